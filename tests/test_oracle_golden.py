@@ -1,0 +1,404 @@
+"""Pins the CPU oracle against every known-answer vector and identity the
+reference's own tests hold for the hot path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import _ptr
+from pdesolver_jl_b200 import mesh as pmesh
+from pdesolver_jl_b200 import sbp
+
+G = 1.4
+L = oracle.lib()
+
+
+def pressure(q):
+    q = np.asarray(q, float)
+    return L.orc_calc_pressure(len(q) - 2, G, _ptr(q))
+
+
+def euler_flux(q, n):
+    q, n = np.asarray(q, float), np.asarray(n, float)
+    F = np.zeros(len(q))
+    L.orc_euler_flux(len(q) - 2, G, _ptr(q), _ptr(n), _ptr(F))
+    return F
+
+
+def roe(qL, qR, n):
+    qL, qR, n = (np.asarray(a, float) for a in (qL, qR, n))
+    F = np.zeros(len(qL))
+    L.orc_roe_solver(len(qL) - 2, G, _ptr(qL), _ptr(qR), _ptr(n), _ptr(F))
+    return F
+
+
+def ir(qL, qR, n):
+    qL, qR = np.asarray(qL, float), np.asarray(qR, float)
+    n = np.asfortranarray(np.asarray(n, float))
+    dim = len(qL) - 2
+    ndir = 1 if n.ndim == 1 else n.shape[1]
+    F = np.zeros((len(qL), ndir), order="F")
+    L.orc_ir_flux(dim, G, _ptr(qL), _ptr(qR), _ptr(n), ndir, _ptr(F))
+    return F[:, 0] if n.ndim == 1 else F
+
+
+def irslf(qL, qR, n):
+    qL, qR, n = (np.asarray(a, float) for a in (qL, qR, n))
+    F = np.zeros(len(qL))
+    L.orc_irslf_flux(len(qL) - 2, G, _ptr(qL), _ptr(qR), _ptr(n), _ptr(F))
+    return F
+
+
+# --- test/euler/test_lowlevel.jl:491-521 -------------------------------------
+def test_pressure_and_flux_2d():
+    q = [1.0, 2.0, 3.0, 7.0]
+    assert abs(pressure(q) - 0.2) < 1e-14
+    assert np.allclose(euler_flux(q, [1.0, 0.0]), [2.0, 4.2, 6, 14.4], atol=1e-14, rtol=0)
+
+
+# --- test/euler/test_3d.jl:163-201 -------------------------------------------
+def test_pressure_and_flux_3d():
+    q = [1.0, 2, 3, 4, 15]
+    assert abs(pressure(q) - 0.2) < 1e-12
+    assert np.allclose(euler_flux(q, [1, 0, 0]), [2, 4.2, 6, 8, 30.4], atol=1e-12, rtol=0)
+    assert np.allclose(euler_flux(q, [0, 1, 0]), [3, 6, 9.2, 12, 45.6], atol=1e-12, rtol=0)
+    assert np.allclose(euler_flux(q, [0, 0, 1]), [4, 8, 12, 16.2, 60.8], atol=1e-12, rtol=0)
+
+
+# --- test/euler/test_lowlevel.jl:626-650 --------------------------------------
+def test_isentropic_vortex_point():
+    s = np.zeros(4)
+    L.orc_isentropic_vortex(2, G, 287.058, _ptr(np.array([1.0, 0.0])), _ptr(s))
+    assert np.allclose(s, [2.0, 0.0, -1.3435, 2.236960], atol=1e-4, rtol=0)
+
+
+# --- test/euler/test_lowlevel.jl:94-146 ---------------------------------------
+def test_ir_variables():
+    q = np.array([1.0, 2.0, 3.0, 7.0])
+    v_analytic = np.array([-2 * 4.99528104378295, 4.0, 6, -2 * 1])
+    w = np.zeros(4)
+    L.orc_convert_to_ir(2, G, _ptr(q), _ptr(w))
+    assert np.linalg.norm(w - v_analytic / (G - 1)) < 1e-12
+    # in-place operation is allowed by the reference
+    q2 = q.copy()
+    L.orc_convert_to_ir(2, G, _ptr(q2), _ptr(q2))
+    assert np.linalg.norm(q2 - v_analytic / (G - 1)) < 1e-12
+
+
+def test_ira0_is_symmetric_dq_dw():
+    """getIRA0 = dq/dw (IR_stab.jl:15-110): check against finite differences of
+    the inverse map w(q)."""
+    for q in ([1.0, 0.3, -0.2, 2.0], [1.1, 0.3, -0.2, 0.4, 2.5]):
+        q = np.array(q)
+        nd = len(q)
+        A0 = np.zeros((nd, nd), order="F")
+        L.orc_ira0(nd - 2, G, _ptr(q), _ptr(A0))
+        assert np.allclose(A0, A0.T, atol=1e-13)
+        J = np.zeros((nd, nd))      # dw/dq
+        for j in range(nd):
+            dq = np.zeros(nd)
+            dq[j] = 1e-6
+            wp, wm = np.zeros(nd), np.zeros(nd)
+            L.orc_convert_to_ir(nd - 2, G, _ptr(q + dq), _ptr(wp))
+            L.orc_convert_to_ir(nd - 2, G, _ptr(q - dq), _ptr(wm))
+            J[:, j] = (wp - wm) / 2e-6
+        assert np.allclose(A0 @ J, np.eye(nd), atol=1e-7)
+
+
+# --- test/euler/test_lowlevel.jl:529-617, test_dg.jl:11-62 --------------------
+def test_roe_consistency_and_bcs():
+    q = np.array([1.0, 2.0, 3.0, 7.0])
+    nrm = np.array([1.0, 0.0])          # dxidx^T*[1,0] for element 1 of tri2l
+    assert np.allclose(roe(q, q, nrm), euler_flux(q, nrm), atol=1e-13)
+    op = sbp.build_operator(2, 1)
+    m = pmesh.two_element_mesh(op)
+    P = oracle.Problem(m, op, {"BC1_name": "isentropicVortexBC"})
+    coords = np.array([1.0, 0.0])
+    qv = np.zeros(4)
+    L.orc_isentropic_vortex(2, G, 287.058, _ptr(coords), _ptr(qv))
+    F = np.zeros(4)
+    L.orc_bc_flux(P.ref(), oracle.BC_IDS["isentropicVortexBC"], _ptr(qv), _ptr(coords), _ptr(nrm), _ptr(F))
+    assert np.allclose(F, euler_flux(qv, nrm), atol=1e-13)
+    qw = qv.copy()
+    qw[2] = 0          # flow parallel to the wall x = const
+    L.orc_bc_flux(P.ref(), oracle.BC_IDS["noPenetrationBC"], _ptr(qw), _ptr(coords), _ptr(nrm), _ptr(F))
+    qproj = qw.copy()
+    qproj[1] = 0.0
+    assert np.allclose(F, euler_flux(qproj, nrm), atol=1e-13)
+    q3 = np.array([1.0, 2, 3, 4, 15])
+    n3 = np.array([0.3, -0.2, 0.9])
+    assert np.allclose(roe(q3, q3, n3), euler_flux(q3, n3), atol=1e-13)
+
+
+# --- test/euler/test_flux.jl:314-367 (testRoe) --------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_roe_upwinding(dim):
+    if dim == 2:
+        qL, nrm = np.array([1.0, 2.0, 3.0, 7.0]), np.array([1.0, 0.0])
+        qI = np.array([1.0, 1.0, 1.0, 7.0])
+    else:
+        qL, nrm = np.array([1.0, 2, 3, 4, 15]), np.array([1.0, 0.0, 0.0])
+        qI = np.array([1.0, 1, 1, 1, 15])
+    qR = qL + 1
+    assert np.linalg.norm(roe(qL, qR, nrm) - euler_flux(qL, nrm)) < 1e-13
+    f = roe(qR, qL, nrm)
+    assert np.linalg.norm(f - euler_flux(qR, nrm)) < 1e-13
+    assert np.linalg.norm(f + roe(qL, qR, -nrm)) < 1e-13
+    assert np.linalg.norm(roe(qI, qI + 1, nrm) + roe(qI + 1, qI, -nrm)) < 1e-13
+
+
+# --- test/euler/test_flux.jl:4-16,87-111: independent slow IR flux -------------
+def _logmean(aL, aR):
+    xi = aL / aR
+    f = (xi - 1) / (xi + 1)
+    u = f * f
+    if u < 1e-2:
+        F = 1.0 + u / 3.0 + u * u / 5.0 + u * u * u / 7.0
+    else:
+        F = np.log(xi) / 2.0 / f
+    return (aL + aR) / (2 * F)
+
+
+def _ir_flux_slow(qL, qR, nrm):
+    pL, pR = pressure(qL), pressure(qR)
+    z5_ln = _logmean(np.sqrt(qL[0] * pL), np.sqrt(qR[0] * pR))
+    z1L, z1R = np.sqrt(qL[0] / pL), np.sqrt(qR[0] / pR)
+    rho_hat = 0.5 * (z1L + z1R) * z5_ln
+    z1_avg = 0.5 * (z1L + z1R)
+    u_hat = 0.5 * (z1L * qL[1] / qL[0] + z1R * qR[1] / qR[0]) / z1_avg
+    v_hat = 0.5 * (z1L * qL[2] / qL[0] + z1R * qR[2] / qR[0]) / z1_avg
+    p1_hat = 0.5 * (np.sqrt(qL[0] * pL) + np.sqrt(qR[0] * pR)) / z1_avg
+    z1_ln = _logmean(z1L, z1R)
+    p2_hat = (G + 1) * z5_ln / (2 * G * z1_ln) + (G - 1) * 0.5 * (np.sqrt(qL[0] * pL) + np.sqrt(qR[0] * pR)) / (2 * G * z1_avg)
+    h_hat = G * p2_hat / (rho_hat * (G - 1)) + 0.5 * (u_hat * u_hat + v_hat * v_hat)
+    fx = np.array([rho_hat * u_hat, rho_hat * u_hat * u_hat + p1_hat, rho_hat * u_hat * v_hat, rho_hat * u_hat * h_hat])
+    fy = np.array([rho_hat * v_hat, rho_hat * u_hat * v_hat, rho_hat * v_hat * v_hat + p1_hat, rho_hat * v_hat * h_hat])
+    return fx * nrm[0] + fy * nrm[1]
+
+
+def test_ir_flux_against_slow_version():
+    qL = np.array([1.0, 2.0, 3.0, 7.0])
+    qR = qL + 1
+    nrm = np.array([1.0, 2.0])
+    assert np.allclose(ir(qL, qR, nrm), _ir_flux_slow(qL, qR, nrm), atol=1e-12, rtol=0)
+    # logavg: both branches of the series switch agree
+    for a, b in [(1.0, 1.0 + 1e-9), (1.0, 1.06), (1.0, 1.07), (2.0, 0.3)]:
+        exact = (a - b) / np.log(a / b)
+        assert abs(L.orc_logavg(a, b) - exact) < 1e-12 * max(1.0, abs(exact)) + 1e-7 * (abs(a - b) < 1e-8)
+
+
+# --- test/euler/test_flux.jl:26-79: symmetry / antisymmetry / consistency / multi-D
+@pytest.mark.parametrize("dim", [2, 3])
+def test_two_point_flux_properties(dim):
+    rng = np.random.default_rng(5)
+    if dim == 2:
+        qL, nrm = np.array([1.0, 2.0, 3.0, 7.0]), np.array([1.0, 1.0])
+    else:
+        qL, nrm = np.array([1.0, 2, 3, 4, 15]), np.array([1.0, 1, 1])
+    qR = qL + 1
+    assert np.allclose(ir(qL, qR, nrm), ir(qR, qL, nrm), atol=1e-12)
+    assert np.allclose(ir(qL, qR, nrm), -ir(qR, qL, -nrm), atol=1e-12)
+    assert np.allclose(ir(qL, qL, nrm), euler_flux(qL, nrm), atol=1e-12)
+    nD = np.asfortranarray(rng.random((dim, dim)))
+    FD = ir(qL, qR, nD)
+    for i in range(dim):
+        assert np.allclose(FD[:, i], ir(qL, qR, nD[:, i].copy()), atol=1e-13)
+    # IRSLF: consistent, conservative under (swap, -n), and dissipative in entropy
+    assert np.allclose(irslf(qL, qL, nrm), euler_flux(qL, nrm), atol=1e-12)
+    assert np.allclose(irslf(qL, qR, nrm), -irslf(qR, qL, -nrm), atol=1e-11)
+    wL, wR = np.zeros(dim + 2), np.zeros(dim + 2)
+    L.orc_convert_to_ir(dim, G, _ptr(qL), _ptr(wL))
+    L.orc_convert_to_ir(dim, G, _ptr(qR), _ptr(wR))
+    assert (wL - wR) @ (irslf(qL, qR, nrm) - ir(qL, qR, nrm)) >= 0
+
+
+# --- test/euler/test_lowlevel.jl:685-827: integral-level goldens (tri2l mesh) --
+def _tri2l(kind):
+    op = sbp.build_operator(2, 1, kind)
+    m = pmesh.two_element_mesh(op)
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "FreeStreamBC", "Ma": 0.5, "aoa": 45.0}
+    P = oracle.Problem(m, op, opts)
+    q = np.zeros(P.shape, order="F")
+    q[:] = np.array([1.0, 0.35355, 0.35355, 2.0])[:, None, None]   # ICRho1E2U3
+    return op, m, P, q
+
+
+def test_golden_flux_parametric_and_volume_blocks():
+    op, m, P, q = _tri2l("gamma")
+    fp = P.euler_flux_parametric(q)
+    # reference element 2 is our element index 1, element 1 is index 0
+    for i in range(3):
+        assert np.allclose(fp[:, i, 0, 1], [0.0, -0.750001, 0.750001, 0.0], atol=1e-5)
+        assert np.allclose(fp[:, i, 1, 1], [0.35355, 0.12499, 0.874999, 0.972263], atol=1e-5)
+        assert np.allclose(fp[:, i, 0, 0], [0.35355, 0.874999, 0.124998, .972263], atol=1e-5)
+        assert np.allclose(fp[:, i, 1, 0], [0.0, 0.750001, -0.750001, 0.0], atol=1e-5)
+    res = P.volume_integrals(q)
+    el1_res = np.array([[-0.35355, 0, 0.35355], [-0.874999, 0.750001, 0.124998],
+                        [-0.124998, -0.750001, 0.874999], [-0.972263, 0, 0.972263]])
+    el2_res = np.array([[-0.35355, 0.35355, 0], [-0.124998, 0.874999, -0.75001],
+                        [-0.874999, 0.124998, 0.75001], [-0.972263, 0.972263, 0]])
+    assert np.allclose(res[:, :, 1], el1_res, atol=1e-4)
+    assert np.allclose(res[:, :, 0], el2_res, atol=1e-4)
+    assert np.allclose(P.volume_integrals(q, precompute=False), res, atol=1e-14)
+
+
+def test_golden_boundary_flux_and_blocks():
+    op, m, P, q = _tri2l("gamma")
+    # the golden bndryflux of a uniform state is the Euler flux along the outward normal
+    P2 = oracle.Problem(m, op, {"BC1_name": "noPenetrationBC"})
+    F = np.zeros(4)
+    gold = {0: [-0.35355, -0.874999, -0.124998, -0.972263], 1: [-0.35355, -0.124998, -0.874999, -0.972263],
+            2: [0.35355, 0.124998, 0.874999, 0.972263], 3: [0.35355, 0.874999, 0.124998, 0.972263]}
+    for b in range(4):
+        n = np.ascontiguousarray(m.nrm_bndry[:, 0, b])
+        assert np.allclose(euler_flux(q[:, 0, 0], n), gold[b], atol=1e-5)
+    # boundary integral of that (constant) flux: -R^T W f, independent of the face rule
+    bf = np.zeros((4, op.face.numnodes, 4), order="F")
+    for b in range(4):
+        bf[:, :, b] = np.array(gold[b])[:, None]
+    res = np.zeros(P.shape, order="F")
+    R = sbp.face_matrices(op)
+    for b in range(4):
+        e, f = int(m.bndryfaces[b]["element"]), int(m.bndryfaces[b]["face"])
+        res[:, :, e] -= bf[:, :, b] @ np.diag(op.face.wface) @ R[f]
+    el1_res = np.array([[0.35355, 0, -0.35355], [0.124998, -0.750001, -0.874999],
+                        [0.874999, 0.750001, -0.124998], [0.972263, 0, -0.972263]])
+    el2_res = np.array([[0.35355, -0.35355, 0], [0.874999, -0.124998, 0.750001],
+                        [0.124998, -0.874999, -0.750001], [0.972263, -0.972263, 0]])
+    assert np.allclose(res[:, :, 1], el1_res, atol=1e-5)
+    assert np.allclose(res[:, :, 0], el2_res, atol=1e-5)
+    # and the oracle's own interpolate -> BC flux -> integrate pass agrees when
+    # the BC state equals the interior state (FreeStream, Ma=0.5, aoa=45deg)
+    qfs = P.exact_state("ICFreeStream")
+    resb, bflux = P.boundary_integrals(qfs)
+    for b in range(4):
+        n = np.ascontiguousarray(m.nrm_bndry[:, 0, b])
+        assert np.allclose(bflux[:, 0, b], euler_flux(qfs[:, 0, 0], n), atol=1e-13)
+
+
+# --- test_lowlevel.jl:813-821, test_dg.jl:71-128: uniform flow => zero residual --
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_uniform_flow_zero_residual(dim, p):
+    op = sbp.build_operator(dim, p)
+    m = pmesh.structured_mesh(op, 3, shuffle_seed=1)
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "FreeStreamBC", "Ma": 0.4, "aoa": 10.0}
+    P = oracle.Problem(m, op, opts)
+    q = P.exact_state("ICFreeStream")
+    qb = P.interpolate_boundary(q)
+    assert np.abs(qb - q[:, :1, :1]).max() < 1e-13        # exact interpolation (test_dg.jl:79-84)
+    assert np.abs(P.eval_residual(q)).max() < 1e-13
+    assert np.abs(P.eval_residual(q, precompute=False)).max() < 1e-13
+
+
+# --- test/euler/test_flux.jl:255-296: precompute == no-precompute ---------------
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_precompute_equals_nopre(dim, p):
+    op = sbp.build_operator(dim, p)
+    m = pmesh.structured_mesh(op, 3, shuffle_seed=2, domain=(0.0, 1.0))
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}
+    P = oracle.Problem(m, op, opts)
+    q = P.exact_state("ICExp")
+    assert np.linalg.norm(P.volume_integrals(q) - P.volume_integrals(q, False)) < 1e-13
+    assert np.linalg.norm(P.face_integrals(q) - P.face_integrals(q, False)) < 1e-13
+    assert np.linalg.norm(P.eval_residual(q) - P.eval_residual(q, False)) < 1e-13
+
+
+# --- test/euler/test_flux.jl:167-234: split form identities ----------------------
+def test_split_form_identities():
+    op = sbp.build_operator(2, 2, "diage")
+    m = pmesh.structured_mesh(op, 3, domain=(0.0, 1.0))
+    opts = {"Flux_name": "IRSLFFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2,
+            "BC1_name": "FreeStreamBC", "Ma": 0.4, "aoa": 5.0}
+    P = oracle.Problem(m, op, opts)
+    q = P.exact_state("ICExp")
+    res = P.volume_integrals(q)
+    # S skew, F* symmetric => 1^T (S o F*) 1 = 0 per element and equation
+    assert np.abs(res.sum(axis=1)).max() < 1e-13
+    # constant field => zero residual for the entropy-stable scheme (test_flux.jl:236-253)
+    qf = P.exact_state("ICFreeStream")
+    assert np.abs(P.eval_residual(qf)).max() < 1e-12
+
+
+# --- test/euler/test_ESS.jl:722-740: IR flux + diag-E type-1 face integrals conserve entropy
+def test_entropy_conservation_diagE():
+    op = sbp.build_operator(2, 2, "diage")
+    m = pmesh.structured_mesh(op, 3)
+    opts = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2,
+            "BC1_name": "FreeStreamBC", "Ma": 0.4}
+    P = oracle.Problem(m, op, opts)
+    q = P.exact_state("ICIsentropicVortex")
+    q *= 1 + 1e-2 * np.sin(np.arange(q.size).reshape(q.shape, order="F"))
+    w = np.zeros_like(q)
+    for e in range(m.numEl):
+        for j in range(op.numnodes):
+            qq = np.ascontiguousarray(q[:, j, e])
+            ww = np.zeros(4)
+            L.orc_convert_to_ir(2, G, _ptr(qq), _ptr(ww))
+            w[:, j, e] = ww
+    res = P.volume_integrals(q) + P.face_integrals(q, precompute=False)
+    # w^T R = - sum over boundary faces of psi_n; evaluate the boundary term explicitly
+    # psi = rho*u (IR potential flux), so w^T R + sum_bndry wface * psi.n == 0
+    total = np.sum(w * res)
+    R = sbp.face_matrices(op)
+    bterm = 0.0
+    for b in range(m.numBoundaryFaces):
+        e, f = int(m.bndryfaces[b]["element"]), int(m.bndryfaces[b]["face"])
+        qb = q[:, :, e] @ R[f].T
+        for i in range(op.face.numnodes):
+            bterm += op.face.wface[i] * (qb[1:3, i] @ m.nrm_bndry[:, i, b])
+    assert abs(total - bterm) < 1e-12 * max(1.0, abs(bterm))
+
+
+# --- test/euler/test_rk4.jl:23-43: rk4 integrates a quartic exactly ---------------
+def test_rk4_quartic():
+    RHS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double)
+    POST = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+
+    def f(ctx, q, r, t):
+        r[0] = 4 * t ** 3 + 3 * t ** 2 + 2 * t + 1
+        return 0
+    q = np.array([1.0])
+    r = np.zeros(1)
+    ns, st = C.c_int64(0), C.c_int(0)
+    h, t_max = 0.1, 1.0
+    L.orc_rk4.argtypes = [RHS, POST, C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                          C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    t = L.orc_rk4(RHS(f), POST(lambda c, r, n: 1.0), None, h, t_max, 1, _ptr(q), _ptr(r), -1, -1.0, 1,
+                  None, 0, C.byref(ns), C.byref(st))
+    exact = t_max ** 4 + t_max ** 3 + t_max ** 2 + t_max + 1
+    assert abs(q[0] - exact) < 1e-14 * 10
+    assert abs(t - t_max) < 1e-14
+    assert ns.value == 10
+
+
+# --- mesh/operator consistency (test/euler/test_curvilinear.jl:3-118) -------------
+@pytest.mark.parametrize("dim,p,kind", [(2, 1, "omega"), (2, 2, "omega"), (3, 1, "omega"),
+                                        (3, 2, "omega"), (2, 2, "diage")])
+def test_freestream_preservation_operator(dim, p, kind):
+    """(S_x + 0.5 E_x) 1 = 0 with E_x assembled from nrm_face / nrm_bndry."""
+    op = sbp.build_operator(dim, p, kind)
+    m = pmesh.structured_mesh(op, 2, shuffle_seed=3)
+    R = sbp.face_matrices(op)
+    nn = op.numnodes
+    Ex = np.zeros((m.numEl, dim, nn, nn))
+    for k, I in enumerate(m.interfaces):
+        eL, eR, fL, fR, o = (int(I[n]) for n in ("elementL", "elementR", "faceL", "faceR", "orient"))
+        pr = op.face.nbrperm[:, o]
+        for d in range(dim):
+            nL = m.nrm_face[d, :, k]
+            Ex[eL, d] += R[fL].T @ np.diag(nL * op.face.wface) @ R[fL]
+            RR = R[fR][pr, :]
+            Ex[eR, d] += RR.T @ np.diag(-nL * op.face.wface) @ RR
+    for b, B in enumerate(m.bndryfaces):
+        e, f = int(B["element"]), int(B["face"])
+        for d in range(dim):
+            Ex[e, d] += R[f].T @ np.diag(m.nrm_bndry[d, :, b] * op.face.wface) @ R[f]
+    one = np.ones(nn)
+    for e in range(m.numEl):
+        for d in range(dim):
+            Qx = sum(op.Q[:, :, k] * m.dxidx[k, d, 0, e] for k in range(dim))
+            Sx = 0.5 * (Qx - Qx.T)
+            assert abs(one @ Ex[e, d] @ one) < 1e-12
+            assert np.abs(Ex[e, d] - Ex[e, d].T).max() < 1e-12
+            assert np.abs((Sx + 0.5 * Ex[e, d]) @ one).max() < 1e-12
