@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the Euler residual + RK4 hot path (BASELINE.json metric: DOF-residual-evals/s).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
+
+A "step" is one classical RK4 step = 4 fused residual+stage launches.  Default workload at N=1 is
+BASELINE.json configs[2]: 3D Euler, p=2 SBP-Omega tets, Roe flux, ExpBC + SRCExp, 31^3*6 = 178,746 tets =
+9.83 M DOF (the configuration the north-star target is quoted on; at N>1 every rank owns a block of the
+same size -- weak scaling -- so N=8 is the 62^3*6-tet, 78.6 M-DOF partitioned mesh of configs[3]).
+Synthetic structured mesh, ICExp state with a deterministic 1e-3 perturbation; q is resident in HBM for
+`value`; `e2e` goes through the public `rk4(evalResidual, h, t_max, mesh, sbp, eqn, opts)` call with host
+arrays (H2D of eqn.q, D2H of the result and the convergence norms inside the timed region).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dim, degree, per-rank cells per side, IC, h, opts
+    "c3_3d_p2_roe": dict(dim=3, p=2, n=31, ic="ICExp", h=5e-5,
+                         opts={"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
+    "c1_2d_p1_roe": dict(dim=2, p=1, n=50, ic="ICIsentropicVortex", h=1e-3,
+                         opts={"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}),
+    "3d_p1_roe": dict(dim=3, p=1, n=60, ic="ICExp", h=5e-5,
+                      opts={"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
+    "2d_p2_roe": dict(dim=2, p=2, n=1000, ic="ICIsentropicVortex", h=1e-4,
+                      opts={"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}),
+}
+PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def algorithmic_bytes_per_dof(dim, nn, nfn, fused_stage):
+    """compulsory traffic per DOF-residual-evaluation with every array touched once."""
+    nd = dim + 2
+    b_el = 8 * nd * nn * 2 + 8 * dim * dim * nn + 8 * nn + ((dim + 1) / 2) * (8 * dim * nfn + 12)
+    b = b_el / (nd * nn)
+    return b + 24 if fused_stage else b
+
+
+def perturbed(q, amp=1e-3):
+    nd, nn, nE = q.shape
+    k = np.arange(nd)[:, None, None]
+    j = np.arange(nn)[None, :, None]
+    e = np.arange(nE)[None, None, :]
+    return np.asfortranarray(q * (1.0 + amp * np.sin(k + 7.0 * j + 13.0 * e)))
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.1):
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:     # region shorter than the sampling period: use everything we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    smax = float(f[1])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(wl, rank, nranks):
+    import pdesolver_jl_b200 as pd
+    from pdesolver_jl_b200 import ic
+    op = pd.build_operator(wl["dim"], wl["p"], "omega")
+    parts = PARTS[nranks][:wl["dim"]]
+    if nranks > 1 and wl["dim"] == 2:
+        parts = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
+    n = tuple(wl["n"] * p for p in parts)
+    mesh = pd.structured_mesh(op, n, parts=parts, rank=rank)
+    opts = dict(wl["opts"])
+    opts["use_itermax"] = False
+    params = pd.ParamType(opts)
+    q0 = perturbed(ic.ICDict[wl["ic"]](mesh.coords, params))
+    return pd, op, mesh, opts, q0, parts, n
+
+
+def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
+    """The reference's algorithm on the host cores: the oracle port (reference-faithful precompute pass
+    structure, OpenMP over elements/faces) on a bounded sample of the same workload."""
+    import oracle
+    import pdesolver_jl_b200 as pd
+    from pdesolver_jl_b200 import ic
+    op = pd.build_operator(wl["dim"], wl["p"], "omega")
+    n = sample_cells or wl["n"]
+    mesh = pd.structured_mesh(op, n)
+    opts = dict(wl["opts"])
+    P = oracle.Problem(mesh, op, opts)
+    q0 = perturbed(ic.ICDict[wl["ic"]](mesh.coords, pd.ParamType(opts)))
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    h = wl["h"]
+    for _ in range(warmup):
+        P.eval_residual(q0, omp=True)
+    t0 = time.perf_counter()
+    nsteps = max(steps, 1)
+    P.rk4(q0, h, nsteps * h, omp=True)
+    dt = time.perf_counter() - t0
+    ndof = mesh.numDof
+    return ndof * 4 * nsteps / dt, dt / nsteps, cores, ndof, n
+
+
+def run_reference(args, wl, rank, nranks):
+    if rank != 0:
+        return
+    # bounded sample: the per-rank mesh of the B200 arm, a few RK4 steps (~7 s each on 8 cores)
+    steps = min(args.steps, 2)
+    rate, spstep, cores, ndof, n = cpu_reference_rate(wl, steps, min(args.warmup, 1))
+    sample = f"{steps} RK4 steps ({4 * steps} evalResidual) of the {n}^{wl['dim']}-cell mesh ({ndof} DOF), OpenMP"
+    line = {
+        "impl": "reference", "metric": "DOF-residual-evals/sec", "value": rate, "unit": "DOF-evals/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": spstep * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "cells_per_side": n, "dof": ndof,
+                   "note": "CPU port of the reference algorithm (oracle/, Julia reference cannot run here)"},
+        "cpu_baseline": {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "DOF-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_3d_p2_roe", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=None, help="override per-rank cells per side")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-rk-steps", type=int, default=10, help="RK4 steps per public rk4() call in the e2e leg")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.cells:
+        wl["n"] = args.cells
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    nranks = world
+
+    pd, op, mesh, opts, q0, parts, ncells = build_problem(wl, rank, nranks)
+    eqn = pd.EulerData(mesh, op, opts, device=local_rank)
+    L, ctx = eqn._L, eqn._ctx
+    if nranks > 1:
+        ids = [pd.EulerData.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eqn.set_comm(ids[0], rank, nranks)
+    h = wl["h"]
+    ndof = mesh.numDof
+    eqn.q[...] = q0
+    eqn._check(L.pdes_set_q(ctx, eqn.q.ctypes.data_as(ctypes.c_void_p)))
+    stream = torch.cuda.ExternalStream(L.pdes_stream(ctx), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if nranks > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: `value` --------------------------------------------------------------
+    for _ in range(args.warmup):
+        eqn._check(L.pdes_rk4_steps_async(ctx, h, 1))
+    eqn._check(L.pdes_sync(ctx))
+    launches0 = eqn.kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eqn._check(L.pdes_rk4_steps_async(ctx, h, 1))
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    eqn._check(L.pdes_sync(ctx))
+    ms = ev0.elapsed_time(ev1)
+    launches = eqn.kernel_launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if nranks > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([float(ndof)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ndof_total = int(tot.item())
+    else:
+        ndof_total = ndof
+    value = ndof_total * 4 * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg through the public API with host arrays --------------------------------------
+    S = args.e2e_rk_steps
+    e2e_calls = max(2, min(args.steps, 5))
+    eqn.q[...] = q0
+    pd.rk4(pd.evalResidual, h, S * h, mesh, op, eqn, opts)          # warm-up call
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        pd.rk4(pd.evalResidual, h, S * h, mesh, op, eqn, opts)
+    barrier()
+    dt_e2e = time.perf_counter() - t0
+    if nranks > 1:
+        t = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+    e2e_value = ndof_total * 4 * S * e2e_calls / dt_e2e
+    # single evalResidual calls (q up, res down every call)
+    pd.evalResidual(mesh, op, eqn, opts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pd.evalResidual(mesh, op, eqn, opts)
+    barrier()
+    dt_res = (time.perf_counter() - t0) / 3
+
+    if rank != 0:
+        if nranks > 1:
+            dist.destroy_process_group()
+        return
+
+    nn, nfn, dim = op.numnodes, op.face.numnodes, mesh.dim
+    b_stage = algorithmic_bytes_per_dof(dim, nn, nfn, True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dominant kernel = k_residual_roe<EPI_RK>: 4 launches per step; the two norm kernels (one CTA each)
+    # are inside the bracket, so the per-launch duration is slightly over-estimated
+    launch_s = (ms * 1e-3) / (4 * args.steps)
+    achieved = b_stage * ndof * 1e-9 / launch_s
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "DOF-residual-evals/sec", "value": value, "unit": "DOF-evals/s", "n_gpus": nranks,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "dim": dim, "degree": wl["p"], "operator": "SBPOmega",
+                   "flux": opts["Flux_name"], "cells_per_rank": [int(c // p) for c, p in zip(ncells, parts)],
+                   "partition": list(parts), "elements_per_rank": mesh.numEl, "dof_total": ndof_total,
+                   "step": "1 RK4 step = 4 fused residual+stage launches", "delta_t": h,
+                   "l2": "working set (4 state vectors + metrics, %.0f MB) exceeds the 126 MB L2; no flush"
+                         % ((4 * ndof * 8 + mesh.dxidx.nbytes) / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "DOF-evals/s", "h2d_bytes_per_step": int(ndof * 8),
+                "d2h_bytes_per_step": int(ndof * 8 + S * 8), "rk4_steps_per_call": S, "calls": e2e_calls,
+                "api": "rk4(evalResidual, h, t_max, mesh, sbp, eqn, opts)",
+                "evalResidual_call_ms": dt_res * 1e3,
+                "evalResidual_dof_per_s": ndof_total / dt_res},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_residual_roe<EPI_RK>",
+                     "algorithmic_bytes_per_dof": b_stage,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+    }
+    if nranks == 1 and not args.no_cpu_baseline:
+        rate, spstep, cores, nd_s, n_s = cpu_reference_rate(wl, 1, 0)
+        line["cpu_baseline"] = {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port",
+                                "sample": f"1 RK4 step (4 evalResidual) of the same {n_s}^{dim}-cell mesh ({nd_s} DOF), "
+                                          f"oracle port with OpenMP, {spstep:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if nranks > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

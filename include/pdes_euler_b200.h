@@ -1,0 +1,170 @@
+/*
+ * pdes_euler_b200.h -- C ABI of libpdes_euler_b200.so
+ *
+ * Drop-in boundary for PDESolver.jl's Euler hot path on one B200 (sm_100a):
+ *
+ *   evalResidual(mesh, sbp, eqn::EulerData, opts, t)   src/solver/euler/euler.jl:111-175
+ *   rk4(f, h, t_max, mesh, sbp, eqn, opts; res_tol, real_time)
+ *                                                       src/NonlinearSolvers/rk4.jl:144-344,404-410
+ *   startSolutionExchange / finishExchangeData          src/Utils/parallel.jl:29-49,178-208
+ *
+ * The Julia host keeps the PumiInterface mesh, the SummationByParts operators
+ * and the options dictionary; it uploads operator matrices, metrics and
+ * connectivity once (pdes_set_operator / pdes_set_mesh / pdes_set_peer), then
+ * drives pdes_eval_residual or pdes_rk4.  All array arguments are HOST pointers
+ * in the reference's (Julia, column-major) layouts unless the name ends in
+ * _dev.  No torch / CUDA types appear in any signature.  There is no CPU
+ * fallback: every entry point fails with PDES_ERR_CUDA if no sm_100 device is
+ * usable.
+ *
+ * Return convention (reference: Julia exceptions, euler.jl:552-556,598-603,653):
+ *    0  success
+ *   >0  physics error: PDES_ERR_NEG_DENSITY / PDES_ERR_NEG_PRESSURE; element and
+ *       node (index_base applied) via pdes_last_error_location
+ *   <0  usage / CUDA error; text via pdes_last_error
+ */
+#ifndef PDES_EULER_B200_H
+#define PDES_EULER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PdesCtx PdesCtx;
+
+enum {
+  PDES_OK = 0,
+  PDES_ERR_NEG_DENSITY = 1,   /* euler.jl:543-570 checkDensity  */
+  PDES_ERR_NEG_PRESSURE = 2,  /* euler.jl:586-611 checkPressure */
+  PDES_ERR_USAGE = -1,
+  PDES_ERR_CUDA = -2,
+  PDES_ERR_UNSUPPORTED = -3,  /* euler.jl:653,796,855,863 ErrorException for option combos */
+  PDES_ERR_COMM = -4
+};
+
+/* FluxDict names (src/solver/euler/flux.jl) -> ids */
+enum { PDES_FLUX_ROE = 1, PDES_FLUX_IR = 2, PDES_FLUX_IRSLF = 3, PDES_FLUX_STANDARD = 4 };
+/* BCDict names (src/solver/euler/bc.jl:2342-2369) -> ids */
+enum { PDES_BC_ISENTROPIC_VORTEX = 1, PDES_BC_EXP = 2, PDES_BC_FREESTREAM = 3, PDES_BC_NOPENETRATION = 4 };
+/* SRCDict names (src/solver/euler/source.jl) -> ids */
+enum { PDES_SRC_NONE = 0, PDES_SRC_EXP = 1 };
+
+/* ODLCommonTools Interface / Boundary records as Julia lays them out
+ * (constructor order: src/solver/euler/shock_capturing_mesh.jl:248). */
+typedef struct { uint32_t elementL, elementR; uint8_t faceL, faceR, orient, pad; } PdesInterface; /* 12 B */
+typedef struct { uint32_t element; uint8_t face, pad[3]; } PdesBoundary;                          /* 8 B  */
+
+typedef struct {
+  int32_t dim;                  /* mesh.dim: 2 | 3                                  */
+  int32_t nn;                   /* mesh.numNodesPerElement = sbp.numnodes           */
+  int32_t nfn;                  /* mesh.numNodesPerFace = sbpface.numnodes          */
+  int32_t ss;                   /* sbpface.stencilsize (dense faces); 1 for sparse  */
+  int32_t norient;              /* size(sbpface.nbrperm, 2)                         */
+  int32_t sparse_face;          /* 1: SparseFace of SBPDiagonalE operators          */
+  int32_t index_base;           /* 1 when called from Julia, 0 from C/Python        */
+  int32_t device;               /* CUDA device ordinal                              */
+  int64_t nE, nF, nB;           /* numEl, numInterfaces, numBoundaryFaces           */
+  int32_t numBC;                /* mesh.numBC                                       */
+  int32_t npeers;               /* mesh.npeers                                      */
+  int32_t volume_integral_type; /* opts["volume_integral_type"]: 1 | 2              */
+  int32_t face_integral_type;   /* opts["face_integral_type"]: 1                    */
+  int32_t flux_id;              /* opts["Flux_name"]                                */
+  int32_t volume_flux_id;       /* opts["Volume_flux_name"] (type 2 only)           */
+  int32_t src_id;               /* opts["SRCname"]                                  */
+  int32_t check_density;        /* opts["check_density"]                            */
+  int32_t check_pressure;       /* opts["check_pressure"]                           */
+  int32_t reserved;
+  double gamma, R;              /* params.gamma, params.R   (types.jl:241-244)      */
+  double Ma, aoa;               /* params.Ma, params.aoa [rad] (types.jl:246-247)   */
+  double rho_free, E_free;      /* params.rho_free, params.E_free (types.jl:249-252)*/
+} PdesConfig;
+
+/* Timings: same field meaning as the reference's Timings struct
+ * (src/Utils/Utils.jl:567-613), seconds accumulated since pdes_create, measured
+ * with CUDA events on the library's streams. */
+typedef struct {
+  double t_send, t_dataprep, t_volume, t_face, t_sharedface, t_source, t_func, t_timemarch,
+         t_wait, t_allreduce;
+  int64_t n_residual_evals, n_kernel_launches;
+} PdesTimings;
+
+int pdes_create(const PdesConfig *cfg, PdesCtx **out);
+void pdes_destroy(PdesCtx *ctx);
+const char *pdes_last_error(const PdesCtx *ctx);       /* ctx may be NULL: last global error */
+int pdes_last_error_location(const PdesCtx *ctx, int64_t *element, int64_t *node);
+
+/* sbp.Q[nn,nn,dim], sbp.w[nn], sbpface.interp[ss,nfn], sbpface.perm[ss,dim+1]
+ * (sparse faces: [nfn,dim+1]), sbpface.nbrperm[nfn,norient], sbpface.wface[nfn] */
+int pdes_set_operator(PdesCtx *ctx, const double *Q, const double *w, const double *interp,
+                      const int64_t *perm, const int64_t *nbrperm, const double *wface);
+
+/* mesh.dxidx[dim,dim,nn,nE], jac[nn,nE], coords[dim,nn,nE], nrm_face[dim,nfn,nF],
+ * nrm_bndry[dim,nfn,nB], coords_bndry[dim,nfn,nB], interfaces[nF], bndryfaces[nB],
+ * bndry_offsets[numBC+1] (BC i owns [offsets[i], offsets[i+1])), bc_ids[numBC].
+ * Valid until the metrics change (reference: updateMetricDependents, types.jl:898-915):
+ * call again to invalidate. */
+int pdes_set_mesh(PdesCtx *ctx, const double *dxidx, const double *jac, const double *coords,
+                  const double *nrm_face, const double *nrm_bndry, const double *coords_bndry,
+                  const PdesInterface *interfaces, const PdesBoundary *bndryfaces,
+                  const int64_t *bndry_offsets, const int32_t *bc_ids);
+
+/* One SharedFaceData (Utils/parallel_types.jl:70-183): peer rank, its
+ * bndries_local[nfaces], shared interfaces[nfaces] (elementL local) and
+ * mesh.nrm_sharedface[peer][dim,nfn,nfaces]. */
+int pdes_set_peer(PdesCtx *ctx, int32_t peer_idx, int32_t peer_rank, int64_t nfaces,
+                  const PdesBoundary *bndries_local, const PdesInterface *shared_interfaces,
+                  const double *nrm_sharedface);
+
+/* Multi-GPU: NCCL communicator from a 128-byte ncclUniqueId the host broadcast
+ * (replaces mesh.comm / MPI.Isend/Irecv!, parallel_types.jl:620-684). */
+int pdes_get_unique_id(uint8_t id_out[128]);
+int pdes_set_comm(PdesCtx *ctx, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* Test hook when no second GPU exists: expose the packed send buffer and
+ * inject the receive buffer by hand (host pointers, [nd,nfn,nfaces]). */
+int pdes_pack_send(PdesCtx *ctx, int32_t peer_idx, double *q_send_out);
+int pdes_inject_recv(PdesCtx *ctx, int32_t peer_idx, const double *q_recv);
+
+/* eqn.q / eqn.res [nd,nn,nE] (alias eqn.q_vec / eqn.res_vec for DG). */
+int pdes_set_q(PdesCtx *ctx, const double *q);
+int pdes_get_q(PdesCtx *ctx, double *q);
+int pdes_get_res(PdesCtx *ctx, double *res);
+double *pdes_q_dev(PdesCtx *ctx);      /* device views, for callers that keep state in HBM */
+double *pdes_res_dev(PdesCtx *ctx);
+/* copy eqn.q from a DEVICE pointer (same layout), asynchronously on the library's compute stream */
+int pdes_set_q_dev(PdesCtx *ctx, const double *q_dev);
+/* page-lock / unlock a host array the caller will pass to pdes_set_q / pdes_get_q / pdes_get_res repeatedly
+ * (eqn.q, eqn.res), so that the copies run at full PCIe rate */
+int pdes_pin_host(void *ptr, int64_t bytes);
+int pdes_unpin_host(void *ptr);
+/* the library's compute stream (a cudaStream_t) so that a caller can bracket launches with its own events */
+void *pdes_stream(PdesCtx *ctx);
+
+/* evalResidual: q -> res (no Minv), synchronous.  euler.jl:111-175 */
+int pdes_eval_residual(PdesCtx *ctx, double t);
+/* same, but returns after enqueueing; pdes_sync reports errors (bench / overlap) */
+int pdes_eval_residual_async(PdesCtx *ctx, double t);
+int pdes_sync(PdesCtx *ctx);
+
+/* rk4 (rk4.jl:144-344) on the resident q.  itermax < 0: use_itermax=false.
+ * norms_out[norms_cap] receives the stage-1 norm of every executed step (the
+ * convergence.dat column); nsteps_out the number of executed step heads;
+ * t_out the value rk4 returns.  With itermax, q is left at x_old + (h/2) k1
+ * exactly as the reference leaves it. */
+int pdes_rk4(PdesCtx *ctx, double h, double t_max, int64_t itermax, double res_tol,
+             int32_t real_time, double *t_out, double *norms_out, int64_t norms_cap,
+             int64_t *nsteps_out);
+/* n plain RK4 steps, no host sync inside (bench inner loop; CUDA-graph replay) */
+int pdes_rk4_steps_async(PdesCtx *ctx, double h, int64_t nsteps);
+
+/* eqn.Minv[nd,nn,nE] as the reference computes it (mass_matrix.jl:20-44) */
+int pdes_get_minv(PdesCtx *ctx, double *Minv);
+int pdes_get_timings(PdesCtx *ctx, PdesTimings *out);
+/* number of CUDA kernels this library has launched on ctx so far */
+int64_t pdes_kernel_launch_count(const PdesCtx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,256 @@
+// Node-level Euler physics as device functions (fp64).  Each function states
+// the reference routine whose arithmetic it reproduces (paths relative to
+// /root/reference/src/solver/euler).  Templated on the spatial dimension and a
+// scalar type T so the same code serves the real residual and, later, the
+// dual-number (Jacobian-vector) residual.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace pdes {
+
+template <int DIM> struct Dims { static constexpr int ND = DIM + 2; };
+
+__device__ __forceinline__ double absv(double x) { return fabs(x); }   // Utils/complexify.jl:25-44 absvalue
+__device__ __forceinline__ double maxv(double a, double b) { return fmax(a, b); }
+
+// euler_funcs.jl:856-863 / 897-903 calcPressure
+template <int DIM, typename T>
+__device__ __forceinline__ T calc_pressure(const T* q, double gami) {
+  T ke = q[1] * q[1];
+#pragma unroll
+  for (int d = 1; d < DIM; ++d) ke += q[1 + d] * q[1 + d];
+  return gami * (q[DIM + 1] - 0.5 * ke / q[0]);
+}
+
+// euler_funcs.jl:512-536 / 749-774 calcEulerFlux
+template <int DIM, typename T>
+__device__ __forceinline__ void euler_flux(const T* q, const double* n, double gami, T* F) {
+  T press = calc_pressure<DIM>(q, gami);
+  T U = q[1] * n[0];
+#pragma unroll
+  for (int d = 1; d < DIM; ++d) U += q[1 + d] * n[d];
+  U = U / q[0];
+  F[0] = q[0] * U;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) F[1 + d] = q[1 + d] * U + n[d] * press;
+  F[DIM + 1] = (q[DIM + 1] + press) * U;
+}
+
+// bc_solvers.jl:29-187 RoeSolver + :207-420 calcSAT:
+//   flux = 0.5*(|A_hat| - A_hat)(q - qg) + F_euler(q, n), eigenvalue floors 0.025*rhoA
+template <int DIM, typename T>
+__device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* n, double gamma, T* flux) {
+  constexpr int ND = DIM + 2;
+  const double gami = gamma - 1.0;
+  const double sat_Vn = 0.025, sat_Vl = 0.025;
+  T fac = 1.0 / q[0];
+  T vL[DIM], vR[DIM];
+  T phi = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { vL[d] = q[1 + d] * fac; phi += vL[d] * vL[d]; }
+  phi = 0.5 * phi;
+  T HL = gamma * q[DIM + 1] * fac - gami * phi;
+  // p = gami*(E - rho*phi): reuse for the Euler flux of the left state
+  T pressL = gami * (q[DIM + 1] - q[0] * phi);
+  fac = 1.0 / qg[0];
+  phi = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { vR[d] = qg[1 + d] * fac; phi += vR[d] * vR[d]; }
+  phi = 0.5 * phi;
+  T HR = gamma * qg[DIM + 1] * fac - gami * phi;
+  T sqL = sqrt(q[0]), sqR = sqrt(qg[0]);
+  fac = 1.0 / (sqL + sqR);
+  T v[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) v[d] = (sqL * vL[d] + sqR * vR[d]) * fac;
+  T H = (sqL * HL + sqR * HR) * fac;
+  T dq[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) dq[i] = q[i] - qg[i];
+
+  // ---- calcSAT ----
+  double dA2 = 0.0;
+  T Un = 0.0;
+  phi = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { dA2 += n[d] * n[d]; phi += v[d] * v[d]; Un += v[d] * n[d]; }
+  double dA = sqrt(dA2);
+  phi = 0.5 * phi;
+  T a = sqrt(gami * (H - phi));
+  T l1 = Un + dA * a, l2 = Un - dA * a, l3 = Un;
+  T rhoA = absv(Un) + dA * a;
+  l1 = 0.5 * (maxv(absv(l1), sat_Vn * rhoA) - l1);
+  l2 = 0.5 * (maxv(absv(l2), sat_Vn * rhoA) - l2);
+  l3 = 0.5 * (maxv(absv(l3), sat_Vl * rhoA) - l3);
+  T e1 = phi * dq[0];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) e1 -= v[d] * dq[1 + d];
+  e1 += dq[DIM + 1];
+  T e2 = -Un * dq[0];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) e2 += n[d] * dq[1 + d];
+  T tmp1 = 0.5 * (l1 + l2) - l3;
+  T tmp2 = gami / (a * a);
+  T tmp3 = 1.0 / (dA * dA);
+  T tmp4 = 0.5 * (l1 - l2) / (dA * a);
+  // sat = l3*dq + tmp1*(tmp2*E1dq + tmp3*E2dq) + tmp4*(E3dq + gami*E4dq)
+  T c1 = tmp1 * tmp2 * e1 + tmp4 * e2;      // multiplies [1, v, H]
+  T c2 = tmp1 * tmp3 * e2 + tmp4 * gami * e1;  // multiplies [0, n, Un]
+
+  // ---- Euler flux of the left state ----
+  T U = vL[0] * n[0];
+#pragma unroll
+  for (int d = 1; d < DIM; ++d) U += vL[d] * n[d];
+  flux[0] = l3 * dq[0] + c1 + q[0] * U;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) flux[1 + d] = l3 * dq[1 + d] + c1 * v[d] + c2 * n[d] + (q[1 + d] * U + n[d] * pressL);
+  flux[DIM + 1] = l3 * dq[DIM + 1] + c1 * H + c2 * Un + (q[DIM + 1] + pressL) * U;
+}
+
+// common_funcs.jl:25-78 calcIsentropicVortex (2D), :204-283 (3D)
+template <int DIM>
+__device__ inline void isentropic_vortex(const double* c, double gamma, double R, double* sol) {
+  const double cv = R / (gamma - 1.0);
+  const double r_in = 1, rho_in = 2, M_in = 0.95, p_in = 1 / gamma;
+  double x = c[0], y = c[1];
+  double theta, theta3 = 0.0;
+  if (DIM == 3) {
+    double z = c[2];
+    const double phi_z = M_PI / 4;
+    double theta1 = atan2(z, x);
+    double phi2 = 0.5 * M_PI - theta1;
+    double r_xz = sqrt(x * x + z * z);
+    x = r_xz * sin(phi_z + phi2);
+    theta3 = theta1 + phi_z + phi2 - 0.5 * M_PI;
+    theta = atan2(x, y);
+  } else {
+    theta = atan2(y, x);
+  }
+  double r = sqrt(x * x + y * y);
+  double tmp1 = ((gamma - 1) / 2) * M_in * M_in;
+  double rho_r = rho_in * pow(1 + tmp1 * (1 - (r_in * r_in) / (r * r)), 1 / (gamma - 1));
+  double p_r = p_in * pow(rho_r / rho_in, gamma);
+  double a_r = sqrt(gamma * p_r / rho_r);
+  double M_r = sqrt((2 / (gamma - 1)) * (pow(rho_in / rho_r, gamma - 1)) * (1 + tmp1) - 2 / (gamma - 1));
+  double U_r = M_r * a_r;
+  double e_r = cv * p_r / (rho_r * R);
+  double E_r = rho_r * e_r + 0.5 * rho_r * U_r * U_r;
+  sol[0] = rho_r;
+  if (DIM == 2) {
+    sol[1] = rho_r * (U_r * sin(theta));
+    sol[2] = rho_r * (-U_r * cos(theta));
+  } else {
+    double v_r = U_r * sin(theta), u_r = -U_r * cos(theta);
+    double w_r = u_r * sin(theta3);
+    u_r = u_r * cos(theta3);
+    sol[1] = rho_r * u_r;
+    sol[2] = rho_r * v_r;
+    sol[3] = rho_r * w_r;
+  }
+  sol[DIM + 1] = E_r;
+}
+
+// source.jl:85-96 MMSExp constants; common_funcs.jl:841-857 / 899-936 calcExp
+struct MMSExp {
+  static constexpr double a = 1.0 / 500, b = 0.01, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 20,
+                          d1 = 1, d2 = 0.05, d3 = 0.15, d4 = 0.25, d5 = 1;
+};
+
+template <int DIM>
+__device__ inline void calc_exp(const double* c, double gamma, double* q) {
+  const double gamma_1 = gamma - 1.0;
+  if (DIM == 2) {
+    double x = c[0], y = c[1];
+    const double af = 1.0 / 5, b = 0.01;
+    q[0] = exp(af * x * y + b);
+    q[1] = exp(af * 2 * x * y + b);
+    q[2] = exp(af * 3 * x * y + b);
+    q[3] = (1 / gamma_1 + 0.5) * exp(af * 5 * x * y + b) + 0.5 * exp(af * 3 * x * y + b);
+  } else {
+    typedef MMSExp M;
+    double xyz = c[0] * c[1] * c[2];
+    double t2 = exp(M::b);
+    double t3 = M::a * M::c1 * xyz;
+    q[0] = M::d1 * t2 * exp(t3);
+    q[1] = M::d2 * t2 * exp(M::a * M::c2 * xyz);
+    q[2] = M::d3 * t2 * exp(M::a * M::c3 * xyz);
+    q[3] = M::d4 * t2 * exp(M::a * M::c4 * xyz);
+    q[4] = (t2 * exp(-t3) * ((M::d2 * M::d2) * exp(M::a * M::c2 * xyz * 2.0) + (M::d3 * M::d3) * exp(M::a * M::c3 * xyz * 2.0)
+            + (M::d4 * M::d4) * exp(M::a * M::c4 * xyz * 2.0)) * (1.0 / 2.0)) / M::d1 + (M::d5 * t2 * exp(M::a * M::c5 * xyz)) / gamma_1;
+  }
+}
+
+// common_funcs.jl:312-351 calcFreeStream
+template <int DIM>
+__device__ inline void free_stream(double rho_free, double E_free, double Ma, double aoa, double* sol) {
+  sol[0] = rho_free;
+  sol[DIM + 1] = E_free;
+  sol[1] = rho_free * Ma * cos(aoa);
+  if (DIM == 2) {
+    sol[2] = rho_free * Ma * sin(aoa);
+  } else {
+    sol[2] = 0.0;
+    sol[3] = -rho_free * Ma * sin(aoa);
+  }
+}
+
+// source.jl:65-81 (2D) / 98-177 (3D) SRCExp = div F(q_exact).  Written here as
+// the analytic divergence of the flux of the calcExp fields (all of the form
+// C*exp(k*phi), phi = x*y (2D) or x*y*z (3D), grad g = k*g*grad phi) instead of
+// the reference's machine-generated expression; tests compare the two.
+template <int DIM>
+__device__ inline void src_exp(const double* c, double gamma, double* S) {
+  const double gamma_1 = gamma - 1.0;
+  double k[5], A[5];       // rho, m_1..m_DIM, p as A*exp(k*phi)
+  double phi, gphi[3];
+  if (DIM == 2) {
+    const double af = 1.0 / 5, eb = exp(0.01);
+    phi = c[0] * c[1];
+    gphi[0] = c[1]; gphi[1] = c[0]; gphi[2] = 0.0;
+    k[0] = af; k[1] = 2 * af; k[2] = 3 * af; k[3] = 0.0; k[4] = 5 * af;
+    A[0] = eb; A[1] = eb; A[2] = eb; A[3] = 0.0; A[4] = eb;   // p = exp(5 af xy + b)
+  } else {
+    typedef MMSExp M;
+    const double eb = exp(M::b);
+    phi = c[0] * c[1] * c[2];
+    gphi[0] = c[1] * c[2]; gphi[1] = c[0] * c[2]; gphi[2] = c[0] * c[1];
+    k[0] = M::a * M::c1; k[1] = M::a * M::c2; k[2] = M::a * M::c3; k[3] = M::a * M::c4; k[4] = M::a * M::c5;
+    A[0] = M::d1 * eb; A[1] = M::d2 * eb; A[2] = M::d3 * eb; A[3] = M::d4 * eb; A[4] = M::d5 * eb;
+  }
+  double rho = A[0] * exp(k[0] * phi);
+  double m[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) m[d] = A[1 + d] * exp(k[1 + d] * phi);
+  double p = A[4] * exp(k[4] * phi);
+  // E = p/gamma_1 + 0.5*sum m_d^2/rho ; each term is an exponential of phi
+  double ke[3], kke[3];
+  double E = p / gamma_1;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { ke[d] = 0.5 * m[d] * m[d] / rho; kke[d] = 2 * k[1 + d] - k[0]; E += ke[d]; }
+  // dE/dphi
+  double dE = k[4] * p / gamma_1;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) dE += kke[d] * ke[d];
+  double S0 = 0.0, SE = 0.0, Sm[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    // flux in direction d: [m_d, m_i m_d/rho + delta p, (E+p) m_d/rho]; d/dx_d = (d/dphi) * gphi[d]
+    double g = gphi[d];
+    S0 += k[1 + d] * m[d] * g;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      double mm = m[i] * m[d] / rho;
+      Sm[i] += (k[1 + i] + k[1 + d] - k[0]) * mm * g;
+    }
+    Sm[d] += k[4] * p * g;
+    double ud = m[d] / rho;
+    SE += ((dE + k[4] * p) * ud + (E + p) * (k[1 + d] - k[0]) * ud) * g;
+  }
+  S[0] = S0;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) S[1 + i] = Sm[i];
+  S[DIM + 1] = SE;
+}
+
+}  // namespace pdes

@@ -1,0 +1,862 @@
+// libpdes_euler_b200.so -- C ABI of the B200 Euler residual / RK4 hot path (include/pdes_euler_b200.h).
+//
+// Host-side runtime: owns the device copies of the operator tables, metrics and connectivity, builds the
+// element-centric face table the kernels gather through, sequences the fused residual/RK4-stage kernels
+// on a compute stream and the halo exchange (NCCL send/recv) on a communication stream.  There is no CPU
+// fallback: without a usable CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pdes_euler_b200.h"
+#include "residual_kernels.cuh"
+
+using namespace pdes;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+void set_err(PdesCtx* ctx, const char* fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      set_err(ctx, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+      return PDES_ERR_CUDA;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+// ---- NCCL, resolved at run time so that single-GPU users need no libnccl ---------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string* why) {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) { *why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) { *why = std::string("missing symbol ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+  }
+} g_nccl;
+
+struct Peer {
+  int32_t rank = -1;
+  int64_t nfaces = 0, offset = 0;   // offset into the concatenated shared-face arrays
+  std::vector<PdesBoundary> bndries_local;
+  std::vector<PdesInterface> ifaces;
+  std::vector<double> nrm;
+};
+
+// type-erased launcher for one (DIM, NN, NFN) operator family
+struct Ops {
+  virtual ~Ops() {}
+  virtual void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp,
+                            const int64_t* perm, const int64_t* nbrperm, const double* wface, int base) = 0;
+  virtual cudaError_t launch_residual(const ResArgs& a, int mode, int64_t nelems, cudaStream_t s) = 0;
+  virtual cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS,
+                                  double* q_send, const Ctl* ctl, cudaStream_t s) = 0;
+  virtual int64_t grid_for(int64_t nelems) const = 0;
+  virtual int tile_elems() const = 0;
+};
+
+template <int DIM, int NN, int NFN, int E>
+struct OpsImpl : Ops {
+  using Tab = OpTab<DIM, NN, NFN>;
+  using Cfg = TileCfg<DIM, NN, NFN, E>;
+  Tab tab;
+  bool attr_set = false;
+  void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
+                    const int64_t* nbrperm, const double* wface, int base) override {
+    memset(&tab, 0, sizeof(tab));
+    const int ss = c.ss;
+    for (int d = 0; d < DIM; ++d)
+      for (int j = 0; j < NN; ++j)
+        for (int i = 0; i < NN; ++i) tab.Qt[d][j][i] = Q[j + NN * (i + NN * d)];
+    for (int f = 0; f < DIM + 1; ++f)
+      for (int j = 0; j < NN; ++j) tab.perm[f][j] = j < ss ? (int)(perm[j + (int64_t)ss * f] - base) : 0;
+    for (int j = 0; j < NN; ++j)
+      for (int i = 0; i < NFN; ++i) tab.interp[j][i] = j < ss ? interp[j + ss * i] : 0.0;
+    for (int f = 0; f < DIM + 1; ++f)
+      for (int i = 0; i < NFN; ++i)
+        for (int j = 0; j < ss; ++j) tab.Rf[f][i][tab.perm[f][j]] += interp[j + ss * i];
+    for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
+    for (int o = 0; o < Tab::NOR; ++o)
+      for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
+    (void)w;
+  }
+  int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
+  int tile_elems() const override { return E; }
+  cudaError_t launch_residual(const ResArgs& a, int mode, int64_t nelems, cudaStream_t s) override {
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg::smem_bytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    if (nelems <= 0) return cudaSuccess;
+    dim3 grid((unsigned)grid_for(nelems)), block(Cfg::T);
+    if (mode == EPI_RES)
+      k_residual_roe<DIM, NN, NFN, E, EPI_RES><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+    else
+      k_residual_roe<DIM, NN, NFN, E, EPI_RK><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
+                          const Ctl* ctl, cudaStream_t s) override {
+    if (nS <= 0) return cudaSuccess;
+    int64_t n = nS * NFN * (DIM + 2);
+    k_pack_send<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, ctl);
+    return cudaGetLastError();
+  }
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+Ops* make_ops(const PdesConfig& c) {
+  if (c.sparse_face) return nullptr;
+  const int big = env_int("PDES_TILE", 0);
+  if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64>();
+  if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32>();
+  if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32>();
+  if (c.dim == 3 && c.nn == 11 && c.nfn == 6) {
+    if (big == 32) return new OpsImpl<3, 11, 6, 32>();
+    return new OpsImpl<3, 11, 6, 16>();
+  }
+  return nullptr;
+}
+
+// one-time uploads: stream-ordered with the kernels of the (non-blocking) compute stream, then synchronised so
+// that the host buffer may be released
+template <typename T>
+cudaError_t dev_upload(cudaStream_t st, T** dst, const T* src, size_t n) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (n == 0) n = 1, src = nullptr;
+  cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (src) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+  else e = cudaMemsetAsync(*dst, 0, n * sizeof(T), st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
+}  // namespace
+
+struct PdesCtx {
+  PdesConfig cfg;
+  int nd = 0, nf = 0;
+  int64_t ndof = 0;
+  std::string err;
+  int64_t err_element = -1, err_node = -1;
+  std::unique_ptr<Ops> ops;
+  bool have_op = false, have_mesh = false, finalized = false;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  // state
+  double* qbuf[3] = {nullptr, nullptr, nullptr};
+  int cur = 0;
+  double *ksum = nullptr, *res = nullptr;
+  // mesh
+  double *dxidx = nullptr, *minv = nullptr, *srcw = nullptr, *nrm_face = nullptr, *nrm_bndry = nullptr,
+         *coords_bndry = nullptr, *w_dev = nullptr;
+  EFace* efaces = nullptr;
+  std::vector<EFace> h_efaces;
+  std::vector<double> h_w;
+  // partition
+  std::vector<Peer> peers;
+  int64_t nS = 0;
+  double *nrm_shared = nullptr, *q_send = nullptr, *q_recv = nullptr;
+  int32_t *sh_el = nullptr, *surf_list = nullptr;
+  uint8_t* sh_face = nullptr;
+  int64_t n_surf = 0;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // control
+  Ctl* ctl = nullptr;
+  Ctl* h_ctl = nullptr;   // pinned
+  double *norm_partials = nullptr, *norm_partials2 = nullptr, *norm_sq = nullptr, *norms_dev = nullptr;
+  int64_t norms_cap = 0;
+  int64_t launches = 0, n_evals = 0;
+  PdesTimings tm{};
+};
+
+namespace {
+
+void set_err(PdesCtx* ctx, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+}
+
+int usage(PdesCtx* ctx, const char* msg) {
+  set_err(ctx, "%s", msg);
+  return PDES_ERR_USAGE;
+}
+
+PhysPar phys_of(const PdesConfig& c) {
+  PhysPar p;
+  p.gamma = c.gamma; p.R = c.R; p.Ma = c.Ma; p.aoa = c.aoa; p.rho_free = c.rho_free; p.E_free = c.E_free;
+  p.check_density = c.check_density; p.check_pressure = c.check_pressure;
+  return p;
+}
+
+int reset_ctl(PdesCtx* ctx) {
+  Ctl z;
+  z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.pad = 0;
+  *ctx->h_ctl = z;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
+  return PDES_OK;
+}
+
+// reads the control block back (synchronises the compute stream) and converts a device-side physics error into
+// the reference's exception semantics (euler.jl:552-556, 598-603)
+int fetch_ctl(PdesCtx* ctx) {
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->h_ctl->err_code) {
+    unsigned long long key = ctx->h_ctl->err_loc;
+    int code = (int)(key >> 62) + 1;
+    unsigned long long loc = key & ((1ull << 62) - 1);
+    ctx->err_element = (int64_t)(loc >> 8) + ctx->cfg.index_base;
+    ctx->err_node = (int64_t)(loc & 0xff) + ctx->cfg.index_base;
+    set_err(ctx, "%s detected at element %lld, node %lld", code == 1 ? "Negative density" : "Negative pressure",
+            (long long)ctx->err_element, (long long)ctx->err_node);
+    return code == 1 ? PDES_ERR_NEG_DENSITY : PDES_ERR_NEG_PRESSURE;
+  }
+  return PDES_OK;
+}
+
+// builds the device copies that depend on both the mesh and the peer lists
+int finalize(PdesCtx* ctx) {
+  if (ctx->finalized) return PDES_OK;
+  if (!ctx->have_op || !ctx->have_mesh) return usage(ctx, "pdes_set_operator and pdes_set_mesh must be called first");
+  const PdesConfig& c = ctx->cfg;
+  const int NF = ctx->nf, base = c.index_base;
+  // shared faces -> element face table, concatenated normals, pack lists
+  ctx->nS = 0;
+  for (auto& p : ctx->peers) { p.offset = ctx->nS; ctx->nS += p.nfaces; }
+  std::vector<int32_t> sh_el(ctx->nS);
+  std::vector<uint8_t> sh_face(ctx->nS);
+  std::vector<double> nrm_sh((size_t)ctx->nS * c.nfn * c.dim);
+  std::vector<EFace> ef = ctx->h_efaces;
+  for (auto& p : ctx->peers) {
+    if (p.rank < 0) return usage(ctx, "pdes_set_peer was not called for every peer");
+    for (int64_t j = 0; j < p.nfaces; ++j) {
+      int64_t el = (int64_t)p.ifaces[j].elementL - base;
+      int f = (int)p.ifaces[j].faceL - base;
+      if (el < 0 || el >= c.nE || f < 0 || f >= NF) return usage(ctx, "shared interface out of range");
+      if ((int64_t)p.bndries_local[j].element - base != el || (int)p.bndries_local[j].face - base != f)
+        return usage(ctx, "bndries_local and shared_interfaces disagree");
+      EFace& r = ef[el * NF + f];
+      if (r.kind != 255) return usage(ctx, "shared face already claimed by an interface or boundary face");
+      r.kind = FK_SHARED; r.idx = (int32_t)(p.offset + j); r.nbr = -1; r.fnbr = 0;
+      r.orient = (uint8_t)(p.ifaces[j].orient - base); r.bc = 0;
+      sh_el[p.offset + j] = (int32_t)el;
+      sh_face[p.offset + j] = (uint8_t)f;
+    }
+    memcpy(nrm_sh.data() + (size_t)p.offset * c.nfn * c.dim, p.nrm.data(), sizeof(double) * p.nrm.size());
+  }
+  std::vector<int32_t> surf;
+  for (int64_t e = 0; e < c.nE; ++e) {
+    bool sh = false;
+    for (int f = 0; f < NF; ++f) {
+      if (ef[e * NF + f].kind == 255) {
+        set_err(ctx, "face %d of element %lld belongs to no interface, boundary face or shared face", f, (long long)e);
+        return PDES_ERR_USAGE;
+      }
+      sh = sh || ef[e * NF + f].kind == FK_SHARED;
+    }
+    if (sh) surf.push_back((int32_t)e);
+  }
+  ctx->n_surf = (int64_t)surf.size();
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->efaces, ef.data(), ef.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_el, sh_el.data(), sh_el.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_face, sh_face.data(), sh_face.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_shared, nrm_sh.data(), nrm_sh.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->surf_list, surf.data(), surf.size()));
+  size_t nsend = (size_t)ctx->nS * c.nfn * ctx->nd;
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
+  int64_t g1 = ctx->ops->grid_for(c.nE), g2 = ctx->ops->grid_for(ctx->n_surf);
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)g1));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials2, nullptr, (size_t)(g2 > 0 ? g2 : 1)));
+  ctx->finalized = true;
+  return PDES_OK;
+}
+
+void fill_args(PdesCtx* ctx, ResArgs* a, const double* q) {
+  memset(a, 0, sizeof(*a));
+  a->q = q; a->dxidx = ctx->dxidx; a->efaces = ctx->efaces; a->nrm_face = ctx->nrm_face;
+  a->nrm_bndry = ctx->nrm_bndry; a->coords_bndry = ctx->coords_bndry; a->nrm_shared = ctx->nrm_shared;
+  a->q_recv = ctx->q_recv; a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
+  a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
+}
+
+// startSolutionExchange (Utils/parallel.jl:29-49): pack on the compute stream, send/recv on the comm stream
+int start_exchange(PdesCtx* ctx, const double* q) {
+  if (ctx->nS == 0) return PDES_OK;
+  CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl, ctx->stream));
+  ctx->launches++;
+  if (!ctx->comm) return PDES_OK;   // test mode: receive buffer injected by hand
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+  const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
+  ncclResult_t r = g_nccl.GroupStart();
+  for (auto& p : ctx->peers) {
+    if (r != ncclSuccess) break;
+    r = g_nccl.Recv(ctx->q_recv + p.offset * per_face, p.nfaces * per_face, ncclFloat64, p.rank, ctx->comm, ctx->comm_stream);
+    if (r != ncclSuccess) break;
+    r = g_nccl.Send(ctx->q_send + p.offset * per_face, p.nfaces * per_face, ncclFloat64, p.rank, ctx->comm, ctx->comm_stream);
+  }
+  ncclResult_t r2 = g_nccl.GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+    return PDES_ERR_COMM;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
+  return PDES_OK;
+}
+
+// one residual evaluation = [pack+exchange] + interior launch + (after the receive) surface launch
+int enqueue_residual(PdesCtx* ctx, ResArgs& a, int mode) {
+  int rc = start_exchange(ctx, a.q);
+  if (rc) return rc;
+  const bool split = ctx->nS > 0;
+  a.elist = nullptr; a.nlist = 0; a.skip_shared = split ? 1 : 0;
+  double* np1 = ctx->norm_partials;
+  a.norm_partials = np1;
+  CUDA_TRY(ctx, ctx->ops->launch_residual(a, mode, ctx->cfg.nE, ctx->stream));
+  ctx->launches++;
+  if (split) {
+    if (ctx->comm) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
+    a.elist = ctx->surf_list; a.nlist = ctx->n_surf; a.skip_shared = 0;
+    a.norm_partials = ctx->norm_partials2;
+    CUDA_TRY(ctx, ctx->ops->launch_residual(a, mode, ctx->n_surf, ctx->stream));
+    ctx->launches++;
+  }
+  ctx->n_evals++;
+  return PDES_OK;
+}
+
+int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
+  int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE), n2 = ctx->nS > 0 ? (int)ctx->ops->grid_for(ctx->n_surf) : 0;
+  k_norm_reduce<<<1, 256, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_partials2, n2, ctx->norm_sq, ctx->ctl);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  double quirk = 1.0;
+  if (ctx->comm && ctx->nranks > 1) {
+    // calcNorm's Allreduce (Utils.jl:443-448); issued on the compute stream: 8 bytes, once per step
+    ncclResult_t r = g_nccl.AllReduce(ctx->norm_sq, ctx->norm_sq, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+    quirk = (double)ctx->nranks;   // rk4.jl:451-453 reduces the already-reduced norm again
+  }
+  k_norm_commit<<<1, 1, 0, ctx->stream>>>(ctx->norm_sq, quirk, ctx->norms_dev, slot, res_tol, pseudo_time, ctx->ctl);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return PDES_OK;
+}
+
+// the four fused stages of one RK4 step (rk4.jl:238-319); stops after stage 1 when only_head is set
+int enqueue_rk4_step(PdesCtx* ctx, double h, int64_t norm_slot, double res_tol, int pseudo_time, bool only_head) {
+  double* A = ctx->qbuf[ctx->cur];
+  double* B = ctx->qbuf[(ctx->cur + 1) % 3];
+  double* Cb = ctx->qbuf[(ctx->cur + 2) % 3];
+  ResArgs a;
+  const double* in[4] = {A, B, Cb, B};
+  double* out[4] = {B, Cb, B, Cb};
+  const double ah[4] = {h / 2, h / 2, h, 0.0};
+  for (int s = 0; s < 4; ++s) {
+    fill_args(ctx, &a, in[s]);
+    a.x_old = A; a.ksum = ctx->ksum; a.q_next = out[s]; a.ah = ah[s]; a.h6 = h / 6; a.stage = s + 1;
+    int rc = enqueue_residual(ctx, a, EPI_RK);
+    if (rc) return rc;
+    if (s == 0) {
+      if (norm_slot >= 0) { rc = enqueue_norm(ctx, norm_slot, res_tol, pseudo_time); if (rc) return rc; }
+      if (only_head) { ctx->cur = (ctx->cur + 1) % 3; return PDES_OK; }
+    }
+  }
+  ctx->cur = (ctx->cur + 2) % 3;
+  return PDES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pdes_last_error(const PdesCtx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int pdes_last_error_location(const PdesCtx* ctx, int64_t* element, int64_t* node) {
+  if (!ctx) return PDES_ERR_USAGE;
+  if (element) *element = ctx->err_element;
+  if (node) *node = ctx->err_node;
+  return PDES_OK;
+}
+
+int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
+  if (!cfg || !out) return usage(nullptr, "pdes_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_err(nullptr, "no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return PDES_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return usage(nullptr, "pdes_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_err(nullptr, "device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
+    return PDES_ERR_CUDA;
+  }
+  if (cfg->dim != 2 && cfg->dim != 3) return usage(nullptr, "pdes_create: dim must be 2 or 3");
+  if (cfg->face_integral_type != 1) {
+    set_err(nullptr, "face_integral_type %d is not supported (type 1 only)", cfg->face_integral_type);
+    return PDES_ERR_UNSUPPORTED;
+  }
+  if (cfg->nE <= 0 || cfg->nE > 0x7fffff00ll) return usage(nullptr, "pdes_create: numEl out of range");
+  std::unique_ptr<PdesCtx> ctx(new PdesCtx());
+  ctx->cfg = *cfg;
+  ctx->nd = cfg->dim + 2;
+  ctx->nf = cfg->dim + 1;
+  ctx->ndof = (int64_t)ctx->nd * cfg->nn * cfg->nE;
+  if (cfg->volume_integral_type == 1 && cfg->flux_id == PDES_FLUX_ROE && !cfg->sparse_face) {
+    ctx->ops.reset(make_ops(*cfg));
+  }
+  if (!ctx->ops) {
+    set_err(nullptr,
+            "unsupported operator/flux combination (dim=%d nn=%d nfn=%d sparse=%d volume_integral_type=%d flux=%d)",
+            cfg->dim, cfg->nn, cfg->nfn, cfg->sparse_face, cfg->volume_integral_type, cfg->flux_id);
+    return PDES_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
+  PdesCtx* c = ctx.get();
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreate(&c->ev_t0));
+  CUDA_TRY(c, cudaEventCreate(&c->ev_t1));
+  for (int i = 0; i < 3; ++i) CUDA_TRY(c, dev_upload<double>(c->stream, &c->qbuf[i], nullptr, (size_t)c->ndof));
+  CUDA_TRY(c, dev_upload<double>(c->stream, &c->ksum, nullptr, (size_t)c->ndof));
+  CUDA_TRY(c, dev_upload<double>(c->stream, &c->res, nullptr, (size_t)c->ndof));
+  CUDA_TRY(c, cudaMalloc((void**)&c->ctl, sizeof(Ctl)));
+  CUDA_TRY(c, cudaMallocHost((void**)&c->h_ctl, sizeof(Ctl)));
+  CUDA_TRY(c, cudaMalloc((void**)&c->norm_sq, sizeof(double)));
+  c->peers.resize(cfg->npeers > 0 ? cfg->npeers : 0);
+  int rc = reset_ctl(c);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  *out = ctx.release();
+  return PDES_OK;
+}
+
+void pdes_destroy(PdesCtx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
+                  ctx->nrm_face, ctx->nrm_bndry, ctx->coords_bndry, ctx->w_dev, ctx->efaces, ctx->nrm_shared,
+                  ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->surf_list, ctx->sh_face, ctx->ctl, ctx->norm_partials,
+                  ctx->norm_partials2, ctx->norm_sq, ctx->norms_dev};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+  if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+  if (ctx->ev_recv) cudaEventDestroy(ctx->ev_recv);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+}
+
+int pdes_set_operator(PdesCtx* ctx, const double* Q, const double* w, const double* interp, const int64_t* perm,
+                      const int64_t* nbrperm, const double* wface) {
+  if (!ctx || !Q || !w || !interp || !perm || !nbrperm || !wface) return usage(ctx, "pdes_set_operator: null argument");
+  const PdesConfig& c = ctx->cfg;
+  if (c.ss != c.nn) return usage(ctx, "dense face operators need stencilsize == numnodes");
+  const int nor = c.dim == 2 ? 1 : 3;
+  if (c.norient != nor) return usage(ctx, "norient must be 1 (2D) or 3 (3D)");
+  for (int f = 0; f < ctx->nf; ++f)
+    for (int j = 0; j < c.ss; ++j) {
+      int64_t p = perm[j + (int64_t)c.ss * f] - c.index_base;
+      if (p < 0 || p >= c.nn) return usage(ctx, "sbpface.perm entry out of range");
+    }
+  for (int o = 0; o < nor; ++o)
+    for (int i = 0; i < c.nfn; ++i) {
+      int64_t p = nbrperm[i + c.nfn * o] - c.index_base;
+      if (p < 0 || p >= c.nfn) return usage(ctx, "sbpface.nbrperm entry out of range");
+    }
+  CUDA_TRY(ctx, cudaSetDevice(c.device));
+  ctx->ops->build_tables(c, Q, w, interp, perm, nbrperm, wface, c.index_base);
+  ctx->h_w.assign(w, w + c.nn);
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->w_dev, w, (size_t)c.nn));
+  ctx->have_op = true;
+  ctx->finalized = false;
+  return PDES_OK;
+}
+
+int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const double* coords, const double* nrm_face,
+                  const double* nrm_bndry, const double* coords_bndry, const PdesInterface* interfaces,
+                  const PdesBoundary* bndryfaces, const int64_t* bndry_offsets, const int32_t* bc_ids) {
+  if (!ctx || !dxidx || !jac) return usage(ctx, "pdes_set_mesh: null argument");
+  if (!ctx->have_op) return usage(ctx, "pdes_set_operator must precede pdes_set_mesh");
+  const PdesConfig& c = ctx->cfg;
+  const int NF = ctx->nf, base = c.index_base;
+  if (c.nF > 0 && (!interfaces || !nrm_face)) return usage(ctx, "pdes_set_mesh: interfaces missing");
+  if (c.nB > 0 && (!bndryfaces || !nrm_bndry || !coords_bndry || !bndry_offsets || !bc_ids))
+    return usage(ctx, "pdes_set_mesh: boundary arrays missing");
+  if (c.src_id != PDES_SRC_NONE && !coords) return usage(ctx, "pdes_set_mesh: coords needed for the source term");
+  CUDA_TRY(ctx, cudaSetDevice(c.device));
+  std::vector<EFace>& ef = ctx->h_efaces;
+  EFace blank;
+  memset(&blank, 0, sizeof(blank));
+  blank.kind = 255; blank.nbr = -1; blank.idx = -1;
+  ef.assign((size_t)c.nE * NF, blank);
+  for (int64_t f = 0; f < c.nF; ++f) {
+    const PdesInterface& I = interfaces[f];
+    int64_t eL = (int64_t)I.elementL - base, eR = (int64_t)I.elementR - base;
+    int fL = (int)I.faceL - base, fR = (int)I.faceR - base, o = (int)I.orient - base;
+    if (eL < 0 || eL >= c.nE || eR < 0 || eR >= c.nE || fL < 0 || fL >= NF || fR < 0 || fR >= NF || o < 0 ||
+        o >= c.norient)
+      return usage(ctx, "mesh.interfaces entry out of range");
+    EFace& L = ef[eL * NF + fL];
+    EFace& Rr = ef[eR * NF + fR];
+    if (L.kind != 255 || Rr.kind != 255) return usage(ctx, "element face referenced by two interfaces");
+    L.kind = FK_INTERIOR_L; L.nbr = (int32_t)eR; L.idx = (int32_t)f; L.fnbr = (uint8_t)fR; L.orient = (uint8_t)o;
+    Rr.kind = FK_INTERIOR_R; Rr.nbr = (int32_t)eL; Rr.idx = (int32_t)f; Rr.fnbr = (uint8_t)fL; Rr.orient = (uint8_t)o;
+  }
+  for (int i = 0; i < c.numBC; ++i) {
+    if (bc_ids[i] < 1 || bc_ids[i] > 4) {
+      set_err(ctx, "BC id %d is not supported", bc_ids[i]);
+      return PDES_ERR_UNSUPPORTED;
+    }
+    for (int64_t b = bndry_offsets[i] - base; b < bndry_offsets[i + 1] - base; ++b) {
+      if (b < 0 || b >= c.nB) return usage(ctx, "bndry_offsets out of range");
+      int64_t el = (int64_t)bndryfaces[b].element - base;
+      int f = (int)bndryfaces[b].face - base;
+      if (el < 0 || el >= c.nE || f < 0 || f >= NF) return usage(ctx, "mesh.bndryfaces entry out of range");
+      EFace& r = ef[el * NF + f];
+      if (r.kind != 255) return usage(ctx, "boundary face already claimed by an interface");
+      r.kind = FK_BOUNDARY; r.idx = (int32_t)b; r.bc = (uint8_t)bc_ids[i];
+    }
+  }
+  const size_t nnE = (size_t)c.nn * c.nE;
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->dxidx, dxidx, nnE * c.dim * c.dim));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_face, nrm_face, (size_t)c.nF * c.nfn * c.dim));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_bndry, nrm_bndry, (size_t)c.nB * c.nfn * c.dim));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->coords_bndry, coords_bndry, (size_t)c.nB * c.nfn * c.dim));
+  // Minv and the tabulated source are produced on the device from jac / coords
+  double* jac_dev = nullptr;
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &jac_dev, jac, nnE));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->minv, nullptr, nnE));
+  unsigned nb = (unsigned)((nnE + 255) / 256);
+  k_minv<<<nb, 256, 0, ctx->stream>>>(jac_dev, ctx->w_dev, c.nn, c.nE, ctx->minv);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  if (c.src_id == PDES_SRC_EXP) {
+    double* coords_dev = nullptr;
+    CUDA_TRY(ctx, dev_upload(ctx->stream, &coords_dev, coords, nnE * c.dim));
+    CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->srcw, nullptr, (size_t)ctx->ndof));
+    if (c.dim == 2) k_tabulate_source<2><<<nb, 256, 0, ctx->stream>>>(coords_dev, jac_dev, ctx->w_dev, c.nn, c.nE, c.gamma, ctx->srcw);
+    else k_tabulate_source<3><<<nb, 256, 0, ctx->stream>>>(coords_dev, jac_dev, ctx->w_dev, c.nn, c.nE, c.gamma, ctx->srcw);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(coords_dev);
+  } else if (c.src_id != PDES_SRC_NONE) {
+    set_err(ctx, "source id %d is not supported", c.src_id);
+    return PDES_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(jac_dev);
+  ctx->have_mesh = true;
+  ctx->finalized = false;
+  return PDES_OK;
+}
+
+int pdes_set_peer(PdesCtx* ctx, int32_t peer_idx, int32_t peer_rank, int64_t nfaces, const PdesBoundary* bndries_local,
+                  const PdesInterface* shared_interfaces, const double* nrm_sharedface) {
+  if (!ctx) return usage(ctx, "pdes_set_peer: null ctx");
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size()) return usage(ctx, "pdes_set_peer: peer index out of range");
+  if (nfaces < 0 || (nfaces > 0 && (!bndries_local || !shared_interfaces || !nrm_sharedface)))
+    return usage(ctx, "pdes_set_peer: null argument");
+  Peer& p = ctx->peers[peer_idx];
+  p.rank = peer_rank;
+  p.nfaces = nfaces;
+  p.bndries_local.assign(bndries_local, bndries_local + nfaces);
+  p.ifaces.assign(shared_interfaces, shared_interfaces + nfaces);
+  p.nrm.assign(nrm_sharedface, nrm_sharedface + (size_t)nfaces * ctx->cfg.nfn * ctx->cfg.dim);
+  ctx->finalized = false;
+  return PDES_OK;
+}
+
+int pdes_get_unique_id(uint8_t id_out[128]) {
+  std::string why;
+  if (!g_nccl.load(&why)) { set_err(nullptr, "%s", why.c_str()); return PDES_ERR_COMM; }
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) { set_err(nullptr, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  memcpy(id_out, &id, 128);
+  return PDES_OK;
+}
+
+int pdes_set_comm(PdesCtx* ctx, const uint8_t id[128], int32_t rank, int32_t nranks) {
+  if (!ctx || !id) return usage(ctx, "pdes_set_comm: null argument");
+  std::string why;
+  if (!g_nccl.load(&why)) { set_err(ctx, "%s", why.c_str()); return PDES_ERR_COMM; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, nranks, uid, rank);
+  if (r != ncclSuccess) { set_err(ctx, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return PDES_OK;
+}
+
+int pdes_pack_send(PdesCtx* ctx, int32_t peer_idx, double* q_send_out) {
+  if (!ctx || !q_send_out) return usage(ctx, "pdes_pack_send: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size()) return usage(ctx, "peer index out of range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  CUDA_TRY(ctx, ctx->ops->launch_pack(ctx->qbuf[ctx->cur], ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl,
+                                      ctx->stream));
+  ctx->launches++;
+  const Peer& p = ctx->peers[peer_idx];
+  const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
+  CUDA_TRY(ctx, cudaMemcpyAsync(q_send_out, ctx->q_send + p.offset * per_face, sizeof(double) * p.nfaces * per_face,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_inject_recv(PdesCtx* ctx, int32_t peer_idx, const double* q_recv) {
+  if (!ctx || !q_recv) return usage(ctx, "pdes_inject_recv: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size()) return usage(ctx, "peer index out of range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const Peer& p = ctx->peers[peer_idx];
+  const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->q_recv + p.offset * per_face, q_recv, sizeof(double) * p.nfaces * per_face,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_set_q(PdesCtx* ctx, const double* q) {
+  if (!ctx || !q) return usage(ctx, "pdes_set_q: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->qbuf[ctx->cur], q, sizeof(double) * ctx->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_get_q(PdesCtx* ctx, double* q) {
+  if (!ctx || !q) return usage(ctx, "pdes_get_q: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(q, ctx->qbuf[ctx->cur], sizeof(double) * ctx->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_get_res(PdesCtx* ctx, double* res) {
+  if (!ctx || !res) return usage(ctx, "pdes_get_res: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(res, ctx->res, sizeof(double) * ctx->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_set_q_dev(PdesCtx* ctx, const double* q_dev) {
+  if (!ctx || !q_dev) return usage(ctx, "pdes_set_q_dev: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->qbuf[ctx->cur], q_dev, sizeof(double) * ctx->ndof, cudaMemcpyDeviceToDevice, ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_pin_host(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return usage(nullptr, "pdes_pin_host: bad argument");
+  CUDA_TRY(nullptr, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return PDES_OK;
+}
+
+int pdes_unpin_host(void* ptr) {
+  if (!ptr) return usage(nullptr, "pdes_unpin_host: null");
+  CUDA_TRY(nullptr, cudaHostUnregister(ptr));
+  return PDES_OK;
+}
+
+void* pdes_stream(PdesCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+double* pdes_q_dev(PdesCtx* ctx) { return ctx ? ctx->qbuf[ctx->cur] : nullptr; }
+double* pdes_res_dev(PdesCtx* ctx) { return ctx ? ctx->res : nullptr; }
+
+int pdes_eval_residual_async(PdesCtx* ctx, double t) {
+  (void)t;  // the scoped BCs and SRCExp are time independent
+  if (!ctx) return usage(ctx, "null ctx");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  ResArgs a;
+  fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
+  a.res = ctx->res;
+  return enqueue_residual(ctx, a, EPI_RES);
+}
+
+int pdes_sync(PdesCtx* ctx) {
+  if (!ctx) return usage(ctx, "null ctx");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc = fetch_ctl(ctx);
+  if (rc > 0) reset_ctl(ctx);
+  return rc;
+}
+
+int pdes_eval_residual(PdesCtx* ctx, double t) {
+  int rc = pdes_eval_residual_async(ctx, t);
+  if (rc) return rc;
+  return pdes_sync(ctx);
+}
+
+int pdes_rk4_steps_async(PdesCtx* ctx, double h, int64_t nsteps) {
+  if (!ctx) return usage(ctx, "null ctx");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  for (int64_t i = 0; i < nsteps; ++i) {
+    rc = enqueue_rk4_step(ctx, h, -1, -1.0, 0, false);
+    if (rc) return rc;
+  }
+  return PDES_OK;
+}
+
+int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_tol, int32_t real_time, double* t_out,
+             double* norms_out, int64_t norms_cap, int64_t* nsteps_out) {
+  if (!ctx) return usage(ctx, "null ctx");
+  if (!(h > 0.0)) return usage(ctx, "pdes_rk4: h must be positive");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const int64_t t_steps = (int64_t)llround(t_max / h);          // rk4.jl:170
+  int64_t max_heads = t_steps;
+  if (itermax >= 0 && itermax < max_heads) max_heads = itermax > 0 ? itermax : 1;
+  if (max_heads < 0) max_heads = 0;
+  if (ctx->norms_cap < max_heads + 1) {
+    if (ctx->norms_dev) cudaFree(ctx->norms_dev);
+    ctx->norms_dev = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->norms_dev, sizeof(double) * (size_t)(max_heads + 1)));
+    ctx->norms_cap = max_heads + 1;
+  }
+  rc = reset_ctl(ctx);
+  if (rc) return rc;
+  const int pseudo = real_time ? 0 : 1;
+  const int cur0 = ctx->cur;
+  int64_t heads = 0;       // executed step heads (stage 1 + norm)
+  int64_t full = 0;        // completed full steps
+  double t = 0.0;
+  int status = PDES_OK;
+  bool stopped_head = false;
+  const int64_t poll = 32;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+  for (int64_t i = 2; i <= t_steps + 1; ++i) {
+    t = (double)(i - 2) * h;
+    const bool head_only = (itermax >= 0 && i > itermax);       // rk4.jl:269-276, after stage 1
+    rc = enqueue_rk4_step(ctx, h, heads, res_tol, pseudo, head_only);
+    if (rc) return rc;
+    ++heads;
+    if (head_only) { stopped_head = true; break; }
+    ++full;
+    if ((full % poll) == 0 || i == t_steps + 1) {
+      status = fetch_ctl(ctx);
+      if (status || ctx->h_ctl->stop) break;
+    }
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+  if (!status) status = fetch_ctl(ctx);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
+  ctx->tm.t_timemarch += ms * 1e-3;
+  if (status == PDES_OK && ctx->h_ctl->stop && ctx->h_ctl->converged_step >= 0 && !stopped_head) {
+    // norm < res_tol at step head c: the reference breaks right after stage 1 (rk4.jl:258-267); every later
+    // kernel was a no-op, so the state is x_old + (h/2) k1 in buffer B of that step
+    const int64_t c = ctx->h_ctl->converged_step;
+    heads = c + 1;
+    ctx->cur = (int)((cur0 + 2 * c + 1) % 3);
+    t = (double)c * h;
+  }
+  t += h;                                                        // rk4.jl:323
+  if (t_out) *t_out = t;
+  if (nsteps_out) *nsteps_out = heads;
+  if (norms_out && heads > 0) {
+    int64_t n = heads < norms_cap ? heads : norms_cap;
+    if (n > 0) CUDA_TRY(ctx, cudaMemcpy(norms_out, ctx->norms_dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  }
+  if (ctx->h_ctl->stop) reset_ctl(ctx);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return status;
+}
+
+int pdes_get_minv(PdesCtx* ctx, double* Minv) {
+  if (!ctx || !Minv) return usage(ctx, "pdes_get_minv: null argument");
+  if (!ctx->have_mesh) return usage(ctx, "pdes_set_mesh must be called first");
+  const PdesConfig& c = ctx->cfg;
+  std::vector<double> m((size_t)c.nn * c.nE);
+  CUDA_TRY(ctx, cudaSetDevice(c.device));
+  CUDA_TRY(ctx, cudaMemcpy(m.data(), ctx->minv, sizeof(double) * m.size(), cudaMemcpyDeviceToHost));
+  for (int64_t e = 0; e < c.nE; ++e)
+    for (int j = 0; j < c.nn; ++j)
+      for (int k = 0; k < ctx->nd; ++k) Minv[k + ctx->nd * (j + (int64_t)c.nn * e)] = m[j + (size_t)c.nn * e];
+  return PDES_OK;
+}
+
+int pdes_get_timings(PdesCtx* ctx, PdesTimings* out) {
+  if (!ctx || !out) return usage(ctx, "pdes_get_timings: null argument");
+  *out = ctx->tm;
+  out->n_residual_evals = ctx->n_evals;
+  out->n_kernel_launches = ctx->launches;
+  return PDES_OK;
+}
+
+int64_t pdes_kernel_launch_count(const PdesCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

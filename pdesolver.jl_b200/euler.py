@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's physics-module API for the Euler hot path.
+
+Same names, argument meaning and error behaviour as the reference:
+
+* ``evalResidual(mesh, sbp, eqn, opts, t=0.0)`` -- ``src/solver/euler/euler.jl:111-175``:
+  reads only ``eqn.q``, overwrites ``eqn.res`` (no Minv applied).
+* ``rk4(f, h, t_max, mesh, sbp, eqn, opts, res_tol=-1.0, real_time=False)`` --
+  ``src/NonlinearSolvers/rk4.jl:404-410``: advances ``eqn.q_vec`` and returns ``t``.
+* ``EulerData`` -- the fields of ``EulerData_`` the path touches
+  (``src/solver/euler/types.jl:401-721``): ``q, res, q_vec, res_vec, M, Minv, params``.
+
+Everything numerical happens in ``libpdes_euler_b200.so`` (hand-written sm_100a
+kernels) through the C ABI of ``include/pdes_euler_b200.h``; this module only
+marshals the host arrays, exactly as the Julia shim in INTEGRATION.md does with
+``ccall``.  There is no CPU fallback: without the library or without a B200 the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import BC_IDS, FLUX_IDS, SRC_IDS
+
+
+class PDESolverError(RuntimeError):
+    """ErrorException of the reference (unsupported option combinations, usage errors)."""
+
+
+class PhysicsError(FloatingPointError):
+    """``error("Negative density detected")`` / ``error("Negative pressure detected")``
+    (euler.jl:552-556, 598-603); carries the offending element and node."""
+
+    def __init__(self, msg, element, node):
+        super().__init__(msg)
+        self.element, self.node = element, node
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+class ParamType:
+    """``ParamType`` (types.jl:57-173, 241-256): the scalars the kernels need."""
+
+    def __init__(self, opts):
+        g = float(opts.get("gamma", 1.4))
+        self.gamma, self.gamma_1 = g, g - 1
+        self.R = float(opts.get("R", 287.058))
+        self.cv = self.R / (g - 1)
+        self.Ma = float(opts.get("Ma", -1.0))
+        self.aoa = float(opts.get("aoa", 0.0)) * np.pi / 180
+        self.rho_free = 1.0
+        self.p_free = float(opts.get("p_free", 1 / g))
+        self.E_free = self.p_free / (g - 1) + 0.5 * self.Ma * self.Ma
+        self.t = 0.0
+
+
+class EulerData:
+    """Solution data object of the Euler physics module, backed by a device context.
+
+    ``q``/``res`` are Fortran-ordered ``[numDofPerNode, numNodesPerElement, numEl]``
+    host arrays; ``q_vec``/``res_vec`` alias them (DG: types.jl:600-602).
+    """
+
+    def __init__(self, mesh, sbp, opts, device=0, comm=None):
+        self.mesh, self.sbp, self.opts = mesh, sbp, opts
+        self.params = ParamType(opts)
+        nd, nn, nE = mesh.numDofPerNode, sbp.numnodes, mesh.numEl
+        self.q = np.zeros((nd, nn, nE), order="F")
+        self.res = np.zeros((nd, nn, nE), order="F")
+        self.q_vec = self.q.reshape(-1, order="F")     # views: share memory with q / res
+        self.res_vec = self.res.reshape(-1, order="F")
+        assert np.shares_memory(self.q, self.q_vec)
+        self._ctx = C.c_void_p(None)
+        self._keep = []
+        self._L = _cabi.lib()
+        self._create(device)
+        Minv = np.zeros((nd, nn, nE), order="F")
+        self._check(self._L.pdes_get_minv(self._ctx, _ptr(Minv)))
+        self.Minv = Minv.reshape(-1, order="F")
+        self.M = 1.0 / self.Minv
+        # page-lock eqn.q / eqn.res: they cross PCIe on every evalResidual / rk4 call
+        self._pinned = [a for a in (self.q, self.res) if self._L.pdes_pin_host(_ptr(a), a.nbytes) == 0]
+        if comm is not None:
+            self.set_comm(*comm)
+
+    # -- context ---------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._L.pdes_last_error(self._ctx if self._ctx else None)
+        msg = msg.decode() if msg else f"pdes error {rc}"
+        if rc > 0:
+            e, n = C.c_int64(-1), C.c_int64(-1)
+            self._L.pdes_last_error_location(self._ctx, C.byref(e), C.byref(n))
+            raise PhysicsError(msg, e.value, n.value)
+        raise PDESolverError(msg)
+
+    def _create(self, device):
+        mesh, sbp, opts, f = self.mesh, self.sbp, self.opts, self.sbp.face
+        cfg = _cabi.PdesConfig()
+        cfg.dim, cfg.nn, cfg.nfn, cfg.ss = mesh.dim, sbp.numnodes, f.numnodes, f.stencilsize
+        cfg.norient, cfg.sparse_face = f.nbrperm.shape[1], int(f.sparse)
+        cfg.index_base, cfg.device = 0, device
+        cfg.nE, cfg.nF, cfg.nB = mesh.numEl, mesh.numInterfaces, mesh.numBoundaryFaces
+        cfg.numBC, cfg.npeers = mesh.numBC, mesh.npeers
+        cfg.volume_integral_type = int(opts.get("volume_integral_type", 1))
+        cfg.face_integral_type = int(opts.get("face_integral_type", 1))
+        try:
+            cfg.flux_id = FLUX_IDS[opts.get("Flux_name", "RoeFlux")]
+            cfg.volume_flux_id = FLUX_IDS[opts.get("Volume_flux_name", "StandardFlux")]
+            cfg.src_id = SRC_IDS[opts.get("SRCname", "SRC0")]
+            bc = [BC_IDS[opts.get(f"BC{i + 1}_name", "isentropicVortexBC")] for i in range(mesh.numBC)]
+        except KeyError as e:
+            raise PDESolverError(f"unsupported functor name {e}") from None
+        cfg.check_density = int(opts.get("check_density", True))
+        cfg.check_pressure = int(opts.get("check_pressure", True))
+        p = self.params
+        cfg.gamma, cfg.R, cfg.Ma, cfg.aoa = p.gamma, p.R, p.Ma, p.aoa
+        cfg.rho_free, cfg.E_free = p.rho_free, p.E_free
+        rc = self._L.pdes_create(C.byref(cfg), C.byref(self._ctx))
+        if rc:
+            self._ctx = C.c_void_p(None)
+            self._check(rc)
+        L, ctx = self._L, self._ctx
+        perm = np.asfortranarray(np.asarray(f.perm, dtype=np.int64))
+        nbr = np.asfortranarray(np.asarray(f.nbrperm, dtype=np.int64))
+        self._check(L.pdes_set_operator(ctx, _ptr(_f64(sbp.Q)), _ptr(_f64(sbp.w)), _ptr(_f64(f.interp)),
+                                        _ptr(perm), _ptr(nbr), _ptr(_f64(f.wface))))
+        ifaces = np.ascontiguousarray(mesh.interfaces)
+        bfaces = np.ascontiguousarray(mesh.bndryfaces)
+        bo = np.ascontiguousarray(mesh.bndry_offsets, dtype=np.int64)
+        bcs = np.ascontiguousarray(bc, dtype=np.int32)
+        self._check(L.pdes_set_mesh(ctx, _ptr(_f64(mesh.dxidx)), _ptr(_f64(mesh.jac)), _ptr(_f64(mesh.coords)),
+                                    _ptr(_f64(mesh.nrm_face)), _ptr(_f64(mesh.nrm_bndry)),
+                                    _ptr(_f64(mesh.coords_bndry)), _ptr(ifaces), _ptr(bfaces), _ptr(bo), _ptr(bcs)))
+        for pi in range(mesh.npeers):
+            bl = np.ascontiguousarray(mesh.bndries_local[pi])
+            si = np.ascontiguousarray(mesh.shared_interfaces[pi])
+            ns = _f64(mesh.nrm_sharedface[pi])
+            self._check(L.pdes_set_peer(ctx, pi, int(mesh.peer_parts[pi]), len(bl), _ptr(bl), _ptr(si), _ptr(ns)))
+
+    def set_comm(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._L.pdes_set_comm(self._ctx, buf, rank, nranks))
+
+    @staticmethod
+    def get_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = _cabi.lib().pdes_get_unique_id(buf)
+        if rc:
+            raise PDESolverError(_cabi.lib().pdes_last_error(None).decode())
+        return bytes(buf)
+
+    def close(self):
+        for a in getattr(self, "_pinned", []):
+            self._L.pdes_unpin_host(_ptr(a))
+        self._pinned = []
+        if getattr(self, "_ctx", None):
+            self._L.pdes_destroy(self._ctx)
+            self._ctx = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- test hooks for the halo exchange without a second GPU ----------------------------------------
+    def pack_send(self, peer_idx):
+        n = len(self.mesh.bndries_local[peer_idx])
+        out = np.zeros((self.mesh.numDofPerNode, self.sbp.face.numnodes, n), order="F")
+        self._check(self._L.pdes_set_q(self._ctx, _ptr(self.q)))
+        self._check(self._L.pdes_pack_send(self._ctx, peer_idx, _ptr(out)))
+        return out
+
+    def inject_recv(self, peer_idx, q_recv):
+        self._check(self._L.pdes_inject_recv(self._ctx, peer_idx, _ptr(_f64(q_recv))))
+
+    def timings(self):
+        t = _cabi.PdesTimings()
+        self._check(self._L.pdes_get_timings(self._ctx, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in t._fields_}
+
+    def kernel_launch_count(self):
+        return int(self._L.pdes_kernel_launch_count(self._ctx))
+
+
+def evalResidual(mesh, sbp, eqn: EulerData, opts, t=0.0):
+    """``evalResidual(mesh, sbp, eqn, opts, t)`` of the Euler module (euler.jl:111-175)."""
+    eqn.params.t = t
+    L, ctx = eqn._L, eqn._ctx
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_eval_residual(ctx, float(t)))
+    eqn._check(L.pdes_get_res(ctx, _ptr(eqn.res)))
+    return None
+
+
+def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=False):
+    """``rk4(f, h, t_max, mesh, sbp, eqn, opts; res_tol, real_time)`` (rk4.jl:404-410).
+
+    ``f`` must be this module's ``evalResidual`` (the fused stage kernels evaluate
+    it on the device).  Advances ``eqn.q_vec`` in place and returns ``t``; the
+    per-step residual norms (the ``convergence.dat`` column) are left in
+    ``eqn.convergence``.
+    """
+    if f is not evalResidual:
+        raise PDESolverError("rk4: f must be pdesolver_jl_b200.evalResidual (device-resident right-hand side)")
+    use_itermax = bool(opts.get("use_itermax", "itermax" in opts))
+    itermax = int(opts["itermax"]) if use_itermax else -1
+    L, ctx = eqn._L, eqn._ctx
+    t_steps = int(round(t_max / h))
+    cap = max(min(t_steps, max(itermax, 1)) if use_itermax else t_steps, 1)
+    norms = np.zeros(cap)
+    t_out, ns = C.c_double(0.0), C.c_int64(0)
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    rc = L.pdes_rk4(ctx, float(h), float(t_max), itermax, float(res_tol), int(bool(real_time)),
+                    C.byref(t_out), _ptr(norms), cap, C.byref(ns))
+    eqn._check(rc)
+    eqn._check(L.pdes_get_q(ctx, _ptr(eqn.q)))
+    eqn.convergence = norms[:ns.value].copy()
+    return t_out.value
+
+
+def createObjects(mesh, sbp, opts, device=0):
+    """Synthetic-mesh analogue of ``createObjects`` (solver/euler/startup_func.jl:45-66):
+    returns ``(mesh, sbp, eqn, opts)`` with the device context initialised."""
+    return mesh, sbp, EulerData(mesh, sbp, opts, device=device), opts

@@ -111,21 +111,29 @@ def _kuhn_tets():
 
 
 def block_ranges(n, parts, rank):
-    """Cube-index range [lo, hi) per dimension owned by ``rank``."""
+    """Cube-index range [lo, hi) per dimension owned by ``rank`` (``n`` cells per
+    dimension: an int or one count per dimension)."""
     dim = len(parts)
+    n = _per_dim(n, dim)
     idx = []
     r = rank
     for d in range(dim):
         idx.append(r % parts[d])
         r //= parts[d]
-    lo = [(n * idx[d]) // parts[d] for d in range(dim)]
-    hi = [(n * (idx[d] + 1)) // parts[d] for d in range(dim)]
+    lo = [(n[d] * idx[d]) // parts[d] for d in range(dim)]
+    hi = [(n[d] * (idx[d] + 1)) // parts[d] for d in range(dim)]
     return lo, hi, idx
 
 
-def structured_mesh(op: SBPOperator, n: int, parts=None, rank: int = 0,
+def _per_dim(n, dim):
+    return [int(n)] * dim if np.isscalar(n) else [int(v) for v in n]
+
+
+def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
                     domain=None, bc_sides=None, shuffle_seed=None) -> Mesh:
-    """Structured simplex mesh of ``n^dim`` cells.
+    """Structured simplex mesh of ``n^dim`` cells; ``n`` may also be
+    one cell count per dimension (the cell size then stays ``(domain[1]-domain[0])/n[0]``
+    in every direction, i.e. the box grows: used for weak-scaling runs).
 
     parts: block partition (px,py[,pz]); ``rank`` selects the local block.
     bc_sides: optional list, one BC index per geometric side
@@ -141,10 +149,12 @@ def structured_mesh(op: SBPOperator, n: int, parts=None, rank: int = 0,
     if parts is None:
         parts = (1,) * dim
     nranks = int(np.prod(parts))
-    lo, hi, _ = block_ranges(n, parts, rank)
+    nv = _per_dim(n, dim)
+    n = nv[0]
+    lo, hi, _ = block_ranges(nv, parts, rank)
     # extended block: one ghost layer wherever a neighbour exists
     elo = [max(lo[d] - 1, 0) for d in range(dim)]
-    ehi = [min(hi[d] + 1, n) for d in range(dim)]
+    ehi = [min(hi[d] + 1, nv[d]) for d in range(dim)]
     ext = [ehi[d] - elo[d] for d in range(dim)]
 
     # cells of the extended block, x fastest
@@ -158,7 +168,7 @@ def structured_mesh(op: SBPOperator, n: int, parts=None, rank: int = 0,
             # inverse of block_ranges: part index whose [lo,hi) contains c
             pidx = np.zeros(len(c), dtype=np.int64)
             for k in range(parts[d]):
-                a, b = (n * k) // parts[d], (n * (k + 1)) // parts[d]
+                a, b = (nv[d] * k) // parts[d], (nv[d] * (k + 1)) // parts[d]
                 pidx[(c[:, d] >= a) & (c[:, d] < b)] = k
             r += mult * pidx
             mult *= parts[d]
@@ -178,12 +188,12 @@ def structured_mesh(op: SBPOperator, n: int, parts=None, rank: int = 0,
     vgrid = cells[:, None, None, :] + simp[None, :, :, :]      # [nc, ns, dim+1, dim]
     vgrid = vgrid.reshape(-1, dim + 1, dim)
     el_owner = np.repeat(cell_owner, ns)
-    mult = np.array([(n + 1) ** d for d in range(dim)], dtype=np.int64)
+    mult = np.cumprod([1] + [nv[d] + 1 for d in range(dim - 1)]).astype(np.int64)
     gvid = (vgrid * mult).sum(axis=2)                           # [ne_ext, dim+1]
     h = (domain[1] - domain[0]) / n
     vcoord = domain[0] + h * vgrid.astype(np.float64)           # [ne_ext, dim+1, dim]
     # global element number (cell lexicographic, x fastest, then simplex)
-    gcell = (cells * np.array([n ** d for d in range(dim)], dtype=np.int64)).sum(axis=1)
+    gcell = (cells * np.cumprod([1] + nv[:-1]).astype(np.int64)).sum(axis=1)
     gel = (gcell[:, None] * ns + np.arange(ns)[None, :]).ravel()
 
     if shuffle_seed is not None:
@@ -284,7 +294,7 @@ def structured_mesh(op: SBPOperator, n: int, parts=None, rank: int = 0,
     side = np.full(len(be), -1, dtype=np.int64)
     for d in range(dim):
         side[np.abs(cen[:, d] - domain[0]) < 1e-9 * h + 1e-12] = 2 * d
-        side[np.abs(cen[:, d] - domain[1]) < 1e-9 * h + 1e-12] = 2 * d + 1
+        side[np.abs(cen[:, d] - (domain[0] + h * nv[d])) < 1e-9 * h + 1e-12] = 2 * d + 1
     assert side.min() >= 0, "unpaired face not on the domain boundary"
     if bc_sides is None:
         bc_sides = [0] * (2 * dim)

@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.
+
+Tolerances are BASELINE.json's: 1e-12 relative L2 per residual, 1e-10 on an RK4
+trajectory (fp64)."""
+import numpy as np
+import pytest
+
+import oracle
+import pdesolver_jl_b200 as pd
+from common import CASES, perturbed, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+RES_TOL = 1e-12
+RK_TOL = 1e-10
+
+
+def setup(case, n, shuffle_seed=None, extra=None, bc_sides=None):
+    dim, p, ic, opts = CASES[case]
+    opts = dict(opts)
+    opts.update(extra or {})
+    op = pd.build_operator(dim, p, "omega")
+    mesh = pd.structured_mesh(op, n, shuffle_seed=shuffle_seed, bc_sides=bc_sides)
+    orc = oracle.Problem(mesh, op, opts)
+    q0 = perturbed(orc.exact_state(ic))
+    eqn = pd.EulerData(mesh, op, opts)
+    return op, mesh, opts, orc, q0, eqn
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 12), ("2d_p2_roe", 9), ("3d_p1_roe_src", 5),
+                                    ("c3_3d_p2_roe_src", 4)])
+@pytest.mark.parametrize("seed", [None, 3])
+def test_residual_matches_oracle(case, n, seed):
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=seed)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    ref = orc.eval_residual(q0)                     # reference-faithful precompute path
+    assert rel_l2(eqn.res, ref) < RES_TOL
+    ref2 = orc.eval_residual(q0, precompute=False)  # fused forms (test_flux.jl:255-296)
+    assert rel_l2(eqn.res, ref2) < RES_TOL
+    assert np.array_equal(eqn.q, q0), "evalResidual must only read eqn.q"
+
+
+def test_residual_ragged_tile_sizes():
+    # element counts that are not multiples of the CTA tile, down to a single cell
+    for n in (1, 2, 3, 7):
+        op, mesh, opts, orc, q0, eqn = setup("c3_3d_p2_roe_src", n, shuffle_seed=n)
+        eqn.q[...] = q0
+        pd.evalResidual(mesh, op, eqn, opts)
+        assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+
+
+@pytest.mark.parametrize("bc", ["FreeStreamBC", "noPenetrationBC", "isentropicVortexBC", "ExpBC"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_boundary_conditions(bc, dim):
+    case = "c1_2d_p1_roe" if dim == 2 else "3d_p1_roe_src"
+    sides = [0, 1, 0, 1] if dim == 2 else [0, 1, 0, 1, 0, 1]
+    extra = {"BC1_name": bc, "BC2_name": "FreeStreamBC" if bc != "FreeStreamBC" else "noPenetrationBC",
+             "Ma": 0.5, "aoa": 5.0}
+    op, mesh, opts, orc, q0, eqn = setup(case, 4, shuffle_seed=5, extra=extra, bc_sides=sides)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_uniform_flow_zero_residual(dim, p):
+    # test_dg.jl:115-128 / test_lowlevel.jl:813-821
+    op = pd.build_operator(dim, p)
+    mesh = pd.structured_mesh(op, 3, shuffle_seed=1)
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "FreeStreamBC", "Ma": 0.4, "aoa": 10.0}
+    orc = oracle.Problem(mesh, op, opts)
+    eqn = pd.EulerData(mesh, op, opts)
+    eqn.q[...] = orc.exact_state("ICFreeStream")
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert np.abs(eqn.res).max() < 1e-13
+
+
+def test_mass_matrix_inverse():
+    op, mesh, opts, orc, q0, eqn = setup("c3_3d_p2_roe_src", 3)
+    assert np.array_equal(eqn.Minv, orc.mass_matrix_inverse().reshape(-1, order="F"))
+
+
+@pytest.mark.parametrize("case,n,h", [("c1_2d_p1_roe", 10, 1e-3), ("c3_3d_p2_roe_src", 3, 5e-5),
+                                       ("2d_p2_roe", 6, 1e-3), ("3d_p1_roe_src", 4, 5e-5)])
+def test_rk4_trajectory(case, n, h):
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=2)
+    nsteps = 20
+    opts["use_itermax"] = False
+    eqn.q[...] = q0
+    t = pd.rk4(pd.evalResidual, h, nsteps * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, nsteps * h)
+    assert t == t_ref
+    assert rel_l2(eqn.q, q_ref) < RK_TOL
+    assert len(eqn.convergence) == len(norms_ref) == nsteps
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+
+
+def test_rk4_itermax_quirk():
+    # rk4.jl:244-247 then :269-276: the itermax exit leaves q = x_old + (h/2) k1
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 8)
+    opts.update({"use_itermax": True, "itermax": 5})
+    eqn.q[...] = q0
+    h = 1e-3
+    t = pd.rk4(pd.evalResidual, h, 1.0, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 1.0, itermax=5)
+    assert t == t_ref and len(eqn.convergence) == len(norms_ref) == 5
+    assert rel_l2(eqn.q, q_ref) < RK_TOL
+
+
+def test_rk4_res_tol_stop():
+    # pseudo-time stopping test (rk4.jl:258-267): stops at the first step head whose norm < res_tol
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 8)
+    opts["use_itermax"] = False
+    h = 1e-3
+    _, _, norms = orc.rk4(q0, h, 40 * h)
+    tol = 0.5 * (norms[10] + norms[11]) if norms[11] < norms[10] else norms[0] * 2
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 40 * h, res_tol=tol)
+    eqn.q[...] = q0
+    t = pd.rk4(pd.evalResidual, h, 40 * h, mesh, op, eqn, opts, res_tol=tol)
+    assert len(eqn.convergence) == len(norms_ref)
+    assert abs(t - t_ref) < 1e-15
+    assert rel_l2(eqn.q, q_ref) < RK_TOL
+    # real_time=True ignores res_tol
+    eqn.q[...] = q0
+    pd.rk4(pd.evalResidual, h, 40 * h, mesh, op, eqn, opts, res_tol=tol, real_time=True)
+    assert len(eqn.convergence) == 40
+
+
+def test_negative_density_and_pressure_raise():
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 6)
+    q = q0.copy(order="F")
+    q[0, 1, 17] = -1.0
+    eqn.q[...] = q
+    with pytest.raises(pd.PhysicsError, match="Negative density") as ei:
+        pd.evalResidual(mesh, op, eqn, opts)
+    assert (ei.value.element, ei.value.node) == (17, 1)
+    with pytest.raises(FloatingPointError):
+        orc.eval_residual(q)
+    q = q0.copy(order="F")
+    q[3, 2, 40] = 1e-3          # energy below kinetic energy -> negative pressure
+    eqn.q[...] = q
+    with pytest.raises(pd.PhysicsError, match="Negative pressure") as ei:
+        pd.evalResidual(mesh, op, eqn, opts)
+    assert (ei.value.element, ei.value.node) == (40, 2)
+    # the context recovers
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+    # checks off: no exception (read_input.jl:334-335 keys)
+    opts2 = dict(opts, check_density=False, check_pressure=False)
+    eqn2 = pd.EulerData(mesh, op, opts2)
+    eqn2.q[...] = q
+    pd.evalResidual(mesh, op, eqn2, opts2)
+
+
+@pytest.mark.parametrize("case,n,parts", [("c1_2d_p1_roe", 8, (2, 2)), ("c3_3d_p2_roe_src", 4, (2, 2, 2)),
+                                          ("3d_p1_roe_src", 4, (2, 1, 1))])
+def test_partitioned_equals_serial(case, n, parts):
+    """runtests_parallel2.jl strategy: the P-way result equals the serial one.  The exchange is done by
+    hand here (pack on the device -> host copy into the peer's receive buffer); NCCL itself is covered by
+    test_gpu_multi.py when more than one GPU is visible."""
+    dim, p, ic, opts = CASES[case]
+    op = pd.build_operator(dim, p)
+    nranks = int(np.prod(parts))
+    meshes = [pd.structured_mesh(op, n, parts=parts, rank=r, shuffle_seed=4) for r in range(nranks)]
+    serial = pd.structured_mesh(op, n, shuffle_seed=4)
+    orc_s = oracle.Problem(serial, op, opts)
+    q_s = perturbed(orc_s.exact_state(ic))
+    res_s = orc_s.eval_residual(q_s)
+    # scatter the serial state by global element number
+    pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
+    eqns, qs = [], []
+    for m in meshes:
+        idx = np.array([pos[int(g)] for g in m.global_elnum])
+        eq = pd.EulerData(m, op, opts)
+        eq.q[...] = q_s[:, :, idx]
+        eqns.append(eq)
+        qs.append(idx)
+    sends = [[eq.pack_send(pi) for pi in range(m.npeers)] for eq, m in zip(eqns, meshes)]
+    for r, (eq, m) in enumerate(zip(eqns, meshes)):
+        for pi, pr in enumerate(m.peer_parts):
+            po = meshes[pr].peer_parts.index(r)
+            eq.inject_recv(pi, sends[pr][po])
+    for eq, m, idx in zip(eqns, meshes, qs):
+        pd.evalResidual(m, op, eq, opts)
+        assert rel_l2(eq.res, res_s[:, :, idx]) < RES_TOL
