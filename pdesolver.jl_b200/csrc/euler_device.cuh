@@ -39,47 +39,49 @@ __device__ __forceinline__ void euler_flux(const T* q, const double* n, double g
 
 // bc_solvers.jl:29-187 RoeSolver + :207-420 calcSAT:
 //   flux = 0.5*(|A_hat| - A_hat)(q - qg) + F_euler(q, n), eigenvalue floors 0.025*rhoA
+// Same formulas, with the ten divisions / square roots of the reference regrouped into three rsqrt and three
+// reciprocals (1/rho = rsqrt(rho)^2, sqrt(rho) = rho*rsqrt(rho), dA*a = x*rsqrt(x) with x = dA^2 a^2,
+// gami/a^2 = 1/(H - phi)); every regrouping is exact up to a few ulp (parity budget: 1e-12).
 template <int DIM, typename T>
 __device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* n, double gamma, T* flux) {
   constexpr int ND = DIM + 2;
   const double gami = gamma - 1.0;
   const double sat_Vn = 0.025, sat_Vl = 0.025;
-  T fac = 1.0 / q[0];
+  const T rL = rsqrt(q[0]), rR = rsqrt(qg[0]);
+  const T sqL = q[0] * rL, sqR = qg[0] * rR;
+  const T invL = rL * rL, invR = rR * rR;
   T vL[DIM], vR[DIM];
-  T phi = 0.0;
+  T phiL = 0.0, phiR = 0.0;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) { vL[d] = q[1 + d] * fac; phi += vL[d] * vL[d]; }
-  phi = 0.5 * phi;
-  T HL = gamma * q[DIM + 1] * fac - gami * phi;
-  // p = gami*(E - rho*phi): reuse for the Euler flux of the left state
-  T pressL = gami * (q[DIM + 1] - q[0] * phi);
-  fac = 1.0 / qg[0];
-  phi = 0.0;
-#pragma unroll
-  for (int d = 0; d < DIM; ++d) { vR[d] = qg[1 + d] * fac; phi += vR[d] * vR[d]; }
-  phi = 0.5 * phi;
-  T HR = gamma * qg[DIM + 1] * fac - gami * phi;
-  T sqL = sqrt(q[0]), sqR = sqrt(qg[0]);
-  fac = 1.0 / (sqL + sqR);
+  for (int d = 0; d < DIM; ++d) {
+    vL[d] = q[1 + d] * invL; phiL += vL[d] * vL[d];
+    vR[d] = qg[1 + d] * invR; phiR += vR[d] * vR[d];
+  }
+  phiL = 0.5 * phiL; phiR = 0.5 * phiR;
+  const T HL = gamma * q[DIM + 1] * invL - gami * phiL;
+  const T HR = gamma * qg[DIM + 1] * invR - gami * phiR;
+  const T pressL = gami * (q[DIM + 1] - q[0] * phiL);     // p of the left state, reused by its Euler flux
+  const T fac = 1.0 / (sqL + sqR);
   T v[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) v[d] = (sqL * vL[d] + sqR * vR[d]) * fac;
-  T H = (sqL * HL + sqR * HR) * fac;
+  const T H = (sqL * HL + sqR * HR) * fac;
   T dq[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) dq[i] = q[i] - qg[i];
 
   // ---- calcSAT ----
   double dA2 = 0.0;
-  T Un = 0.0;
-  phi = 0.0;
+  T Un = 0.0, phi = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { dA2 += n[d] * n[d]; phi += v[d] * v[d]; Un += v[d] * n[d]; }
-  double dA = sqrt(dA2);
   phi = 0.5 * phi;
-  T a = sqrt(gami * (H - phi));
-  T l1 = Un + dA * a, l2 = Un - dA * a, l3 = Un;
-  T rhoA = absv(Un) + dA * a;
+  const T Hm = H - phi;                 // a^2 = gami*(H - phi)
+  const T x = dA2 * (gami * Hm);        // (dA a)^2
+  const T rx = rsqrt(x);
+  const T dAa = x * rx;                 // dA * a
+  T l1 = Un + dAa, l2 = Un - dAa, l3 = Un;
+  const T rhoA = absv(Un) + dAa;
   l1 = 0.5 * (maxv(absv(l1), sat_Vn * rhoA) - l1);
   l2 = 0.5 * (maxv(absv(l2), sat_Vn * rhoA) - l2);
   l3 = 0.5 * (maxv(absv(l3), sat_Vl * rhoA) - l3);
@@ -90,13 +92,13 @@ __device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* 
   T e2 = -Un * dq[0];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) e2 += n[d] * dq[1 + d];
-  T tmp1 = 0.5 * (l1 + l2) - l3;
-  T tmp2 = gami / (a * a);
-  T tmp3 = 1.0 / (dA * dA);
-  T tmp4 = 0.5 * (l1 - l2) / (dA * a);
+  const T tmp1 = 0.5 * (l1 + l2) - l3;
+  const T tmp2 = 1.0 / Hm;              // gami / a^2
+  const T tmp3 = 1.0 / dA2;
+  const T tmp4 = 0.5 * (l1 - l2) * rx;  // 0.5*(l1-l2)/(dA a)
   // sat = l3*dq + tmp1*(tmp2*E1dq + tmp3*E2dq) + tmp4*(E3dq + gami*E4dq)
-  T c1 = tmp1 * tmp2 * e1 + tmp4 * e2;      // multiplies [1, v, H]
-  T c2 = tmp1 * tmp3 * e2 + tmp4 * gami * e1;  // multiplies [0, n, Un]
+  const T c1 = tmp1 * tmp2 * e1 + tmp4 * e2;          // multiplies [1, v, H]
+  const T c2 = tmp1 * tmp3 * e2 + tmp4 * gami * e1;   // multiplies [0, n, Un]
 
   // ---- Euler flux of the left state ----
   T U = vL[0] * n[0];

@@ -99,6 +99,8 @@ struct ResArgs {
   PhysPar ph;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __host__ __device__ constexpr int pad_stride(int n, int nd) {
   // smallest m >= n with m % 16 == nd % 16: (element, variable)-indexed fp64 accesses of a half-warp
   // then fall into distinct banks
@@ -208,6 +210,37 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
     s_skip[tid] = sk;
   }
   __syncthreads();
+  // L2 prefetch of everything the later stages gather: neighbour elements, face normals, and the
+  // epilogue's streams (the loads themselves are issued much later; this converts their HBM latency into L2 latency)
+  for (int idx = tid; idx < ne * NF; idx += T) {
+    const EFace ef = sEf[idx];
+    if (ef.kind <= FK_INTERIOR_R) {
+      const char* pq = reinterpret_cast<const char*>(a.q + (int64_t)ef.nbr * EL);
+#pragma unroll
+      for (int o = 0; o < EL * 8 + 127; o += 128) prefetch_l2(pq + o);
+      const char* pn = reinterpret_cast<const char*>(a.nrm_face + (int64_t)ef.idx * NFN * DIM);
+      prefetch_l2(pn);
+      prefetch_l2(pn + NFN * DIM * 8 - 8);
+    } else if (ef.kind == FK_BOUNDARY) {
+      prefetch_l2(a.nrm_bndry + (int64_t)ef.idx * NFN * DIM);
+      prefetch_l2(a.coords_bndry + (int64_t)ef.idx * NFN * DIM);
+    }
+  }
+  if (a.elist == nullptr) {
+    const int64_t b0 = e0 * EL * 8, nb = (int64_t)ne * EL * 8;
+    for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
+      if (a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
+      if (MODE == EPI_RK) {
+        if (a.stage > 1) {
+          prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+          prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+        }
+      }
+    }
+    if (MODE == EPI_RK)
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.minv) + e0 * NN * 8 + o);
+  }
   const int v = tid;                     // variable-thread id
   const int vs = v / ND, vk = v - vs * ND;
   const bool v_active = (v < ne * ND) && !s_skip[vs];
@@ -319,43 +352,47 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   __syncthreads();
 
   // ---- S5: numerical flux at every face node, scaled by -/+ wface (in place in sOwn) ---------
+  // one instance of the Roe solver (rolled loop: the unrolled operator products already fill the
+  // instruction cache); the left/right roles are selected on the data.  Normals were prefetched to L2.
+#pragma unroll 1
   for (int it = tid; it < ne * NF * NFN; it += T) {
-    int s = it / (NF * NFN), r = it - s * (NF * NFN);
-    int f = r / NFN, i = r - f * NFN;
+    const int s = it / (NF * NFN), r = it - s * (NF * NFN);
     if (s_skip[s]) continue;
-    EFace ef = sEf[s * NF + f];
+    const int f = r / NFN, i = r - f * NFN;
+    const EFace ef = sEf[s * NF + f];
+    const bool right = ef.kind == FK_INTERIOR_R;
+    const int ii = right ? s_nbrperm[ef.orient][i] : i;   // node index in the left element's ordering
+    const double* base = a.nrm_face;
+    if (ef.kind == FK_BOUNDARY) base = a.nrm_bndry;
+    else if (ef.kind == FK_SHARED) base = a.nrm_shared;
+    const double* np_ = base + ((int64_t)ef.idx * NFN + ii) * DIM;
+    double nrm[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
     double* po = sOwn + s * FS + r * ND;
-    double own[ND], flux[ND], nrm[DIM];
-#pragma unroll
-    for (int k = 0; k < ND; ++k) own[k] = po[k];
-    double scale;
+    const double* pn = sNbr + s * FS + r * ND;
+    double flux[ND];
+    double scale = right ? op.wface[ii] : -op.wface[ii];
     if (ef.kind == FK_BOUNDARY) {
-      const double* np_ = a.nrm_bndry + ((int64_t)ef.idx * NFN + i) * DIM;
+      // separate copies so that only this (rare) path touches local memory
       const double* xp = a.coords_bndry + ((int64_t)ef.idx * NFN + i) * DIM;
-      double x[DIM];
+      double xb[DIM], nb_[DIM], qb[ND], fb[ND];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) { nrm[d] = np_[d]; x[d] = xp[d]; }
-      bc_flux<DIM>(ef.bc, own, x, nrm, a.ph, flux);
-      scale = -op.wface[i];
+      for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
+#pragma unroll
+      for (int k = 0; k < ND; ++k) qb[k] = po[k];
+      bc_flux<DIM>(ef.bc, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) flux[k] = fb[k];
     } else {
-      double nb[ND];
-      const double* pn = sNbr + s * FS + r * ND;
+      double qa[ND], qb[ND];
 #pragma unroll
-      for (int k = 0; k < ND; ++k) nb[k] = pn[k];
-      if (ef.kind == FK_INTERIOR_R) {
-        int ii = s_nbrperm[ef.orient][i];        // node index in the left element's ordering
-        const double* np_ = a.nrm_face + ((int64_t)ef.idx * NFN + ii) * DIM;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) nrm[d] = np_[d];
-        roe_flux<DIM>(nb, own, nrm, a.ph.gamma, flux);
-        scale = op.wface[ii];
-      } else {
-        const double* np_ = (ef.kind == FK_SHARED ? a.nrm_shared : a.nrm_face) + ((int64_t)ef.idx * NFN + i) * DIM;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) nrm[d] = np_[d];
-        roe_flux<DIM>(own, nb, nrm, a.ph.gamma, flux);
-        scale = -op.wface[i];
+      for (int k = 0; k < ND; ++k) {
+        const double o = po[k], nb = pn[k];
+        qa[k] = right ? nb : o;
+        qb[k] = right ? o : nb;
       }
+      roe_flux<DIM>(qa, qb, nrm, a.ph.gamma, flux);
     }
 #pragma unroll
     for (int k = 0; k < ND; ++k) po[k] = scale * flux[k];
@@ -378,29 +415,49 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   __syncthreads();
 
   // ---- S7: epilogue (coalesced): source, then either res or the fused RK4 stage ----------------
+  // loads of a chunk of CH dofs per thread are issued together before any of them is consumed
   double nrm2 = 0.0;
-  for (int idx = tid; idx < ne * EL; idx += T) {
-    int s = idx / EL, r = idx - s * EL;
-    if (s_skip[s]) continue;
-    int64_t dof = (int64_t)s_el[s] * EL + r;
-    double val = sq[s * SQ + r];
-    if (a.srcw) val += a.srcw[dof];
-    if (MODE == EPI_RES) {
-      a.res[dof] = val;
-    } else {
-      int j = r / ND;
-      double mi = a.minv[(int64_t)s_el[s] * NN + j];
-      double k = mi * val;                       // pde_post_func: res_vec *= Minv
-      double xo = a.x_old[dof];
-      if (a.stage == 1) {
-        nrm2 += k * k / mi;                      // calcNorm: sum res*M*res (Utils.jl:427-449)
-        a.ksum[dof] = k;
-        a.q_next[dof] = xo + a.ah * k;
-      } else if (a.stage < 4) {
-        a.ksum[dof] = a.ksum[dof] + 2.0 * k;
-        a.q_next[dof] = xo + a.ah * k;
-      } else {
-        a.q_next[dof] = xo + a.h6 * (a.ksum[dof] + k);
+  {
+    constexpr int CH = 4;
+    const int ntile = ne * EL;
+    for (int base = 0; base < ntile; base += CH * T) {
+      double val[CH], sv[CH], mi[CH], xo[CH], ks[CH];
+      int64_t dof[CH];
+      bool ok[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int idx = base + u * T + tid;
+        ok[u] = idx < ntile;
+        int s = 0, r = 0;
+        if (ok[u]) { s = idx / EL; r = idx - s * EL; ok[u] = !s_skip[s]; }
+        dof[u] = ok[u] ? (int64_t)s_el[s] * EL + r : 0;
+        val[u] = ok[u] ? sq[s * SQ + r] : 0.0;
+        sv[u] = (ok[u] && a.srcw) ? a.srcw[dof[u]] : 0.0;
+        if (MODE == EPI_RK) {
+          mi[u] = ok[u] ? a.minv[(int64_t)s_el[s] * NN + r / ND] : 1.0;
+          xo[u] = ok[u] ? a.x_old[dof[u]] : 0.0;
+          ks[u] = (ok[u] && a.stage > 1) ? a.ksum[dof[u]] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        if (!ok[u]) continue;
+        const double v = val[u] + sv[u];
+        if (MODE == EPI_RES) {
+          a.res[dof[u]] = v;
+        } else {
+          const double k = mi[u] * v;              // pde_post_func: res_vec *= Minv
+          if (a.stage == 1) {
+            nrm2 += k * k / mi[u];                 // calcNorm: sum res*M*res (Utils.jl:427-449)
+            a.ksum[dof[u]] = k;
+            a.q_next[dof[u]] = xo[u] + a.ah * k;
+          } else if (a.stage < 4) {
+            a.ksum[dof[u]] = ks[u] + 2.0 * k;
+            a.q_next[dof[u]] = xo[u] + a.ah * k;
+          } else {
+            a.q_next[dof[u]] = xo[u] + a.h6 * (ks[u] + k);
+          }
+        }
       }
     }
   }
