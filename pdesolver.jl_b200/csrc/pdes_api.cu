@@ -86,7 +86,7 @@ struct Ops {
   virtual int tile_elems() const = 0;
 };
 
-template <int DIM, int NN, int NFN, int E>
+template <int DIM, int NN, int NFN, int E, int MINB = 1>
 struct OpsImpl : Ops {
   using Tab = OpTab<DIM, NN, NFN>;
   using Cfg = TileCfg<DIM, NN, NFN, E>;
@@ -98,14 +98,17 @@ struct OpsImpl : Ops {
     const int ss = c.ss;
     for (int d = 0; d < DIM; ++d)
       for (int j = 0; j < NN; ++j)
-        for (int i = 0; i < NN; ++i) tab.Qt[d][j][i] = Q[j + NN * (i + NN * d)];
+        for (int i = 0; i < NN; ++i) tab.Qt[d * NN + j][i] = Q[j + NN * (i + NN * d)];
     for (int f = 0; f < DIM + 1; ++f)
       for (int j = 0; j < NN; ++j) tab.perm[f][j] = j < ss ? (int)(perm[j + (int64_t)ss * f] - base) : 0;
     for (int j = 0; j < NN; ++j)
       for (int i = 0; i < NFN; ++i) tab.interp[j][i] = j < ss ? interp[j + ss * i] : 0.0;
     for (int f = 0; f < DIM + 1; ++f)
       for (int i = 0; i < NFN; ++i)
-        for (int j = 0; j < ss; ++j) tab.Rf[f][i][tab.perm[f][j]] += interp[j + ss * i];
+        for (int j = 0; j < ss; ++j) {
+          tab.RfN[f * NFN + i][tab.perm[f][j]] += interp[j + ss * i];
+          tab.RfT[tab.perm[f][j]][f * NFN + i] += interp[j + ss * i];
+        }
     for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
     for (int o = 0; o < Tab::NOR; ++o)
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
@@ -115,10 +118,10 @@ struct OpsImpl : Ops {
   int tile_elems() const override { return E; }
   cudaError_t launch_residual(const ResArgs& a, int mode, int64_t nelems, cudaStream_t s) override {
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RES>,
+      cudaError_t e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RES, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg::smem_bytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
@@ -126,9 +129,9 @@ struct OpsImpl : Ops {
     if (nelems <= 0) return cudaSuccess;
     dim3 grid((unsigned)grid_for(nelems)), block(Cfg::T);
     if (mode == EPI_RES)
-      k_residual_roe<DIM, NN, NFN, E, EPI_RES><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+      k_residual_roe<DIM, NN, NFN, E, EPI_RES, MINB><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     else
-      k_residual_roe<DIM, NN, NFN, E, EPI_RK><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+      k_residual_roe<DIM, NN, NFN, E, EPI_RK, MINB><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     return cudaGetLastError();
   }
   cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
@@ -147,13 +150,17 @@ int env_int(const char* name, int dflt) {
 
 Ops* make_ops(const PdesConfig& c) {
   if (c.sparse_face) return nullptr;
-  const int big = env_int("PDES_TILE", 0);
+  const int tile = env_int("PDES_TILE", 0), minb = env_int("PDES_MINB", 0);   // tuning knobs (tools/bench_variants.sh)
   if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64>();
   if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32>();
   if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32>();
   if (c.dim == 3 && c.nn == 11 && c.nfn == 6) {
-    if (big == 32) return new OpsImpl<3, 11, 6, 32>();
-    return new OpsImpl<3, 11, 6, 16>();
+    if (tile == 32) return minb == 3 ? (Ops*)new OpsImpl<3, 11, 6, 32, 3>() : (Ops*)new OpsImpl<3, 11, 6, 32, 2>();
+    if (tile == 19) return minb == 5 ? (Ops*)new OpsImpl<3, 11, 6, 19, 5>() : (Ops*)new OpsImpl<3, 11, 6, 19, 4>();
+    if (tile == 12) return new OpsImpl<3, 11, 6, 12, 6>();
+    if (minb == 6) return new OpsImpl<3, 11, 6, 16, 6>();
+    if (minb == 4) return new OpsImpl<3, 11, 6, 16, 4>();
+    return new OpsImpl<3, 11, 6, 16, 5>();
   }
   return nullptr;
 }

@@ -55,8 +55,10 @@ template <int DIM, int NN, int NFN>
 struct OpTab {
   static constexpr int NF = DIM + 1;
   static constexpr int NOR = (DIM == 2) ? 1 : 3;
-  double Qt[DIM][NN][NN];     // Qt[d][j][i] = sbp.Q[j,i,d]   (res_i += Q[j,i,d] F_j : weakdifferentiate!, trans=true)
-  double Rf[NF][NFN][NN];     // Rf[f][i][node] = sum_j interp[j,i] [perm[j,f]==node]
+  static constexpr int NNP = NN, NFP = NF * NFN;
+  double Qt[DIM * NN][NNP];   // Qt[d*NN+j][i] = sbp.Q[j,i,d]   (res_i += Q[j,i,d] F_j : weakdifferentiate!, trans=true)
+  double RfN[NF * NFN][NNP];  // RfN[f*NFN+i][node] = sum_j interp[j,i] [perm[j,f]==node]   (face integration)
+  double RfT[NN][NFP];        // RfT[node][f*NFN+i] = the same matrix, transposed               (face interpolation)
   double interp[NN][NFN];     // sbpface.interp[j,i] (stencil order, used for the neighbour side)
   double wface[NFN];
   int32_t perm[NF][NN];       // sbpface.perm[j,f] (0-based)
@@ -112,7 +114,9 @@ __host__ __device__ constexpr int pad_stride(int n, int nd) {
 template <int DIM, int NN, int NFN, int E>
 struct TileCfg {
   static constexpr int ND = DIM + 2, NF = DIM + 1;
-  static constexpr int T = ((E * ND + 31) / 32) * 32;
+  static constexpr int H = 1;                                  // threads per (element, variable) row
+  static constexpr int VT = E * ND * H;                        // variable threads
+  static constexpr int T = ((VT + 31) / 32) * 32;
   static constexpr int SQ = pad_stride(NN * ND, ND);           // per-element stride of the q tile
   static constexpr int FS = pad_stride(NF * NFN * ND, ND);     // per-element stride of face-state tiles
   static constexpr int SF = ND * DIM * NN;                      // per-element stride of the volume-flux tile
@@ -147,8 +151,8 @@ __device__ __noinline__ void bc_flux(int bc, const double* q, const double* x, c
   roe_flux<DIM>(q, qg, n, ph.gamma, flux);
 }
 
-template <int DIM, int NN, int NFN, int E, int MODE>
-__global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T))
+template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
+__global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
 k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ResArgs a) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
   constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ, FS = Cfg::FS;
@@ -241,9 +245,10 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
       for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
         prefetch_l2(reinterpret_cast<const char*>(a.minv) + e0 * NN * 8 + o);
   }
-  const int v = tid;                     // variable-thread id
+  // variable threads: v -> (element vs, variable vk)
+  const int v = tid;
   const int vs = v / ND, vk = v - vs * ND;
-  const bool v_active = (v < ne * ND) && !s_skip[vs];
+  const bool v_active = (v < ne * ND) && !s_skip[vs < E ? vs : 0];
 
   // ---- S1: Euler flux in the parametric directions at every node (getEulerFlux) ---------------
   for (int it = tid; it < ne * NN; it += T) {
@@ -251,6 +256,10 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
     double qn[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) qn[k] = sq[s * SQ + j * ND + k];
+    const double* dx = a.dxidx + ((int64_t)s_el[s] * NN + j) * (DIM * DIM);
+    double dxl[DIM * DIM];
+#pragma unroll
+    for (int m = 0; m < DIM * DIM; ++m) dxl[m] = __ldg(dx + m);
     double press = calc_pressure<DIM>(qn, gami);
     if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
       int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
@@ -261,10 +270,6 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
       atomicExch(&a.ctl->err_code, 1);  // decoded on the host from err_loc
       atomicExch(&a.ctl->stop, 1);
     }
-    const double* dx = a.dxidx + ((int64_t)s_el[s] * NN + j) * (DIM * DIM);
-    double dxl[DIM * DIM];
-#pragma unroll
-    for (int m = 0; m < DIM * DIM; ++m) dxl[m] = dx[m];
     double rinv = 1.0 / qn[0];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
@@ -282,44 +287,39 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   __syncthreads();
 
   // ---- S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j] ---------------------------
+  // (loops over directions / faces stay rolled: the fully unrolled operator products overflow the instruction
+  // cache; one direction or one face at a time keeps >= NN independent DFMA chains in flight)
   double acc[NN];
-  double qk[NN];
 #pragma unroll
-  for (int i = 0; i < NN; ++i) acc[i] = 0.0;
+  for (int u = 0; u < NN; ++u) acc[u] = 0.0;
   if (v_active) {
-#pragma unroll
-    for (int j = 0; j < NN; ++j) qk[j] = sq[vs * SQ + j * ND + vk];
     const double* Fv = sF + (vs * ND + vk) * DIM * NN;
+#pragma unroll 1
+    for (int d = 0; d < DIM; ++d) {
+      double Fj[NN];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d)
+      for (int j = 0; j < NN; ++j) Fj[j] = Fv[d * NN + j];
 #pragma unroll
-      for (int j = 0; j < NN; ++j) {
-        double Fj = Fv[d * NN + j];
+      for (int j = 0; j < NN; ++j)
 #pragma unroll
-        for (int i = 0; i < NN; ++i) acc[i] = fma(op.Qt[d][j][i], Fj, acc[i]);
-      }
+        for (int u = 0; u < NN; ++u) acc[u] = fma(op.Qt[d * NN + j][u], Fj[j], acc[u]);
+    }
   }
   __syncthreads();   // sF is dead; the face-state tiles reuse its storage
 
-  // ---- S3/S4: face interpolation of the own and of the neighbour state ------------------------
+  // ---- S3/S4: face interpolation of the own and of the neighbour state, one face at a time -------
   if (v_active) {
+    double qk[NN];
 #pragma unroll
+    for (int j = 0; j < NN; ++j) qk[j] = sq[vs * SQ + j * ND + vk];
+#pragma unroll 1
     for (int f = 0; f < NF; ++f) {
-#pragma unroll
-      for (int i = 0; i < NFN; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int n = 0; n < NN; ++n) s = fma(op.Rf[f][i][n], qk[n], s);
-        sOwn[vs * FS + (f * NFN + i) * ND + vk] = s;
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      EFace ef = sEf[vs * NF + f];
-      if (ef.kind <= FK_INTERIOR_R) {
-        // neighbour values in the neighbour's stencil order: q[k, perm[j,fnbr], nbr]
-        double qn[NN];
-        int64_t loc = (int64_t)ef.nbr - e0;
+      const EFace ef = sEf[vs * NF + f];
+      // neighbour values in the neighbour's stencil order: q[k, perm[j,fnbr], nbr] (issued first: L2 latency)
+      double qn[NN];
+      const bool interior = ef.kind <= FK_INTERIOR_R;
+      if (interior) {
+        const int64_t loc = (int64_t)ef.nbr - e0;
         if (a.elist == nullptr && loc >= 0 && loc < ne) {
           const double* b = sq + (int)loc * SQ + vk;
 #pragma unroll
@@ -329,21 +329,31 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
           for (int j = 0; j < NN; ++j) qn[j] = __ldg(b + s_perm[ef.fnbr][j] * ND);
         }
+      }
+      // own state at the NFN nodes of face f
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) sacc = fma(op.RfN[f * NFN + i][n], qk[n], sacc);
+        sOwn[vs * FS + (f * NFN + i) * ND + vk] = sacc;
+      }
+      if (interior) {
 #pragma unroll
         for (int i = 0; i < NFN; ++i) {
-          double s = 0.0;
+          double sacc = 0.0;
 #pragma unroll
-          for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], qn[j], s);
+          for (int j = 0; j < NN; ++j) sacc = fma(op.interp[j][i], qn[j], sacc);
           // the neighbour's face node i coincides with own face node nbrperm[i,orient] (involution)
-          int io = s_nbrperm[ef.orient][i];
-          sNbr[vs * FS + (f * NFN + io) * ND + vk] = s;
+          const int io = s_nbrperm[ef.orient][i];
+          sNbr[vs * FS + (f * NFN + io) * ND + vk] = sacc;
         }
       } else if (ef.kind == FK_SHARED) {
         // permuteinterface! (Utils/parallel.jl:198-201): received face-node i of the peer is own node nbrperm[i]
         const double* b = a.q_recv + (int64_t)ef.idx * (NFN * ND) + vk;
 #pragma unroll
         for (int i = 0; i < NFN; ++i) {
-          int io = s_nbrperm[ef.orient][i];
+          const int io = s_nbrperm[ef.orient][i];
           sNbr[vs * FS + (f * NFN + io) * ND + vk] = b[i * ND];
         }
       }
@@ -401,16 +411,19 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 
   // ---- S6: face integration  res[k,node] += sum_f sum_i Rf[f][i][node] * (+-w f*)[k,i] ---------
   if (v_active) {
+    const double* fv = sOwn + vs * FS + vk;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      double fl[NFN];
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
+      for (int i = 0; i < NFN; ++i) fl[i] = fv[(f * NFN + i) * ND];
 #pragma unroll
-      for (int i = 0; i < NFN; ++i) {
-        double fl = sOwn[vs * FS + (f * NFN + i) * ND + vk];
+      for (int i = 0; i < NFN; ++i)
 #pragma unroll
-        for (int n = 0; n < NN; ++n) acc[n] = fma(op.Rf[f][i][n], fl, acc[n]);
-      }
+        for (int u = 0; u < NN; ++u) acc[u] = fma(op.RfN[f * NFN + i][u], fl[i], acc[u]);
+    }
 #pragma unroll
-    for (int n = 0; n < NN; ++n) sq[vs * SQ + n * ND + vk] = acc[n];
+    for (int u = 0; u < NN; ++u) sq[vs * SQ + u * ND + vk] = acc[u];
   }
   __syncthreads();
 
