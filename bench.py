@@ -292,7 +292,7 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel = k_residual_roe<EPI_RK>: 4 launches per step; the two norm kernels (one CTA each)
+    # one residual evaluation = k_face_flux + k_element_rk<EPI_RK>: 4 such pairs per step; the two norm kernels (one CTA each)
     # are inside the bracket, so the per-launch duration is slightly over-estimated
     launch_s = (ms * 1e-3) / (4 * args.steps)
     achieved = b_stage * ndof * 1e-9 / launch_s
@@ -320,7 +320,7 @@ def main():
                 "evalResidual_dof_per_s": ndof_total / dt_res},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_residual_roe<EPI_RK>",
+                     "traffic": traffic, "kernel": "k_face_flux + k_element_rk<EPI_RK> (one residual evaluation + RK4 stage)",
                      "algorithmic_bytes_per_dof": b_stage,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
     }

@@ -79,17 +79,18 @@ struct Ops {
   virtual ~Ops() {}
   virtual void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp,
                             const int64_t* perm, const int64_t* nbrperm, const double* wface, int base) = 0;
-  virtual cudaError_t launch_residual(const ResArgs& a, int mode, int64_t nelems, cudaStream_t s) = 0;
+  virtual cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) = 0;
+  virtual cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) = 0;
   virtual cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS,
                                   double* q_send, const Ctl* ctl, cudaStream_t s) = 0;
   virtual int64_t grid_for(int64_t nelems) const = 0;
-  virtual int tile_elems() const = 0;
 };
 
-template <int DIM, int NN, int NFN, int E, int MINB = 1>
+template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
 struct OpsImpl : Ops {
   using Tab = OpTab<DIM, NN, NFN>;
   using Cfg = TileCfg<DIM, NN, NFN, E>;
+  using FCfg = FaceCfg<DIM, NN, NFN, FT>;
   Tab tab;
   bool attr_set = false;
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
@@ -105,33 +106,34 @@ struct OpsImpl : Ops {
       for (int i = 0; i < NFN; ++i) tab.interp[j][i] = j < ss ? interp[j + ss * i] : 0.0;
     for (int f = 0; f < DIM + 1; ++f)
       for (int i = 0; i < NFN; ++i)
-        for (int j = 0; j < ss; ++j) {
-          tab.RfN[f * NFN + i][tab.perm[f][j]] += interp[j + ss * i];
-          tab.RfT[tab.perm[f][j]][f * NFN + i] += interp[j + ss * i];
-        }
+        for (int j = 0; j < ss; ++j) tab.RfN[f * NFN + i][tab.perm[f][j]] += interp[j + ss * i];
     for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
     for (int o = 0; o < Tab::NOR; ++o)
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
     (void)w;
   }
   int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
-  int tile_elems() const override { return E; }
-  cudaError_t launch_residual(const ResArgs& a, int mode, int64_t nelems, cudaStream_t s) override {
+  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+    if (a.ng <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((a.ng + FT - 1) / FT)), block(FCfg::T);
+    k_face_flux<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RES, MINB>,
+      cudaError_t e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_residual_roe<DIM, NN, NFN, E, EPI_RK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)Cfg::smem_bytes);
+      e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    if (nelems <= 0) return cudaSuccess;
-    dim3 grid((unsigned)grid_for(nelems)), block(Cfg::T);
+    dim3 grid((unsigned)grid_for(a.nE)), block(Cfg::T);
     if (mode == EPI_RES)
-      k_residual_roe<DIM, NN, NFN, E, EPI_RES, MINB><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+      k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     else
-      k_residual_roe<DIM, NN, NFN, E, EPI_RK, MINB><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+      k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     return cudaGetLastError();
   }
   cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
@@ -150,17 +152,20 @@ int env_int(const char* name, int dflt) {
 
 Ops* make_ops(const PdesConfig& c) {
   if (c.sparse_face) return nullptr;
-  const int tile = env_int("PDES_TILE", 0), minb = env_int("PDES_MINB", 0);   // tuning knobs (tools/bench_variants.sh)
-  if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64>();
-  if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32>();
-  if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32>();
+  const int variant = env_int("PDES_VARIANT", 0);   // tuning knob (tools/bench_variants.sh)
+  if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64, 2, 64, 2>();
+  if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32, 2, 32, 2>();
+  if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32, 2, 32, 2>();
   if (c.dim == 3 && c.nn == 11 && c.nfn == 6) {
-    if (tile == 32) return minb == 3 ? (Ops*)new OpsImpl<3, 11, 6, 32, 3>() : (Ops*)new OpsImpl<3, 11, 6, 32, 2>();
-    if (tile == 19) return minb == 5 ? (Ops*)new OpsImpl<3, 11, 6, 19, 5>() : (Ops*)new OpsImpl<3, 11, 6, 19, 4>();
-    if (tile == 12) return new OpsImpl<3, 11, 6, 12, 6>();
-    if (minb == 6) return new OpsImpl<3, 11, 6, 16, 6>();
-    if (minb == 4) return new OpsImpl<3, 11, 6, 16, 4>();
-    return new OpsImpl<3, 11, 6, 16, 5>();
+    switch (variant) {
+      case 1: return new OpsImpl<3, 11, 6, 32, 2, 32, 2>();
+      case 2: return new OpsImpl<3, 11, 6, 32, 3, 32, 3>();
+      case 3: return new OpsImpl<3, 11, 6, 16, 5, 16, 4>();
+      case 4: return new OpsImpl<3, 11, 6, 16, 6, 32, 3>();
+      case 5: return new OpsImpl<3, 11, 6, 32, 3, 64, 1>();
+      case 6: return new OpsImpl<3, 11, 6, 64, 1, 32, 2>();
+      default: return new OpsImpl<3, 11, 6, 16, 4, 32, 2>();
+    }
   }
   return nullptr;
 }
@@ -196,24 +201,26 @@ struct PdesCtx {
   int cur = 0;
   double *ksum = nullptr, *res = nullptr;
   // mesh
-  double *dxidx = nullptr, *minv = nullptr, *srcw = nullptr, *nrm_face = nullptr, *nrm_bndry = nullptr,
-         *coords_bndry = nullptr, *w_dev = nullptr;
+  double *dxidx = nullptr, *minv = nullptr, *srcw = nullptr, *coords_bndry = nullptr, *w_dev = nullptr;
   EFace* efaces = nullptr;
-  std::vector<EFace> h_efaces;
+  FaceRec* faces = nullptr;
+  double *nrm_all = nullptr, *fluxw = nullptr;
+  std::vector<EFace> h_efaces;      // interior + boundary part (shared faces added by finalize)
+  std::vector<FaceRec> h_faces;
+  std::vector<double> h_nrm;        // nrm_face | nrm_bndry
   std::vector<double> h_w;
   // partition
   std::vector<Peer> peers;
   int64_t nS = 0;
-  double *nrm_shared = nullptr, *q_send = nullptr, *q_recv = nullptr;
-  int32_t *sh_el = nullptr, *surf_list = nullptr;
+  double *q_send = nullptr, *q_recv = nullptr;
+  int32_t* sh_el = nullptr;
   uint8_t* sh_face = nullptr;
-  int64_t n_surf = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   // control
   Ctl* ctl = nullptr;
   Ctl* h_ctl = nullptr;   // pinned
-  double *norm_partials = nullptr, *norm_partials2 = nullptr, *norm_sq = nullptr, *norms_dev = nullptr;
+  double *norm_partials = nullptr, *norm_sq = nullptr, *norms_dev = nullptr;
   int64_t norms_cap = 0;
   int64_t launches = 0, n_evals = 0;
   PdesTimings tm{};
@@ -276,64 +283,67 @@ int finalize(PdesCtx* ctx) {
   if (!ctx->have_op || !ctx->have_mesh) return usage(ctx, "pdes_set_operator and pdes_set_mesh must be called first");
   const PdesConfig& c = ctx->cfg;
   const int NF = ctx->nf, base = c.index_base;
-  // shared faces -> element face table, concatenated normals, pack lists
+  const size_t per_nrm = (size_t)c.nfn * c.dim;
+  // shared faces are appended to the face list after the interfaces and the boundary faces
   ctx->nS = 0;
   for (auto& p : ctx->peers) { p.offset = ctx->nS; ctx->nS += p.nfaces; }
+  const int64_t nG = c.nF + c.nB + ctx->nS;
   std::vector<int32_t> sh_el(ctx->nS);
   std::vector<uint8_t> sh_face(ctx->nS);
-  std::vector<double> nrm_sh((size_t)ctx->nS * c.nfn * c.dim);
   std::vector<EFace> ef = ctx->h_efaces;
+  std::vector<FaceRec> faces = ctx->h_faces;
+  std::vector<double> nrm = ctx->h_nrm;
+  faces.resize(nG);
+  nrm.resize((size_t)nG * per_nrm);
   for (auto& p : ctx->peers) {
     if (p.rank < 0) return usage(ctx, "pdes_set_peer was not called for every peer");
     for (int64_t j = 0; j < p.nfaces; ++j) {
       int64_t el = (int64_t)p.ifaces[j].elementL - base;
-      int f = (int)p.ifaces[j].faceL - base;
-      if (el < 0 || el >= c.nE || f < 0 || f >= NF) return usage(ctx, "shared interface out of range");
+      int f = (int)p.ifaces[j].faceL - base, o = (int)p.ifaces[j].orient - base;
+      if (el < 0 || el >= c.nE || f < 0 || f >= NF || o < 0 || o >= c.norient)
+        return usage(ctx, "shared interface out of range");
       if ((int64_t)p.bndries_local[j].element - base != el || (int)p.bndries_local[j].face - base != f)
         return usage(ctx, "bndries_local and shared_interfaces disagree");
       EFace& r = ef[el * NF + f];
-      if (r.kind != 255) return usage(ctx, "shared face already claimed by an interface or boundary face");
-      r.kind = FK_SHARED; r.idx = (int32_t)(p.offset + j); r.nbr = -1; r.fnbr = 0;
-      r.orient = (uint8_t)(p.ifaces[j].orient - base); r.bc = 0;
+      if (r.gface >= 0) return usage(ctx, "shared face already claimed by an interface or boundary face");
+      const int64_t g = c.nF + c.nB + p.offset + j;
+      r.gface = (int32_t)g; r.right = 0; r.orient = (uint8_t)o;
+      FaceRec& fr = faces[g];
+      memset(&fr, 0, sizeof(fr));
+      fr.elL = (int32_t)el; fr.elR = -1; fr.fL = (uint8_t)f; fr.orient = (uint8_t)o; fr.kind = FK_SHARED;
+      fr.aux = (int32_t)(p.offset + j);
       sh_el[p.offset + j] = (int32_t)el;
       sh_face[p.offset + j] = (uint8_t)f;
     }
-    memcpy(nrm_sh.data() + (size_t)p.offset * c.nfn * c.dim, p.nrm.data(), sizeof(double) * p.nrm.size());
+    if (p.nfaces)
+      memcpy(nrm.data() + (size_t)(c.nF + c.nB + p.offset) * per_nrm, p.nrm.data(), sizeof(double) * p.nrm.size());
   }
-  std::vector<int32_t> surf;
-  for (int64_t e = 0; e < c.nE; ++e) {
-    bool sh = false;
-    for (int f = 0; f < NF; ++f) {
-      if (ef[e * NF + f].kind == 255) {
+  for (int64_t e = 0; e < c.nE; ++e)
+    for (int f = 0; f < NF; ++f)
+      if (ef[e * NF + f].gface < 0) {
         set_err(ctx, "face %d of element %lld belongs to no interface, boundary face or shared face", f, (long long)e);
         return PDES_ERR_USAGE;
       }
-      sh = sh || ef[e * NF + f].kind == FK_SHARED;
-    }
-    if (sh) surf.push_back((int32_t)e);
-  }
-  ctx->n_surf = (int64_t)surf.size();
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->efaces, ef.data(), ef.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->faces, faces.data(), faces.size()));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nrm.data(), nrm.size()));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxw, nullptr, (size_t)nG * c.nfn * ctx->nd));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_el, sh_el.data(), sh_el.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_face, sh_face.data(), sh_face.size()));
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_shared, nrm_sh.data(), nrm_sh.size()));
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->surf_list, surf.data(), surf.size()));
   size_t nsend = (size_t)ctx->nS * c.nfn * ctx->nd;
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
-  int64_t g1 = ctx->ops->grid_for(c.nE), g2 = ctx->ops->grid_for(ctx->n_surf);
-  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)g1));
-  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials2, nullptr, (size_t)(g2 > 0 ? g2 : 1)));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
   ctx->finalized = true;
   return PDES_OK;
 }
 
-void fill_args(PdesCtx* ctx, ResArgs* a, const double* q) {
+void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   memset(a, 0, sizeof(*a));
-  a->q = q; a->dxidx = ctx->dxidx; a->efaces = ctx->efaces; a->nrm_face = ctx->nrm_face;
-  a->nrm_bndry = ctx->nrm_bndry; a->coords_bndry = ctx->coords_bndry; a->nrm_shared = ctx->nrm_shared;
-  a->q_recv = ctx->q_recv; a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
+  a->q = q; a->dxidx = ctx->dxidx; a->efaces = ctx->efaces; a->fluxw = ctx->fluxw;
+  a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
   a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
+  a->norm_partials = ctx->norm_partials;
 }
 
 // startSolutionExchange (Utils/parallel.jl:29-49): pack on the compute stream, send/recv on the comm stream
@@ -361,30 +371,34 @@ int start_exchange(PdesCtx* ctx, const double* q) {
   return PDES_OK;
 }
 
-// one residual evaluation = [pack+exchange] + interior launch + (after the receive) surface launch
-int enqueue_residual(PdesCtx* ctx, ResArgs& a, int mode) {
+// one residual evaluation = [pack + exchange on the comm stream] | face fluxes of the interior and boundary
+// faces (overlaps the exchange) -> face fluxes of the shared faces (after the receive) -> element kernel
+int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   int rc = start_exchange(ctx, a.q);
   if (rc) return rc;
-  const bool split = ctx->nS > 0;
-  a.elist = nullptr; a.nlist = 0; a.skip_shared = split ? 1 : 0;
-  double* np1 = ctx->norm_partials;
-  a.norm_partials = np1;
-  CUDA_TRY(ctx, ctx->ops->launch_residual(a, mode, ctx->cfg.nE, ctx->stream));
+  const PdesConfig& c = ctx->cfg;
+  FaceArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
+  fa.q_recv = ctx->q_recv; fa.fluxw = ctx->fluxw; fa.nF = c.nF; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.g0 = 0; fa.ng = c.nF + c.nB;
+  CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
   ctx->launches++;
-  if (split) {
+  if (ctx->nS > 0) {
     if (ctx->comm) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
-    a.elist = ctx->surf_list; a.nlist = ctx->n_surf; a.skip_shared = 0;
-    a.norm_partials = ctx->norm_partials2;
-    CUDA_TRY(ctx, ctx->ops->launch_residual(a, mode, ctx->n_surf, ctx->stream));
+    fa.g0 = c.nF + c.nB; fa.ng = ctx->nS;
+    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
     ctx->launches++;
   }
+  CUDA_TRY(ctx, ctx->ops->launch_elements(a, mode, ctx->stream));
+  ctx->launches++;
   ctx->n_evals++;
   return PDES_OK;
 }
 
 int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
-  int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE), n2 = ctx->nS > 0 ? (int)ctx->ops->grid_for(ctx->n_surf) : 0;
-  k_norm_reduce<<<1, 256, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_partials2, n2, ctx->norm_sq, ctx->ctl);
+  int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE);
+  k_norm_reduce<<<1, 256, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_sq, ctx->ctl);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   double quirk = 1.0;
@@ -405,7 +419,7 @@ int enqueue_rk4_step(PdesCtx* ctx, double h, int64_t norm_slot, double res_tol, 
   double* A = ctx->qbuf[ctx->cur];
   double* B = ctx->qbuf[(ctx->cur + 1) % 3];
   double* Cb = ctx->qbuf[(ctx->cur + 2) % 3];
-  ResArgs a;
+  ElemArgs a;
   const double* in[4] = {A, B, Cb, B};
   double* out[4] = {B, Cb, B, Cb};
   const double ah[4] = {h / 2, h / 2, h, 0.0};
@@ -500,9 +514,9 @@ void pdes_destroy(PdesCtx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
-                  ctx->nrm_face, ctx->nrm_bndry, ctx->coords_bndry, ctx->w_dev, ctx->efaces, ctx->nrm_shared,
-                  ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->surf_list, ctx->sh_face, ctx->ctl, ctx->norm_partials,
-                  ctx->norm_partials2, ctx->norm_sq, ctx->norms_dev};
+                  ctx->nrm_all, ctx->fluxw, ctx->faces, ctx->coords_bndry, ctx->w_dev, ctx->efaces,
+                  ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
+                  ctx->norm_sq, ctx->norms_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
@@ -553,10 +567,12 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
   if (c.src_id != PDES_SRC_NONE && !coords) return usage(ctx, "pdes_set_mesh: coords needed for the source term");
   CUDA_TRY(ctx, cudaSetDevice(c.device));
   std::vector<EFace>& ef = ctx->h_efaces;
+  std::vector<FaceRec>& faces = ctx->h_faces;
   EFace blank;
   memset(&blank, 0, sizeof(blank));
-  blank.kind = 255; blank.nbr = -1; blank.idx = -1;
+  blank.gface = -1;
   ef.assign((size_t)c.nE * NF, blank);
+  faces.assign((size_t)(c.nF + c.nB), FaceRec());
   for (int64_t f = 0; f < c.nF; ++f) {
     const PdesInterface& I = interfaces[f];
     int64_t eL = (int64_t)I.elementL - base, eR = (int64_t)I.elementR - base;
@@ -566,10 +582,15 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
       return usage(ctx, "mesh.interfaces entry out of range");
     EFace& L = ef[eL * NF + fL];
     EFace& Rr = ef[eR * NF + fR];
-    if (L.kind != 255 || Rr.kind != 255) return usage(ctx, "element face referenced by two interfaces");
-    L.kind = FK_INTERIOR_L; L.nbr = (int32_t)eR; L.idx = (int32_t)f; L.fnbr = (uint8_t)fR; L.orient = (uint8_t)o;
-    Rr.kind = FK_INTERIOR_R; Rr.nbr = (int32_t)eL; Rr.idx = (int32_t)f; Rr.fnbr = (uint8_t)fL; Rr.orient = (uint8_t)o;
+    if (L.gface >= 0 || Rr.gface >= 0) return usage(ctx, "element face referenced by two interfaces");
+    L.gface = (int32_t)f; L.right = 0; L.orient = (uint8_t)o;
+    Rr.gface = (int32_t)f; Rr.right = 1; Rr.orient = (uint8_t)o;
+    FaceRec& fr = faces[f];
+    memset(&fr, 0, sizeof(fr));
+    fr.elL = (int32_t)eL; fr.elR = (int32_t)eR; fr.fL = (uint8_t)fL; fr.fR = (uint8_t)fR; fr.orient = (uint8_t)o;
+    fr.kind = FK_INTERIOR;
   }
+  std::vector<char> bseen((size_t)c.nB, 0);
   for (int i = 0; i < c.numBC; ++i) {
     if (bc_ids[i] < 1 || bc_ids[i] > 4) {
       set_err(ctx, "BC id %d is not supported", bc_ids[i]);
@@ -581,14 +602,24 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
       int f = (int)bndryfaces[b].face - base;
       if (el < 0 || el >= c.nE || f < 0 || f >= NF) return usage(ctx, "mesh.bndryfaces entry out of range");
       EFace& r = ef[el * NF + f];
-      if (r.kind != 255) return usage(ctx, "boundary face already claimed by an interface");
-      r.kind = FK_BOUNDARY; r.idx = (int32_t)b; r.bc = (uint8_t)bc_ids[i];
+      if (r.gface >= 0) return usage(ctx, "boundary face already claimed by an interface");
+      r.gface = (int32_t)(c.nF + b); r.right = 0; r.orient = 0;
+      FaceRec& fr = faces[c.nF + b];
+      memset(&fr, 0, sizeof(fr));
+      fr.elL = (int32_t)el; fr.elR = -1; fr.fL = (uint8_t)f; fr.kind = FK_BOUNDARY; fr.aux = bc_ids[i];
+      bseen[b] = 1;
     }
+  }
+  for (int64_t b = 0; b < c.nB; ++b)
+    if (!bseen[b]) return usage(ctx, "boundary face not covered by bndry_offsets");
+  {
+    const size_t per_nrm = (size_t)c.nfn * c.dim;
+    ctx->h_nrm.resize((size_t)(c.nF + c.nB) * per_nrm);
+    if (c.nF) memcpy(ctx->h_nrm.data(), nrm_face, sizeof(double) * (size_t)c.nF * per_nrm);
+    if (c.nB) memcpy(ctx->h_nrm.data() + (size_t)c.nF * per_nrm, nrm_bndry, sizeof(double) * (size_t)c.nB * per_nrm);
   }
   const size_t nnE = (size_t)c.nn * c.nE;
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->dxidx, dxidx, nnE * c.dim * c.dim));
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_face, nrm_face, (size_t)c.nF * c.nfn * c.dim));
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_bndry, nrm_bndry, (size_t)c.nB * c.nfn * c.dim));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->coords_bndry, coords_bndry, (size_t)c.nB * c.nfn * c.dim));
   // Minv and the tabulated source are produced on the device from jac / coords
   double* jac_dev = nullptr;
@@ -745,7 +776,7 @@ int pdes_eval_residual_async(PdesCtx* ctx, double t) {
   int rc = finalize(ctx);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
-  ResArgs a;
+  ElemArgs a;
   fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
   a.res = ctx->res;
   return enqueue_residual(ctx, a, EPI_RES);

@@ -1,52 +1,53 @@
-// Fused Euler residual kernel for sm_100a (dense-face SBP-Omega operators, Roe flux).
+// Euler residual + fused RK4 stage for sm_100a (dense-face SBP-Omega operators, Roe flux), fp64.
 //
-// One CTA evaluates the complete residual of a tile of E elements: every entry
-// of res is produced by exactly one thread, there are no atomics and no
-// materialised intermediates in HBM (the reference makes >= 12 mesh sweeps
-// through aux_vars / flux_parametric / q_face / flux_face / q_bndry / bndryflux,
-// src/solver/euler/euler.jl:441-519).  What one launch replaces:
+// One residual evaluation is two launches, both atomic-free and deterministic:
 //
-//   dataPrep + checkDensity/checkPressure     euler.jl:441-519, 543-611
-//   getEulerFlux + weakdifferentiate!(trans)  euler_funcs.jl:23-58, euler.jl:628-658
-//   interpolateFace + calcFaceFlux (Roe)      flux.jl:613-641, 37-64, bc_solvers.jl:29-420
-//   interiorfaceintegrate!                    euler.jl:770-802
-//   interpolateBoundary + getBCFluxes + boundaryintegrate!   bc.jl:49-80,162-175,251-284, euler.jl:669-690
-//   calcSharedFaceIntegrals_nopre_inner       flux.jl:264-308 (receive buffer filled by the halo exchange)
-//   applySourceTerm                           source.jl:27-47 (time-independent source tabulated at upload)
-//   pde_post_func (Minv, stage-1 norm) + the RK4 axpy loops   rk4.jl:244-319, 446-457
+//   k_face_flux      one numerical flux per face node, evaluated ONCE per interface (the element-centric
+//                    variant that recomputed it on both sides was FP64-pipe bound: profiles/r1_v2_*):
+//                      interpolateFace / interiorFaceInterpolate!        flux.jl:613-641, 79-125
+//                      calcFaceFlux + RoeSolver + calcSAT                flux.jl:37-64, bc_solvers.jl:29-420
+//                      interpolateBoundary + getBCFluxes (BC functors)   bc.jl:49-80, 162-175, 251-284
+//                      calcSharedFaceIntegrals_nopre_inner (flux part)   flux.jl:264-308
+//                    output: wface[i] * flux[:, i] per face, 8*nd*nfn bytes per face in HBM/L2.
+//   k_element_rk     everything that is owned by one element, every res entry produced by one thread:
+//                      dataPrep checks, getEulerFlux, weakdifferentiate! euler.jl:441-519, 543-611, 628-658
+//                      interiorfaceintegrate! / boundaryintegrate! / boundaryFaceIntegrate!  (gather form)
+//                      applySourceTerm (tabulated), pde_post_func, RK4 axpy rk4.jl:244-319, 446-457
 //
-// Work decomposition inside a CTA (T threads, E elements, ND = DIM+2 variables):
-//   * "variable threads": thread v < E*ND owns (element s = v/ND, variable k = v%ND).  All operator
-//     applications (Q^T F, face interpolation R q, face integration R^T W f) are small dense products
-//     whose coefficients are compile-time-indexed entries of the kernel-parameter operator table
-//     (constant bank operands of DFMA); the thread keeps q[k,:] and the residual row res[k,:] in registers.
-//   * "node items" (E*NN) evaluate the Euler flux in the DIM parametric directions.
-//   * "face-node items" (E*NF*NFN) evaluate the numerical (Roe / boundary-condition) flux.
-// Roles exchange data through shared memory.  The face flux is evaluated on both sides of an interior
-// face (element-centric gather) so that no scatter is needed.
+// The reference materialises aux_vars / flux_parametric / q_face / flux_face / q_bndry / bndryflux and makes
+// >= 12 sweeps (euler.jl:441-519); here the only intermediate is the face flux.
+//
+// Thread roles inside a CTA exchange data through shared memory:
+//   "variable threads"  (tile item, variable k): all operator applications (Q^T F, R q, R^T W f) are small dense
+//                       products whose coefficients are compile-time-indexed entries of the kernel-parameter
+//                       operator table (uniform constant loads feeding DFMA); the row lives in registers.
+//   "node threads"      (tile item, node): pointwise nonlinear work (Euler flux, Roe flux, BC functors).
 #pragma once
 #include <stdint.h>
 #include "euler_device.cuh"
 
 namespace pdes {
 
-// per (element, local face) connectivity record built at upload time from mesh.interfaces /
-// mesh.bndryfaces / mesh.shared_interfaces
-struct __align__(16) EFace {
-  int32_t nbr;       // neighbour element (interior faces)
-  int32_t idx;       // interface / boundary-face / shared-face index (normals, coordinates, receive buffer)
-  uint8_t kind;      // FaceKind
-  uint8_t fnbr;      // neighbour's local face
-  uint8_t orient;    // interface orientation
-  uint8_t bc;        // BC functor id (boundary faces)
-  uint32_t pad;
+// per (element, local face): where the element finds its face flux and how to read it
+struct __align__(8) EFace {
+  int32_t gface;     // index into the face-flux array (interfaces, then boundary faces, then shared faces)
+  uint8_t right;     // 1: this element is elementR of the interface (+flux, node order permuted by nbrperm)
+  uint8_t orient;
+  uint8_t pad[2];
 };
-enum FaceKind : uint8_t { FK_INTERIOR_L = 0, FK_INTERIOR_R = 1, FK_BOUNDARY = 2, FK_SHARED = 3 };
+
+// per face: what k_face_flux gathers
+struct __align__(16) FaceRec {
+  int32_t elL, elR;  // elR: right element (interior) | unused
+  uint8_t fL, fR, orient, kind;
+  int32_t aux;       // boundary: BC functor id; shared: index into the receive buffer
+};
+enum FaceKind : uint8_t { FK_INTERIOR = 0, FK_BOUNDARY = 2, FK_SHARED = 3 };
 
 struct Ctl {               // device-resident control block
   int32_t stop;            // kernels return immediately when set (physics error or res_tol reached)
-  int32_t err_code;        // 0 | PDES_ERR_NEG_DENSITY | PDES_ERR_NEG_PRESSURE
-  unsigned long long err_loc;  // (element << 8) | node of the lowest offending location
+  int32_t err_code;        // != 0: physics error, decoded on the host from err_loc
+  unsigned long long err_loc;  // ((code-1) << 62) | (element << 8) | node of the lowest offending location
   int32_t converged_step;  // step head at which norm < res_tol (or -1)
   int32_t pad;
 };
@@ -55,11 +56,9 @@ template <int DIM, int NN, int NFN>
 struct OpTab {
   static constexpr int NF = DIM + 1;
   static constexpr int NOR = (DIM == 2) ? 1 : 3;
-  static constexpr int NNP = NN, NFP = NF * NFN;
-  double Qt[DIM * NN][NNP];   // Qt[d*NN+j][i] = sbp.Q[j,i,d]   (res_i += Q[j,i,d] F_j : weakdifferentiate!, trans=true)
-  double RfN[NF * NFN][NNP];  // RfN[f*NFN+i][node] = sum_j interp[j,i] [perm[j,f]==node]   (face integration)
-  double RfT[NN][NFP];        // RfT[node][f*NFN+i] = the same matrix, transposed               (face interpolation)
-  double interp[NN][NFN];     // sbpface.interp[j,i] (stencil order, used for the neighbour side)
+  double Qt[DIM * NN][NN];    // Qt[d*NN+j][i] = sbp.Q[j,i,d]   (res_i += Q[j,i,d] F_j : weakdifferentiate!, trans=true)
+  double RfN[NF * NFN][NN];   // RfN[f*NFN+i][node] = sum_j interp[j,i] [perm[j,f]==node]   (face integration)
+  double interp[NN][NFN];     // sbpface.interp[j,i] (stencil order: face interpolation after a perm-ordered gather)
   double wface[NFN];
   int32_t perm[NF][NN];       // sbpface.perm[j,f] (0-based)
   int32_t nbrperm[NOR][NFN];  // sbpface.nbrperm[i,orient] (0-based)
@@ -72,15 +71,24 @@ struct PhysPar {
 
 enum EpiMode { EPI_RES = 0, EPI_RK = 1 };
 
-struct ResArgs {
+struct FaceArgs {
+  const double* q;             // [ND,NN,nE]
+  const FaceRec* faces;        // [nF + nB + nS]
+  const double* nrm;           // [DIM,NFN,nF+nB+nS]   nrm_face | nrm_bndry | nrm_sharedface
+  const double* coords_bndry;  // [DIM,NFN,nB]
+  const double* q_recv;        // [ND,NFN,nS] (peer's own face-node order)
+  double* fluxw;               // [ND,NFN,nF+nB+nS]    wface[i] * flux[:,i]
+  int64_t g0, ng;              // face range of this launch
+  int64_t nF;                  // first boundary face
+  const Ctl* ctl;
+  PhysPar ph;
+};
+
+struct ElemArgs {
   const double* q;             // [ND,NN,nE]
   const double* dxidx;         // [DIM,DIM,NN,nE]
   const EFace* efaces;         // [nE][NF]
-  const double* nrm_face;      // [DIM,NFN,nF]
-  const double* nrm_bndry;     // [DIM,NFN,nB]
-  const double* coords_bndry;  // [DIM,NFN,nB]
-  const double* nrm_shared;    // [DIM,NFN,nS]  all peers concatenated
-  const double* q_recv;        // [ND,NFN,nS]   all peers concatenated (peer's own face-node order)
+  const double* fluxw;         // from k_face_flux
   const double* srcw;          // [ND,NN,nE] (w_j/jac_j) * S(x_j), or nullptr
   double* res;                 // EPI_RES: [ND,NN,nE]
   // EPI_RK (rk4.jl:244-319): k = Minv*res; q_next = x_old + ah*k; ksum updated; last stage: x_new
@@ -92,11 +100,7 @@ struct ResArgs {
   double ah;                   // a_s * h
   double h6;                   // h/6 (last stage)
   int32_t stage;               // 1..4
-  // tiling
   int64_t nE;
-  const int32_t* elist;        // optional compacted element list (launch over surface elements)
-  int64_t nlist;
-  int32_t skip_shared;         // 1: elements that own a shared face are left to the elist launch
   Ctl* ctl;
   PhysPar ph;
 };
@@ -104,25 +108,12 @@ struct ResArgs {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __host__ __device__ constexpr int pad_stride(int n, int nd) {
-  // smallest m >= n with m % 16 == nd % 16: (element, variable)-indexed fp64 accesses of a half-warp
+  // smallest m >= n with m % 16 == nd % 16: (item, variable)-indexed fp64 accesses of a half-warp
   // then fall into distinct banks
   int m = n;
   while (m % 16 != nd % 16) ++m;
   return m;
 }
-
-template <int DIM, int NN, int NFN, int E>
-struct TileCfg {
-  static constexpr int ND = DIM + 2, NF = DIM + 1;
-  static constexpr int H = 1;                                  // threads per (element, variable) row
-  static constexpr int VT = E * ND * H;                        // variable threads
-  static constexpr int T = ((VT + 31) / 32) * 32;
-  static constexpr int SQ = pad_stride(NN * ND, ND);           // per-element stride of the q tile
-  static constexpr int FS = pad_stride(NF * NFN * ND, ND);     // per-element stride of face-state tiles
-  static constexpr int SF = ND * DIM * NN;                      // per-element stride of the volume-flux tile
-  static constexpr int UNION = (2 * FS > SF) ? 2 * FS : SF;
-  static constexpr size_t smem_bytes = sizeof(double) * (size_t)E * (SQ + UNION) + sizeof(EFace) * E * NF;
-};
 
 // boundary-condition functors (bc.jl:554-567, 1756-1768, 1573-1587, 717-765): Dirichlet state + Roe, or
 // Euler flux of the wall-projected state
@@ -151,126 +142,221 @@ __device__ __noinline__ void bc_flux(int bc, const double* q, const double* x, c
   roe_flux<DIM>(q, qg, n, ph.gamma, flux);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// k_face_flux: FT faces per CTA
+// ------------------------------------------------------------------------------------------------------
+template <int DIM, int NN, int NFN, int FT>
+struct FaceCfg {
+  static constexpr int ND = DIM + 2;
+  static constexpr int PER = ND > NFN ? ND : NFN;             // threads per face
+  static constexpr int T = ((FT * PER + 31) / 32) * 32;
+  static constexpr int FS = pad_stride(NFN * ND, ND);          // per-face stride of a face-state tile
+};
+
+template <int DIM, int NN, int NFN, int FT, int MINB>
+__global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
+k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  using Cfg = FaceCfg<DIM, NN, NFN, FT>;
+  constexpr int ND = Cfg::ND, T = Cfg::T, FS = Cfg::FS, NF = DIM + 1, EL = NN * ND;
+  __shared__ double sL[FT * FS];
+  __shared__ double sR[FT * FS];
+  __shared__ FaceRec sRec[FT];
+  __shared__ int s_perm[NF][NN];
+  __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
+
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FT;
+  const int64_t rem = a.g0 + a.ng - g0;
+  const int nf = (int)(rem < FT ? rem : FT);
+  if (tid < nf) sRec[tid] = a.faces[g0 + tid];
+  for (int idx = tid; idx < NF * NN; idx += T) s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
+  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
+    s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
+  __syncthreads();
+
+  // ---- A: interpolate both sides to the face nodes (variable threads) ----------------------------------
+  if (tid < nf * ND) {
+    const int fi = tid / ND, k = tid - fi * ND;
+    const FaceRec r = sRec[fi];
+    double ql[NN], qr[NN];
+    {
+      const double* b = a.q + (int64_t)r.elL * EL + k;
+#pragma unroll
+      for (int j = 0; j < NN; ++j) ql[j] = __ldg(b + s_perm[r.fL][j] * ND);
+    }
+    if (r.kind == FK_INTERIOR) {
+      const double* b = a.q + (int64_t)r.elR * EL + k;
+#pragma unroll
+      for (int j = 0; j < NN; ++j) qr[j] = __ldg(b + s_perm[r.fR][j] * ND);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NN; ++j) qr[j] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NFN; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], ql[j], s);
+      sL[fi * FS + i * ND + k] = s;
+    }
+    if (r.kind == FK_INTERIOR) {
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], qr[j], s);
+        // elementR's face node i coincides with elementL's face node nbrperm[i,orient] (involution)
+        sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = s;
+      }
+    } else if (r.kind == FK_SHARED) {
+      // permuteinterface! (Utils/parallel.jl:198-201): received node i of the peer is own node nbrperm[i,orient]
+      const double* b = a.q_recv + (int64_t)r.aux * (NFN * ND) + k;
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = b[i * ND];
+    }
+  }
+  __syncthreads();
+
+  // ---- B: numerical flux at every face node (node threads), scaled by wface ------------------------------
+  if (tid < nf * NFN) {
+    const int fi = tid / NFN, i = tid - fi * NFN;
+    const FaceRec r = sRec[fi];
+    const int64_t g = g0 + fi;
+    const double* np_ = a.nrm + (g * NFN + i) * DIM;
+    double nrm[DIM], qL[ND], flux[ND];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
+    double* po = sL + fi * FS + i * ND;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qL[k] = po[k];
+    if (r.kind == FK_BOUNDARY) {
+      // separate copies so that only this (rare) path touches local memory
+      const double* xp = a.coords_bndry + ((g - a.nF) * NFN + i) * DIM;
+      double xb[DIM], nb_[DIM], qb[ND], fb[ND];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
+#pragma unroll
+      for (int k = 0; k < ND; ++k) qb[k] = qL[k];
+      bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) flux[k] = fb[k];
+    } else {
+      double qR[ND];
+      const double* pn = sR + fi * FS + i * ND;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) qR[k] = pn[k];
+      roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
+    }
+    const double w = op.wface[i];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) po[k] = w * flux[k];
+  }
+  __syncthreads();
+
+  // ---- C: coalesced store of the tile ----------------------------------------------------------------------
+  double* dst = a.fluxw + g0 * (NFN * ND);
+  for (int idx = tid; idx < nf * NFN * ND; idx += T) {
+    const int fi = idx / (NFN * ND), r = idx - fi * (NFN * ND);
+    dst[idx] = sL[fi * FS + r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_element_rk: E elements per CTA
+// ------------------------------------------------------------------------------------------------------
+template <int DIM, int NN, int NFN, int E>
+struct TileCfg {
+  static constexpr int ND = DIM + 2, NF = DIM + 1;
+  static constexpr int VT = E * ND;                             // variable threads
+  static constexpr int T = ((VT + 31) / 32) * 32;
+  static constexpr int SQ = pad_stride(NN * ND, ND);           // per-element stride of the q tile
+  static constexpr int SF = ND * DIM * NN;                      // per-element stride of the volume-flux tile
+  static constexpr size_t smem_bytes = sizeof(double) * (size_t)E * (SQ + SF);
+};
+
 template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
 __global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
-k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ResArgs a) {
+k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
-  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ, FS = Cfg::FS;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ;
   constexpr int EL = NN * ND;                       // doubles per element
+  constexpr int FL = NFN * ND;                      // doubles per face
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sq = reinterpret_cast<double*>(smem_raw);             // [E][SQ]
-  double* sU = sq + E * SQ;                                     // union
-  double* sF = sU;                                              // [E][ND][DIM][NN]
-  double* sOwn = sU;                                            // [E][FS]
-  double* sNbr = sU + E * FS;                                   // [E][FS]
-  EFace* sEf = reinterpret_cast<EFace*>(sU + E * Cfg::UNION);   // [E][NF]
-  __shared__ int s_el[E];
-  __shared__ int s_skip[E];
-  __shared__ int s_perm[NF][NN];
+  double* sF = sq + E * SQ;                                     // [E][ND][DIM][NN]
   __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
   __shared__ double s_red[T / 32];
 
   if (a.ctl->stop) return;
   const int tid = threadIdx.x;
-  const int64_t ntot = a.elist ? a.nlist : a.nE;
   const int64_t e0 = (int64_t)blockIdx.x * E;
-  const int ne = (int)((ntot - e0) < E ? (ntot - e0) : E);
+  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
   const double gami = a.ph.gamma - 1.0;
 
-  // ---- S0: tile load --------------------------------------------------------------------------
-  if (tid < E) {
-    int el = -1;
-    if (tid < ne) el = a.elist ? a.elist[e0 + tid] : (int)(e0 + tid);
-    s_el[tid] = el;
-  }
-  for (int idx = tid; idx < NF * NN; idx += T) s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
-  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T) s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
-  __syncthreads();
-  for (int idx = tid; idx < ne * NF; idx += T) {
-    int s = idx / NF, f = idx - s * NF;
-    sEf[idx] = a.efaces[(int64_t)s_el[s] * NF + f];
-  }
-  if (a.elist == nullptr) {
+  // ---- S0: tile load; variable threads fetch their element's face records and prefetch the face fluxes ------
+  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
+    s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
+  {
     const double* src = a.q + e0 * EL;
     for (int idx = tid; idx < ne * EL; idx += T) {
-      int s = idx / EL, r = idx - s * EL;
+      const int s = idx / EL, r = idx - s * EL;
       sq[s * SQ + r] = src[idx];
     }
-  } else {
-    for (int idx = tid; idx < ne * EL; idx += T) {
-      int s = idx / EL, r = idx - s * EL;
-      sq[s * SQ + r] = a.q[(int64_t)s_el[s] * EL + r];
-    }
   }
-  __syncthreads();
-
-  // elements this launch must not touch (they own a shared face and are done by the elist launch)
-  if (tid < E) {
-    int sk = 0;
-    if (tid < ne && a.skip_shared) {
+  const int v = tid;
+  const int vs = v / ND, vk = v - vs * ND;
+  const bool v_active = v < ne * ND;
+  EFace ef[NF];
+  if (v_active) {
+    const EFace* pe = a.efaces + (e0 + vs) * NF;
 #pragma unroll
-      for (int f = 0; f < NF; ++f) sk |= (sEf[tid * NF + f].kind == FK_SHARED);
-    }
-    s_skip[tid] = sk;
-  }
-  __syncthreads();
-  // L2 prefetch of everything the later stages gather: neighbour elements, face normals, and the
-  // epilogue's streams (the loads themselves are issued much later; this converts their HBM latency into L2 latency)
-  for (int idx = tid; idx < ne * NF; idx += T) {
-    const EFace ef = sEf[idx];
-    if (ef.kind <= FK_INTERIOR_R) {
-      const char* pq = reinterpret_cast<const char*>(a.q + (int64_t)ef.nbr * EL);
+    for (int f = 0; f < NF; ++f) ef[f] = pe[f];
+    if (vk == 0) {
 #pragma unroll
-      for (int o = 0; o < EL * 8 + 127; o += 128) prefetch_l2(pq + o);
-      const char* pn = reinterpret_cast<const char*>(a.nrm_face + (int64_t)ef.idx * NFN * DIM);
-      prefetch_l2(pn);
-      prefetch_l2(pn + NFN * DIM * 8 - 8);
-    } else if (ef.kind == FK_BOUNDARY) {
-      prefetch_l2(a.nrm_bndry + (int64_t)ef.idx * NFN * DIM);
-      prefetch_l2(a.coords_bndry + (int64_t)ef.idx * NFN * DIM);
+      for (int f = 0; f < NF; ++f) {
+        const char* pf = reinterpret_cast<const char*>(a.fluxw + (int64_t)ef[f].gface * FL);
+        prefetch_l2(pf);
+        if (FL * 8 > 128) prefetch_l2(pf + FL * 8 - 8);
+      }
     }
   }
-  if (a.elist == nullptr) {
+  // L2 prefetch of the epilogue's streams
+  {
     const int64_t b0 = e0 * EL * 8, nb = (int64_t)ne * EL * 8;
     for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
       if (a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
-      if (MODE == EPI_RK) {
-        if (a.stage > 1) {
-          prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
-          prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
-        }
+      if (MODE == EPI_RK && a.stage > 1) {
+        prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+        prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
       }
     }
     if (MODE == EPI_RK)
       for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
         prefetch_l2(reinterpret_cast<const char*>(a.minv) + e0 * NN * 8 + o);
   }
-  // variable threads: v -> (element vs, variable vk)
-  const int v = tid;
-  const int vs = v / ND, vk = v - vs * ND;
-  const bool v_active = (v < ne * ND) && !s_skip[vs < E ? vs : 0];
+  __syncthreads();
 
   // ---- S1: Euler flux in the parametric directions at every node (getEulerFlux) ---------------
   for (int it = tid; it < ne * NN; it += T) {
-    int s = it / NN, j = it - s * NN;
+    const int s = it / NN, j = it - s * NN;
     double qn[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) qn[k] = sq[s * SQ + j * ND + k];
-    const double* dx = a.dxidx + ((int64_t)s_el[s] * NN + j) * (DIM * DIM);
+    const double* dx = a.dxidx + ((e0 + s) * NN + j) * (DIM * DIM);
     double dxl[DIM * DIM];
 #pragma unroll
     for (int m = 0; m < DIM * DIM; ++m) dxl[m] = __ldg(dx + m);
-    double press = calc_pressure<DIM>(qn, gami);
+    const double press = calc_pressure<DIM>(qn, gami);
     if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
-      int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
-      unsigned long long loc = ((unsigned long long)s_el[s] << 8) | (unsigned)j;
+      const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
+      const unsigned long long loc = ((unsigned long long)(e0 + s) << 8) | (unsigned)j;
       // density errors win over pressure errors (checkDensity runs first), lowest location wins
-      unsigned long long key = ((unsigned long long)(code - 1) << 62) | loc;
-      atomicMin(&a.ctl->err_loc, key);
-      atomicExch(&a.ctl->err_code, 1);  // decoded on the host from err_loc
+      atomicMin(&a.ctl->err_loc, ((unsigned long long)(code - 1) << 62) | loc);
+      atomicExch(&a.ctl->err_code, 1);
       atomicExch(&a.ctl->stop, 1);
     }
-    double rinv = 1.0 / qn[0];
+    const double rinv = 1.0 / qn[0];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       double U = 0.0;
@@ -286,13 +372,24 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   }
   __syncthreads();
 
-  // ---- S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j] ---------------------------
-  // (loops over directions / faces stay rolled: the fully unrolled operator products overflow the instruction
-  // cache; one direction or one face at a time keeps >= NN independent DFMA chains in flight)
   double acc[NN];
 #pragma unroll
   for (int u = 0; u < NN; ++u) acc[u] = 0.0;
   if (v_active) {
+    // face fluxes of this (element, variable) row: issued now (L2 hits after the prefetch), consumed after S2.
+    // interiorfaceintegrate!: elementL subtracts, elementR adds and reads node nbrperm[i,orient]
+    double fl[NF][NFN];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const double* b = a.fluxw + (int64_t)ef[f].gface * FL + vk;
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) {
+        const int ii = ef[f].right ? s_nbrperm[ef[f].orient][i] : i;
+        fl[f][i] = __ldg(b + ii * ND);
+      }
+    }
+    // ---- S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j] ---------------------------
+    // (the loop over directions stays rolled: fully unrolled operator products overflow the instruction cache)
     const double* Fv = sF + (vs * ND + vk) * DIM * NN;
 #pragma unroll 1
     for (int d = 0; d < DIM; ++d) {
@@ -304,130 +401,23 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
         for (int u = 0; u < NN; ++u) acc[u] = fma(op.Qt[d * NN + j][u], Fj[j], acc[u]);
     }
-  }
-  __syncthreads();   // sF is dead; the face-state tiles reuse its storage
-
-  // ---- S3/S4: face interpolation of the own and of the neighbour state, one face at a time -------
-  if (v_active) {
-    double qk[NN];
+    // ---- S3: face integration  res[k,node] -+= sum_f sum_i Rf[f][i][node] * w_i f*[k,i] -----------
 #pragma unroll
-    for (int j = 0; j < NN; ++j) qk[j] = sq[vs * SQ + j * ND + vk];
-#pragma unroll 1
     for (int f = 0; f < NF; ++f) {
-      const EFace ef = sEf[vs * NF + f];
-      // neighbour values in the neighbour's stencil order: q[k, perm[j,fnbr], nbr] (issued first: L2 latency)
-      double qn[NN];
-      const bool interior = ef.kind <= FK_INTERIOR_R;
-      if (interior) {
-        const int64_t loc = (int64_t)ef.nbr - e0;
-        if (a.elist == nullptr && loc >= 0 && loc < ne) {
-          const double* b = sq + (int)loc * SQ + vk;
-#pragma unroll
-          for (int j = 0; j < NN; ++j) qn[j] = b[s_perm[ef.fnbr][j] * ND];
-        } else {
-          const double* b = a.q + (int64_t)ef.nbr * EL + vk;
-#pragma unroll
-          for (int j = 0; j < NN; ++j) qn[j] = __ldg(b + s_perm[ef.fnbr][j] * ND);
-        }
-      }
-      // own state at the NFN nodes of face f
+      const double sgn = ef[f].right ? 1.0 : -1.0;
 #pragma unroll
       for (int i = 0; i < NFN; ++i) {
-        double sacc = 0.0;
+        const double x = sgn * fl[f][i];
 #pragma unroll
-        for (int n = 0; n < NN; ++n) sacc = fma(op.RfN[f * NFN + i][n], qk[n], sacc);
-        sOwn[vs * FS + (f * NFN + i) * ND + vk] = sacc;
-      }
-      if (interior) {
-#pragma unroll
-        for (int i = 0; i < NFN; ++i) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int j = 0; j < NN; ++j) sacc = fma(op.interp[j][i], qn[j], sacc);
-          // the neighbour's face node i coincides with own face node nbrperm[i,orient] (involution)
-          const int io = s_nbrperm[ef.orient][i];
-          sNbr[vs * FS + (f * NFN + io) * ND + vk] = sacc;
-        }
-      } else if (ef.kind == FK_SHARED) {
-        // permuteinterface! (Utils/parallel.jl:198-201): received face-node i of the peer is own node nbrperm[i]
-        const double* b = a.q_recv + (int64_t)ef.idx * (NFN * ND) + vk;
-#pragma unroll
-        for (int i = 0; i < NFN; ++i) {
-          const int io = s_nbrperm[ef.orient][i];
-          sNbr[vs * FS + (f * NFN + io) * ND + vk] = b[i * ND];
-        }
+        for (int u = 0; u < NN; ++u) acc[u] = fma(op.RfN[f * NFN + i][u], x, acc[u]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < NN; ++u) sq[vs * SQ + u * ND + vk] = acc[u];   // only this thread reads/writes its row
   }
   __syncthreads();
 
-  // ---- S5: numerical flux at every face node, scaled by -/+ wface (in place in sOwn) ---------
-  // one instance of the Roe solver (rolled loop: the unrolled operator products already fill the
-  // instruction cache); the left/right roles are selected on the data.  Normals were prefetched to L2.
-#pragma unroll 1
-  for (int it = tid; it < ne * NF * NFN; it += T) {
-    const int s = it / (NF * NFN), r = it - s * (NF * NFN);
-    if (s_skip[s]) continue;
-    const int f = r / NFN, i = r - f * NFN;
-    const EFace ef = sEf[s * NF + f];
-    const bool right = ef.kind == FK_INTERIOR_R;
-    const int ii = right ? s_nbrperm[ef.orient][i] : i;   // node index in the left element's ordering
-    const double* base = a.nrm_face;
-    if (ef.kind == FK_BOUNDARY) base = a.nrm_bndry;
-    else if (ef.kind == FK_SHARED) base = a.nrm_shared;
-    const double* np_ = base + ((int64_t)ef.idx * NFN + ii) * DIM;
-    double nrm[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
-    double* po = sOwn + s * FS + r * ND;
-    const double* pn = sNbr + s * FS + r * ND;
-    double flux[ND];
-    double scale = right ? op.wface[ii] : -op.wface[ii];
-    if (ef.kind == FK_BOUNDARY) {
-      // separate copies so that only this (rare) path touches local memory
-      const double* xp = a.coords_bndry + ((int64_t)ef.idx * NFN + i) * DIM;
-      double xb[DIM], nb_[DIM], qb[ND], fb[ND];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
-#pragma unroll
-      for (int k = 0; k < ND; ++k) qb[k] = po[k];
-      bc_flux<DIM>(ef.bc, qb, xb, nb_, a.ph, fb);
-#pragma unroll
-      for (int k = 0; k < ND; ++k) flux[k] = fb[k];
-    } else {
-      double qa[ND], qb[ND];
-#pragma unroll
-      for (int k = 0; k < ND; ++k) {
-        const double o = po[k], nb = pn[k];
-        qa[k] = right ? nb : o;
-        qb[k] = right ? o : nb;
-      }
-      roe_flux<DIM>(qa, qb, nrm, a.ph.gamma, flux);
-    }
-#pragma unroll
-    for (int k = 0; k < ND; ++k) po[k] = scale * flux[k];
-  }
-  __syncthreads();
-
-  // ---- S6: face integration  res[k,node] += sum_f sum_i Rf[f][i][node] * (+-w f*)[k,i] ---------
-  if (v_active) {
-    const double* fv = sOwn + vs * FS + vk;
-#pragma unroll 1
-    for (int f = 0; f < NF; ++f) {
-      double fl[NFN];
-#pragma unroll
-      for (int i = 0; i < NFN; ++i) fl[i] = fv[(f * NFN + i) * ND];
-#pragma unroll
-      for (int i = 0; i < NFN; ++i)
-#pragma unroll
-        for (int u = 0; u < NN; ++u) acc[u] = fma(op.RfN[f * NFN + i][u], fl[i], acc[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < NN; ++u) sq[vs * SQ + u * ND + vk] = acc[u];
-  }
-  __syncthreads();
-
-  // ---- S7: epilogue (coalesced): source, then either res or the fused RK4 stage ----------------
+  // ---- S4: epilogue (coalesced): source, then either res or the fused RK4 stage ----------------
   // loads of a chunk of CH dofs per thread are issued together before any of them is consumed
   double nrm2 = 0.0;
   {
@@ -442,12 +432,12 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
         const int idx = base + u * T + tid;
         ok[u] = idx < ntile;
         int s = 0, r = 0;
-        if (ok[u]) { s = idx / EL; r = idx - s * EL; ok[u] = !s_skip[s]; }
-        dof[u] = ok[u] ? (int64_t)s_el[s] * EL + r : 0;
+        if (ok[u]) { s = idx / EL; r = idx - s * EL; }
+        dof[u] = ok[u] ? (e0 + s) * EL + r : 0;
         val[u] = ok[u] ? sq[s * SQ + r] : 0.0;
         sv[u] = (ok[u] && a.srcw) ? a.srcw[dof[u]] : 0.0;
         if (MODE == EPI_RK) {
-          mi[u] = ok[u] ? a.minv[(int64_t)s_el[s] * NN + r / ND] : 1.0;
+          mi[u] = ok[u] ? a.minv[(e0 + s) * NN + r / ND] : 1.0;
           xo[u] = ok[u] ? a.x_old[dof[u]] : 0.0;
           ks[u] = (ok[u] && a.stage > 1) ? a.ksum[dof[u]] : 0.0;
         }
@@ -455,11 +445,11 @@ k_residual_roe(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         if (!ok[u]) continue;
-        const double v = val[u] + sv[u];
+        const double vv = val[u] + sv[u];
         if (MODE == EPI_RES) {
-          a.res[dof[u]] = v;
+          a.res[dof[u]] = vv;
         } else {
-          const double k = mi[u] * v;              // pde_post_func: res_vec *= Minv
+          const double k = mi[u] * vv;             // pde_post_func: res_vec *= Minv
           if (a.stage == 1) {
             nrm2 += k * k / mi[u];                 // calcNorm: sum res*M*res (Utils.jl:427-449)
             a.ksum[dof[u]] = k;
@@ -508,13 +498,11 @@ __global__ void k_pack_send(const __grid_constant__ OpTab<DIM, NN, NFN> op, cons
 }
 
 // second pass of the stage-1 norm: deterministic sum of the per-CTA partials of this rank
-__global__ void k_norm_reduce(const double* __restrict__ partials, int n1, const double* __restrict__ partials2, int n2,
-                              double* norm_sq_out, const Ctl* ctl) {
+__global__ void k_norm_reduce(const double* __restrict__ partials, int n1, double* norm_sq_out, const Ctl* ctl) {
   __shared__ double sh[256];
   if (ctl->stop) return;
   double s = 0.0;
   for (int i = threadIdx.x; i < n1; i += 256) s += partials[i];
-  for (int i = threadIdx.x; i < n2; i += 256) s += partials2[i];
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
