@@ -84,6 +84,7 @@ struct Ops {
   virtual cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS,
                                   double* q_send, const Ctl* ctl, cudaStream_t s) = 0;
   virtual int64_t grid_for(int64_t nelems) const = 0;
+  virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
 };
 
 template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
@@ -113,6 +114,16 @@ struct OpsImpl : Ops {
     (void)w;
   }
   int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
+  int resident_element_ctas() override {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)Cfg::smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, Cfg::T,
+                                                  Cfg::smem_bytes);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
+  }
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
     if (a.ng <= 0) return cudaSuccess;
     dim3 grid((unsigned)((a.ng + FT - 1) / FT)), block(FCfg::T);
@@ -208,6 +219,8 @@ struct PdesCtx {
   std::vector<EFace> h_efaces;      // interior + boundary part (shared faces added by finalize)
   std::vector<FaceRec> h_faces;
   std::vector<double> h_nrm;        // nrm_face | nrm_bndry
+  bool dx_compact = false, nrm_compact = false;   // node-independent metrics detected at upload
+  int prefetch_ahead = 0;
   std::vector<double> h_w;
   // partition
   std::vector<Peer> peers;
@@ -326,7 +339,21 @@ int finalize(PdesCtx* ctx) {
       }
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->efaces, ef.data(), ef.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->faces, faces.data(), faces.size()));
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nrm.data(), nrm.size()));
+  {
+    bool compact = env_int("PDES_NO_COMPACT", 0) == 0;
+    for (int64_t g = 0; g < nG && compact; ++g)
+      for (int i = 1; i < c.nfn && compact; ++i)
+        compact = memcmp(nrm.data() + (size_t)g * per_nrm + (size_t)i * c.dim, nrm.data() + (size_t)g * per_nrm,
+                         sizeof(double) * c.dim) == 0;
+    ctx->nrm_compact = compact;
+    if (compact) {
+      std::vector<double> nc((size_t)nG * c.dim);
+      for (int64_t g = 0; g < nG; ++g) memcpy(nc.data() + (size_t)g * c.dim, nrm.data() + (size_t)g * per_nrm, sizeof(double) * c.dim);
+      CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nc.data(), nc.size()));
+    } else {
+      CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nrm.data(), nrm.size()));
+    }
+  }
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxw, nullptr, (size_t)nG * c.nfn * ctx->nd));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_el, sh_el.data(), sh_el.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_face, sh_face.data(), sh_face.size()));
@@ -334,6 +361,7 @@ int finalize(PdesCtx* ctx) {
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
+  ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas());
   ctx->finalized = true;
   return PDES_OK;
 }
@@ -344,6 +372,10 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
   a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
   a->norm_partials = ctx->norm_partials;
+  const int dd = ctx->cfg.dim * ctx->cfg.dim;
+  a->dx_el_stride = ctx->dx_compact ? dd : ctx->cfg.nn * dd;
+  a->dx_node_stride = ctx->dx_compact ? 0 : dd;
+  a->prefetch_ahead = ctx->prefetch_ahead;
 }
 
 // startSolutionExchange (Utils/parallel.jl:29-49): pack on the compute stream, send/recv on the comm stream
@@ -381,6 +413,8 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   memset(&fa, 0, sizeof(fa));
   fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
   fa.q_recv = ctx->q_recv; fa.fluxw = ctx->fluxw; fa.nF = c.nF; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
+  fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.g0 = 0; fa.ng = c.nF + c.nB;
   CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
   ctx->launches++;
@@ -619,7 +653,23 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
     if (c.nB) memcpy(ctx->h_nrm.data() + (size_t)c.nF * per_nrm, nrm_bndry, sizeof(double) * (size_t)c.nB * per_nrm);
   }
   const size_t nnE = (size_t)c.nn * c.nE;
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->dxidx, dxidx, nnE * c.dim * c.dim));
+  {
+    // straight-sided elements have node-independent dxidx: store one matrix per element (the reference stores it
+    // per node, docs/src/interfaces.md:351-357); exact comparison, so curved meshes take the general path
+    const int dd = c.dim * c.dim;
+    bool compact = env_int("PDES_NO_COMPACT", 0) == 0;
+    for (int64_t e = 0; e < c.nE && compact; ++e)
+      for (int j = 1; j < c.nn && compact; ++j)
+        compact = memcmp(dxidx + ((size_t)e * c.nn + j) * dd, dxidx + (size_t)e * c.nn * dd, sizeof(double) * dd) == 0;
+    ctx->dx_compact = compact;
+    if (compact) {
+      std::vector<double> dc((size_t)c.nE * dd);
+      for (int64_t e = 0; e < c.nE; ++e) memcpy(dc.data() + (size_t)e * dd, dxidx + (size_t)e * c.nn * dd, sizeof(double) * dd);
+      CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->dxidx, dc.data(), dc.size()));
+    } else {
+      CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->dxidx, dxidx, nnE * c.dim * c.dim));
+    }
+  }
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->coords_bndry, coords_bndry, (size_t)c.nB * c.nfn * c.dim));
   // Minv and the tabulated source are produced on the device from jac / coords
   double* jac_dev = nullptr;

@@ -74,7 +74,9 @@ enum EpiMode { EPI_RES = 0, EPI_RK = 1 };
 struct FaceArgs {
   const double* q;             // [ND,NN,nE]
   const FaceRec* faces;        // [nF + nB + nS]
-  const double* nrm;           // [DIM,NFN,nF+nB+nS]   nrm_face | nrm_bndry | nrm_sharedface
+  const double* nrm;           // [DIM,NFN,nF+nB+nS]   nrm_face | nrm_bndry | nrm_sharedface  (or [DIM,nG] when every
+                               // face has node-independent normals: straight-sided meshes, detected at upload)
+  int32_t nrm_face_stride, nrm_node_stride;   // in doubles: (NFN*DIM, DIM) or (DIM, 0)
   const double* coords_bndry;  // [DIM,NFN,nB]
   const double* q_recv;        // [ND,NFN,nS] (peer's own face-node order)
   double* fluxw;               // [ND,NFN,nF+nB+nS]    wface[i] * flux[:,i]
@@ -86,7 +88,8 @@ struct FaceArgs {
 
 struct ElemArgs {
   const double* q;             // [ND,NN,nE]
-  const double* dxidx;         // [DIM,DIM,NN,nE]
+  const double* dxidx;         // [DIM,DIM,NN,nE]  (or [DIM,DIM,nE] when node-independent: straight-sided elements)
+  int32_t dx_el_stride, dx_node_stride;       // in doubles: (NN*DIM*DIM, DIM*DIM) or (DIM*DIM, 0)
   const EFace* efaces;         // [nE][NF]
   const double* fluxw;         // from k_face_flux
   const double* srcw;          // [ND,NN,nE] (w_j/jac_j) * S(x_j), or nullptr
@@ -100,6 +103,7 @@ struct ElemArgs {
   double ah;                   // a_s * h
   double h6;                   // h/6 (last stage)
   int32_t stage;               // 1..4
+  int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
   int64_t nE;
   Ctl* ctl;
   PhysPar ph;
@@ -223,7 +227,7 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
     const int fi = tid / NFN, i = tid - fi * NFN;
     const FaceRec r = sRec[fi];
     const int64_t g = g0 + fi;
-    const double* np_ = a.nrm + (g * NFN + i) * DIM;
+    const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
     double nrm[DIM], qL[ND], flux[ND];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
@@ -321,19 +325,29 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
       }
     }
   }
-  // L2 prefetch of the epilogue's streams
+  // L2 prefetch of the contiguous streams of the tile that will run on this SM slot next (CTAs are dispatched
+  // in order, so tile blockIdx + gridDim-resident runs when this one retires): turns its HBM latency into L2 latency
   {
-    const int64_t b0 = e0 * EL * 8, nb = (int64_t)ne * EL * 8;
-    for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
-      if (a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
-      if (MODE == EPI_RK && a.stage > 1) {
-        prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
-        prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+    const int64_t ea = e0 + (int64_t)a.prefetch_ahead * E;
+    if (ea < a.nE) {
+      const int na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
+      const int64_t b0 = ea * EL * 8, nb = (int64_t)na * EL * 8;
+      for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
+        prefetch_l2(reinterpret_cast<const char*>(a.q) + b0 + o);
+        if (a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
+        if (MODE == EPI_RK && a.stage > 1) {
+          prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+          prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+        }
       }
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * a.dx_el_stride * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.dxidx) + ea * a.dx_el_stride * 8 + o);
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NF * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.efaces) + ea * NF * 8 + o);
+      if (MODE == EPI_RK)
+        for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NN * 8; o += (int64_t)T * 128)
+          prefetch_l2(reinterpret_cast<const char*>(a.minv) + ea * NN * 8 + o);
     }
-    if (MODE == EPI_RK)
-      for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
-        prefetch_l2(reinterpret_cast<const char*>(a.minv) + e0 * NN * 8 + o);
   }
   __syncthreads();
 
@@ -343,7 +357,7 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
     double qn[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) qn[k] = sq[s * SQ + j * ND + k];
-    const double* dx = a.dxidx + ((e0 + s) * NN + j) * (DIM * DIM);
+    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
     double dxl[DIM * DIM];
 #pragma unroll
     for (int m = 0; m < DIM * DIM; ++m) dxl[m] = __ldg(dx + m);
