@@ -206,7 +206,7 @@ struct PdesCtx {
   std::unique_ptr<Ops> ops;
   bool have_op = false, have_mesh = false, finalized = false;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_norm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   // state
   double* qbuf[3] = {nullptr, nullptr, nullptr};
   int cur = 0;
@@ -432,19 +432,31 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
 
 int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
   int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE);
+  const bool parallel = ctx->comm && ctx->nranks > 1;
+  // the norm only feeds back into the time loop through the res_tol test; when that test is off the
+  // Allreduce + commit run on the communication stream and never stall the stage kernels
+  const bool async = parallel && !(pseudo_time && res_tol >= 0.0);
+  if (parallel) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_norm, 0));   // norm_sq of the previous step consumed
   k_norm_reduce<<<1, 256, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_sq, ctx->ctl);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   double quirk = 1.0;
-  if (ctx->comm && ctx->nranks > 1) {
-    // calcNorm's Allreduce (Utils.jl:443-448); issued on the compute stream: 8 bytes, once per step
-    ncclResult_t r = g_nccl.AllReduce(ctx->norm_sq, ctx->norm_sq, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+  cudaStream_t st = ctx->stream;
+  if (parallel) {
+    if (async) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+      st = ctx->comm_stream;
+    }
+    // calcNorm's Allreduce (Utils.jl:443-448): 8 bytes, once per step
+    ncclResult_t r = g_nccl.AllReduce(ctx->norm_sq, ctx->norm_sq, 1, ncclFloat64, ncclSum, ctx->comm, st);
     if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
     quirk = (double)ctx->nranks;   // rk4.jl:451-453 reduces the already-reduced norm again
   }
-  k_norm_commit<<<1, 1, 0, ctx->stream>>>(ctx->norm_sq, quirk, ctx->norms_dev, slot, res_tol, pseudo_time, ctx->ctl);
+  k_norm_commit<<<1, 1, 0, st>>>(ctx->norm_sq, quirk, ctx->norms_dev, slot, res_tol, pseudo_time, ctx->ctl);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
+  if (parallel) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_norm, st));
   return PDES_OK;
 }
 
@@ -526,6 +538,7 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_norm, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreate(&c->ev_t0));
   CUDA_TRY(c, cudaEventCreate(&c->ev_t1));
   for (int i = 0; i < 3; ++i) CUDA_TRY(c, dev_upload<double>(c->stream, &c->qbuf[i], nullptr, (size_t)c->ndof));
@@ -555,6 +568,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
   if (ctx->ev_recv) cudaEventDestroy(ctx->ev_recv);
+  if (ctx->ev_norm) cudaEventDestroy(ctx->ev_norm);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -1,0 +1,116 @@
+"""Worker for the multi-process tests (launched by torchrun or mp.spawn).
+
+mode "gloo-oracle": CPU, gloo backend -- each rank owns one block of the partitioned mesh, packs its shared-face
+    states with the oracle's getSendDataFace, exchanges them with dist.send/recv (the MPI Isend/Irecv of
+    Utils/parallel.jl:82-141) and evaluates the oracle residual; the result must equal the serial one.
+mode "nccl-b200": one GPU per rank -- the same comparison for the CUDA path with the NCCL halo exchange inside
+    libpdes_euler_b200.so, for evalResidual and for an RK4 trajectory (norms carry the reference's sqrt(P) quirk).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PARTS = {2: {2: (2, 1), 3: (2, 1, 1)}, 4: {2: (2, 2), 3: (2, 2, 1)}, 8: {2: (4, 2), 3: (2, 2, 2)}}
+
+
+def serial_and_local(case, n, rank, world, seed=4):
+    import oracle
+    import pdesolver_jl_b200 as pd
+    from common import CASES, perturbed
+    dim, p, ic, opts = CASES[case]
+    op = pd.build_operator(dim, p)
+    parts = PARTS[world][dim]
+    serial = pd.structured_mesh(op, n, shuffle_seed=seed)
+    local = pd.structured_mesh(op, n, parts=parts, rank=rank, shuffle_seed=seed)
+    orc_s = oracle.Problem(serial, op, opts)
+    q_s = perturbed(orc_s.exact_state(ic))
+    pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
+    idx = np.array([pos[int(g)] for g in local.global_elnum])
+    return pd, op, dict(opts), serial, local, orc_s, q_s, idx
+
+
+def run_gloo_oracle(rank, world, case="c3_3d_p2_roe_src", n=4):
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from common import rel_l2
+    pd, op, opts, serial, local, orc_s, q_s, idx = serial_and_local(case, n, rank, world)
+    orc = oracle.Problem(local, op, opts)
+    q = np.asfortranarray(q_s[:, :, idx])
+    orc.start_exchange(q)
+    reqs, bufs = [], []
+    for pi, pr in enumerate(local.peer_parts):
+        send = torch.from_numpy(np.ascontiguousarray(orc.q_send[pi].ravel(order="F")))
+        recv = torch.empty_like(send)
+        bufs.append((pi, recv))
+        reqs.append(dist.isend(send, dst=pr))
+        reqs.append(dist.irecv(recv, src=pr))
+    for r in reqs:
+        r.wait()
+    for pi, recv in bufs:
+        orc.q_recv[pi][...] = recv.numpy().reshape(orc.q_recv[pi].shape, order="F")
+    res = orc.eval_residual(q)
+    err = rel_l2(res, orc_s.eval_residual(q_s)[:, :, idx])
+    assert err < 1e-13, f"rank {rank}: partitioned oracle != serial oracle ({err:.2e})"
+    # global norm through the process group == serial norm (calcNorm + Allreduce, Utils.jl:427-449)
+    M = 1.0 / orc.mass_matrix_inverse()
+    loc = torch.tensor([float(np.sum(res * M * res))], dtype=torch.float64)
+    dist.all_reduce(loc)
+    Ms = 1.0 / orc_s.mass_matrix_inverse()
+    rs = orc_s.eval_residual(q_s)
+    assert abs(loc.item() - float(np.sum(rs * Ms * rs))) < 1e-12 * loc.item()
+
+
+def run_nccl_b200(rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from common import rel_l2
+    torch.cuda.set_device(local_rank)
+    for case, n, h in [("c3_3d_p2_roe_src", 4, 5e-5), ("c1_2d_p1_roe", 8, 1e-3), ("3d_p1_roe_src", 4, 5e-5)]:
+        pd, op, opts, serial, local, orc_s, q_s, idx = serial_and_local(case, n, rank, world)
+        ids = [pd.EulerData.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eqn = pd.EulerData(local, op, opts, device=local_rank, comm=(ids[0], rank, world))
+        eqn.q[...] = q_s[:, :, idx]
+        pd.evalResidual(local, op, eqn, opts)
+        err = rel_l2(eqn.res, orc_s.eval_residual(q_s)[:, :, idx])
+        assert err < 1e-12, f"rank {rank} {case}: residual parity {err:.2e}"
+        nsteps = 10
+        opts["use_itermax"] = False
+        eqn.q[...] = q_s[:, :, idx]
+        t = pd.rk4(pd.evalResidual, h, nsteps * h, local, op, eqn, opts)
+        t_ref, q_ref, norms_ref = orc_s.rk4(q_s, h, nsteps * h)
+        errq = rel_l2(eqn.q, q_ref[:, :, idx])
+        assert t == t_ref and errq < 1e-10, f"rank {rank} {case}: rk4 parity {errq:.2e}"
+        # the parallel norm is reduced twice -> sqrt(P) * serial norm
+        assert np.allclose(eqn.convergence, np.sqrt(world) * norms_ref, rtol=1e-11, atol=0), \
+            f"rank {rank} {case}: norms"
+        eqn.close()
+        dist.barrier()
+    if rank == 0:
+        print(f"nccl-b200 ok on {world} ranks")
+
+
+def main():
+    import torch.distributed as dist
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    if mode == "gloo-oracle":
+        dist.init_process_group("gloo")
+        run_gloo_oracle(rank, world)
+    else:
+        import torch
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        run_nccl_b200(rank, world, local_rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+"""N>1 path: world_size-2 gloo test on the CPU (partition bookkeeping + exchange through a real process boundary)
+and, when >= 2 GPUs are visible, the NCCL halo exchange inside the CUDA library."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _torchrun(mode, nproc, timeout):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "mp_worker.py"), mode]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_partitioned_oracle_gloo_world2():
+    _torchrun("gloo-oracle", 2, 300)
+
+
+@pytest.mark.gpu
+def test_nccl_halo_exchange_matches_serial():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    out = _torchrun("nccl-b200", 2 if n < 4 else 4, 600)
+    assert "nccl-b200 ok" in out
