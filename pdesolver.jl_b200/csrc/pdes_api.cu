@@ -85,6 +85,7 @@ struct Ops {
                                   double* q_send, const Ctl* ctl, cudaStream_t s) = 0;
   virtual int64_t grid_for(int64_t nelems) const = 0;
   virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
+  virtual int resident_face_ctas() = 0;
 };
 
 template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
@@ -120,6 +121,13 @@ struct OpsImpl : Ops {
                          (int)Cfg::smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, Cfg::T,
                                                   Cfg::smem_bytes);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
+  }
+  int resident_face_ctas() override {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_face_flux<DIM, NN, NFN, FT, MINB_F>, FCfg::T, 0);
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return per_sm * sms;
@@ -169,13 +177,13 @@ Ops* make_ops(const PdesConfig& c) {
   if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32, 2, 32, 2>();
   if (c.dim == 3 && c.nn == 11 && c.nfn == 6) {
     switch (variant) {
-      case 1: return new OpsImpl<3, 11, 6, 32, 2, 32, 2>();
-      case 2: return new OpsImpl<3, 11, 6, 32, 3, 32, 3>();
-      case 3: return new OpsImpl<3, 11, 6, 16, 5, 16, 4>();
-      case 4: return new OpsImpl<3, 11, 6, 16, 6, 32, 3>();
-      case 5: return new OpsImpl<3, 11, 6, 32, 3, 64, 1>();
-      case 6: return new OpsImpl<3, 11, 6, 64, 1, 32, 2>();
-      default: return new OpsImpl<3, 11, 6, 16, 4, 32, 2>();
+      case 1: return new OpsImpl<3, 11, 6, 32, 3, 16, 8>();
+      case 2: return new OpsImpl<3, 11, 6, 32, 5, 16, 8>();
+      case 3: return new OpsImpl<3, 11, 6, 64, 1, 16, 8>();
+      case 4: return new OpsImpl<3, 11, 6, 64, 2, 16, 8>();
+      case 5: return new OpsImpl<3, 11, 6, 38, 3, 16, 8>();
+      case 6: return new OpsImpl<3, 11, 6, 24, 5, 16, 8>();
+      default: return new OpsImpl<3, 11, 6, 32, 4, 16, 8>();
     }
   }
   return nullptr;
@@ -213,14 +221,13 @@ struct PdesCtx {
   double *ksum = nullptr, *res = nullptr;
   // mesh
   double *dxidx = nullptr, *minv = nullptr, *srcw = nullptr, *coords_bndry = nullptr, *w_dev = nullptr;
-  EFace* efaces = nullptr;
   FaceRec* faces = nullptr;
-  double *nrm_all = nullptr, *fluxw = nullptr;
+  double *nrm_all = nullptr, *fluxe = nullptr, *srcm = nullptr;
   std::vector<EFace> h_efaces;      // interior + boundary part (shared faces added by finalize)
   std::vector<FaceRec> h_faces;
   std::vector<double> h_nrm;        // nrm_face | nrm_bndry
   bool dx_compact = false, nrm_compact = false;   // node-independent metrics detected at upload
-  int prefetch_ahead = 0;
+  int prefetch_ahead = 0, prefetch_ahead_faces = 0;
   std::vector<double> h_w;
   // partition
   std::vector<Peer> peers;
@@ -337,7 +344,6 @@ int finalize(PdesCtx* ctx) {
         set_err(ctx, "face %d of element %lld belongs to no interface, boundary face or shared face", f, (long long)e);
         return PDES_ERR_USAGE;
       }
-  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->efaces, ef.data(), ef.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->faces, faces.data(), faces.size()));
   {
     bool compact = env_int("PDES_NO_COMPACT", 0) == 0;
@@ -354,22 +360,24 @@ int finalize(PdesCtx* ctx) {
       CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nrm.data(), nrm.size()));
     }
   }
-  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxw, nullptr, (size_t)nG * c.nfn * ctx->nd));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxe, nullptr, (size_t)c.nE * NF * c.nfn * ctx->nd + 2));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_el, sh_el.data(), sh_el.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_face, sh_face.data(), sh_face.size()));
   size_t nsend = (size_t)ctx->nS * c.nfn * ctx->nd;
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
-  ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas());
+  ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas() / 8);   // measured optimum: ~half a wave
+  ctx->prefetch_ahead_faces = env_int("PDES_PREFETCH_AHEAD_F", ctx->ops->resident_face_ctas());
   ctx->finalized = true;
   return PDES_OK;
 }
 
 void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   memset(a, 0, sizeof(*a));
-  a->q = q; a->dxidx = ctx->dxidx; a->efaces = ctx->efaces; a->fluxw = ctx->fluxw;
+  a->q = q; a->dxidx = ctx->dxidx; a->fluxe = ctx->fluxe;
   a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
+  a->srcm = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcm : nullptr;
   a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
   a->norm_partials = ctx->norm_partials;
   const int dd = ctx->cfg.dim * ctx->cfg.dim;
@@ -412,9 +420,10 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   FaceArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
-  fa.q_recv = ctx->q_recv; fa.fluxw = ctx->fluxw; fa.nF = c.nF; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.nF = c.nF; fa.ctl = ctx->ctl; fa.ph = a.ph;
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
+  fa.prefetch_ahead = ctx->prefetch_ahead_faces;
   fa.g0 = 0; fa.ng = c.nF + c.nB;
   CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
   ctx->launches++;
@@ -561,7 +570,7 @@ void pdes_destroy(PdesCtx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
-                  ctx->nrm_all, ctx->fluxw, ctx->faces, ctx->coords_bndry, ctx->w_dev, ctx->efaces,
+                  ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
                   ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -699,6 +708,10 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
     CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->srcw, nullptr, (size_t)ctx->ndof));
     if (c.dim == 2) k_tabulate_source<2><<<nb, 256, 0, ctx->stream>>>(coords_dev, jac_dev, ctx->w_dev, c.nn, c.nE, c.gamma, ctx->srcw);
     else k_tabulate_source<3><<<nb, 256, 0, ctx->stream>>>(coords_dev, jac_dev, ctx->w_dev, c.nn, c.nE, c.gamma, ctx->srcw);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->srcm, nullptr, (size_t)ctx->ndof));
+    k_srcm<<<(unsigned)((ctx->ndof + 255) / 256), 256, 0, ctx->stream>>>(ctx->srcw, ctx->minv, ctx->nd, (int64_t)nnE, ctx->srcm);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -28,12 +28,11 @@
 
 namespace pdes {
 
-// per (element, local face): where the element finds its face flux and how to read it
-struct __align__(8) EFace {
-  int32_t gface;     // index into the face-flux array (interfaces, then boundary faces, then shared faces)
-  uint8_t right;     // 1: this element is elementR of the interface (+flux, node order permuted by nbrperm)
-  uint8_t orient;
-  uint8_t pad[2];
+// host-side bookkeeping per (element, local face): which face covers it (every element face must be claimed by
+// exactly one interface, boundary face or shared face)
+struct EFace {
+  int32_t gface;
+  uint8_t right, orient, pad[2];
 };
 
 // per face: what k_face_flux gathers
@@ -79,9 +78,11 @@ struct FaceArgs {
   int32_t nrm_face_stride, nrm_node_stride;   // in doubles: (NFN*DIM, DIM) or (DIM, 0)
   const double* coords_bndry;  // [DIM,NFN,nB]
   const double* q_recv;        // [ND,NFN,nS] (peer's own face-node order)
-  double* fluxw;               // [ND,NFN,nF+nB+nS]    wface[i] * flux[:,i]
+  double* fluxe;               // [ND,NFN,dim+1,nE]: per (element, local face) the contribution the element integrates,
+                               // -wface_i f*(:,i) for elementL, +wface_i f*(:,i) in elementR's own node order
   int64_t g0, ng;              // face range of this launch
   int64_t nF;                  // first boundary face
+  int32_t prefetch_ahead;      // tiles between this CTA and the one whose gathers it prefetches into L2
   const Ctl* ctl;
   PhysPar ph;
 };
@@ -90,9 +91,9 @@ struct ElemArgs {
   const double* q;             // [ND,NN,nE]
   const double* dxidx;         // [DIM,DIM,NN,nE]  (or [DIM,DIM,nE] when node-independent: straight-sided elements)
   int32_t dx_el_stride, dx_node_stride;       // in doubles: (NN*DIM*DIM, DIM*DIM) or (DIM*DIM, 0)
-  const EFace* efaces;         // [nE][NF]
-  const double* fluxw;         // from k_face_flux
-  const double* srcw;          // [ND,NN,nE] (w_j/jac_j) * S(x_j), or nullptr
+  const double* fluxe;         // [ND,NFN,dim+1,nE] from k_face_flux
+  const double* srcw;          // [ND,NN,nE] (w_j/jac_j) * S(x_j), or nullptr   (EPI_RES)
+  const double* srcm;          // [ND,NN,nE] Minv_j * srcw                     (EPI_RK)
   double* res;                 // EPI_RES: [ND,NN,nE]
   // EPI_RK (rk4.jl:244-319): k = Minv*res; q_next = x_old + ah*k; ksum updated; last stage: x_new
   const double* minv;          // [NN,nE]  1/(w_j/jac_j)   (mass_matrix.jl:20-44)
@@ -110,6 +111,26 @@ struct ElemArgs {
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Ampere-style asynchronous global->shared copies (LDGSTS): issued at the top of a tile, consumed stages later
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// contiguous tile of n doubles, both sides 16-byte aligned (tile bases are: even tile sizes, 256-B aligned arrays)
+__device__ __forceinline__ void async_tile(double* dst, const double* src, int n, int tid, int T) {
+  const int n2 = n >> 1;
+  for (int i = tid; i < n2; i += T) cp_async16(dst + 2 * i, src + 2 * i);
+  if ((n & 1) && tid == 0) cp_async8(dst + n - 1, src + n - 1);
+}
 
 __host__ __device__ constexpr int pad_stride(int n, int nd) {
   // smallest m >= n with m % 16 == nd % 16: (item, variable)-indexed fp64 accesses of a half-warp
@@ -154,7 +175,7 @@ struct FaceCfg {
   static constexpr int ND = DIM + 2;
   static constexpr int PER = ND > NFN ? ND : NFN;             // threads per face
   static constexpr int T = ((FT * PER + 31) / 32) * 32;
-  static constexpr int FS = pad_stride(NFN * ND, ND);          // per-face stride of a face-state tile
+  static constexpr int FS = (pad_stride(NFN * ND, ND) + 1) & ~1;   // per-face stride of a face-state tile (even: LDS.128)
 };
 
 template <int DIM, int NN, int NFN, int FT, int MINB>
@@ -165,6 +186,7 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   __shared__ double sL[FT * FS];
   __shared__ double sR[FT * FS];
   __shared__ FaceRec sRec[FT];
+  __shared__ int s_dst[2 * FT];            // (element*NF + face) of the record each side of a face writes, or -1
   __shared__ int s_perm[NF][NN];
   __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
 
@@ -173,7 +195,22 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FT;
   const int64_t rem = a.g0 + a.ng - g0;
   const int nf = (int)(rem < FT ? rem : FT);
-  if (tid < nf) sRec[tid] = a.faces[g0 + tid];
+  if (tid < nf) {
+    const FaceRec r = a.faces[g0 + tid];
+    sRec[tid] = r;
+    s_dst[2 * tid] = r.elL * NF + r.fL;
+    s_dst[2 * tid + 1] = r.kind == FK_INTERIOR ? r.elR * NF + r.fR : -1;
+  }
+  // the tile that will run on this SM slot next: fetch its records now, prefetch what they point at when done
+  FaceRec nxt;
+  nxt.kind = 255;
+  const int64_t ga = g0 + (int64_t)a.prefetch_ahead * FT;
+  if (a.prefetch_ahead > 0 && tid < FT && ga + tid < a.g0 + a.ng) nxt = a.faces[ga + tid];
+  if (a.prefetch_ahead > 0 && tid == 0 && ga + (int64_t)a.prefetch_ahead * FT < a.g0 + a.ng) {
+    const char* pr = reinterpret_cast<const char*>(a.faces + ga + (int64_t)a.prefetch_ahead * FT);
+#pragma unroll
+    for (int o = 0; o < FT * 16; o += 128) prefetch_l2(pr + o);
+  }
   for (int idx = tid; idx < NF * NN; idx += T) s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
   for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
     s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
@@ -222,74 +259,106 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   }
   __syncthreads();
 
-  // ---- B: numerical flux at every face node (node threads), scaled by wface ------------------------------
-  if (tid < nf * NFN) {
-    const int fi = tid / NFN, i = tid - fi * NFN;
+  // ---- B: numerical flux at every face node (node threads) ------------------------------------------------
+  // results overwrite the face-state tiles: sL <- -w f* in elementL's node order, sR <- +w f* in elementR's
+  // node order (the contributions interiorfaceintegrate! hands to the two elements)
+  {
+    const bool nact = tid < nf * NFN;
+    const int fi = nact ? tid / NFN : 0, i = tid - fi * NFN;
     const FaceRec r = sRec[fi];
     const int64_t g = g0 + fi;
-    const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
-    double nrm[DIM], qL[ND], flux[ND];
+    double nrm[DIM], qL[ND], qR[ND], flux[ND];
+    if (nact) {
+      const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
-    double* po = sL + fi * FS + i * ND;
+      for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
 #pragma unroll
-    for (int k = 0; k < ND; ++k) qL[k] = po[k];
-    if (r.kind == FK_BOUNDARY) {
-      // separate copies so that only this (rare) path touches local memory
-      const double* xp = a.coords_bndry + ((g - a.nF) * NFN + i) * DIM;
-      double xb[DIM], nb_[DIM], qb[ND], fb[ND];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
-#pragma unroll
-      for (int k = 0; k < ND; ++k) qb[k] = qL[k];
-      bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
-#pragma unroll
-      for (int k = 0; k < ND; ++k) flux[k] = fb[k];
-    } else {
-      double qR[ND];
-      const double* pn = sR + fi * FS + i * ND;
-#pragma unroll
-      for (int k = 0; k < ND; ++k) qR[k] = pn[k];
-      roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
+      for (int k = 0; k < ND; ++k) { qL[k] = sL[fi * FS + i * ND + k]; qR[k] = sR[fi * FS + i * ND + k]; }
     }
-    const double w = op.wface[i];
+    __syncthreads();       // every node thread holds its inputs: the tiles may be overwritten
+    if (nact) {
+      if (r.kind == FK_BOUNDARY) {
+        // separate copies so that only this (rare) path touches local memory
+        const double* xp = a.coords_bndry + ((g - a.nF) * NFN + i) * DIM;
+        double xb[DIM], nb_[DIM], qb[ND], fb[ND];
 #pragma unroll
-    for (int k = 0; k < ND; ++k) po[k] = w * flux[k];
+        for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
+#pragma unroll
+        for (int k = 0; k < ND; ++k) qb[k] = qL[k];
+        bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) flux[k] = fb[k];
+      } else {
+        roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
+      }
+      const double w = op.wface[i];
+      const int ir = (r.kind == FK_INTERIOR) ? s_nbrperm[r.orient][i] : i;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        const double wf = w * flux[k];
+        sL[fi * FS + i * ND + k] = -wf;
+        sR[fi * FS + ir * ND + k] = wf;
+      }
+    }
   }
   __syncthreads();
 
-  // ---- C: coalesced store of the tile ----------------------------------------------------------------------
-  double* dst = a.fluxw + g0 * (NFN * ND);
-  for (int idx = tid; idx < nf * NFN * ND; idx += T) {
-    const int fi = idx / (NFN * ND), r = idx - fi * (NFN * ND);
-    dst[idx] = sL[fi * FS + r];
+  // ---- C: store one record per (element, local face): 8*ND*NFN contiguous bytes each, half a warp per record ---
+  constexpr int FL = NFN * ND;
+  {
+    const int half = tid >> 4, hl = tid & 15;
+    for (int rec = half; rec < 2 * nf; rec += T / 16) {
+      const int di = s_dst[rec];
+      if (di < 0) continue;
+      const double* src = ((rec & 1) ? sR : sL) + (rec >> 1) * FS;
+      double* dst = a.fluxe + (int64_t)di * FL;
+      if (FL % 2 == 0) {       // records are 16-byte aligned: move them as double2
+        for (int c2 = hl; c2 < FL / 2; c2 += 16)
+          reinterpret_cast<double2*>(dst)[c2] = reinterpret_cast<const double2*>(src)[c2];
+      } else {
+        for (int c1 = hl; c1 < FL; c1 += 16) dst[c1] = src[c1];
+      }
+    }
+  }
+  if (nxt.kind != 255) {
+    const char* pq = reinterpret_cast<const char*>(a.q + (int64_t)nxt.elL * EL);
+#pragma unroll
+    for (int o = 0; o < EL * 8 + 127; o += 128) prefetch_l2(pq + o);
+    if (nxt.kind == FK_INTERIOR) {
+      const char* pr = reinterpret_cast<const char*>(a.q + (int64_t)nxt.elR * EL);
+#pragma unroll
+      for (int o = 0; o < EL * 8 + 127; o += 128) prefetch_l2(pr + o);
+    }
+    prefetch_l2(a.nrm + (ga + tid) * a.nrm_face_stride);
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_element_rk: E elements per CTA
+// k_element_rk: E elements per CTA; every variable thread owns TWO (element, variable) rows -- elements p and
+// p + E/2 -- so that each uniform coefficient load feeds two DFMAs
 // ------------------------------------------------------------------------------------------------------
 template <int DIM, int NN, int NFN, int E>
 struct TileCfg {
   static constexpr int ND = DIM + 2, NF = DIM + 1;
-  static constexpr int VT = E * ND;                             // variable threads
+  static constexpr int HP = E / 2;                              // row pairs
+  static constexpr int VT = HP * ND;                            // variable threads
   static constexpr int T = ((VT + 31) / 32) * 32;
-  static constexpr int SQ = pad_stride(NN * ND, ND);           // per-element stride of the q tile
+  static constexpr int SQ = NN * ND;                            // per-element stride of the q tile (contiguous: cp.async)
   static constexpr int SF = ND * DIM * NN;                      // per-element stride of the volume-flux tile
   static constexpr size_t smem_bytes = sizeof(double) * (size_t)E * (SQ + SF);
+  static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
 };
 
 template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
 __global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
 k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
-  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ, HP = Cfg::HP;
   constexpr int EL = NN * ND;                       // doubles per element
   constexpr int FL = NFN * ND;                      // doubles per face
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sq = reinterpret_cast<double*>(smem_raw);             // [E][SQ]
+  double* sq = reinterpret_cast<double*>(smem_raw);             // [E][EL]
   double* sF = sq + E * SQ;                                     // [E][ND][DIM][NN]
-  __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
   __shared__ double s_red[T / 32];
 
   if (a.ctl->stop) return;
@@ -298,57 +367,44 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
   const double gami = a.ph.gamma - 1.0;
 
-  // ---- S0: tile load; variable threads fetch their element's face records and prefetch the face fluxes ------
-  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
-    s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
-  {
-    const double* src = a.q + e0 * EL;
-    for (int idx = tid; idx < ne * EL; idx += T) {
-      const int s = idx / EL, r = idx - s * EL;
-      sq[s * SQ + r] = src[idx];
-    }
-  }
-  const int v = tid;
-  const int vs = v / ND, vk = v - vs * ND;
-  const bool v_active = v < ne * ND;
-  EFace ef[NF];
-  if (v_active) {
-    const EFace* pe = a.efaces + (e0 + vs) * NF;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) ef[f] = pe[f];
-    if (vk == 0) {
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const char* pf = reinterpret_cast<const char*>(a.fluxw + (int64_t)ef[f].gface * FL);
-        prefetch_l2(pf);
-        if (FL * 8 > 128) prefetch_l2(pf + FL * 8 - 8);
-      }
-    }
-  }
-  // L2 prefetch of the contiguous streams of the tile that will run on this SM slot next (CTAs are dispatched
-  // in order, so tile blockIdx + gridDim-resident runs when this one retires): turns its HBM latency into L2 latency
+  // ---- S0: q tile (asynchronous copy) + L2 prefetch of the streams of the tile this SM slot runs next --------
+  async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
+  cp_async_commit();
   {
     const int64_t ea = e0 + (int64_t)a.prefetch_ahead * E;
-    if (ea < a.nE) {
+    if (a.prefetch_ahead > 0 && ea < a.nE) {
       const int na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
       const int64_t b0 = ea * EL * 8, nb = (int64_t)na * EL * 8;
       for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
         prefetch_l2(reinterpret_cast<const char*>(a.q) + b0 + o);
-        if (a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
-        if (MODE == EPI_RK && a.stage > 1) {
+        if (MODE == EPI_RES && a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
+        if (MODE == EPI_RK) {
+          if (a.srcm) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
           prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
-          prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+          if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
         }
       }
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NF * FL * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + ea * NF * FL * 8 + o);
       for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * a.dx_el_stride * 8; o += (int64_t)T * 128)
         prefetch_l2(reinterpret_cast<const char*>(a.dxidx) + ea * a.dx_el_stride * 8 + o);
-      for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NF * 8; o += (int64_t)T * 128)
-        prefetch_l2(reinterpret_cast<const char*>(a.efaces) + ea * NF * 8 + o);
-      if (MODE == EPI_RK)
-        for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NN * 8; o += (int64_t)T * 128)
-          prefetch_l2(reinterpret_cast<const char*>(a.minv) + ea * NN * 8 + o);
     }
   }
+  // this tile's own epilogue streams and face contributions: in L2 by the time S3 / S4 ask for them
+  {
+    const int64_t b0 = e0 * EL * 8, nb = (int64_t)ne * EL * 8;
+    for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
+      if (MODE == EPI_RES && a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
+      if (MODE == EPI_RK) {
+        if (a.srcm) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
+        prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+        if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+      }
+    }
+    for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NF * FL * 8; o += (int64_t)T * 128)
+      prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + e0 * NF * FL * 8 + o);
+  }
+  cp_async_wait<0>();
   __syncthreads();
 
   // ---- S1: Euler flux in the parametric directions at every node (getEulerFlux) ---------------
@@ -384,96 +440,136 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
       Fo[(DIM + 1) * DIM * NN] = (qn[DIM + 1] + press) * U;
     }
   }
-  __syncthreads();
+  __syncthreads();       // sF complete; nobody reads the q tile any more (it becomes the output staging tile)
 
-  double acc[NN];
+  // ---- S2 + S3: variable threads -------------------------------------------------------------------
+  const int vp = tid / ND, vk = tid - vp * ND;
+  const int s0 = vp, s1 = vp + HP;
+  const bool act0 = tid < Cfg::VT && s0 < ne, act1 = tid < Cfg::VT && s1 < ne;
+  if (act0) {
+    double acc0[NN], acc1[NN];
 #pragma unroll
-  for (int u = 0; u < NN; ++u) acc[u] = 0.0;
-  if (v_active) {
-    // face fluxes of this (element, variable) row: issued now (L2 hits after the prefetch), consumed after S2.
-    // interiorfaceintegrate!: elementL subtracts, elementR adds and reads node nbrperm[i,orient]
-    double fl[NF][NFN];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const double* b = a.fluxw + (int64_t)ef[f].gface * FL + vk;
-#pragma unroll
-      for (int i = 0; i < NFN; ++i) {
-        const int ii = ef[f].right ? s_nbrperm[ef[f].orient][i] : i;
-        fl[f][i] = __ldg(b + ii * ND);
-      }
-    }
-    // ---- S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j] ---------------------------
+    for (int u = 0; u < NN; ++u) { acc0[u] = 0.0; acc1[u] = 0.0; }
+    const int s1c = act1 ? s1 : s0;        // the second row of a ragged tile recomputes the first (never stored)
+    // S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j]   (weakdifferentiate!, trans=true)
     // (the loop over directions stays rolled: fully unrolled operator products overflow the instruction cache)
-    const double* Fv = sF + (vs * ND + vk) * DIM * NN;
+    const double* F0 = sF + (s0 * ND + vk) * DIM * NN;
+    const double* F1 = sF + (s1c * ND + vk) * DIM * NN;
 #pragma unroll 1
     for (int d = 0; d < DIM; ++d) {
-      double Fj[NN];
 #pragma unroll
-      for (int j = 0; j < NN; ++j) Fj[j] = Fv[d * NN + j];
+      for (int j = 0; j < NN; ++j) {
+        const double f0 = F0[d * NN + j], f1 = F1[d * NN + j];
 #pragma unroll
-      for (int j = 0; j < NN; ++j)
-#pragma unroll
-        for (int u = 0; u < NN; ++u) acc[u] = fma(op.Qt[d * NN + j][u], Fj[j], acc[u]);
-    }
-    // ---- S3: face integration  res[k,node] -+= sum_f sum_i Rf[f][i][node] * w_i f*[k,i] -----------
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const double sgn = ef[f].right ? 1.0 : -1.0;
-#pragma unroll
-      for (int i = 0; i < NFN; ++i) {
-        const double x = sgn * fl[f][i];
-#pragma unroll
-        for (int u = 0; u < NN; ++u) acc[u] = fma(op.RfN[f * NFN + i][u], x, acc[u]);
+        for (int u = 0; u < NN; ++u) {
+          const double c = op.Qt[d * NN + j][u];
+          acc0[u] = fma(c, f0, acc0[u]);
+          acc1[u] = fma(c, f1, acc1[u]);
+        }
       }
     }
+    // S3: face integration  res[k,node] += sum_f sum_i Rf[f][i][node] * (-+ w_i f*[k,i]); the contributions
+    // arrive signed and in this element's node order (interiorfaceintegrate!, boundaryintegrate!)
+    const double* G0 = a.fluxe + (e0 + s0) * (NF * FL) + vk;
+    const double* G1 = a.fluxe + (e0 + s1c) * (NF * FL) + vk;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      double g0v[NFN], g1v[NFN];
 #pragma unroll
-    for (int u = 0; u < NN; ++u) sq[vs * SQ + u * ND + vk] = acc[u];   // only this thread reads/writes its row
+      for (int i = 0; i < NFN; ++i) { g0v[i] = __ldg(G0 + (f * NFN + i) * ND); g1v[i] = __ldg(G1 + (f * NFN + i) * ND); }
+#pragma unroll
+      for (int i = 0; i < NFN; ++i)
+#pragma unroll
+        for (int u = 0; u < NN; ++u) {
+          const double c = op.RfN[f * NFN + i][u];
+          acc0[u] = fma(c, g0v[i], acc0[u]);
+          acc1[u] = fma(c, g1v[i], acc1[u]);
+        }
+    }
+    // pde_post_func: res_vec *= Minv (EPI_RK); staged for the coalesced epilogue
+    if (MODE == EPI_RK) {
+      const double* m0 = a.minv + (e0 + s0) * NN;
+      const double* m1 = a.minv + (e0 + s1c) * NN;
+#pragma unroll
+      for (int u = 0; u < NN; ++u) { acc0[u] *= __ldg(m0 + u); acc1[u] *= __ldg(m1 + u); }
+    }
+#pragma unroll
+    for (int u = 0; u < NN; ++u) sq[s0 * SQ + u * ND + vk] = acc0[u];
+    if (act1) {
+#pragma unroll
+      for (int u = 0; u < NN; ++u) sq[s1 * SQ + u * ND + vk] = acc1[u];
+    }
   }
   __syncthreads();
 
-  // ---- S4: epilogue (coalesced): source, then either res or the fused RK4 stage ----------------
-  // loads of a chunk of CH dofs per thread are issued together before any of them is consumed
+  // ---- S4: epilogue, linear and coalesced over the tile, two dofs per access, CH accesses in flight per thread ---
+  // EPI_RES: res = acc + srcw.  EPI_RK: k = Minv*acc + Minv*srcw, then the RK4 stage update (rk4.jl:244-319)
   double nrm2 = 0.0;
   {
-    constexpr int CH = 4;
+    constexpr int CH = 3;
     const int ntile = ne * EL;
-    for (int base = 0; base < ntile; base += CH * T) {
-      double val[CH], sv[CH], mi[CH], xo[CH], ks[CH];
-      int64_t dof[CH];
-      bool ok[CH];
+    const int npair = (ntile + 1) / 2;
+    const int64_t base = e0 * EL;            // even: 16-byte aligned in every array
+    const double2* sq2 = reinterpret_cast<const double2*>(sq);
+    const double* psrc = MODE == EPI_RES ? a.srcw : a.srcm;
+    for (int i0 = 0; i0 < npair; i0 += CH * T) {
+      double2 v[CH], sv[CH], xo[CH], ks[CH];
+      bool ok[CH], two[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
-        const int idx = base + u * T + tid;
-        ok[u] = idx < ntile;
-        int s = 0, r = 0;
-        if (ok[u]) { s = idx / EL; r = idx - s * EL; }
-        dof[u] = ok[u] ? (e0 + s) * EL + r : 0;
-        val[u] = ok[u] ? sq[s * SQ + r] : 0.0;
-        sv[u] = (ok[u] && a.srcw) ? a.srcw[dof[u]] : 0.0;
-        if (MODE == EPI_RK) {
-          mi[u] = ok[u] ? a.minv[(e0 + s) * NN + r / ND] : 1.0;
-          xo[u] = ok[u] ? a.x_old[dof[u]] : 0.0;
-          ks[u] = (ok[u] && a.stage > 1) ? a.ksum[dof[u]] : 0.0;
+        const int i2 = i0 + u * T + tid;
+        ok[u] = i2 < npair;
+        two[u] = ok[u] && (2 * i2 + 1 < ntile);
+        const int64_t dof = base + 2 * i2;
+        sv[u] = xo[u] = ks[u] = make_double2(0.0, 0.0);
+        if (two[u]) {
+          v[u] = sq2[i2];
+          if (psrc) sv[u] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
+          if (MODE == EPI_RK) {
+            xo[u] = __ldg(reinterpret_cast<const double2*>(a.x_old + dof));
+            if (a.stage > 1) ks[u] = *reinterpret_cast<const double2*>(a.ksum + dof);
+          }
+        } else if (ok[u]) {
+          v[u] = make_double2(sq[2 * i2], 0.0);
+          if (psrc) sv[u].x = __ldg(psrc + dof);
+          if (MODE == EPI_RK) {
+            xo[u].x = __ldg(a.x_old + dof);
+            if (a.stage > 1) ks[u].x = a.ksum[dof];
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         if (!ok[u]) continue;
-        const double vv = val[u] + sv[u];
-        if (MODE == EPI_RES) {
-          a.res[dof[u]] = vv;
-        } else {
-          const double k = mi[u] * vv;             // pde_post_func: res_vec *= Minv
+        const int i2 = i0 + u * T + tid;
+        const int64_t dof = base + 2 * i2;
+        const double2 k = make_double2(v[u].x + sv[u].x, v[u].y + sv[u].y);
+        double2 o1 = k, o2 = k;
+        if (MODE == EPI_RK) {
           if (a.stage == 1) {
-            nrm2 += k * k / mi[u];                 // calcNorm: sum res*M*res (Utils.jl:427-449)
-            a.ksum[dof[u]] = k;
-            a.q_next[dof[u]] = xo[u] + a.ah * k;
+            // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
+            const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
+            nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
+            if (two[u]) {
+              const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
+              nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
+            }
+            o1 = k;                                                                   // ksum
+            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);            // q_next
           } else if (a.stage < 4) {
-            a.ksum[dof[u]] = ks[u] + 2.0 * k;
-            a.q_next[dof[u]] = xo[u] + a.ah * k;
+            o1 = make_double2(ks[u].x + 2.0 * k.x, ks[u].y + 2.0 * k.y);
+            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);
           } else {
-            a.q_next[dof[u]] = xo[u] + a.h6 * (ks[u] + k);
+            o2 = make_double2(xo[u].x + a.h6 * (ks[u].x + k.x), xo[u].y + a.h6 * (ks[u].y + k.y));
           }
+        }
+        if (MODE == EPI_RES) {
+          if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
+        } else {
+          if (a.stage < 4) {
+            if (two[u]) *reinterpret_cast<double2*>(a.ksum + dof) = o1; else a.ksum[dof] = o1.x;
+          }
+          if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;
         }
       }
     }
@@ -552,6 +648,14 @@ __global__ void k_tabulate_source(const double* __restrict__ coords, const doubl
   double fac = w[j] / jac[t];
 #pragma unroll
   for (int k = 0; k < ND; ++k) srcw[t * ND + k] = fac * S[k];
+}
+
+// srcm = Minv * srcw (EPI_RK epilogue)
+__global__ void k_srcm(const double* __restrict__ srcw, const double* __restrict__ minv, int nd, int64_t n_nodes,
+                       double* __restrict__ srcm) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes * nd) return;
+  srcm[t] = minv[t / nd] * srcw[t];
 }
 
 __global__ void k_minv(const double* __restrict__ jac, const double* __restrict__ w, int nn, int64_t nE,
