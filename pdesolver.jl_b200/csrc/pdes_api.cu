@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,6 +87,7 @@ struct Ops {
   virtual int64_t grid_for(int64_t nelems) const = 0;
   virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
   virtual int resident_face_ctas() = 0;
+  virtual int tile_elems() const = 0;
 };
 
 template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
@@ -115,6 +117,7 @@ struct OpsImpl : Ops {
     (void)w;
   }
   int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
+  int tile_elems() const override { return E; }
   int resident_element_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
     cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -148,7 +151,8 @@ struct OpsImpl : Ops {
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    dim3 grid((unsigned)grid_for(a.nE)), block(Cfg::T);
+    if (a.nE <= a.e_begin) return cudaSuccess;
+    dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES)
       k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     else
@@ -213,7 +217,13 @@ struct PdesCtx {
   int64_t err_element = -1, err_node = -1;
   std::unique_ptr<Ops> ops;
   bool have_op = false, have_mesh = false, finalized = false;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, face_stream = nullptr;
+  // the face-flux and element kernels of one evaluation are cut into chunks that run concurrently on two streams
+  // (k_face_flux is issue-bound, k_element_rk is HBM-bound): chunk c of the elements needs face chunks <= c
+  static const int MAXC = 16;
+  int nchunks = 1;
+  int64_t chunk_e[MAXC + 1] = {0}, chunk_g[MAXC + 1] = {0};
+  cudaEvent_t ev_face[MAXC] = {nullptr}, ev_elem = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_norm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   // state
   double* qbuf[3] = {nullptr, nullptr, nullptr};
@@ -338,6 +348,40 @@ int finalize(PdesCtx* ctx) {
     if (p.nfaces)
       memcpy(nrm.data() + (size_t)(c.nF + c.nB + p.offset) * per_nrm, p.nrm.data(), sizeof(double) * p.nrm.size());
   }
+  {
+    // order the interior + boundary faces by the lowest element they touch: the faces an element chunk needs are then a
+    // prefix of the list, which lets element chunk c start while face chunk c+1 is still running
+    const int64_t nIB = c.nF + c.nB;
+    std::vector<int64_t> order(nIB);
+    for (int64_t g = 0; g < nIB; ++g) order[g] = g;
+    auto key = [&](int64_t g) {
+      const FaceRec& r = faces[g];
+      return (r.kind == FK_INTERIOR && r.elR < r.elL) ? r.elR : r.elL;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return key(x) < key(y); });
+    std::vector<FaceRec> fs(faces);
+    std::vector<double> ns(nrm);
+    for (int64_t g = 0; g < nIB; ++g) {
+      faces[g] = fs[order[g]];
+      if (faces[g].kind == FK_BOUNDARY) faces[g].elR = (int32_t)(order[g] - c.nF);
+      memcpy(nrm.data() + (size_t)g * per_nrm, ns.data() + (size_t)order[g] * per_nrm, sizeof(double) * per_nrm);
+    }
+    const int tile = ctx->ops->tile_elems();
+    int nc = env_int("PDES_CHUNKS", 0);
+    if (nc <= 0) nc = 1;   // measured on C3: more chunks only add tail waves
+    if (nc > PdesCtx::MAXC) nc = PdesCtx::MAXC;
+    const int64_t ntiles = (c.nE + tile - 1) / tile;
+    if (nc > ntiles) nc = (int)ntiles;
+    ctx->nchunks = nc;
+    int64_t g = 0;
+    for (int k = 0; k <= nc; ++k) {
+      int64_t e = k == nc ? c.nE : (ntiles * k / nc) * tile;
+      ctx->chunk_e[k] = e;
+      while (g < nIB && key(g) < e) ++g;      // faces[] is sorted: key(g) uses the permuted list
+      ctx->chunk_g[k] = k == nc ? nIB : g;
+    }
+    ctx->chunk_g[0] = 0;
+  }
   for (int64_t e = 0; e < c.nE; ++e)
     for (int f = 0; f < NF; ++f)
       if (ef[e * NF + f].gface < 0) {
@@ -380,6 +424,7 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->srcm = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcm : nullptr;
   a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
   a->norm_partials = ctx->norm_partials;
+  a->e_begin = 0;
   const int dd = ctx->cfg.dim * ctx->cfg.dim;
   a->dx_el_stride = ctx->dx_compact ? dd : ctx->cfg.nn * dd;
   a->dx_node_stride = ctx->dx_compact ? 0 : dd;
@@ -411,8 +456,11 @@ int start_exchange(PdesCtx* ctx, const double* q) {
   return PDES_OK;
 }
 
-// one residual evaluation = [pack + exchange on the comm stream] | face fluxes of the interior and boundary
-// faces (overlaps the exchange) -> face fluxes of the shared faces (after the receive) -> element kernel
+// one residual evaluation:
+//   compute stream : pack -> [event] ............ shared-face fluxes (after the receive) -> element chunk 1..C
+//   comm stream    :          send/recv
+//   face stream    : face chunk 1..C (interior + boundary faces; overlaps the exchange and the element chunks)
+// element chunk c waits for face chunk c; the next evaluation's face chunks wait for this evaluation's elements
 int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   int rc = start_exchange(ctx, a.q);
   if (rc) return rc;
@@ -420,21 +468,36 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   FaceArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
-  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.nF = c.nF; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.prefetch_ahead = ctx->prefetch_ahead_faces;
-  fa.g0 = 0; fa.ng = c.nF + c.nB;
-  CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
-  ctx->launches++;
+  const int nc = ctx->nchunks;
+  cudaStream_t fs = nc > 1 ? ctx->face_stream : ctx->stream;
+  if (nc > 1) {
+    // q of this evaluation is complete once everything enqueued so far on the compute stream has run
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_elem, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->ev_elem, 0));
+  }
+  for (int k = 0; k < nc; ++k) {
+    fa.g0 = ctx->chunk_g[k]; fa.ng = ctx->chunk_g[k + 1] - ctx->chunk_g[k];
+    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, fs));
+    ctx->launches += fa.ng > 0;
+    if (nc > 1) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_face[k], fs));
+  }
   if (ctx->nS > 0) {
     if (ctx->comm) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
     fa.g0 = c.nF + c.nB; fa.ng = ctx->nS;
     CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
     ctx->launches++;
   }
-  CUDA_TRY(ctx, ctx->ops->launch_elements(a, mode, ctx->stream));
-  ctx->launches++;
+  for (int k = 0; k < nc; ++k) {
+    if (nc > 1) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_face[k], 0));
+    a.e_begin = ctx->chunk_e[k]; a.nE = ctx->chunk_e[k + 1];
+    CUDA_TRY(ctx, ctx->ops->launch_elements(a, mode, ctx->stream));
+    ctx->launches += a.nE > a.e_begin;
+  }
+  a.e_begin = 0; a.nE = c.nE;
   ctx->n_evals++;
   return PDES_OK;
 }
@@ -545,6 +608,9 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   PdesCtx* c = ctx.get();
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->face_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < PdesCtx::MAXC; ++i) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_face[i], cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_elem, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_norm, cudaEventDisableTiming));
@@ -580,6 +646,9 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->ev_norm) cudaEventDestroy(ctx->ev_norm);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  for (int i = 0; i < PdesCtx::MAXC; ++i) if (ctx->ev_face[i]) cudaEventDestroy(ctx->ev_face[i]);
+  if (ctx->ev_elem) cudaEventDestroy(ctx->ev_elem);
+  if (ctx->face_stream) cudaStreamDestroy(ctx->face_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   delete ctx;

@@ -37,7 +37,7 @@ struct EFace {
 
 // per face: what k_face_flux gathers
 struct __align__(16) FaceRec {
-  int32_t elL, elR;  // elR: right element (interior) | unused
+  int32_t elL, elR;  // elR: right element (interior) | index into mesh.bndryfaces (boundary) | unused (shared)
   uint8_t fL, fR, orient, kind;
   int32_t aux;       // boundary: BC functor id; shared: index into the receive buffer
 };
@@ -81,7 +81,6 @@ struct FaceArgs {
   double* fluxe;               // [ND,NFN,dim+1,nE]: per (element, local face) the contribution the element integrates,
                                // -wface_i f*(:,i) for elementL, +wface_i f*(:,i) in elementR's own node order
   int64_t g0, ng;              // face range of this launch
-  int64_t nF;                  // first boundary face
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose gathers it prefetches into L2
   const Ctl* ctl;
   PhysPar ph;
@@ -105,7 +104,7 @@ struct ElemArgs {
   double h6;                   // h/6 (last stage)
   int32_t stage;               // 1..4
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
-  int64_t nE;
+  int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
 };
@@ -279,7 +278,7 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
     if (nact) {
       if (r.kind == FK_BOUNDARY) {
         // separate copies so that only this (rare) path touches local memory
-        const double* xp = a.coords_bndry + ((g - a.nF) * NFN + i) * DIM;
+        const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + i) * DIM;   // elR of a boundary face: its index in bndryfaces
         double xb[DIM], nb_[DIM], qb[ND], fb[ND];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
@@ -363,7 +362,7 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
 
   if (a.ctl->stop) return;
   const int tid = threadIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.x * E;
+  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
   const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
   const double gami = a.ph.gamma - 1.0;
 
@@ -582,7 +581,7 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
     if (tid == 0) {
       double t = 0.0;
       for (int w = 0; w < T / 32; ++w) t += s_red[w];
-      a.norm_partials[blockIdx.x] = t;
+      a.norm_partials[e0 / E] = t;
     }
   }
 }
