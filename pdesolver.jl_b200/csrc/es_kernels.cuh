@@ -1,0 +1,235 @@
+// Entropy-stable path (BASELINE config 2): SBPDiagonalE operators (sparse faces: face node i IS volume node
+// perm[i,f]), split-form volume integrals with the Ismail-Roe two-point flux, IRSLF / IR / Roe interface flux.
+//
+//   k_face_flux_sparse   calcFaceIntegral_nopre with a SparseFace (flux.jl:79-125; index rule
+//                        sbp_sat_reduced_sc.jl:969-972: iL = perm[i,faceL], iR = perm[nbrperm[i,orient],faceR]),
+//                        IRSLFFlux (flux.jl:964-976 -> bc_solvers.jl:898-909), boundary functors (bc.jl:251-284)
+//   k_element_split      calcVolumeIntegralsSplitFormLinear (euler_funcs.jl:240-288, S = (Q - Q^T)/2
+//                        flux_types.jl:969-971) + face records + source + fused RK4 stage
+//
+// The volume kernel evaluates each of the nn(nn-1)/2 two-point fluxes of an element ONCE (pair threads), with
+// the square roots and logarithms of the Ismail-Roe parameter vector tabulated per node, then node threads gather
+// -2 S[i,m,d] F_d over their nn-1 partners.  The kernel is FP64-pipe bound (~150 FP64 instructions per pair).
+#pragma once
+#include "residual_kernels.cuh"
+
+namespace pdes {
+
+template <int DIM, int NN, int NFN>
+struct OpTabS {
+  static constexpr int NF = DIM + 1;
+  static constexpr int NOR = (DIM == 2) ? 1 : 3;
+  double S2[DIM][NN][NN];     // 2*S[i][m][d] = Q[i,m,d] - Q[m,i,d]
+  double wface[NFN];
+  int32_t perm[NF][NFN];      // sparse face: volume node of face node i on face f
+  int32_t nbrperm[NOR][NFN];
+  int32_t inv[NN][DIM];       // face-node slots (f*NFN+i) that coincide with volume node n, or -1
+};
+
+enum FluxId { FLUX_ROE = 1, FLUX_IR = 2, FLUX_IRSLF = 3 };
+
+template <int DIM>
+__device__ __forceinline__ void numerical_flux(int flux_id, const double* qL, const double* qR, const double* n,
+                                               double gamma, double* F) {
+  if (flux_id == FLUX_IRSLF) irslf_flux<DIM>(qL, qR, n, gamma, F);
+  else if (flux_id == FLUX_IR) ir_flux_single<DIM>(qL, qR, n, gamma, F);
+  else roe_flux<DIM>(qL, qR, n, gamma, F);
+}
+
+// one thread per (face, face node): no interpolation, states are read at the coinciding volume nodes
+template <int DIM, int NN, int NFN>
+__global__ void __launch_bounds__(128)
+k_face_flux_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a, int flux_id) {
+  constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, FL = NFN * ND;
+  if (a.ctl->stop) return;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.ng * NFN) return;
+  const int64_t g = a.g0 + t / NFN;
+  const int i = (int)(t % NFN);
+  const FaceRec r = a.faces[g];
+  double qL[ND], qR[ND], nrm[DIM], flux[ND];
+  {
+    const double* b = a.q + (int64_t)r.elL * EL + op.perm[r.fL][i] * ND;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qL[k] = __ldg(b + k);
+    const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
+  }
+  int iR = i;
+  if (r.kind == FK_BOUNDARY) {
+    const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + i) * DIM;
+    double xb[DIM], nb_[DIM], qb[ND], fb[ND];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qb[k] = qL[k];
+    bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) flux[k] = fb[k];
+  } else {
+    iR = op.nbrperm[r.orient][i];
+    const double* b = r.kind == FK_INTERIOR ? a.q + (int64_t)r.elR * EL + op.perm[r.fR][iR] * ND
+                                            : a.q_recv + ((int64_t)r.aux * NFN + iR) * ND;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qR[k] = __ldg(b + k);
+    numerical_flux<DIM>(flux_id, qL, qR, nrm, a.ph.gamma, flux);
+  }
+  const double w = op.wface[i];
+  double* dl = a.fluxe + ((int64_t)r.elL * NF + r.fL) * FL + i * ND;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) dl[k] = -w * flux[k];
+  if (r.kind == FK_INTERIOR) {
+    double* dr = a.fluxe + ((int64_t)r.elR * NF + r.fR) * FL + iR * ND;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) dr[k] = w * flux[k];
+  }
+}
+
+// getSendDataFace for sparse faces: q_send[:, i, j] = q[:, perm[i, face], element]
+template <int DIM, int NN, int NFN>
+__global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const double* __restrict__ q,
+                                   const int32_t* __restrict__ sh_el, const uint8_t* __restrict__ sh_face, int64_t nS,
+                                   double* __restrict__ q_send, const Ctl* ctl) {
+  constexpr int ND = DIM + 2;
+  if (ctl->stop) return;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nS * NFN * ND) return;
+  int k = (int)(t % ND);
+  int i = (int)((t / ND) % NFN);
+  int64_t j = t / (ND * NFN);
+  q_send[t] = q[((int64_t)sh_el[j] * NN + op.perm[sh_face[j]][i]) * ND + k];
+}
+
+template <int DIM, int NN, int NFN, int E>
+struct SplitCfg {
+  static constexpr int ND = DIM + 2, NF = DIM + 1;
+  static constexpr int NP = NN * (NN - 1) / 2;                   // node pairs
+  static constexpr int NZ = DIM + 4;                             // z1, zv[DIM], z5, log z1, log z5
+  static constexpr int T = 192;
+  static constexpr size_t smem_bytes =
+      sizeof(double) * ((size_t)E * (NN * ND + NN * NZ + NP * DIM * ND) + DIM * NN * NN);
+  static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
+};
+
+template <int DIM, int NN, int NFN, int E, int MODE>
+__global__ void __launch_bounds__((SplitCfg<DIM, NN, NFN, E>::T), 2)
+k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
+  using Cfg = SplitCfg<DIM, NN, NFN, E>;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, NP = Cfg::NP, NZ = Cfg::NZ, T = Cfg::T;
+  constexpr int EL = NN * ND, FL = NFN * ND;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sq = reinterpret_cast<double*>(smem_raw);     // [E][EL]   q tile, later the staged output
+  double* sZ = sq + E * EL;                             // [E][NN][NZ]
+  double* sFp = sZ + E * NN * NZ;                       // [E][NP][DIM][ND]
+  double* sS2 = sFp + E * NP * DIM * ND;                // [DIM][NN][NN]
+  __shared__ double s_red[T / 32];
+
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
+  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
+  const double gami = a.ph.gamma - 1.0;
+
+  async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
+  cp_async_commit();
+  for (int idx = tid; idx < DIM * NN * NN; idx += T) sS2[idx] = (&op.S2[0][0][0])[idx];
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- node threads: checks + Ismail-Roe parameter vector and its logarithms ---------------------------------
+  for (int it = tid; it < ne * NN; it += T) {
+    const int s = it / NN, j = it - s * NN;
+    double qn[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qn[k] = sq[it * ND + k];
+    const double press = calc_pressure<DIM>(qn, gami);
+    if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
+      const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
+      const unsigned long long loc = ((unsigned long long)(e0 + s) << 8) | (unsigned)j;
+      atomicMin(&a.ctl->err_loc, ((unsigned long long)(code - 1) << 62) | loc);
+      atomicExch(&a.ctl->err_code, 1);
+      atomicExch(&a.ctl->stop, 1);
+      qn[0] = 1.0; qn[DIM + 1] = 1.0;       // keep the arithmetic finite; the result is discarded
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) qn[1 + d] = 0.0;
+    }
+    const IRNode<DIM> z = ir_node<DIM>(qn, gami);
+    double* o = sZ + it * NZ;
+    o[0] = z.z1;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) o[1 + d] = z.zv[d];
+    o[DIM + 1] = z.z5; o[DIM + 2] = z.l1; o[DIM + 3] = z.l5;
+  }
+  __syncthreads();
+
+  // ---- pair threads: F_d(q_j, q_k) for k < j in the DIM parametric directions of node j ------------------------
+  for (int it = tid; it < ne * NP; it += T) {
+    const int s = it / NP, pr = it - s * NP;
+    // pr -> (j, k), j > k: pr = j(j-1)/2 + k
+    int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f);
+    while (j * (j - 1) / 2 > pr) --j;
+    while ((j + 1) * j / 2 <= pr) ++j;
+    const int k = pr - j * (j - 1) / 2;
+    IRNode<DIM> zj, zk;
+    const double* pj = sZ + (s * NN + j) * NZ;
+    const double* pk = sZ + (s * NN + k) * NZ;
+    zj.z1 = pj[0]; zk.z1 = pk[0];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { zj.zv[d] = pj[1 + d]; zk.zv[d] = pk[1 + d]; }
+    zj.z5 = pj[DIM + 1]; zj.l1 = pj[DIM + 2]; zj.l5 = pj[DIM + 3];
+    zk.z5 = pk[DIM + 1]; zk.l1 = pk[DIM + 2]; zk.l5 = pk[DIM + 3];
+    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
+    double dirs[DIM][DIM], F[DIM][ND];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int p = 0; p < DIM; ++p) dirs[d][p] = __ldg(dx + d + DIM * p);
+    ir_flux<DIM, DIM>(zj, zk, dirs, a.ph.gamma, F);
+    double* o = sFp + (int64_t)it * (DIM * ND);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int c = 0; c < ND; ++c) o[d * ND + c] = F[d][c];
+  }
+  __syncthreads();
+
+  // ---- node threads: res[:,i] = -sum_m 2 S[i,m,d] F_d(pair(i,m)) + face records + (Minv) -----------------------
+  for (int it = tid; it < ne * NN; it += T) {
+    const int s = it / NN, i = it - s * NN;
+    double acc[ND];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) acc[c] = 0.0;
+    for (int m = 0; m < NN; ++m) {
+      if (m == i) continue;
+      const int jj = m > i ? m : i, kk = m > i ? i : m;
+      const double* F = sFp + ((int64_t)s * NP + jj * (jj - 1) / 2 + kk) * (DIM * ND);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const double c2 = sS2[(d * NN + i) * NN + m];
+#pragma unroll
+        for (int c = 0; c < ND; ++c) acc[c] = fma(-c2, F[d * ND + c], acc[c]);
+      }
+    }
+    const double* G = a.fluxe + (e0 + s) * (NF * FL);
+#pragma unroll
+    for (int u = 0; u < DIM; ++u) {
+      const int slot = op.inv[i][u];
+      if (slot >= 0) {
+#pragma unroll
+        for (int c = 0; c < ND; ++c) acc[c] += __ldg(G + slot * ND + c);
+      }
+    }
+    if (MODE == EPI_RK) {
+      const double mi = __ldg(a.minv + (e0 + s) * NN + i);
+#pragma unroll
+      for (int c = 0; c < ND; ++c) acc[c] *= mi;
+    }
+#pragma unroll
+    for (int c = 0; c < ND; ++c) sq[it * ND + c] = acc[c];
+  }
+  __syncthreads();
+  epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
+}
+
+}  // namespace pdes

@@ -131,6 +131,151 @@ __device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* 
   flux[DIM + 1] = l3 * dq[DIM + 1] + c1 * H + c2 * Un + (q[DIM + 1] + pressL) * U;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// entropy-stable two-point fluxes (config 2)
+// ---------------------------------------------------------------------------------------------------------
+
+// bc_solvers.jl:942-956 logavg(aL, aR) with log(aL/aR) supplied as lL - lR (logs tabulated per node: two per
+// node instead of two per node pair); f = (xi-1)/(xi+1) is evaluated as (aL-aR)/(aL+aR)
+__device__ __forceinline__ double logavg_pre(double aL, double aR, double lL, double lR, double inv_sum) {
+  const double f = (aL - aR) * inv_sum;
+  const double u = f * f;
+  double F;
+  if (u < 1e-3) F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0 + u * (1.0 / 9.0))));
+  else F = 0.5 * (lL - lR) * fast_rcp(f);
+  return (aL + aR) * fast_rcp(2.0 * F);
+}
+
+// per-node quantities of the Ismail-Roe flux: z1 = sqrt(rho/p), z_{1+d} = z1*u_d, z5 = sqrt(rho*p), log z1, log z5
+template <int DIM>
+struct IRNode {
+  double z1, zv[DIM], z5, l1, l5;
+};
+
+template <int DIM>
+__device__ __forceinline__ IRNode<DIM> ir_node(const double* q, double gami) {
+  IRNode<DIM> z;
+  const double p = calc_pressure<DIM>(q, gami);
+  const double rinv = fast_rcp(q[0]);
+  z.z1 = sqrt(q[0] * fast_rcp(p));
+  z.z5 = sqrt(q[0] * p);
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) z.zv[d] = z.z1 * q[1 + d] * rinv;
+  z.l1 = log(z.z1);
+  z.l5 = log(z.z5);
+  return z;
+}
+
+// bc_solvers.jl:776-805 (2D) / 842-874 (3D) calcEulerFlux_IR for NDIR directions (dir[d][:]), F[d][:]
+template <int DIM, int NDIR>
+__device__ __forceinline__ void ir_flux(const IRNode<DIM>& L, const IRNode<DIM>& R, const double (*dir)[DIM],
+                                        double gamma, double (*F)[DIM + 2]) {
+  const double gamma_1 = gamma - 1.0;
+  const double s1 = L.z1 + R.z1, s5 = L.z5 + R.z5;
+  const double is1 = fast_rcp(s1), is5 = fast_rcp(s5);
+  const double la5 = logavg_pre(L.z5, R.z5, L.l5, R.l5, is5);
+  const double la1 = logavg_pre(L.z1, R.z1, L.l1, R.l1, is1);
+  const double rho_hat = 0.5 * s1 * la5;
+  double vh[DIM], vv = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { vh[d] = (L.zv[d] + R.zv[d]) * is1; vv += vh[d] * vh[d]; }
+  const double p1_hat = s5 * is1;
+  const double p2_hat = ((gamma + 1) / (2 * gamma)) * la5 * fast_rcp(la1) + (gamma_1 / (2 * gamma)) * p1_hat;
+  const double h_hat = gamma * p2_hat * fast_rcp(rho_hat * gamma_1) + 0.5 * vv;
+#pragma unroll
+  for (int i = 0; i < NDIR; ++i) {
+    double un = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) un += dir[i][d] * vh[d];
+    const double mv_n = rho_hat * un;
+    F[i][0] = mv_n;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) F[i][1 + d] = mv_n * vh[d] + dir[i][d] * p1_hat;
+    F[i][DIM + 1] = mv_n * h_hat;
+  }
+}
+
+// bc_solvers.jl:898-909 calcEulerFlux_IRSLF = IR flux + applyEntropyKernel_diagE with the LFKernel
+// (faceElementIntegrals.jl:455-468, 510-575): F += lambda_max(q_avg) * A0(q_avg) * (w(qL) - w(qR));
+// convertToIR_ conversion.jl:160-204, getIRA0 IR_stab.jl:15-110, getLambdaMax euler_funcs.jl:1887-1913 with
+// absvalue3 (Utils/complexify.jl:157-172)
+template <int DIM>
+__device__ __forceinline__ void convert_to_ir(const double* qc, double gamma, double* qe) {
+  const double gamma_1 = gamma - 1.0, gamma_1i = 1.0 / gamma_1;
+  double k1 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) k1 += qc[1 + d] * qc[1 + d];
+  k1 = 0.5 * k1 / qc[0];
+  const double rho_int = qc[DIM + 1] - k1;
+  const double s = log(gamma_1 * rho_int / pow(qc[0], gamma));
+  const double fac = 1.0 / rho_int;
+  qe[0] = ((rho_int * (gamma + 1 - s) - qc[DIM + 1]) * fac) * gamma_1i;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) qe[1 + d] = qc[1 + d] * fac * gamma_1i;
+  qe[DIM + 1] = -qc[0] * fac * gamma_1i;
+}
+
+template <int DIM>
+__device__ __forceinline__ void irslf_flux(const double* qL, const double* qR, const double* n, double gamma, double* F) {
+  constexpr int ND = DIM + 2;
+  const double gami = gamma - 1.0;
+  const IRNode<DIM> zL = ir_node<DIM>(qL, gami), zR = ir_node<DIM>(qR, gami);
+  double dirs[1][DIM], Fi[1][ND];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) dirs[0][d] = n[d];
+  ir_flux<DIM, 1>(zL, zR, dirs, gamma, Fi);
+  double qa[ND], vL[ND], vR[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) qa[i] = 0.5 * (qL[i] + qR[i]);
+  convert_to_ir<DIM>(qL, gamma, vL);
+  convert_to_ir<DIM>(qR, gamma, vR);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) vL[i] -= vR[i];
+  // A0 = dq/dw at q_avg (symmetric), applied to delta w
+  const double p = calc_pressure<DIM>(qa, gami);
+  const double rho = qa[0], rhoe = qa[DIM + 1], rhoinv = 1.0 / rho;
+  const double h = (rhoe + p) * rhoinv, a2 = gamma * p * rhoinv;
+  double out[ND];
+  out[0] = rho * vL[0] + rhoe * vL[DIM + 1];
+  out[DIM + 1] = rhoe * vL[0] + (rho * h * h - a2 * p / gami) * vL[DIM + 1];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    out[0] += qa[1 + c] * vL[1 + c];
+    out[DIM + 1] += qa[1 + c] * h * vL[1 + c];
+    double r = qa[1 + c] * vL[0] + h * qa[1 + c] * vL[DIM + 1];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double a = qa[1 + d] * qa[1 + c] * rhoinv;
+      if (d == c) a += p;
+      r += a * vL[1 + d];
+    }
+    out[1 + c] = r;
+  }
+  // lambda_max = absvalue3(Un) + dA * a
+  double Un = 0.0, dA = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { Un += n[d] * qa[1 + d] * rhoinv; dA += n[d] * n[d]; }
+  dA = sqrt(dA);
+  const double delta = 1e-7;
+  const double v1 = fabs(Un);
+  const double aUn = v1 > delta ? v1 : ((Un * Un) / delta + delta) / 2;
+  const double lambda_max = aUn + dA * sqrt(a2);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) F[i] = Fi[0][i] + out[i] * lambda_max;
+}
+
+template <int DIM>
+__device__ __forceinline__ void ir_flux_single(const double* qL, const double* qR, const double* n, double gamma, double* F) {
+  constexpr int ND = DIM + 2;
+  const IRNode<DIM> zL = ir_node<DIM>(qL, gamma - 1.0), zR = ir_node<DIM>(qR, gamma - 1.0);
+  double dirs[1][DIM], Fi[1][ND];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) dirs[0][d] = n[d];
+  ir_flux<DIM, 1>(zL, zR, dirs, gamma, Fi);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) F[i] = Fi[0][i];
+}
+
 // common_funcs.jl:25-78 calcIsentropicVortex (2D), :204-283 (3D)
 template <int DIM>
 __device__ inline void isentropic_vortex(const double* c, double gamma, double R, double* sol) {

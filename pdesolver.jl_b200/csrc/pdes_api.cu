@@ -20,6 +20,7 @@
 
 #include "../../include/pdes_euler_b200.h"
 #include "residual_kernels.cuh"
+#include "es_kernels.cuh"
 
 using namespace pdes;
 
@@ -168,13 +169,84 @@ struct OpsImpl : Ops {
   }
 };
 
+// SBPDiagonalE operators (sparse faces) with the split-form entropy-stable volume integral (config 2)
+template <int DIM, int NN, int NFN, int E>
+struct OpsImplS : Ops {
+  using Tab = OpTabS<DIM, NN, NFN>;
+  using Cfg = SplitCfg<DIM, NN, NFN, E>;
+  Tab tab;
+  int flux_id = FLUX_IRSLF;
+  bool attr_set = false;
+  void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
+                    const int64_t* nbrperm, const double* wface, int base) override {
+    memset(&tab, 0, sizeof(tab));
+    flux_id = c.flux_id;
+    for (int d = 0; d < DIM; ++d)
+      for (int i = 0; i < NN; ++i)
+        for (int m = 0; m < NN; ++m) tab.S2[d][i][m] = Q[i + NN * (m + NN * d)] - Q[m + NN * (i + NN * d)];
+    for (int n = 0; n < NN; ++n)
+      for (int u = 0; u < DIM; ++u) tab.inv[n][u] = -1;
+    for (int f = 0; f < DIM + 1; ++f)
+      for (int i = 0; i < NFN; ++i) {
+        const int n = (int)(perm[i + (int64_t)NFN * f] - base);
+        tab.perm[f][i] = n;
+        for (int u = 0; u < DIM; ++u)
+          if (tab.inv[n][u] < 0) { tab.inv[n][u] = f * NFN + i; break; }
+      }
+    for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
+    for (int o = 0; o < Tab::NOR; ++o)
+      for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
+    (void)w; (void)interp;
+  }
+  int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
+  int tile_elems() const override { return E; }
+  int resident_element_ctas() override { return 0; }
+  int resident_face_ctas() override { return 0; }
+  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+    if (a.ng <= 0) return cudaSuccess;
+    const int64_t n = a.ng * NFN;
+    k_face_flux_sparse<DIM, NN, NFN><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(tab, a, flux_id);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg::smem_bytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    if (a.nE <= a.e_begin) return cudaSuccess;
+    dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
+    if (mode == EPI_RES) k_element_split<DIM, NN, NFN, E, EPI_RES><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+    else k_element_split<DIM, NN, NFN, E, EPI_RK><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
+                          const Ctl* ctl, cudaStream_t s) override {
+    if (nS <= 0) return cudaSuccess;
+    int64_t n = nS * NFN * (DIM + 2);
+    k_pack_send_sparse<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, ctl);
+    return cudaGetLastError();
+  }
+};
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
 Ops* make_ops(const PdesConfig& c) {
-  if (c.sparse_face) return nullptr;
+  if (c.sparse_face) {
+    // entropy-stable configuration: diag-E operator, split-form IR volume flux, Roe / IR / IRSLF interface flux
+    if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR) return nullptr;
+    if (c.flux_id != PDES_FLUX_ROE && c.flux_id != PDES_FLUX_IR && c.flux_id != PDES_FLUX_IRSLF) return nullptr;
+    if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 8>();
+    return nullptr;
+  }
+  if (c.volume_integral_type != 1 || c.flux_id != PDES_FLUX_ROE) return nullptr;
   const int variant = env_int("PDES_VARIANT", 0);   // tuning knob (tools/bench_variants.sh)
   if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64, 2, 64, 2>();
   if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32, 2, 32, 2>();
@@ -595,9 +667,7 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   ctx->nd = cfg->dim + 2;
   ctx->nf = cfg->dim + 1;
   ctx->ndof = (int64_t)ctx->nd * cfg->nn * cfg->nE;
-  if (cfg->volume_integral_type == 1 && cfg->flux_id == PDES_FLUX_ROE && !cfg->sparse_face) {
-    ctx->ops.reset(make_ops(*cfg));
-  }
+  ctx->ops.reset(make_ops(*cfg));
   if (!ctx->ops) {
     set_err(nullptr,
             "unsupported operator/flux combination (dim=%d nn=%d nfn=%d sparse=%d volume_integral_type=%d flux=%d)",
@@ -658,12 +728,13 @@ int pdes_set_operator(PdesCtx* ctx, const double* Q, const double* w, const doub
                       const int64_t* nbrperm, const double* wface) {
   if (!ctx || !Q || !w || !interp || !perm || !nbrperm || !wface) return usage(ctx, "pdes_set_operator: null argument");
   const PdesConfig& c = ctx->cfg;
-  if (c.ss != c.nn) return usage(ctx, "dense face operators need stencilsize == numnodes");
+  if (!c.sparse_face && c.ss != c.nn) return usage(ctx, "dense face operators need stencilsize == numnodes");
   const int nor = c.dim == 2 ? 1 : 3;
   if (c.norient != nor) return usage(ctx, "norient must be 1 (2D) or 3 (3D)");
+  const int nperm = c.sparse_face ? c.nfn : c.ss;     // sbpface.perm is [nfn, numfaces] for a SparseFace
   for (int f = 0; f < ctx->nf; ++f)
-    for (int j = 0; j < c.ss; ++j) {
-      int64_t p = perm[j + (int64_t)c.ss * f] - c.index_base;
+    for (int j = 0; j < nperm; ++j) {
+      int64_t p = perm[j + (int64_t)nperm * f] - c.index_base;
       if (p < 0 || p >= c.nn) return usage(ctx, "sbpface.perm entry out of range");
     }
   for (int o = 0; o < nor; ++o)

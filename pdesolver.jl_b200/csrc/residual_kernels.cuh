@@ -332,6 +332,96 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   }
 }
 
+// Coalesced epilogue shared by the element kernels: the tile of staged values (EPI_RES: acc; EPI_RK: Minv*acc) is
+// combined with the tabulated source and either stored as res or pushed through the fused RK4 stage
+// (rk4.jl:244-319); two dofs per access, CH accesses in flight per thread.
+template <int NN, int ND, int E, int T, int MODE>
+__device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* sq, int ne, int64_t e0, int tid,
+                                              double* s_red) {
+  constexpr int EL = NN * ND;
+  double nrm2 = 0.0;
+  {
+    constexpr int CH = 3;
+    const int ntile = ne * EL;
+    const int npair = (ntile + 1) / 2;
+    const int64_t base = e0 * EL;            // even: 16-byte aligned in every array
+    const double2* sq2 = reinterpret_cast<const double2*>(sq);
+    const double* psrc = MODE == EPI_RES ? a.srcw : a.srcm;
+    for (int i0 = 0; i0 < npair; i0 += CH * T) {
+      double2 v[CH], sv[CH], xo[CH], ks[CH];
+      bool ok[CH], two[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int i2 = i0 + u * T + tid;
+        ok[u] = i2 < npair;
+        two[u] = ok[u] && (2 * i2 + 1 < ntile);
+        const int64_t dof = base + 2 * i2;
+        sv[u] = xo[u] = ks[u] = make_double2(0.0, 0.0);
+        if (two[u]) {
+          v[u] = sq2[i2];
+          if (psrc) sv[u] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
+          if (MODE == EPI_RK) {
+            xo[u] = __ldg(reinterpret_cast<const double2*>(a.x_old + dof));
+            if (a.stage > 1) ks[u] = *reinterpret_cast<const double2*>(a.ksum + dof);
+          }
+        } else if (ok[u]) {
+          v[u] = make_double2(sq[2 * i2], 0.0);
+          if (psrc) sv[u].x = __ldg(psrc + dof);
+          if (MODE == EPI_RK) {
+            xo[u].x = __ldg(a.x_old + dof);
+            if (a.stage > 1) ks[u].x = a.ksum[dof];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        if (!ok[u]) continue;
+        const int i2 = i0 + u * T + tid;
+        const int64_t dof = base + 2 * i2;
+        const double2 k = make_double2(v[u].x + sv[u].x, v[u].y + sv[u].y);
+        double2 o1 = k, o2 = k;
+        if (MODE == EPI_RK) {
+          if (a.stage == 1) {
+            // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
+            const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
+            nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
+            if (two[u]) {
+              const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
+              nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
+            }
+            o1 = k;                                                                   // ksum
+            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);            // q_next
+          } else if (a.stage < 4) {
+            o1 = make_double2(ks[u].x + 2.0 * k.x, ks[u].y + 2.0 * k.y);
+            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);
+          } else {
+            o2 = make_double2(xo[u].x + a.h6 * (ks[u].x + k.x), xo[u].y + a.h6 * (ks[u].y + k.y));
+          }
+        }
+        if (MODE == EPI_RES) {
+          if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
+        } else {
+          if (a.stage < 4) {
+            if (two[u]) *reinterpret_cast<double2*>(a.ksum + dof) = o1; else a.ksum[dof] = o1.x;
+          }
+          if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;
+        }
+      }
+    }
+  }
+  if (MODE == EPI_RK && a.stage == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = nrm2;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < T / 32; ++w) t += s_red[w];
+      a.norm_partials[e0 / E] = t;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // k_element_rk: E elements per CTA; every variable thread owns TWO (element, variable) rows -- elements p and
 // p + E/2 -- so that each uniform coefficient load feeds two DFMAs
@@ -501,89 +591,8 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   }
   __syncthreads();
 
-  // ---- S4: epilogue, linear and coalesced over the tile, two dofs per access, CH accesses in flight per thread ---
-  // EPI_RES: res = acc + srcw.  EPI_RK: k = Minv*acc + Minv*srcw, then the RK4 stage update (rk4.jl:244-319)
-  double nrm2 = 0.0;
-  {
-    constexpr int CH = 3;
-    const int ntile = ne * EL;
-    const int npair = (ntile + 1) / 2;
-    const int64_t base = e0 * EL;            // even: 16-byte aligned in every array
-    const double2* sq2 = reinterpret_cast<const double2*>(sq);
-    const double* psrc = MODE == EPI_RES ? a.srcw : a.srcm;
-    for (int i0 = 0; i0 < npair; i0 += CH * T) {
-      double2 v[CH], sv[CH], xo[CH], ks[CH];
-      bool ok[CH], two[CH];
-#pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int i2 = i0 + u * T + tid;
-        ok[u] = i2 < npair;
-        two[u] = ok[u] && (2 * i2 + 1 < ntile);
-        const int64_t dof = base + 2 * i2;
-        sv[u] = xo[u] = ks[u] = make_double2(0.0, 0.0);
-        if (two[u]) {
-          v[u] = sq2[i2];
-          if (psrc) sv[u] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
-          if (MODE == EPI_RK) {
-            xo[u] = __ldg(reinterpret_cast<const double2*>(a.x_old + dof));
-            if (a.stage > 1) ks[u] = *reinterpret_cast<const double2*>(a.ksum + dof);
-          }
-        } else if (ok[u]) {
-          v[u] = make_double2(sq[2 * i2], 0.0);
-          if (psrc) sv[u].x = __ldg(psrc + dof);
-          if (MODE == EPI_RK) {
-            xo[u].x = __ldg(a.x_old + dof);
-            if (a.stage > 1) ks[u].x = a.ksum[dof];
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        if (!ok[u]) continue;
-        const int i2 = i0 + u * T + tid;
-        const int64_t dof = base + 2 * i2;
-        const double2 k = make_double2(v[u].x + sv[u].x, v[u].y + sv[u].y);
-        double2 o1 = k, o2 = k;
-        if (MODE == EPI_RK) {
-          if (a.stage == 1) {
-            // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
-            const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
-            nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
-            if (two[u]) {
-              const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
-              nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
-            }
-            o1 = k;                                                                   // ksum
-            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);            // q_next
-          } else if (a.stage < 4) {
-            o1 = make_double2(ks[u].x + 2.0 * k.x, ks[u].y + 2.0 * k.y);
-            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);
-          } else {
-            o2 = make_double2(xo[u].x + a.h6 * (ks[u].x + k.x), xo[u].y + a.h6 * (ks[u].y + k.y));
-          }
-        }
-        if (MODE == EPI_RES) {
-          if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
-        } else {
-          if (a.stage < 4) {
-            if (two[u]) *reinterpret_cast<double2*>(a.ksum + dof) = o1; else a.ksum[dof] = o1.x;
-          }
-          if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;
-        }
-      }
-    }
-  }
-  if (MODE == EPI_RK && a.stage == 1) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
-    if ((tid & 31) == 0) s_red[tid >> 5] = nrm2;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < T / 32; ++w) t += s_red[w];
-      a.norm_partials[e0 / E] = t;
-    }
-  }
+  // ---- S4: coalesced epilogue (source, res | fused RK4 stage, stage-1 norm partial) ----------------------------
+  epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
 }
 
 // getSendDataFace (Utils/parallel.jl:249-258): q_send[:, i, j] = R q on the shared faces, one thread per

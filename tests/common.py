@@ -16,8 +16,15 @@ def rel_l2(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
 
 
+ES_OPTS = {"Flux_name": "IRSLFFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2,
+           "BC1_name": "isentropicVortexBC"}
+KIND = {"c2_2d_p2_es": "diage", "2d_p2_es_ir": "diage", "2d_p2_es_roe": "diage"}
+
 CASES = {
     # name: (dim, degree, IC, opts)
+    "c2_2d_p2_es": (2, 2, "ICIsentropicVortex", dict(ES_OPTS)),
+    "2d_p2_es_ir": (2, 2, "ICIsentropicVortex", dict(ES_OPTS, Flux_name="IRFlux")),
+    "2d_p2_es_roe": (2, 2, "ICIsentropicVortex", dict(ES_OPTS, Flux_name="RoeFlux")),
     "c1_2d_p1_roe": (2, 1, "ICIsentropicVortex",
                      {"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}),
     "2d_p2_roe": (2, 2, "ICIsentropicVortex",

@@ -21,14 +21,14 @@ PARTS = {2: {2: (2, 1), 3: (2, 1, 1)}, 4: {2: (2, 2), 3: (2, 2, 1)}, 8: {2: (4, 
 def serial_and_local(case, n, rank, world, seed=4):
     import oracle
     import pdesolver_jl_b200 as pd
-    from common import CASES, perturbed
+    from common import CASES, KIND, perturbed
     dim, p, ic, opts = CASES[case]
-    op = pd.build_operator(dim, p)
+    op = pd.build_operator(dim, p, KIND.get(case, "omega"))
     parts = PARTS[world][dim]
     serial = pd.structured_mesh(op, n, shuffle_seed=seed)
     local = pd.structured_mesh(op, n, parts=parts, rank=rank, shuffle_seed=seed)
     orc_s = oracle.Problem(serial, op, opts)
-    q_s = perturbed(orc_s.exact_state(ic))
+    q_s = perturbed(orc_s.exact_state(ic), amp=1e-2 if case in KIND else 1e-3)
     pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
     idx = np.array([pos[int(g)] for g in local.global_elnum])
     return pd, op, dict(opts), serial, local, orc_s, q_s, idx
@@ -71,7 +71,8 @@ def run_nccl_b200(rank, world, local_rank):
     import torch.distributed as dist
     from common import rel_l2
     torch.cuda.set_device(local_rank)
-    for case, n, h in [("c3_3d_p2_roe_src", 4, 5e-5), ("c1_2d_p1_roe", 8, 1e-3), ("3d_p1_roe_src", 4, 5e-5)]:
+    for case, n, h in [("c3_3d_p2_roe_src", 4, 5e-5), ("c1_2d_p1_roe", 8, 1e-3), ("3d_p1_roe_src", 4, 5e-5),
+                       ("c2_2d_p2_es", 6, 1e-3)]:
         pd, op, opts, serial, local, orc_s, q_s, idx = serial_and_local(case, n, rank, world)
         ids = [pd.EulerData.get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
