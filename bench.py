@@ -30,6 +30,9 @@ WORKLOADS = {
     # name: dim, degree, per-rank cells per side, IC, h, opts
     "c3_3d_p2_roe": dict(dim=3, p=2, n=31, ic="ICExp", h=5e-5,
                          opts={"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
+    "c2_2d_p2_es": dict(dim=2, p=2, n=1000, kind="diage", ic="ICIsentropicVortex", h=2e-5, cpu_cells=160,
+                        opts={"Flux_name": "IRSLFFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2,
+                              "BC1_name": "isentropicVortexBC"}),
     "c1_2d_p1_roe": dict(dim=2, p=1, n=50, ic="ICIsentropicVortex", h=1e-3,
                          opts={"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}),
     "3d_p1_roe": dict(dim=3, p=1, n=60, ic="ICExp", h=5e-5,
@@ -112,7 +115,7 @@ class ClockSampler:
 def build_problem(wl, rank, nranks):
     import pdesolver_jl_b200 as pd
     from pdesolver_jl_b200 import ic
-    op = pd.build_operator(wl["dim"], wl["p"], "omega")
+    op = pd.build_operator(wl["dim"], wl["p"], wl.get("kind", "omega"))
     parts = PARTS[nranks][:wl["dim"]]
     if nranks > 1 and wl["dim"] == 2:
         parts = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
@@ -131,8 +134,8 @@ def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
     import oracle
     import pdesolver_jl_b200 as pd
     from pdesolver_jl_b200 import ic
-    op = pd.build_operator(wl["dim"], wl["p"], "omega")
-    n = sample_cells or wl["n"]
+    op = pd.build_operator(wl["dim"], wl["p"], wl.get("kind", "omega"))
+    n = sample_cells or wl.get("cpu_cells", wl["n"])
     mesh = pd.structured_mesh(op, n)
     opts = dict(wl["opts"])
     P = oracle.Problem(mesh, op, opts)
@@ -306,7 +309,8 @@ def main():
         "metric": "DOF-residual-evals/sec", "value": value, "unit": "DOF-evals/s", "n_gpus": nranks,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "dim": dim, "degree": wl["p"], "operator": "SBPOmega",
+        "config": {"workload": args.workload, "dim": dim, "degree": wl["p"],
+                   "operator": "SBPDiagonalE" if wl.get("kind") == "diage" else "SBPOmega",
                    "flux": opts["Flux_name"], "cells_per_rank": [int(c // p) for c, p in zip(ncells, parts)],
                    "partition": list(parts), "elements_per_rank": mesh.numEl, "dof_total": ndof_total,
                    "step": "1 RK4 step = 4 fused residual+stage launches", "delta_t": h,
@@ -327,7 +331,7 @@ def main():
     if nranks == 1 and not args.no_cpu_baseline:
         rate, spstep, cores, nd_s, n_s = cpu_reference_rate(wl, 1, 0)
         line["cpu_baseline"] = {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port",
-                                "sample": f"1 RK4 step (4 evalResidual) of the same {n_s}^{dim}-cell mesh ({nd_s} DOF), "
+                                "sample": f"1 RK4 step (4 evalResidual) of the {n_s}^{dim}-cell mesh ({nd_s} DOF), "
                                           f"oracle port with OpenMP, {spstep:.1f} s"}
     print(json.dumps(line), flush=True)
     if nranks > 1:

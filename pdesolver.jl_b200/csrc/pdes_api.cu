@@ -89,6 +89,7 @@ struct Ops {
   virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
   virtual int resident_face_ctas() = 0;
   virtual int tile_elems() const = 0;
+  virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
 };
 
 template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
@@ -142,16 +143,19 @@ struct OpsImpl : Ops {
     k_face_flux<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
     return cudaGetLastError();
   }
+  cudaError_t prepare() override {
+    if (attr_set) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+    return cudaSuccess;
+  }
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES)
@@ -208,16 +212,19 @@ struct OpsImplS : Ops {
     k_face_flux_sparse<DIM, NN, NFN><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(tab, a, flux_id);
     return cudaGetLastError();
   }
+  cudaError_t prepare() override {
+    if (attr_set) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+    return cudaSuccess;
+  }
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RES>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)Cfg::smem_bytes);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES) k_element_split<DIM, NN, NFN, E, EPI_RES><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
@@ -310,6 +317,11 @@ struct PdesCtx {
   std::vector<double> h_nrm;        // nrm_face | nrm_bndry
   bool dx_compact = false, nrm_compact = false;   // node-independent metrics detected at upload
   int prefetch_ahead = 0, prefetch_ahead_faces = 0;
+  // CUDA graphs of one RK4 step, one per state-buffer rotation; key = (h, norm?, res_tol, pseudo_time)
+  cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr};
+  double g_h = -1.0, g_tol = 0.0;
+  bool g_norm = false, no_graph = false;
+  int g_pseudo = 0, g_launches = 0;
   std::vector<double> h_w;
   // partition
   std::vector<Peer> peers;
@@ -354,7 +366,7 @@ PhysPar phys_of(const PdesConfig& c) {
 
 int reset_ctl(PdesCtx* ctx) {
   Ctl z;
-  z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.pad = 0;
+  z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.norm_count = 0;
   *ctx->h_ctl = z;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
   return PDES_OK;
@@ -483,6 +495,10 @@ int finalize(PdesCtx* ctx) {
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
+  for (int i = 0; i < 3; ++i)
+    if (ctx->step_graph[i]) { cudaGraphExecDestroy(ctx->step_graph[i]); ctx->step_graph[i] = nullptr; }
+  ctx->no_graph = env_int("PDES_NO_GRAPH", 0) != 0;
+  CUDA_TRY(ctx, ctx->ops->prepare());
   ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas() / 8);   // measured optimum: ~half a wave
   ctx->prefetch_ahead_faces = env_int("PDES_PREFETCH_AHEAD_F", ctx->ops->resident_face_ctas());
   ctx->finalized = true;
@@ -574,7 +590,7 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   return PDES_OK;
 }
 
-int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
+int enqueue_norm(PdesCtx* ctx, double res_tol, int pseudo_time) {
   int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE);
   const bool parallel = ctx->comm && ctx->nranks > 1;
   // the norm only feeds back into the time loop through the res_tol test; when that test is off the
@@ -597,7 +613,7 @@ int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
     if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
     quirk = (double)ctx->nranks;   // rk4.jl:451-453 reduces the already-reduced norm again
   }
-  k_norm_commit<<<1, 1, 0, st>>>(ctx->norm_sq, quirk, ctx->norms_dev, slot, res_tol, pseudo_time, ctx->ctl);
+  k_norm_commit<<<1, 1, 0, st>>>(ctx->norm_sq, quirk, ctx->norms_dev, ctx->norms_cap, res_tol, pseudo_time, ctx->ctl);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   if (parallel) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_norm, st));
@@ -605,7 +621,7 @@ int enqueue_norm(PdesCtx* ctx, int64_t slot, double res_tol, int pseudo_time) {
 }
 
 // the four fused stages of one RK4 step (rk4.jl:238-319); stops after stage 1 when only_head is set
-int enqueue_rk4_step(PdesCtx* ctx, double h, int64_t norm_slot, double res_tol, int pseudo_time, bool only_head) {
+int enqueue_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int pseudo_time, bool only_head) {
   double* A = ctx->qbuf[ctx->cur];
   double* B = ctx->qbuf[(ctx->cur + 1) % 3];
   double* Cb = ctx->qbuf[(ctx->cur + 2) % 3];
@@ -619,10 +635,42 @@ int enqueue_rk4_step(PdesCtx* ctx, double h, int64_t norm_slot, double res_tol, 
     int rc = enqueue_residual(ctx, a, EPI_RK);
     if (rc) return rc;
     if (s == 0) {
-      if (norm_slot >= 0) { rc = enqueue_norm(ctx, norm_slot, res_tol, pseudo_time); if (rc) return rc; }
+      if (with_norm) { rc = enqueue_norm(ctx, res_tol, pseudo_time); if (rc) return rc; }
       if (only_head) { ctx->cur = (ctx->cur + 1) % 3; return PDES_OK; }
     }
   }
+  ctx->cur = (ctx->cur + 2) % 3;
+  return PDES_OK;
+}
+
+// One full RK4 step as a CUDA graph (single-GPU, single-stream schedule): the ten launches of a step are
+// captured once per buffer rotation (three graphs) and replayed; small meshes are launch-bound otherwise.
+int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int pseudo_time) {
+  const bool graphable = !ctx->comm && ctx->nS == 0 && ctx->nchunks == 1 && !ctx->no_graph;
+  if (!graphable) return enqueue_rk4_step(ctx, h, with_norm, res_tol, pseudo_time, false);
+  if (ctx->g_h != h || ctx->g_norm != with_norm || ctx->g_tol != res_tol || ctx->g_pseudo != pseudo_time) {
+    for (int i = 0; i < 3; ++i)
+      if (ctx->step_graph[i]) { cudaGraphExecDestroy(ctx->step_graph[i]); ctx->step_graph[i] = nullptr; }
+    ctx->g_h = h; ctx->g_norm = with_norm; ctx->g_tol = res_tol; ctx->g_pseudo = pseudo_time;
+  }
+  const int slot = ctx->cur;
+  if (!ctx->step_graph[slot]) {
+    const int64_t l0 = ctx->launches, n0 = ctx->n_evals;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_rk4_step(ctx, h, with_norm, res_tol, pseudo_time, false);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    ctx->cur = slot;                       // the capture only recorded the step; it is executed below
+    ctx->g_launches = (int)(ctx->launches - l0);
+    ctx->launches = l0; ctx->n_evals = n0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    CUDA_TRY(ctx, e);
+    CUDA_TRY(ctx, cudaGraphInstantiate(&ctx->step_graph[slot], g, 0));
+    cudaGraphDestroy(g);
+  }
+  CUDA_TRY(ctx, cudaGraphLaunch(ctx->step_graph[slot], ctx->stream));
+  ctx->launches += ctx->g_launches;
+  ctx->n_evals += 4;
   ctx->cur = (ctx->cur + 2) % 3;
   return PDES_OK;
 }
@@ -704,6 +752,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
+  for (int i = 0; i < 3; ++i) if (ctx->step_graph[i]) cudaGraphExecDestroy(ctx->step_graph[i]);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
@@ -1019,7 +1068,7 @@ int pdes_rk4_steps_async(PdesCtx* ctx, double h, int64_t nsteps) {
   if (rc) return rc;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   for (int64_t i = 0; i < nsteps; ++i) {
-    rc = enqueue_rk4_step(ctx, h, -1, -1.0, 0, false);
+    rc = launch_rk4_step(ctx, h, false, -1.0, 0);
     if (rc) return rc;
   }
   return PDES_OK;
@@ -1041,6 +1090,7 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
     ctx->norms_dev = nullptr;
     CUDA_TRY(ctx, cudaMalloc((void**)&ctx->norms_dev, sizeof(double) * (size_t)(max_heads + 1)));
     ctx->norms_cap = max_heads + 1;
+    ctx->g_h = -1.0;      // captured graphs hold the old norms pointer
   }
   rc = reset_ctl(ctx);
   if (rc) return rc;
@@ -1056,7 +1106,7 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
   for (int64_t i = 2; i <= t_steps + 1; ++i) {
     t = (double)(i - 2) * h;
     const bool head_only = (itermax >= 0 && i > itermax);       // rk4.jl:269-276, after stage 1
-    rc = enqueue_rk4_step(ctx, h, heads, res_tol, pseudo, head_only);
+    rc = head_only ? enqueue_rk4_step(ctx, h, true, res_tol, pseudo, true) : launch_rk4_step(ctx, h, true, res_tol, pseudo);
     if (rc) return rc;
     ++heads;
     if (head_only) { stopped_head = true; break; }

@@ -48,7 +48,7 @@ struct Ctl {               // device-resident control block
   int32_t err_code;        // != 0: physics error, decoded on the host from err_loc
   unsigned long long err_loc;  // ((code-1) << 62) | (element << 8) | node of the lowest offending location
   int32_t converged_step;  // step head at which norm < res_tol (or -1)
-  int32_t pad;
+  int32_t norm_count;      // step heads whose norm has been committed (the slot the next commit writes)
 };
 
 template <int DIM, int NN, int NFN>
@@ -632,12 +632,15 @@ __global__ void k_norm_reduce(const double* __restrict__ partials, int n1, doubl
 
 // norm_sq is the (all-reduced) sum over ranks.  quirk_scale reproduces the reference's double reduction in
 // parallel runs (Utils.jl:443-448 then rk4.jl:451-453: the logged norm is sqrt(P) too large); 1 in serial.
-__global__ void k_norm_commit(const double* norm_sq, double quirk_scale, double* norms, int64_t slot, double res_tol,
-                              int pseudo_time, Ctl* ctl) {
+// The slot is a device-side counter so that a captured CUDA graph of one RK4 step can be replayed unchanged.
+__global__ void k_norm_commit(const double* norm_sq, double quirk_scale, double* norms, int64_t norms_cap,
+                              double res_tol, int pseudo_time, Ctl* ctl) {
   if (ctl->stop) return;
-  double nv = sqrt(*norm_sq * quirk_scale);
-  norms[slot] = nv;
-  if (pseudo_time && nv < res_tol) { ctl->converged_step = (int32_t)slot; ctl->stop = 1; }
+  const double nv = sqrt(*norm_sq * quirk_scale);
+  const int slot = ctl->norm_count;
+  if (slot < norms_cap) norms[slot] = nv;
+  ctl->norm_count = slot + 1;
+  if (pseudo_time && nv < res_tol) { ctl->converged_step = slot; ctl->stop = 1; }
 }
 
 // applySourceTerm tabulation (source.jl:27-47): srcw[:,j,e] = (w_j / jac[j,e]) * SRCExp(coords[:,j,e])
