@@ -147,6 +147,11 @@ int pdes_eval_residual(PdesCtx *ctx, double t);
 int pdes_eval_residual_async(PdesCtx *ctx, double t);
 int pdes_sync(PdesCtx *ctx);
 
+/* Jacobian-vector product out = dR/dq(q) * v at the resident q (no Minv), v/out [nd,nn,nE] host arrays: the
+ * product the reference forms as imag(R(q + i*eps*v))/eps with eps = 1e-20 (evaldRdqProduct interface2.jl:454-498,
+ * applyLinearOperator NonlinearSolvers/newton_setup.jl:632-662); evaluated here on dual numbers, exact to round-off. */
+int pdes_eval_jvp(PdesCtx *ctx, const double *v, double *out);
+
 /* rk4 (rk4.jl:144-344) on the resident q.  itermax < 0: use_itermax=false.
  * norms_out[norms_cap] receives the stage-1 norm of every executed step (the
  * convergence.dat column); nsteps_out the number of executed step heads;

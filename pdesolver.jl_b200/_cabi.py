@@ -31,7 +31,7 @@ EXPORTS = [
     "pdes_pack_send", "pdes_inject_recv", "pdes_set_q", "pdes_get_q", "pdes_get_res", "pdes_q_dev",
     "pdes_res_dev", "pdes_eval_residual", "pdes_eval_residual_async", "pdes_sync", "pdes_rk4",
     "pdes_rk4_steps_async", "pdes_get_minv", "pdes_get_timings", "pdes_kernel_launch_count",
-    "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host",
+    "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp",
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
         L.pdes_q_dev.restype = p
         L.pdes_res_dev.argtypes = [p]
         L.pdes_res_dev.restype = p
+        L.pdes_eval_jvp.argtypes = [p, p, p]
         L.pdes_pin_host.argtypes = [p, i64]
         L.pdes_unpin_host.argtypes = [p]
         L.pdes_stream.argtypes = [p]

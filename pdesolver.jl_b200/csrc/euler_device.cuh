@@ -35,6 +35,35 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 __device__ __forceinline__ double absv(double x) { return fabs(x); }   // Utils/complexify.jl:25-44 absvalue
 __device__ __forceinline__ double maxv(double a, double b) { return fmax(a, b); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dual numbers {value, tangent}: the device-side counterpart of the reference's complex-step residual
+// (Complex128 + Utils/complexify.jl): J*v = tangent of R(q + eps*v), exact to round-off.  absvalue flips the
+// sign by the real part, max/isless compare real parts (complexify.jl:25-44, 207-217).
+// ---------------------------------------------------------------------------------------------------------
+struct Dual {
+  double v, d;
+  __host__ __device__ Dual() : v(0.0), d(0.0) {}
+  __host__ __device__ Dual(double a) : v(a), d(0.0) {}
+  __host__ __device__ Dual(double a, double b) : v(a), d(b) {}
+};
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.v * b.d + a.d * b.v); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  const double r = 1.0 / b.v, q = a.v * r;
+  return Dual(q, (a.d - q * b.d) * r);
+}
+__device__ __forceinline__ Dual& operator+=(Dual& a, Dual b) { a.v += b.v; a.d += b.d; return a; }
+__device__ __forceinline__ Dual& operator-=(Dual& a, Dual b) { a.v -= b.v; a.d -= b.d; return a; }
+__device__ __forceinline__ Dual fast_rcp(Dual x) { const double r = fast_rcp(x.v); return Dual(r, -r * r * x.d); }
+__device__ __forceinline__ Dual fast_rsqrt(Dual x) {
+  const double y = fast_rsqrt(x.v);
+  return Dual(y, -0.5 * y * y * y * x.d);
+}
+__device__ __forceinline__ Dual absv(Dual x) { return x.v < 0.0 ? -x : x; }
+__device__ __forceinline__ Dual maxv(Dual a, Dual b) { return a.v > b.v ? a : b; }
+
 // euler_funcs.jl:856-863 / 897-903 calcPressure
 template <int DIM, typename T>
 __device__ __forceinline__ T calc_pressure(const T* q, double gami) {

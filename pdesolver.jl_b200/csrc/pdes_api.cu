@@ -21,6 +21,7 @@
 #include "../../include/pdes_euler_b200.h"
 #include "residual_kernels.cuh"
 #include "es_kernels.cuh"
+#include "jvp_kernels.cuh"
 
 using namespace pdes;
 
@@ -90,6 +91,11 @@ struct Ops {
   virtual int resident_face_ctas() = 0;
   virtual int tile_elems() const = 0;
   virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
+  // J*v kernels (dual numbers); cudaErrorNotSupported when the operator family has none
+  virtual cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) {
+    (void)fa; (void)a; (void)v; (void)out; (void)s;
+    return cudaErrorNotSupported;
+  }
 };
 
 template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
@@ -169,6 +175,12 @@ struct OpsImpl : Ops {
     if (nS <= 0) return cudaSuccess;
     int64_t n = nS * NFN * (DIM + 2);
     k_pack_send<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, ctl);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) override {
+    const int64_t nfn = fa.ng * NFN, nen = a.nE * NN;
+    if (nfn > 0) k_jvp_face<DIM, NN, NFN><<<(unsigned)((nfn + 127) / 128), 128, 0, s>>>(tab, fa, v);
+    k_jvp_element<DIM, NN, NFN><<<(unsigned)((nen + 127) / 128), 128, 0, s>>>(tab, a, v, out);
     return cudaGetLastError();
   }
 };
@@ -1060,6 +1072,42 @@ int pdes_eval_residual(PdesCtx* ctx, double t) {
   int rc = pdes_eval_residual_async(ctx, t);
   if (rc) return rc;
   return pdes_sync(ctx);
+}
+
+// evaldRdqProduct / applyLinearOperator (interface2.jl:454-498, newton_setup.jl:632-662): out = dR/dq(q) * v at the
+// resident q, without Minv (the reference's physicsRhs residual), v and out in the layout of eqn.q
+int pdes_eval_jvp(PdesCtx* ctx, const double* v, double* out) {
+  if (!ctx || !v || !out) return usage(ctx, "pdes_eval_jvp: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (ctx->nS > 0) {
+    set_err(ctx, "pdes_eval_jvp is not implemented for partitioned meshes");
+    return PDES_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const PdesConfig& c = ctx->cfg;
+  double* vdev = ctx->qbuf[(ctx->cur + 1) % 3];     // RK4 scratch buffers double as (v, out) storage
+  double* odev = ctx->qbuf[(ctx->cur + 2) % 3];
+  CUDA_TRY(ctx, cudaMemcpyAsync(vdev, v, sizeof(double) * ctx->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  ElemArgs a;
+  fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
+  FaceArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
+  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
+  fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
+  fa.g0 = 0; fa.ng = c.nF + c.nB;
+  cudaError_t e = ctx->ops->launch_jvp(fa, a, vdev, odev, ctx->stream);
+  if (e == cudaErrorNotSupported) {
+    set_err(ctx, "pdes_eval_jvp is implemented for dense-face operators with the Roe flux only");
+    return PDES_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(ctx, e);
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, odev, sizeof(double) * ctx->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
 }
 
 int pdes_rk4_steps_async(PdesCtx* ctx, double h, int64_t nsteps) {

@@ -203,6 +203,20 @@ def evalResidual(mesh, sbp, eqn: EulerData, opts, t=0.0):
     return None
 
 
+def evaldRdqProduct(mesh, sbp, eqn: EulerData, opts, v, out=None):
+    """``evaldRdqProduct(mesh, sbp, eqn, opts, input_array, output_array)`` (src/interface2.jl:454-498):
+    ``out = dR/dq(eqn.q) * v`` -- the matrix-free operator of the Jacobian-free Newton-Krylov path
+    (NonlinearSolvers/newton_setup.jl:632-662).  The reference perturbs q by ``i*eps*v`` and takes
+    ``imag(res)/eps``; the device evaluates the same residual on dual numbers."""
+    v = np.asfortranarray(np.asarray(v, dtype=np.float64).reshape(eqn.q.shape, order="F"))
+    if out is None:
+        out = np.zeros_like(eqn.q, order="F")
+    L, ctx = eqn._L, eqn._ctx
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_eval_jvp(ctx, _ptr(v), _ptr(out)))
+    return out
+
+
 def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=False):
     """``rk4(f, h, t_max, mesh, sbp, eqn, opts; res_tol, real_time)`` (rk4.jl:404-410).
 

@@ -227,3 +227,24 @@ def test_unsupported_combination_raises():
     mesh = pd.structured_mesh(op, 2)
     with pytest.raises(pd.PDESolverError, match="unsupported"):
         pd.EulerData(mesh, op, {"Flux_name": "RoeFlux", "volume_integral_type": 1})
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 8), ("c3_3d_p2_roe_src", 3), ("2d_p2_roe", 5)])
+def test_jacobian_vector_product(case, n):
+    """Config 5: J*v from dual numbers vs central differences of the oracle residual, plus the
+    properties the complex-step product has: linear in v and independent of the source term."""
+    sides = [0, 1, 0, 1] if CASES[case][0] == 2 else [0, 1, 0, 1, 0, 1]
+    extra = {"BC2_name": "noPenetrationBC"}
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=6, extra=extra, bc_sides=sides)
+    rng = np.random.RandomState(0)
+    v = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+    w = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+    eqn.q[...] = q0
+    Jv = pd.evaldRdqProduct(mesh, op, eqn, opts, v)
+    eps = 1e-6
+    fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
+    assert rel_l2(Jv, fd) < 1e-8
+    Jw = pd.evaldRdqProduct(mesh, op, eqn, opts, w)
+    Jc = pd.evaldRdqProduct(mesh, op, eqn, opts, 2.0 * v - 3.0 * w)
+    assert rel_l2(Jc, 2.0 * Jv - 3.0 * Jw) < 1e-12
+    assert np.array_equal(eqn.q, q0)
