@@ -160,6 +160,11 @@ int pdes_eval_jvp(PdesCtx *ctx, const double *v, double *out);
 int pdes_rk4(PdesCtx *ctx, double h, double t_max, int64_t itermax, double res_tol,
              int32_t real_time, double *t_out, double *norms_out, int64_t norms_cap,
              int64_t *nsteps_out);
+/* lserk54 (NonlinearSolvers/lserk.jl:39-248; run_type 30, solver/common.jl:603-605): same arguments as pdes_rk4.
+ * The res_tol / itermax tests precede the stage-1 update there, so those exits leave q untouched. */
+int pdes_lserk54(PdesCtx *ctx, double h, double t_max, int64_t itermax, double res_tol,
+                 int32_t real_time, double *t_out, double *norms_out, int64_t norms_cap,
+                 int64_t *nsteps_out);
 /* n plain RK4 steps, no host sync inside (bench inner loop; CUDA-graph replay) */
 int pdes_rk4_steps_async(PdesCtx *ctx, double h, int64_t nsteps);
 

@@ -85,6 +85,9 @@ def lib(omp=False):
         L.orc_fill_exact.argtypes = [p, i, p, C.c_int64, p]
         L.orc_rk4_euler.restype = d
         L.orc_rk4_euler.argtypes = [p, p, d, d, C.c_int64, d, i, i, p, C.c_int64, p, p]
+        L.orc_lserk54.restype = d
+        L.orc_lserk54_euler.restype = d
+        L.orc_lserk54_euler.argtypes = [p, p, d, d, C.c_int64, d, i, i, p, C.c_int64, p, p]
         _libs[name] = L
     return _libs[name]
 
@@ -211,14 +214,19 @@ class Problem:
         lib().orc_mass_matrix_inverse(self.ref(), _ptr(Minv))
         return Minv
 
-    def rk4(self, q, h, t_max, itermax=-1, res_tol=-1.0, real_time=False, precompute=True, omp=False):
+    def lserk54(self, q, h, t_max, itermax=-1, res_tol=-1.0, real_time=False, precompute=True, omp=False):
+        """lserk54 (NonlinearSolvers/lserk.jl).  Returns (t, q_final, norms)."""
+        return self.rk4(q, h, t_max, itermax, res_tol, real_time, precompute, omp, _fn="orc_lserk54_euler")
+
+    def rk4(self, q, h, t_max, itermax=-1, res_tol=-1.0, real_time=False, precompute=True, omp=False,
+            _fn="orc_rk4_euler"):
         """Returns (t, q_final, norms).  q is not modified."""
         qv = np.asfortranarray(q, dtype=np.float64).copy(order="F")
         cap = int(round(t_max / h)) + 2
         norms = np.zeros(cap)
         ns = C.c_int64(0)
         st = C.c_int(0)
-        t = lib(omp).orc_rk4_euler(self.ref(), _ptr(qv), float(h), float(t_max), int(itermax),
+        t = getattr(lib(omp), _fn)(self.ref(), _ptr(qv), float(h), float(t_max), int(itermax),
                                    float(res_tol), int(real_time), int(precompute), _ptr(norms), cap,
                                    C.byref(ns), C.byref(st))
         if st.value:

@@ -948,6 +948,73 @@ double orc_rk4_euler(const OrcProblem *P, double *q_vec, double h, double t_max,
   return t;
 }
 
+/* ------------------------------------------------------------------------ */
+/* NonlinearSolvers/lserk.jl:39-248: lserk54 (Carpenter-Kennedy 5-stage 2N-storage RK).  Note the stopping   */
+/* tests come BEFORE the stage-1 update (lserk.jl:161-181), unlike rk4.                                      */
+/* ------------------------------------------------------------------------ */
+double orc_lserk54(orc_rhs_fn f, orc_post_fn post, void *ctx, double delta_t, double t_max, int64_t m,
+                   double *q_vec, double *res_vec, int64_t itermax, double res_tol, int real_time,
+                   double *norms_out, int64_t norms_cap, int64_t *nsteps_out, int *status_out) {
+  const double a_coeffs[5] = {0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                              -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+  const double b_coeffs[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                              1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                              2277821191437.0 / 14882151754819.0};
+  const double c_coeffs[5] = {0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                              2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+  double t = 0.0, treal = 0.0;
+  int64_t t_steps = (int64_t)llround(t_max / delta_t);
+  double *dq_vec = (double *)calloc(m, sizeof(double));
+  int64_t nsteps = 0;
+  int status = 0;
+  for (int64_t i = 2; i <= t_steps + 1; ++i) {
+    t = (i - 2) * delta_t;
+    if (real_time) treal = t;
+    if ((status = f(ctx, q_vec, res_vec, treal))) break;
+    double sol_norm = post(ctx, res_vec, 1);
+    if (norms_out && nsteps < norms_cap) norms_out[nsteps] = sol_norm;
+    ++nsteps;
+    if ((sol_norm < res_tol) && !real_time) break;
+    if (itermax >= 0 && i > itermax) break;
+    double fac = b_coeffs[0];
+    for (int64_t j = 0; j < m; ++j) { dq_vec[j] = delta_t * res_vec[j]; q_vec[j] += fac * dq_vec[j]; }
+    for (int stage = 1; stage < 5; ++stage) {
+      if (real_time) treal = t + c_coeffs[stage] * delta_t;
+      if ((status = f(ctx, q_vec, res_vec, treal))) break;
+      post(ctx, res_vec, 0);
+      fac = a_coeffs[stage];
+      double fac2 = b_coeffs[stage];
+      for (int64_t j = 0; j < m; ++j) { dq_vec[j] = fac * dq_vec[j] + delta_t * res_vec[j]; q_vec[j] += fac2 * dq_vec[j]; }
+    }
+    if (status) break;
+  }
+  t += delta_t;
+  free(dq_vec);
+  if (nsteps_out) *nsteps_out = nsteps;
+  if (status_out) *status_out = status;
+  return t;
+}
+
+double orc_lserk54_euler(const OrcProblem *P, double *q_vec, double h, double t_max, int64_t itermax,
+                         double res_tol, int real_time, int precompute, double *norms_out,
+                         int64_t norms_cap, int64_t *nsteps_out, int *status_out) {
+  int64_t m = (int64_t)P->nd * P->nn * P->nE;
+  EulerRkCtx C;
+  C.P = P; C.precompute = precompute;
+  C.Minv = (double *)malloc(sizeof(double) * m);
+  C.M = (double *)malloc(sizeof(double) * m);
+  orc_mass_matrix_inverse(P, C.Minv);
+  for (int64_t e = 0; e < P->nE; ++e)
+    for (int j = 0; j < P->nn; ++j)
+      for (int k = 0; k < P->nd; ++k)
+        C.M[IDX3(k, j, e, P->nd, P->nn)] = P->w[j] / P->jac[j + (int64_t)P->nn * e];
+  double *res_vec = (double *)malloc(sizeof(double) * m);
+  double t = orc_lserk54(euler_rhs, euler_post, &C, h, t_max, m, q_vec, res_vec, itermax, res_tol, real_time,
+                         norms_out, norms_cap, nsteps_out, status_out);
+  free(res_vec); free(C.Minv); free(C.M);
+  return t;
+}
+
 /* ic.jl (macro-generated ICs): evaluate calc<Name>(params, coords_j, sol) at n nodes.
  * kind: 1 ICIsentropicVortex, 2 ICExp, 3 ICFreeStream */
 void orc_fill_exact(const OrcProblem *P, int kind, const double *coords, int64_t n, double *out) {

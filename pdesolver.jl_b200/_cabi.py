@@ -31,7 +31,7 @@ EXPORTS = [
     "pdes_pack_send", "pdes_inject_recv", "pdes_set_q", "pdes_get_q", "pdes_get_res", "pdes_q_dev",
     "pdes_res_dev", "pdes_eval_residual", "pdes_eval_residual_async", "pdes_sync", "pdes_rk4",
     "pdes_rk4_steps_async", "pdes_get_minv", "pdes_get_timings", "pdes_kernel_launch_count",
-    "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp",
+    "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp", "pdes_lserk54",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.pdes_eval_residual_async.argtypes = [p, d]
         L.pdes_sync.argtypes = [p]
         L.pdes_rk4.argtypes = [p, d, d, i64, d, i32, C.POINTER(d), p, i64, C.POINTER(i64)]
+        L.pdes_lserk54.argtypes = [p, d, d, i64, d, i32, C.POINTER(d), p, i64, C.POINTER(i64)]
         L.pdes_rk4_steps_async.argtypes = [p, d, i64]
         L.pdes_get_timings.argtypes = [p, C.POINTER(PdesTimings)]
         L.pdes_kernel_launch_count.argtypes = [p]

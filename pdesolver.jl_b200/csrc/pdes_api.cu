@@ -655,6 +655,36 @@ int enqueue_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int
   return PDES_OK;
 }
 
+// the five stages of one lserk54 step (lserk.jl:183-205).  Two state buffers ping-pong (every stage reads the
+// neighbours' q while it writes its own), ksum holds dq_vec.  head_only: stage-1 evaluation + norm only, q untouched
+// (the reference tests res_tol / itermax BEFORE the stage-1 update, lserk.jl:161-181).
+int enqueue_lserk_step(PdesCtx* ctx, double h, double res_tol, int pseudo_time, bool head_only) {
+  static const double a_c[5] = {0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+  static const double b_c[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                2277821191437.0 / 14882151754819.0};
+  double* P0 = ctx->qbuf[ctx->cur];
+  double* P1 = ctx->qbuf[(ctx->cur + 1) % 3];
+  ElemArgs a;
+  for (int s = 0; s < 5; ++s) {
+    double* in = (s % 2 == 0) ? P0 : P1;
+    double* out = (s % 2 == 0) ? P1 : P0;
+    fill_args(ctx, &a, in);
+    a.scheme = 1; a.stage = s + 1; a.x_old = in; a.ksum = ctx->ksum; a.q_next = out;
+    a.ah = a_c[s]; a.h6 = b_c[s]; a.hh = h;
+    int rc = enqueue_residual(ctx, a, EPI_RK);
+    if (rc) return rc;
+    if (s == 0) {
+      rc = enqueue_norm(ctx, res_tol, pseudo_time);
+      if (rc) return rc;
+      if (head_only) return PDES_OK;
+    }
+  }
+  ctx->cur = (ctx->cur + 1) % 3;     // five ping-pong stages end in P1
+  return PDES_OK;
+}
+
 // One full RK4 step as a CUDA graph (single-GPU, single-stream schedule): the ten launches of a step are
 // captured once per buffer rotation (three graphs) and replayed; small meshes are launch-bound otherwise.
 int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int pseudo_time) {
@@ -1178,6 +1208,64 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
     t = (double)c * h;
   }
   t += h;                                                        // rk4.jl:323
+  if (t_out) *t_out = t;
+  if (nsteps_out) *nsteps_out = heads;
+  if (norms_out && heads > 0) {
+    int64_t n = heads < norms_cap ? heads : norms_cap;
+    if (n > 0) CUDA_TRY(ctx, cudaMemcpy(norms_out, ctx->norms_dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  }
+  if (ctx->h_ctl->stop) reset_ctl(ctx);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return status;
+}
+
+int pdes_lserk54(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_tol, int32_t real_time, double* t_out,
+                 double* norms_out, int64_t norms_cap, int64_t* nsteps_out) {
+  if (!ctx) return usage(ctx, "null ctx");
+  if (!(h > 0.0)) return usage(ctx, "pdes_lserk54: h must be positive");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const int64_t t_steps = (int64_t)llround(t_max / h);
+  int64_t max_heads = t_steps;
+  if (itermax >= 0 && itermax < max_heads) max_heads = itermax > 0 ? itermax : 1;
+  if (max_heads < 0) max_heads = 0;
+  if (ctx->norms_cap < max_heads + 1) {
+    if (ctx->norms_dev) cudaFree(ctx->norms_dev);
+    ctx->norms_dev = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->norms_dev, sizeof(double) * (size_t)(max_heads + 1)));
+    ctx->norms_cap = max_heads + 1;
+    ctx->g_h = -1.0;
+  }
+  rc = reset_ctl(ctx);
+  if (rc) return rc;
+  const int pseudo = real_time ? 0 : 1;
+  const int cur0 = ctx->cur;
+  int64_t heads = 0, full = 0;
+  double t = 0.0;
+  int status = PDES_OK;
+  for (int64_t i = 2; i <= t_steps + 1; ++i) {
+    t = (double)(i - 2) * h;
+    const bool head_only = (itermax >= 0 && i > itermax);
+    rc = enqueue_lserk_step(ctx, h, res_tol, pseudo, head_only);
+    if (rc) return rc;
+    ++heads;
+    if (head_only) break;
+    ++full;
+    if ((full % 32) == 0 || i == t_steps + 1) {
+      status = fetch_ctl(ctx);
+      if (status || ctx->h_ctl->stop) break;
+    }
+  }
+  if (!status) status = fetch_ctl(ctx);
+  if (status == PDES_OK && ctx->h_ctl->stop && ctx->h_ctl->converged_step >= 0) {
+    // norm < res_tol at step head c: q of that step head is untouched (buffer P0 of step c)
+    const int64_t c = ctx->h_ctl->converged_step;
+    heads = c + 1;
+    ctx->cur = (int)((cur0 + c) % 3);
+    t = (double)c * h;
+  }
+  t += h;
   if (t_out) *t_out = t;
   if (nsteps_out) *nsteps_out = heads;
   if (norms_out && heads > 0) {

@@ -102,7 +102,9 @@ struct ElemArgs {
   double* norm_partials;       // [gridDim.x] sum_j M_j k_j^2 per CTA (stage 1 only)
   double ah;                   // a_s * h
   double h6;                   // h/6 (last stage)
-  int32_t stage;               // 1..4
+  double hh;                   // LSERK54: delta_t  (then ah = a_s, h6 = b_s, ksum = dq_vec, x_old = q)
+  int32_t scheme;              // 0: rk4 (rk4.jl:244-319), 1: lserk54 (lserk.jl:183-205)
+  int32_t stage;               // 1..4 (rk4) | 1..5 (lserk54)
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
@@ -380,15 +382,22 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         const int64_t dof = base + 2 * i2;
         const double2 k = make_double2(v[u].x + sv[u].x, v[u].y + sv[u].y);
         double2 o1 = k, o2 = k;
-        if (MODE == EPI_RK) {
+        if (MODE == EPI_RK && a.stage == 1) {
+          // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
+          const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
+          nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
+          if (two[u]) {
+            const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
+            nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
+          }
+        }
+        if (MODE == EPI_RK && a.scheme == 1) {
+          // lserk54: dq = a_s*dq + delta_t*res ; q += b_s*dq
+          if (a.stage == 1) o1 = make_double2(a.hh * k.x, a.hh * k.y);
+          else o1 = make_double2(a.ah * ks[u].x + a.hh * k.x, a.ah * ks[u].y + a.hh * k.y);
+          o2 = make_double2(xo[u].x + a.h6 * o1.x, xo[u].y + a.h6 * o1.y);
+        } else if (MODE == EPI_RK) {
           if (a.stage == 1) {
-            // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
-            const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
-            nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
-            if (two[u]) {
-              const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
-              nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
-            }
             o1 = k;                                                                   // ksum
             o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);            // q_next
           } else if (a.stage < 4) {
@@ -401,7 +410,7 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         if (MODE == EPI_RES) {
           if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
         } else {
-          if (a.stage < 4) {
+          if (a.scheme == 1 || a.stage < 4) {
             if (two[u]) *reinterpret_cast<double2*>(a.ksum + dof) = o1; else a.ksum[dof] = o1.x;
           }
           if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;

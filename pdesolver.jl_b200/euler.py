@@ -217,7 +217,13 @@ def evaldRdqProduct(mesh, sbp, eqn: EulerData, opts, v, out=None):
     return out
 
 
-def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=False):
+def lserk54(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=False):
+    """``lserk54(f, h, t_max, mesh, sbp, eqn, opts; res_tol, real_time)`` (NonlinearSolvers/lserk.jl): the
+    five-stage 2N-storage scheme behind ``run_type = 30``; same contract as ``rk4``."""
+    return rk4(f, h, t_max, mesh, sbp, eqn, opts, res_tol=res_tol, real_time=real_time, _entry="pdes_lserk54")
+
+
+def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=False, _entry="pdes_rk4"):
     """``rk4(f, h, t_max, mesh, sbp, eqn, opts; res_tol, real_time)`` (rk4.jl:404-410).
 
     ``f`` must be this module's ``evalResidual`` (the fused stage kernels evaluate
@@ -235,7 +241,7 @@ def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=Fa
     norms = np.zeros(cap)
     t_out, ns = C.c_double(0.0), C.c_int64(0)
     eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
-    rc = L.pdes_rk4(ctx, float(h), float(t_max), itermax, float(res_tol), int(bool(real_time)),
+    rc = getattr(L, _entry)(ctx, float(h), float(t_max), itermax, float(res_tol), int(bool(real_time)),
                     C.byref(t_out), _ptr(norms), cap, C.byref(ns))
     eqn._check(rc)
     eqn._check(L.pdes_get_q(ctx, _ptr(eqn.q)))

@@ -248,3 +248,23 @@ def test_jacobian_vector_product(case, n):
     Jc = pd.evaldRdqProduct(mesh, op, eqn, opts, 2.0 * v - 3.0 * w)
     assert rel_l2(Jc, 2.0 * Jv - 3.0 * Jw) < 1e-12
     assert np.array_equal(eqn.q, q0)
+
+
+@pytest.mark.parametrize("case,n,h", [("c1_2d_p1_roe", 8, 1e-3), ("c3_3d_p2_roe_src", 3, 5e-5), ("c2_2d_p2_es", 5, 1e-3)])
+def test_lserk54_trajectory(case, n, h):
+    """lserk54 (NonlinearSolvers/lserk.jl) on the fused stage kernels."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=2)
+    opts["use_itermax"] = False
+    eqn.q[...] = q0
+    t = pd.lserk54(pd.evalResidual, h, 12 * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.lserk54(q0, h, 12 * h)
+    assert t == t_ref and len(eqn.convergence) == 12
+    assert rel_l2(eqn.q, q_ref) < RK_TOL
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+    # itermax exit: the tests precede the stage-1 update, q is the state at that step head
+    opts.update({"use_itermax": True, "itermax": 4})
+    eqn.q[...] = q0
+    t = pd.lserk54(pd.evalResidual, h, 1.0, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.lserk54(q0, h, 1.0, itermax=4)
+    assert t == t_ref and len(eqn.convergence) == len(norms_ref) == 4
+    assert rel_l2(eqn.q, q_ref) < RK_TOL

@@ -402,3 +402,25 @@ def test_freestream_preservation_operator(dim, p, kind):
             assert abs(one @ Ex[e, d] @ one) < 1e-12
             assert np.abs(Ex[e, d] - Ex[e, d].T).max() < 1e-12
             assert np.abs((Sx + 0.5 * Ex[e, d]) @ one).max() < 1e-12
+
+
+# --- test/euler/test_rk4.jl:45-64: lserk54 integrates a quartic in t exactly ---------------------
+def test_lserk54_quartic():
+    RHS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double)
+    POST = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_void_p, C.c_int)
+
+    def rhs(ctx, q, res, t):
+        C.cast(res, C.POINTER(C.c_double))[0] = 4 * t ** 3 + 3 * t ** 2 + 2 * t + 1
+        return 0
+
+    def post(ctx, res, calc_norm):
+        return 1.0
+    q = np.array([1.0])
+    res = np.zeros(1)
+    ns, st = C.c_int64(0), C.c_int(0)
+    L.orc_lserk54.argtypes = [RHS, POST, C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                              C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    t = L.orc_lserk54(RHS(rhs), POST(post), None, 0.01, 1.0, 1, _ptr(q), _ptr(res), -1, -1.0, 1, None, 0,
+                      C.byref(ns), C.byref(st))
+    exact = t ** 4 + t ** 3 + t ** 2 + t + 1
+    assert abs(t - 1.0) < 1e-12 and abs(q[0] - exact) < 1e-12
