@@ -337,9 +337,10 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
 // Coalesced epilogue shared by the element kernels: the tile of staged values (EPI_RES: acc; EPI_RK: Minv*acc) is
 // combined with the tabulated source and either stored as res or pushed through the fused RK4 stage
 // (rk4.jl:244-319); two dofs per access, CH accesses in flight per thread.
-template <int NN, int ND, int E, int T, int MODE>
+// STAGED: the source / x_old / ksum tiles were copied to shared memory (sStr = [srcm | x_old | ksum], E*EL each).
+template <int NN, int ND, int E, int T, int MODE, bool STAGED = false>
 __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* sq, int ne, int64_t e0, int tid,
-                                              double* s_red) {
+                                              double* s_red, const double* sStr = nullptr) {
   constexpr int EL = NN * ND;
   double nrm2 = 0.0;
   {
@@ -359,7 +360,20 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         two[u] = ok[u] && (2 * i2 + 1 < ntile);
         const int64_t dof = base + 2 * i2;
         sv[u] = xo[u] = ks[u] = make_double2(0.0, 0.0);
-        if (two[u]) {
+        if (STAGED && ok[u]) {
+          const double2* s2 = reinterpret_cast<const double2*>(sStr);
+          if (two[u]) {
+            v[u] = sq2[i2];
+            if (psrc) sv[u] = s2[i2];
+            xo[u] = s2[(E * EL) / 2 + i2];
+            if (a.stage > 1) ks[u] = s2[E * EL + i2];
+          } else {
+            v[u] = make_double2(sq[2 * i2], 0.0);
+            if (psrc) sv[u].x = sStr[2 * i2];
+            xo[u].x = sStr[E * EL + 2 * i2];
+            if (a.stage > 1) ks[u].x = sStr[2 * E * EL + 2 * i2];
+          }
+        } else if (two[u]) {
           v[u] = sq2[i2];
           if (psrc) sv[u] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
           if (MODE == EPI_RK) {
@@ -443,7 +457,8 @@ struct TileCfg {
   static constexpr int T = ((VT + 31) / 32) * 32;
   static constexpr int SQ = NN * ND;                            // per-element stride of the q tile (contiguous: cp.async)
   static constexpr int SF = ND * DIM * NN;                      // per-element stride of the volume-flux tile
-  static constexpr size_t smem_bytes = sizeof(double) * (size_t)E * (SQ + SF);
+  static constexpr int SU = SF > 3 * SQ ? SF : 3 * SQ;         // the tile is reused for the three epilogue streams
+  static constexpr size_t smem_bytes = sizeof(double) * (size_t)E * (SQ + SU);
   static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
 };
 
@@ -544,11 +559,19 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   const int vp = tid / ND, vk = tid - vp * ND;
   const int s0 = vp, s1 = vp + HP;
   const bool act0 = tid < Cfg::VT && s0 < ne, act1 = tid < Cfg::VT && s1 < ne;
-  if (act0) {
-    double acc0[NN], acc1[NN];
+  const int s1c = act1 ? s1 : s0;          // the second row of a ragged tile recomputes the first (never stored)
+  const int s0c = act0 ? s0 : 0;
+  double acc0[NN], acc1[NN];
 #pragma unroll
-    for (int u = 0; u < NN; ++u) { acc0[u] = 0.0; acc1[u] = 0.0; }
-    const int s1c = act1 ? s1 : s0;        // the second row of a ragged tile recomputes the first (never stored)
+  for (int u = 0; u < NN; ++u) { acc0[u] = 0.0; acc1[u] = 0.0; }
+  // face contributions of the two rows: signed, in the element's node order (k_face_flux).  The records of face
+  // f+1 are requested before the products of face f are issued (software pipeline; they are L2 hits).
+  const double* G0 = a.fluxe + (e0 + s0c) * (NF * FL) + vk;
+  const double* G1 = a.fluxe + (e0 + (act0 ? s1c : 0)) * (NF * FL) + vk;
+  double g0v[NFN], g1v[NFN];
+  if (act0) {
+#pragma unroll
+    for (int i = 0; i < NFN; ++i) { g0v[i] = __ldg(G0 + i * ND); g1v[i] = __ldg(G1 + i * ND); }
     // S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j]   (weakdifferentiate!, trans=true)
     // (the loop over directions stays rolled: fully unrolled operator products overflow the instruction cache)
     const double* F0 = sF + (s0 * ND + vk) * DIM * NN;
@@ -566,15 +589,26 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
         }
       }
     }
-    // S3: face integration  res[k,node] += sum_f sum_i Rf[f][i][node] * (-+ w_i f*[k,i]); the contributions
-    // arrive signed and in this element's node order (interiorfaceintegrate!, boundaryintegrate!)
-    const double* G0 = a.fluxe + (e0 + s0) * (NF * FL) + vk;
-    const double* G1 = a.fluxe + (e0 + s1c) * (NF * FL) + vk;
+  }
+  constexpr bool STAGED = (MODE == EPI_RK);
+  if (STAGED) {
+    // the volume-flux tile is dead: its storage receives the epilogue's streams (srcm | x_old | ksum), which are
+    // in flight while the face products run
+    __syncthreads();
+    if (a.srcm) async_tile(sF, a.srcm + e0 * EL, ne * EL, tid, T);
+    async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);
+    if (a.stage > 1) async_tile(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T);
+    cp_async_commit();
+  }
+  if (act0) {
+    // S3: face integration  res[k,node] += sum_f sum_i Rf[f][i][node] * (-+ w_i f*[k,i])
+    // (interiorfaceintegrate!, boundaryintegrate!, boundaryFaceIntegrate!)
 #pragma unroll 1
     for (int f = 0; f < NF; ++f) {
-      double g0v[NFN], g1v[NFN];
+      double n0v[NFN], n1v[NFN];
+      const int fn = f + 1 < NF ? f + 1 : f;
 #pragma unroll
-      for (int i = 0; i < NFN; ++i) { g0v[i] = __ldg(G0 + (f * NFN + i) * ND); g1v[i] = __ldg(G1 + (f * NFN + i) * ND); }
+      for (int i = 0; i < NFN; ++i) { n0v[i] = __ldg(G0 + (fn * NFN + i) * ND); n1v[i] = __ldg(G1 + (fn * NFN + i) * ND); }
 #pragma unroll
       for (int i = 0; i < NFN; ++i)
 #pragma unroll
@@ -583,6 +617,8 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
           acc0[u] = fma(c, g0v[i], acc0[u]);
           acc1[u] = fma(c, g1v[i], acc1[u]);
         }
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) { g0v[i] = n0v[i]; g1v[i] = n1v[i]; }
     }
     // pde_post_func: res_vec *= Minv (EPI_RK); staged for the coalesced epilogue
     if (MODE == EPI_RK) {
@@ -598,10 +634,11 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
       for (int u = 0; u < NN; ++u) sq[s1 * SQ + u * ND + vk] = acc1[u];
     }
   }
+  if (STAGED) cp_async_wait<0>();
   __syncthreads();
 
   // ---- S4: coalesced epilogue (source, res | fused RK4 stage, stage-1 norm partial) ----------------------------
-  epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
+  epilogue_tile<NN, ND, E, T, MODE, STAGED>(a, sq, ne, e0, tid, s_red, sF);
 }
 
 // getSendDataFace (Utils/parallel.jl:249-258): q_send[:, i, j] = R q on the shared faces, one thread per
