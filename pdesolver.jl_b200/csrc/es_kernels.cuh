@@ -106,9 +106,14 @@ struct SplitCfg {
   static constexpr int ND = DIM + 2, NF = DIM + 1;
   static constexpr int NP = NN * (NN - 1) / 2;                   // node pairs
   static constexpr int NZ = DIM + 4;                             // z1, zv[DIM], z5, log z1, log z5
-  static constexpr int T = 192;
+  static constexpr int NC = DIM * ND;                            // flux components per pair
+  // the pair stage dominates: T divides E*NP (E=16, nn=12: 1056 = 3 * 352) so that every thread evaluates the same
+  // number of two-point fluxes
+  static constexpr int T = (E * NP) % 352 == 0 ? 352 : 192;
+  static constexpr int PS = E * NP + 1;                          // component stride of the pair-flux tile (odd)
+  static constexpr int ZS = E * NN + 1;                          // component stride of the node tile (odd)
   static constexpr size_t smem_bytes =
-      sizeof(double) * ((size_t)E * (NN * ND + NN * NZ + NP * DIM * ND) + DIM * NN * NN);
+      sizeof(double) * ((size_t)E * NN * ND + (size_t)NZ * ZS + (size_t)NC * PS + DIM * NN * NN);
   static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
 };
 
@@ -116,13 +121,14 @@ template <int DIM, int NN, int NFN, int E, int MODE>
 __global__ void __launch_bounds__((SplitCfg<DIM, NN, NFN, E>::T), 2)
 k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = SplitCfg<DIM, NN, NFN, E>;
-  constexpr int ND = Cfg::ND, NF = Cfg::NF, NP = Cfg::NP, NZ = Cfg::NZ, T = Cfg::T;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, NP = Cfg::NP, NZ = Cfg::NZ, NC = Cfg::NC, T = Cfg::T;
+  constexpr int PS = Cfg::PS, ZS = Cfg::ZS;
   constexpr int EL = NN * ND, FL = NFN * ND;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sq = reinterpret_cast<double*>(smem_raw);     // [E][EL]   q tile, later the staged output
-  double* sZ = sq + E * EL;                             // [E][NN][NZ]
-  double* sFp = sZ + E * NN * NZ;                       // [E][NP][DIM][ND]
-  double* sS2 = sFp + E * NP * DIM * ND;                // [DIM][NN][NN]
+  double* sq = reinterpret_cast<double*>(smem_raw);     // [E][EL]       q tile, later the staged output
+  double* sZ = sq + E * EL;                             // [NZ][E*NN]    component-major (conflict-free)
+  double* sFp = sZ + NZ * ZS;                           // [NC][E*NP]    component-major
+  double* sS2 = sFp + NC * PS;                          // [DIM][NN][NN]
   __shared__ double s_red[T / 32];
 
   if (a.ctl->stop) return;
@@ -155,11 +161,10 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
       for (int d = 0; d < DIM; ++d) qn[1 + d] = 0.0;
     }
     const IRNode<DIM> z = ir_node<DIM>(qn, gami);
-    double* o = sZ + it * NZ;
-    o[0] = z.z1;
+    sZ[0 * ZS + it] = z.z1;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) o[1 + d] = z.zv[d];
-    o[DIM + 1] = z.z5; o[DIM + 2] = z.l1; o[DIM + 3] = z.l5;
+    for (int d = 0; d < DIM; ++d) sZ[(1 + d) * ZS + it] = z.zv[d];
+    sZ[(DIM + 1) * ZS + it] = z.z5; sZ[(DIM + 2) * ZS + it] = z.l1; sZ[(DIM + 3) * ZS + it] = z.l5;
   }
   __syncthreads();
 
@@ -172,13 +177,12 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
     while ((j + 1) * j / 2 <= pr) ++j;
     const int k = pr - j * (j - 1) / 2;
     IRNode<DIM> zj, zk;
-    const double* pj = sZ + (s * NN + j) * NZ;
-    const double* pk = sZ + (s * NN + k) * NZ;
-    zj.z1 = pj[0]; zk.z1 = pk[0];
+    const int nj = s * NN + j, nk = s * NN + k;
+    zj.z1 = sZ[nj]; zk.z1 = sZ[nk];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) { zj.zv[d] = pj[1 + d]; zk.zv[d] = pk[1 + d]; }
-    zj.z5 = pj[DIM + 1]; zj.l1 = pj[DIM + 2]; zj.l5 = pj[DIM + 3];
-    zk.z5 = pk[DIM + 1]; zk.l1 = pk[DIM + 2]; zk.l5 = pk[DIM + 3];
+    for (int d = 0; d < DIM; ++d) { zj.zv[d] = sZ[(1 + d) * ZS + nj]; zk.zv[d] = sZ[(1 + d) * ZS + nk]; }
+    zj.z5 = sZ[(DIM + 1) * ZS + nj]; zj.l1 = sZ[(DIM + 2) * ZS + nj]; zj.l5 = sZ[(DIM + 3) * ZS + nj];
+    zk.z5 = sZ[(DIM + 1) * ZS + nk]; zk.l1 = sZ[(DIM + 2) * ZS + nk]; zk.l5 = sZ[(DIM + 3) * ZS + nk];
     const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
     double dirs[DIM][DIM], F[DIM][ND];
 #pragma unroll
@@ -186,47 +190,34 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
 #pragma unroll
       for (int p = 0; p < DIM; ++p) dirs[d][p] = __ldg(dx + d + DIM * p);
     ir_flux<DIM, DIM>(zj, zk, dirs, a.ph.gamma, F);
-    double* o = sFp + (int64_t)it * (DIM * ND);
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
 #pragma unroll
-      for (int c = 0; c < ND; ++c) o[d * ND + c] = F[d][c];
+      for (int c = 0; c < ND; ++c) sFp[(d * ND + c) * PS + it] = F[d][c];
   }
   __syncthreads();
 
-  // ---- node threads: res[:,i] = -sum_m 2 S[i,m,d] F_d(pair(i,m)) + face records + (Minv) -----------------------
-  for (int it = tid; it < ne * NN; it += T) {
-    const int s = it / NN, i = it - s * NN;
-    double acc[ND];
+  // ---- (element, node, variable) threads: res[c,i] = -sum_m 2 S[i,m,d] F_d[c](pair(i,m)) + face records, x Minv ----
+  for (int it = tid; it < ne * EL; it += T) {
+    const int s = it / EL, r = it - s * EL;
+    const int i = r / ND, c = r - i * ND;
+    double acc = 0.0;
 #pragma unroll
-    for (int c = 0; c < ND; ++c) acc[c] = 0.0;
     for (int m = 0; m < NN; ++m) {
       if (m == i) continue;
       const int jj = m > i ? m : i, kk = m > i ? i : m;
-      const double* F = sFp + ((int64_t)s * NP + jj * (jj - 1) / 2 + kk) * (DIM * ND);
+      const int pi = s * NP + jj * (jj - 1) / 2 + kk;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const double c2 = sS2[(d * NN + i) * NN + m];
-#pragma unroll
-        for (int c = 0; c < ND; ++c) acc[c] = fma(-c2, F[d * ND + c], acc[c]);
-      }
+      for (int d = 0; d < DIM; ++d) acc = fma(-sS2[(d * NN + i) * NN + m], sFp[(d * ND + c) * PS + pi], acc);
     }
     const double* G = a.fluxe + (e0 + s) * (NF * FL);
 #pragma unroll
     for (int u = 0; u < DIM; ++u) {
       const int slot = op.inv[i][u];
-      if (slot >= 0) {
-#pragma unroll
-        for (int c = 0; c < ND; ++c) acc[c] += __ldg(G + slot * ND + c);
-      }
+      if (slot >= 0) acc += __ldg(G + slot * ND + c);
     }
-    if (MODE == EPI_RK) {
-      const double mi = __ldg(a.minv + (e0 + s) * NN + i);
-#pragma unroll
-      for (int c = 0; c < ND; ++c) acc[c] *= mi;
-    }
-#pragma unroll
-    for (int c = 0; c < ND; ++c) sq[it * ND + c] = acc[c];
+    if (MODE == EPI_RK) acc *= __ldg(a.minv + (e0 + s) * NN + i);
+    sq[it] = acc;
   }
   __syncthreads();
   epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);

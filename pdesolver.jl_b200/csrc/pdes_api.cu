@@ -262,7 +262,7 @@ Ops* make_ops(const PdesConfig& c) {
     // entropy-stable configuration: diag-E operator, split-form IR volume flux, Roe / IR / IRSLF interface flux
     if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR) return nullptr;
     if (c.flux_id != PDES_FLUX_ROE && c.flux_id != PDES_FLUX_IR && c.flux_id != PDES_FLUX_IRSLF) return nullptr;
-    if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 8>();
+    if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 16>();
     return nullptr;
   }
   if (c.volume_integral_type != 1 || c.flux_id != PDES_FLUX_ROE) return nullptr;
