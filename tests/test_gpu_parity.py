@@ -268,3 +268,70 @@ def test_lserk54_trajectory(case, n, h):
     t_ref, q_ref, norms_ref = orc.lserk54(q0, h, 1.0, itermax=4)
     assert t == t_ref and len(eqn.convergence) == len(norms_ref) == 4
     assert rel_l2(eqn.q, q_ref) < RK_TOL
+
+
+def test_one_based_indices_from_julia():
+    """The Julia host passes mesh.interfaces / bndryfaces / bndry_offsets / perm / nbrperm 1-based
+    (PdesConfig.index_base = 1); the result must equal the 0-based call bit for bit."""
+    import ctypes as C
+    from pdesolver_jl_b200 import _cabi
+    op, mesh, opts, orc, q0, eqn = setup("c3_3d_p2_roe_src", 3, shuffle_seed=8)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    L = _cabi.lib()
+    f = op.face
+    cfg = _cabi.PdesConfig()
+    cfg.dim, cfg.nn, cfg.nfn, cfg.ss = mesh.dim, op.numnodes, f.numnodes, f.stencilsize
+    cfg.norient, cfg.sparse_face, cfg.index_base, cfg.device = f.nbrperm.shape[1], 0, 1, 0
+    cfg.nE, cfg.nF, cfg.nB = mesh.numEl, mesh.numInterfaces, mesh.numBoundaryFaces
+    cfg.numBC, cfg.npeers, cfg.volume_integral_type, cfg.face_integral_type = 1, 0, 1, 1
+    cfg.flux_id, cfg.volume_flux_id, cfg.src_id = 1, 4, 1
+    cfg.check_density = cfg.check_pressure = 1
+    cfg.gamma, cfg.R, cfg.Ma, cfg.aoa, cfg.rho_free, cfg.E_free = 1.4, 287.058, -1.0, 0.0, 1.0, 1 / 1.4 / 0.4 + 0.5
+    ctx = C.c_void_p(None)
+    assert L.pdes_create(C.byref(cfg), C.byref(ctx)) == 0
+    F64 = lambda a: np.asfortranarray(np.asarray(a, dtype=np.float64))   # noqa: E731
+    P = lambda a: a.ctypes.data_as(C.c_void_p)                           # noqa: E731
+    keep = [F64(op.Q), F64(op.w), F64(f.interp), np.asfortranarray(f.perm.astype(np.int64) + 1),
+            np.asfortranarray(f.nbrperm.astype(np.int64) + 1), F64(f.wface)]
+    assert L.pdes_set_operator(ctx, *[P(x) for x in keep]) == 0
+    ifc = mesh.interfaces.copy()
+    for k in ("elementL", "elementR", "faceL", "faceR", "orient"):
+        ifc[k] += 1
+    bf = mesh.bndryfaces.copy()
+    bf["element"] += 1
+    bf["face"] += 1
+    arrs = [F64(mesh.dxidx), F64(mesh.jac), F64(mesh.coords), F64(mesh.nrm_face), F64(mesh.nrm_bndry),
+            F64(mesh.coords_bndry), np.ascontiguousarray(ifc), np.ascontiguousarray(bf),
+            np.ascontiguousarray(mesh.bndry_offsets + 1, dtype=np.int64), np.array([2], dtype=np.int32)]
+    assert L.pdes_set_mesh(ctx, *[P(x) for x in arrs]) == 0
+    res = np.zeros_like(q0, order="F")
+    assert L.pdes_set_q(ctx, P(q0)) == 0 and L.pdes_eval_residual(ctx, 0.0) == 0 and L.pdes_get_res(ctx, P(res)) == 0
+    assert np.array_equal(res, eqn.res)
+    # error locations come back 1-based
+    qb = q0.copy(order="F")
+    qb[0, 3, 10] = -1.0
+    assert L.pdes_set_q(ctx, P(qb)) == 0
+    assert L.pdes_eval_residual(ctx, 0.0) == _cabi.PDES_ERR_NEG_DENSITY
+    e, n = C.c_int64(), C.c_int64()
+    L.pdes_last_error_location(ctx, C.byref(e), C.byref(n))
+    assert (e.value, n.value) == (11, 4)
+    L.pdes_destroy(ctx)
+
+
+def test_usage_errors_are_reported():
+    import ctypes as C
+    from pdesolver_jl_b200 import _cabi
+    L = _cabi.lib()
+    op = pd.build_operator(2, 1)
+    mesh = pd.structured_mesh(op, 3)
+    eqn = pd.EulerData(mesh, op, {"Flux_name": "RoeFlux"})
+    # an interface list that does not cover every element face must be rejected, not silently accepted
+    bad = pd.structured_mesh(op, 3)
+    bad.interfaces = bad.interfaces[:-1]
+    with pytest.raises(pd.PDESolverError, match="belongs to no interface"):
+        e2 = pd.EulerData(bad, op, {"Flux_name": "RoeFlux"})
+        e2.q[...] = 1.0
+        pd.evalResidual(bad, op, e2, {})
+    assert L.pdes_eval_residual(None, 0.0) == _cabi.PDES_ERR_USAGE
+    assert eqn.kernel_launch_count() >= 1
