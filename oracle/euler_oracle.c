@@ -502,12 +502,20 @@ static void face_integrate_el(const OrcProblem *P, const double *flux, int face,
     const double *f = flux + nd * i;
     if (P->sparse_face) {
       int64_t node = P->perm[col + (int64_t)nfn * face];
-      for (int k = 0; k < nd; ++k) res_el[k + nd * node] += sgn * P->wface[i] * f[k];
+      for (int k = 0; k < nd; ++k) {
+        double v = sgn * P->wface[i] * f[k];
+#pragma omp atomic
+        res_el[k + nd * node] += v;
+      }
     } else {
       for (int j = 0; j < ss; ++j) {
         double c = P->interp[j + ss * col] * P->wface[i];
         int64_t node = P->perm[j + (int64_t)ss * face];
-        for (int k = 0; k < nd; ++k) res_el[k + nd * node] += sgn * c * f[k];
+        for (int k = 0; k < nd; ++k) {
+          double v = sgn * c * f[k];
+#pragma omp atomic
+          res_el[k + nd * node] += v;
+        }
       }
     }
   }
@@ -535,7 +543,23 @@ typedef struct {
   double *aux_vars, *flux_parametric, *q_face, *flux_face, *q_bndry, *bndryflux;
 } OrcWork;
 
+/* the intermediates are as large as the state: keep one set per process (the reference allocates them once in the
+ * EulerData constructor, types.jl:584-646) instead of paying malloc + first-touch on every evaluation */
+static OrcWork g_work;
+static size_t g_work_key[4];
+static OrcWork work_alloc_raw(const OrcProblem *P);
+static void work_free_raw(OrcWork *W);
 static OrcWork work_alloc(const OrcProblem *P) {
+  size_t key[4] = {(size_t)P->nd * P->nn * P->nE * P->dim, (size_t)P->nF, (size_t)P->nB, (size_t)P->nfn};
+  if (memcmp(key, g_work_key, sizeof(key)) != 0) {
+    if (g_work_key[0]) work_free_raw(&g_work);
+    g_work = work_alloc_raw(P);
+    memcpy(g_work_key, key, sizeof(key));
+  }
+  return g_work;
+}
+static void work_free(OrcWork *W) { (void)W; }
+static OrcWork work_alloc_raw(const OrcProblem *P) {
   OrcWork W;
   size_t nd = P->nd, nn = P->nn, nfn = P->nfn;
   W.aux_vars = (double *)malloc(sizeof(double) * nn * P->nE);
@@ -546,7 +570,7 @@ static OrcWork work_alloc(const OrcProblem *P) {
   W.bndryflux = (double *)malloc(sizeof(double) * nd * nfn * (P->nB ? P->nB : 1));
   return W;
 }
-static void work_free(OrcWork *W) {
+static void work_free_raw(OrcWork *W) {
   free(W->aux_vars); free(W->flux_parametric); free(W->q_face); free(W->flux_face);
   free(W->q_bndry); free(W->bndryflux);
 }
@@ -557,6 +581,7 @@ static void work_free(OrcWork *W) {
 static int aux_and_checks(const OrcProblem *P, const double *q, double *aux, int64_t *err_loc) {
   int nd = P->nd, nn = P->nn;
   int status = 0;
+#pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < P->nE; ++e)
     for (int j = 0; j < nn; ++j)
       aux[j + nn * e] = orc_calc_pressure(P->dim, P->gamma, q + IDX3(0, j, e, nd, nn));
@@ -618,6 +643,7 @@ static void calc_face_flux(const OrcProblem *P, const double *q_face, double *fl
 /* euler.jl:777-778 interiorfaceintegrate!(sbpface, interfaces, flux_face, res, Subtract) */
 static void interior_face_integrate(const OrcProblem *P, const double *flux_face, double *res) {
   int nd = P->nd, nn = P->nn, nfn = P->nfn;
+#pragma omp parallel for schedule(static)
   for (int64_t f = 0; f < P->nF; ++f) {
     OrcInterface I = P->ifaces[f];
     const double *fl = flux_face + (int64_t)nd * nfn * f;
@@ -629,6 +655,7 @@ static void interior_face_integrate(const OrcProblem *P, const double *flux_face
 /* flux.jl:79-125 calcFaceIntegral_nopre */
 static void calc_face_integral_nopre(const OrcProblem *P, const double *q, double *res) {
   int nd = P->nd, nn = P->nn, nfn = P->nfn, dim = P->dim;
+#pragma omp parallel for schedule(static)
   for (int64_t f = 0; f < P->nF; ++f) {
     OrcInterface I = P->ifaces[f];
     double uL[ORC_MAXD * ORC_MAXFN], uR[ORC_MAXD * ORC_MAXFN], fl[ORC_MAXD * ORC_MAXFN];
@@ -645,6 +672,7 @@ static void calc_face_integral_nopre(const OrcProblem *P, const double *q, doubl
 /* bc.jl:162-175 interpolateBoundary (SBP boundaryinterpolate!) */
 static void interpolate_boundary(const OrcProblem *P, const double *q, double *q_bndry) {
   int nd = P->nd, nn = P->nn, nfn = P->nfn;
+#pragma omp parallel for schedule(static)
   for (int64_t b = 0; b < P->nB; ++b)
     face_interp_el(P, q + (int64_t)nd * nn * P->bfaces[b].element, P->bfaces[b].face, -1,
                    q_bndry + (int64_t)nd * nfn * b);
@@ -654,6 +682,7 @@ static void interpolate_boundary(const OrcProblem *P, const double *q, double *q
 static void get_bc_fluxes(const OrcProblem *P, const double *q_bndry, double *bndryflux) {
   int nd = P->nd, nfn = P->nfn, dim = P->dim;
   for (int i = 0; i < P->numBC; ++i)
+#pragma omp parallel for schedule(static)
     for (int64_t b = P->bndry_offsets[i]; b < P->bndry_offsets[i + 1]; ++b)
       for (int j = 0; j < nfn; ++j)
         orc_bc_flux(P, P->bc_ids[i], q_bndry + nd * (j + (int64_t)nfn * b),
@@ -665,6 +694,7 @@ static void get_bc_fluxes(const OrcProblem *P, const double *q_bndry, double *bn
 /* euler.jl:675 boundaryintegrate!(sbpface, bndryfaces, bndryflux, res, Subtract) */
 static void boundary_integrate(const OrcProblem *P, const double *bndryflux, double *res) {
   int nd = P->nd, nn = P->nn, nfn = P->nfn;
+#pragma omp parallel for schedule(static)
   for (int64_t b = 0; b < P->nB; ++b)
     face_integrate_el(P, bndryflux + (int64_t)nd * nfn * b, P->bfaces[b].face, -1, -1.0,
                       res + (int64_t)nd * nn * P->bfaces[b].element);
