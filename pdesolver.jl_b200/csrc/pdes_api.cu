@@ -1099,9 +1099,15 @@ int pdes_sync(PdesCtx* ctx) {
 }
 
 int pdes_eval_residual(PdesCtx* ctx, double t) {
+  if (!ctx) return usage(ctx, "null ctx");
+  cudaEventRecord(ctx->ev_t0, ctx->stream);
   int rc = pdes_eval_residual_async(ctx, t);
   if (rc) return rc;
-  return pdes_sync(ctx);
+  cudaEventRecord(ctx->ev_t1, ctx->stream);
+  rc = pdes_sync(ctx);
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) ctx->tm.t_func += ms * 1e-3;   // Timings.t_func
+  return rc;
 }
 
 // evaldRdqProduct / applyLinearOperator (interface2.jl:454-498, newton_setup.jl:632-662): out = dR/dq(q) * v at the
