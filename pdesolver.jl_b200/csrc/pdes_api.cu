@@ -766,7 +766,13 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   }
   CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
   PdesCtx* c = ctx.get();
-  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // the compute stream (element kernels) outranks the face stream: when the two kernel families run concurrently
+    // (PDES_CHUNKS > 1) pending element CTAs are dispatched before the queued face CTAs
+    int lo = 0, hi = 0;
+    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+  }
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->face_stream, cudaStreamNonBlocking));
   for (int i = 0; i < PdesCtx::MAXC; ++i) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_face[i], cudaEventDisableTiming));

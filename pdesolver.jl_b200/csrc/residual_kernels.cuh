@@ -122,6 +122,17 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
+// streaming variant: the line is marked evict-first in L2 (data touched once per launch must not push out q / the face
+// records that the next kernel re-reads)
+__device__ __forceinline__ void cp_async16_stream(void* smem, const void* gmem, unsigned long long pol) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -130,6 +141,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void async_tile(double* dst, const double* src, int n, int tid, int T) {
   const int n2 = n >> 1;
   for (int i = tid; i < n2; i += T) cp_async16(dst + 2 * i, src + 2 * i);
+  if ((n & 1) && tid == 0) cp_async8(dst + n - 1, src + n - 1);
+}
+
+__device__ __forceinline__ void async_tile_stream(double* dst, const double* src, int n, int tid, int T,
+                                                  unsigned long long pol) {
+  const int n2 = n >> 1;
+  for (int i = tid; i < n2; i += T) cp_async16_stream(dst + 2 * i, src + 2 * i, pol);
   if ((n & 1) && tid == 0) cp_async8(dst + n - 1, src + n - 1);
 }
 
@@ -425,7 +443,7 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
           if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
         } else {
           if (a.scheme == 1 || a.stage < 4) {
-            if (two[u]) *reinterpret_cast<double2*>(a.ksum + dof) = o1; else a.ksum[dof] = o1.x;
+            if (two[u]) __stcs(reinterpret_cast<double2*>(a.ksum + dof), o1); else __stcs(a.ksum + dof, o1.x);
           }
           if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;
         }
@@ -595,9 +613,11 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
     // the volume-flux tile is dead: its storage receives the epilogue's streams (srcm | x_old | ksum), which are
     // in flight while the face products run
     __syncthreads();
-    if (a.srcm) async_tile(sF, a.srcm + e0 * EL, ne * EL, tid, T);
-    async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);
-    if (a.stage > 1) async_tile(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T);
+    const unsigned long long pol = policy_evict_first();
+    if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
+    if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);   // x_old == q of this stage
+    else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
+    if (a.stage > 1) async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
     cp_async_commit();
   }
   if (act0) {
