@@ -130,6 +130,8 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
   double* sFp = sZ + NZ * ZS;                           // [NC][E*NP]    component-major
   double* sS2 = sFp + NC * PS;                          // [DIM][NN][NN]
   __shared__ double s_red[T / 32];
+  __shared__ unsigned char s_pj[NP], s_pk[NP];          // pair -> (j, k), j > k
+  __shared__ unsigned char s_pidx[NN][NN];              // (i, m) -> pair index
 
   if (a.ctl->stop) return;
   const int tid = threadIdx.x;
@@ -140,6 +142,13 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
   async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
   cp_async_commit();
   for (int idx = tid; idx < DIM * NN * NN; idx += T) sS2[idx] = (&op.S2[0][0][0])[idx];
+  for (int idx = tid; idx < NN * NN; idx += T) {
+    const int i = idx / NN, m = idx - i * NN;
+    const int jj = m > i ? m : i, kk = m > i ? i : m;
+    const int pr = jj * (jj - 1) / 2 + kk;
+    s_pidx[i][m] = (unsigned char)(i == m ? 0 : pr);
+    if (i > m) { s_pj[pr] = (unsigned char)i; s_pk[pr] = (unsigned char)m; }
+  }
   cp_async_wait<0>();
   __syncthreads();
 
@@ -171,11 +180,7 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
   // ---- pair threads: F_d(q_j, q_k) for k < j in the DIM parametric directions of node j ------------------------
   for (int it = tid; it < ne * NP; it += T) {
     const int s = it / NP, pr = it - s * NP;
-    // pr -> (j, k), j > k: pr = j(j-1)/2 + k
-    int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f);
-    while (j * (j - 1) / 2 > pr) --j;
-    while ((j + 1) * j / 2 <= pr) ++j;
-    const int k = pr - j * (j - 1) / 2;
+    const int j = s_pj[pr], k = s_pk[pr];            // pr = j(j-1)/2 + k, j > k
     IRNode<DIM> zj, zk;
     const int nj = s * NN + j, nk = s * NN + k;
     zj.z1 = sZ[nj]; zk.z1 = sZ[nk];
@@ -202,13 +207,14 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
     const int s = it / EL, r = it - s * EL;
     const int i = r / ND, c = r - i * ND;
     double acc = 0.0;
+    const double* Fc = sFp + c * PS + s * NP;
+    const double* Sc = sS2 + i * NN;
 #pragma unroll
     for (int m = 0; m < NN; ++m) {
-      if (m == i) continue;
-      const int jj = m > i ? m : i, kk = m > i ? i : m;
-      const int pi = s * NP + jj * (jj - 1) / 2 + kk;
+      // S2[i][i] = 0, so the diagonal term (which reads pair 0) contributes nothing
+      const int pi = s_pidx[i][m];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) acc = fma(-sS2[(d * NN + i) * NN + m], sFp[(d * ND + c) * PS + pi], acc);
+      for (int d = 0; d < DIM; ++d) acc = fma(-Sc[d * NN * NN + m], Fc[d * ND * PS + pi], acc);
     }
     const double* G = a.fluxe + (e0 + s) * (NF * FL);
 #pragma unroll
