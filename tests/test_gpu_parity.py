@@ -335,3 +335,44 @@ def test_usage_errors_are_reported():
         pd.evalResidual(bad, op, e2, {})
     assert L.pdes_eval_residual(None, 0.0) == _cabi.PDES_ERR_USAGE
     assert eqn.kernel_launch_count() >= 1
+
+
+@pytest.mark.parametrize("case,n", [("c3_3d_p2_roe_src", 3), ("c1_2d_p1_roe", 6), ("c2_2d_p2_es", 5)])
+def test_node_dependent_metrics(case, n):
+    """Curved elements have node-dependent dxidx / jac / normals (docs/src/interfaces.md:351-377).  The library
+    switches to compact per-element storage only when the arrays are exactly node-independent; here every node gets its
+    own (synthetic) metric so that the general path of every kernel is compared with the oracle."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=9)
+    nn, nE = op.numnodes, mesh.numEl
+    j = np.arange(nn)[:, None]
+    e = np.arange(nE)[None, :]
+    mesh.dxidx = np.asfortranarray(mesh.dxidx * (1.0 + 0.02 * np.sin(1.0 + 3.0 * j + 5.0 * e))[None, None])
+    mesh.jac = np.asfortranarray(mesh.jac * (1.0 + 0.03 * np.cos(2.0 + j + 7.0 * e)))
+    i = np.arange(op.face.numnodes)[:, None]
+    f = np.arange(mesh.numInterfaces)[None, :]
+    mesh.nrm_face = np.asfortranarray(mesh.nrm_face * (1.0 + 0.02 * np.sin(i + 2.0 * f))[None])
+    b = np.arange(mesh.numBoundaryFaces)[None, :]
+    mesh.nrm_bndry = np.asfortranarray(mesh.nrm_bndry * (1.0 + 0.02 * np.cos(i + 3.0 * b))[None])
+    orc2 = oracle.Problem(mesh, op, opts)
+    eqn2 = pd.EulerData(mesh, op, opts)
+    eqn2.q[...] = q0
+    pd.evalResidual(mesh, op, eqn2, opts)
+    assert rel_l2(eqn2.res, orc2.eval_residual(q0)) < RES_TOL
+    opts["use_itermax"] = False
+    h = 1e-4
+    eqn2.q[...] = q0
+    pd.rk4(pd.evalResidual, h, 6 * h, mesh, op, eqn2, opts)
+    _, q_ref, _ = orc2.rk4(q0, h, 6 * h)
+    assert rel_l2(eqn2.q, q_ref) < RK_TOL
+
+
+def test_timings_and_launch_counter():
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 6)
+    eqn.q[...] = q0
+    n0 = eqn.kernel_launch_count()
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert eqn.kernel_launch_count() - n0 == 2          # k_face_flux + k_element_rk
+    opts["use_itermax"] = False
+    pd.rk4(pd.evalResidual, 1e-3, 5e-3, mesh, op, eqn, opts)
+    tm = eqn.timings()
+    assert tm["n_residual_evals"] == 1 + 4 * 5 and tm["t_timemarch"] > 0 and tm["t_func"] > 0
