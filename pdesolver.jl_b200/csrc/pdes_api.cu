@@ -77,6 +77,11 @@ struct Peer {
   std::vector<double> nrm;
 };
 
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 // type-erased launcher for one (DIM, NN, NFN) operator family
 struct Ops {
   virtual ~Ops() {}
@@ -105,9 +110,11 @@ struct OpsImpl : Ops {
   using FCfg = FaceCfg<DIM, NN, NFN, FT>;
   Tab tab;
   bool attr_set = false;
+  bool use_tma = false;
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
+    use_tma = env_int("PDES_FACE_TMA", 0) != 0;
     const int ss = c.ss;
     for (int d = 0; d < DIM; ++d)
       for (int j = 0; j < NN; ++j)
@@ -143,9 +150,25 @@ struct OpsImpl : Ops {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return per_sm * sms;
   }
+  int tma_grid = -1;
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
     if (a.ng <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((a.ng + FT - 1) / FT)), block(FCfg::T);
+    const int64_t ntiles = (a.ng + FT - 1) / FT;
+    if constexpr (FaceTmaCfg<DIM, NN, NFN, FT>::FITS) if (use_tma) {
+      // persistent CTAs (one wave), elements staged by the bulk-copy engine one tile ahead
+      if (tma_grid < 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_face_flux_tma<DIM, NN, NFN, FT, MINB_F>,
+                                                      FaceTmaCfg<DIM, NN, NFN, FT>::T, 0);
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        tma_grid = per_sm * sms > 0 ? per_sm * sms : sms;
+      }
+      dim3 grid((unsigned)(ntiles < tma_grid ? ntiles : tma_grid)), block(FaceTmaCfg<DIM, NN, NFN, FT>::T);
+      k_face_flux_tma<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
+      return cudaGetLastError();
+    }
+    dim3 grid((unsigned)ntiles), block(FCfg::T);
     k_face_flux<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
     return cudaGetLastError();
   }
@@ -252,11 +275,6 @@ struct OpsImplS : Ops {
   }
 };
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 Ops* make_ops(const PdesConfig& c) {
   if (c.sparse_face) {
     // entropy-stable configuration: diag-E operator, split-form IR volume flux, Roe / IR / IRSLF interface flux
@@ -278,6 +296,8 @@ Ops* make_ops(const PdesConfig& c) {
       case 4: return new OpsImpl<3, 11, 6, 64, 2, 16, 8>();
       case 5: return new OpsImpl<3, 11, 6, 38, 3, 16, 8>();
       case 6: return new OpsImpl<3, 11, 6, 24, 5, 16, 8>();
+      case 7: return new OpsImpl<3, 11, 6, 32, 4, 16, 4>();
+      case 8: return new OpsImpl<3, 11, 6, 32, 4, 16, 5>();
       default: return new OpsImpl<3, 11, 6, 32, 4, 16, 8>();
     }
   }
@@ -782,7 +802,7 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_norm, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreate(&c->ev_t0));
   CUDA_TRY(c, cudaEventCreate(&c->ev_t1));
-  for (int i = 0; i < 3; ++i) CUDA_TRY(c, dev_upload<double>(c->stream, &c->qbuf[i], nullptr, (size_t)c->ndof));
+  for (int i = 0; i < 3; ++i) CUDA_TRY(c, dev_upload<double>(c->stream, &c->qbuf[i], nullptr, (size_t)c->ndof + 2));
   CUDA_TRY(c, dev_upload<double>(c->stream, &c->ksum, nullptr, (size_t)c->ndof));
   CUDA_TRY(c, dev_upload<double>(c->stream, &c->res, nullptr, (size_t)c->ndof));
   CUDA_TRY(c, cudaMalloc((void**)&c->ctl, sizeof(Ctl)));

@@ -352,6 +352,226 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// k_face_flux_tma: the same computation as k_face_flux with the element gathers done by the bulk-copy (TMA)
+// engine: persistent CTAs, two shared-memory stages; while tile t is interpolated and its fluxes evaluated, the
+// 2*FT element blocks of tile t+gridDim are landing in the other stage (cp.async.bulk + mbarrier complete_tx).
+// The variable threads then read their columns from shared memory instead of issuing 2*NN 40-byte-strided global
+// loads each (the LSU data pipe was 70 % busy in k_face_flux: profiles/r1_final_face_flux_c3.txt).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int DIM, int NN, int NFN, int FT>
+struct FaceTmaCfg {
+  static constexpr int ND = DIM + 2, EL = NN * ND, ELB = EL * 8;
+  static constexpr bool ALIGNED = (ELB % 16) == 0;             // element blocks 16-byte aligned for every element
+  static constexpr int CPY = ALIGNED ? ELB : ELB + 8;          // bytes per bulk copy (from the 16-byte floor)
+  static constexpr int SLOTD = CPY / 8 + 2;                    // doubles per staged element (16-byte multiple)
+  static constexpr int PER = ND > NFN ? ND : NFN;
+  static constexpr int T = ((FT * PER + 31) / 32) * 32;
+  static constexpr int FS = pad_stride(NFN * ND, ND);
+  static constexpr size_t static_smem = sizeof(double) * (4 * FT * SLOTD + 2 * FT * FS) + 32 * FT + 1024;
+  static constexpr bool FITS = static_smem <= 47 * 1024;       // static shared memory limit
+};
+
+template <int DIM, int NN, int NFN, int FT, int MINB>
+__global__ void __launch_bounds__((FaceTmaCfg<DIM, NN, NFN, FT>::T), MINB)
+k_face_flux_tma(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  using Cfg = FaceTmaCfg<DIM, NN, NFN, FT>;
+  constexpr int ND = Cfg::ND, T = Cfg::T, FS = Cfg::FS, NF = DIM + 1, SLOTD = Cfg::SLOTD;
+  constexpr int FL = NFN * ND;
+  __shared__ __align__(16) double sQ[2][2 * FT * SLOTD];
+  __shared__ double sL[FT * FS];
+  __shared__ double sR[FT * FS];
+  __shared__ FaceRec sRec[2][FT];
+  __shared__ int s_dst[2 * FT];
+  __shared__ int s_perm[NF][NN];
+  __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
+  __shared__ __align__(8) unsigned long long bar[2];
+
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (a.ng + FT - 1) / FT;
+  for (int idx = tid; idx < NF * NN; idx += T) s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
+  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
+    s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  auto tile_nf = [&](int64_t tile) {
+    const int64_t rem = a.ng - tile * FT;
+    return (int)(rem < FT ? rem : FT);
+  };
+  auto load_recs = [&](int64_t tile, int st) {
+    if (tid < tile_nf(tile)) sRec[st][tid] = a.faces[a.g0 + tile * FT + tid];
+  };
+  // warp 0: one bulk copy per staged element (the 16-byte aligned block that contains it)
+  auto issue = [&](int64_t tile, int st) {
+    const int nf = tile_nf(tile);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    unsigned total = 0;
+    for (int slot = tid; slot < 2 * FT; slot += 32) {
+      int el = -1;
+      if ((slot >> 1) < nf) {
+        const FaceRec r = sRec[st][slot >> 1];
+        el = (slot & 1) ? (r.kind == FK_INTERIOR ? r.elR : -1) : r.elL;
+      }
+      if (el >= 0) {
+        const char* src = reinterpret_cast<const char*>(a.q) + (int64_t)el * Cfg::ELB;
+        src -= (reinterpret_cast<uintptr_t>(src) & 15);
+        bulk_g2s(&sQ[st][slot * SLOTD], src, Cfg::CPY, &bar[st]);
+        total += Cfg::CPY;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (tid == 0) mbar_expect_tx(&bar[st], total);
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  load_recs(tile, 0);
+  __syncthreads();
+  if (tid < 32) issue(tile, 0);
+  int st = 0;
+  unsigned parity[2] = {0, 0};
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    const int nf = tile_nf(tile);
+    const int64_t g0 = a.g0 + tile * FT;
+    if (next < ntiles) load_recs(next, st ^ 1);
+    if (tid < nf) {
+      const FaceRec r = sRec[st][tid];
+      s_dst[2 * tid] = r.elL * NF + r.fL;
+      s_dst[2 * tid + 1] = r.kind == FK_INTERIOR ? r.elR * NF + r.fR : -1;
+    }
+    __syncthreads();       // records of the next tile visible; the previous tile's stores have read sL / sR
+    if (tid < 32 && next < ntiles) issue(next, st ^ 1);
+    mbar_wait(&bar[st], parity[st]);
+    parity[st] ^= 1;
+
+    // ---- A: interpolate both sides to the face nodes (variable threads), columns read from the staged elements
+    if (tid < nf * ND) {
+      const int fi = tid / ND, k = tid - fi * ND;
+      const FaceRec r = sRec[st][fi];
+      double ql[NN], qr[NN];
+      {
+        const int off = Cfg::ALIGNED ? 0 : (r.elL & 1);
+        const double* b = &sQ[st][(2 * fi) * SLOTD + off + k];
+#pragma unroll
+        for (int j = 0; j < NN; ++j) ql[j] = b[s_perm[r.fL][j] * ND];
+      }
+      if (r.kind == FK_INTERIOR) {
+        const int off = Cfg::ALIGNED ? 0 : (r.elR & 1);
+        const double* b = &sQ[st][(2 * fi + 1) * SLOTD + off + k];
+#pragma unroll
+        for (int j = 0; j < NN; ++j) qr[j] = b[s_perm[r.fR][j] * ND];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NN; ++j) qr[j] = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], ql[j], s);
+        sL[fi * FS + i * ND + k] = s;
+      }
+      if (r.kind == FK_INTERIOR) {
+#pragma unroll
+        for (int i = 0; i < NFN; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], qr[j], s);
+          sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = s;
+        }
+      } else if (r.kind == FK_SHARED) {
+        const double* b = a.q_recv + (int64_t)r.aux * (NFN * ND) + k;
+#pragma unroll
+        for (int i = 0; i < NFN; ++i) sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = b[i * ND];
+      }
+    }
+    __syncthreads();
+
+    // ---- B: numerical flux at every face node (node threads) ---------------------------------------------
+    {
+      const bool nact = tid < nf * NFN;
+      const int fi = nact ? tid / NFN : 0, i = tid - fi * NFN;
+      const FaceRec r = sRec[st][fi];
+      const int64_t g = g0 + fi;
+      double nrm[DIM], qL[ND], qR[ND], flux[ND];
+      if (nact) {
+        const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { qL[k] = sL[fi * FS + i * ND + k]; qR[k] = sR[fi * FS + i * ND + k]; }
+      }
+      __syncthreads();
+      if (nact) {
+        if (r.kind == FK_BOUNDARY) {
+          const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + i) * DIM;
+          double xb[DIM], nb_[DIM], qb[ND], fb[ND];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
+#pragma unroll
+          for (int k = 0; k < ND; ++k) qb[k] = qL[k];
+          bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) flux[k] = fb[k];
+        } else {
+          roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
+        }
+        const double w = op.wface[i];
+        const int ir = (r.kind == FK_INTERIOR) ? s_nbrperm[r.orient][i] : i;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          const double wf = w * flux[k];
+          sL[fi * FS + i * ND + k] = -wf;
+          sR[fi * FS + ir * ND + k] = wf;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- C: store one record per (element, local face), half a warp per record ----------------------------
+    {
+      const int half = tid >> 4, hl = tid & 15;
+      for (int rec = half; rec < 2 * nf; rec += T / 16) {
+        const int di = s_dst[rec];
+        if (di < 0) continue;
+        const double* src = ((rec & 1) ? sR : sL) + (rec >> 1) * FS;
+        double* dst = a.fluxe + (int64_t)di * FL;
+        for (int c1 = hl; c1 < FL; c1 += 16) dst[c1] = src[c1];
+      }
+    }
+    st ^= 1;
+  }
+}
+
 // Coalesced epilogue shared by the element kernels: the tile of staged values (EPI_RES: acc; EPI_RK: Minv*acc) is
 // combined with the tabulated source and either stored as res or pushed through the fused RK4 stage
 // (rk4.jl:244-319); two dofs per access, CH accesses in flight per thread.
