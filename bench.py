@@ -131,6 +131,7 @@ def build_problem(wl, rank, nranks):
 def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
     """The reference's algorithm on the host cores: the oracle port (reference-faithful precompute pass
     structure, OpenMP over elements/faces) on a bounded sample of the same workload."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle
     import pdesolver_jl_b200 as pd
     from pdesolver_jl_b200 import ic
@@ -141,7 +142,9 @@ def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
     P = oracle.Problem(mesh, op, opts)
     q0 = perturbed(ic.ICDict[wl["ic"]](mesh.coords, pd.ParamType(opts)))
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm uses every host core (libgomp reads the
+    # variable when liborc_omp.so is first loaded, i.e. below)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     h = wl["h"]
     for _ in range(warmup):
         P.eval_residual(q0, omp=True)
