@@ -424,3 +424,37 @@ def test_lserk54_quartic():
                       C.byref(ns), C.byref(st))
     exact = t ** 4 + t ** 3 + t ** 2 + t + 1
     assert abs(t - 1.0) < 1e-12 and abs(q[0] - exact) < 1e-12
+
+
+# --- committed fixtures: the oracle must keep reproducing them (tests/golden/make_fixtures.py) ------------
+@pytest.mark.parametrize("case", ["c1_2d_p1_roe", "c3_3d_p2_roe_src", "c2_2d_p2_es", "2d_p2_roe", "3d_p1_roe_src"])
+def test_oracle_reproduces_committed_fixtures(case):
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_fixtures
+    op, mesh, opts, orc, q0, h = make_fixtures.build(case)
+    fx = np.load(os.path.join(gold, case + ".npz"))
+    assert np.array_equal(q0, fx["q0"])
+    res = orc.eval_residual(q0)
+    assert np.linalg.norm(res - fx["res"]) <= 1e-14 * np.linalg.norm(fx["res"])
+    t, q5, norms = orc.rk4(q0, h, 5 * h)
+    assert t == float(fx["t_rk4"]) and np.linalg.norm(q5 - fx["q_rk4"]) <= 1e-14 * np.linalg.norm(q5)
+
+
+def test_reference_known_answers_file():
+    import json
+    import os
+    ka = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")))
+    a = ka["calcPressure_2d"]
+    assert abs(pressure(a["q"]) - a["p"]) < a["tol"]
+    a = ka["calcEulerFlux_2d"]
+    assert np.allclose(euler_flux(a["q"], a["dir"]), a["F"], atol=a["tol"], rtol=0)
+    a = ka["calcEulerFlux_3d"]
+    for d, F in a["F"].items():
+        assert np.allclose(euler_flux(a["q"], [float(c) for c in d]), F, atol=a["tol"], rtol=0)
+    a = ka["calcIsentropicVortex"]
+    sol = np.zeros(4)
+    L.orc_isentropic_vortex(2, G, 287.058, _ptr(np.array(a["coords"])), _ptr(sol))
+    assert np.allclose(sol, a["q"], atol=a["tol"])
