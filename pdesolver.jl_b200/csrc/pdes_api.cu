@@ -771,7 +771,8 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
     set_err(nullptr, "face_integral_type %d is not supported (type 1 only)", cfg->face_integral_type);
     return PDES_ERR_UNSUPPORTED;
   }
-  if (cfg->nE <= 0 || cfg->nE > 0x7fffff00ll) return usage(nullptr, "pdes_create: numEl out of range");
+  if (cfg->nE <= 0 || cfg->nE * (cfg->dim + 1) > 0x7fffff00ll)
+    return usage(nullptr, "pdes_create: numEl out of range (32-bit element-face indices)");
   std::unique_ptr<PdesCtx> ctx(new PdesCtx());
   ctx->cfg = *cfg;
   ctx->nd = cfg->dim + 2;

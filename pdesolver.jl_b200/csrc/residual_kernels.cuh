@@ -253,23 +253,21 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
 #pragma unroll
       for (int j = 0; j < NN; ++j) qr[j] = 0.0;
     }
+    // both sides share every interpolation coefficient (one uniform load feeds two DFMAs)
 #pragma unroll
     for (int i = 0; i < NFN; ++i) {
-      double s = 0.0;
+      double s = 0.0, t = 0.0;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], ql[j], s);
-      sL[fi * FS + i * ND + k] = s;
-    }
-    if (r.kind == FK_INTERIOR) {
-#pragma unroll
-      for (int i = 0; i < NFN; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NN; ++j) s = fma(op.interp[j][i], qr[j], s);
-        // elementR's face node i coincides with elementL's face node nbrperm[i,orient] (involution)
-        sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = s;
+      for (int j = 0; j < NN; ++j) {
+        const double c = op.interp[j][i];
+        s = fma(c, ql[j], s);
+        t = fma(c, qr[j], t);
       }
-    } else if (r.kind == FK_SHARED) {
+      sL[fi * FS + i * ND + k] = s;
+      // elementR's face node i coincides with elementL's face node nbrperm[i,orient] (involution)
+      if (r.kind == FK_INTERIOR) sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = t;
+    }
+    if (r.kind == FK_SHARED) {
       // permuteinterface! (Utils/parallel.jl:198-201): received node i of the peer is own node nbrperm[i,orient]
       const double* b = a.q_recv + (int64_t)r.aux * (NFN * ND) + k;
 #pragma unroll
