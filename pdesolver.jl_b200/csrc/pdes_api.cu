@@ -103,7 +103,7 @@ struct Ops {
   }
 };
 
-template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F>
+template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F, int WMINB = 4>
 struct OpsImpl : Ops {
   using Tab = OpTab<DIM, NN, NFN>;
   using Cfg = TileCfg<DIM, NN, NFN, E>;
@@ -115,6 +115,7 @@ struct OpsImpl : Ops {
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
     use_tma = env_int("PDES_FACE_TMA", 0) != 0;
+    use_warp_kernel = env_int("PDES_ELEM_W", 0) != 0;
     const int ss = c.ss;
     for (int d = 0; d < DIM; ++d)
       for (int j = 0; j < NN; ++j)
@@ -131,8 +132,10 @@ struct OpsImpl : Ops {
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
     (void)w;
   }
-  int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
-  int tile_elems() const override { return E; }
+  int64_t grid_for(int64_t nelems) const override {
+    return use_warp_kernel ? (nelems + GW - 1) / GW : (nelems + E - 1) / E;     // norm partials per tile / per warp
+  }
+  int tile_elems() const override { return use_warp_kernel ? GW * WPC : E; }
   int resident_element_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
     cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -149,6 +152,25 @@ struct OpsImpl : Ops {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return per_sm * sms;
+  }
+  // warp-autonomous element kernel (node-independent metrics only): G elements per warp, WPC warps per CTA
+  static constexpr int GW = (32 / (DIM + 2)) * 2, WPC = 4;
+  using WCfg = WarpCfg<DIM, NN, NFN, GW, WPC>;
+  bool use_warp_kernel = false, w_attr = false;
+  cudaError_t launch_elements_w(const ElemArgs& a, int mode, cudaStream_t s) {
+    if (!w_attr) {
+      cudaFuncSetAttribute(k_element_w<DIM, NN, NFN, GW, WPC, EPI_RES, WMINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)WCfg::smem_bytes);
+      cudaFuncSetAttribute(k_element_w<DIM, NN, NFN, GW, WPC, EPI_RK, WMINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)WCfg::smem_bytes);
+      w_attr = true;
+    }
+    if (a.nE <= a.e_begin) return cudaSuccess;
+    const int64_t ngroups = (a.nE - a.e_begin + GW - 1) / GW;
+    dim3 grid((unsigned)((ngroups + WPC - 1) / WPC)), block(WCfg::T);
+    if (mode == EPI_RES) k_element_w<DIM, NN, NFN, GW, WPC, EPI_RES, WMINB><<<grid, block, WCfg::smem_bytes, s>>>(tab, a);
+    else k_element_w<DIM, NN, NFN, GW, WPC, EPI_RK, WMINB><<<grid, block, WCfg::smem_bytes, s>>>(tab, a);
+    return cudaGetLastError();
   }
   int tma_grid = -1;
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
@@ -185,6 +207,7 @@ struct OpsImpl : Ops {
   }
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    if (use_warp_kernel && a.dx_node_stride == 0) return launch_elements_w(a, mode, s);
     if (a.nE <= a.e_begin) return cudaSuccess;
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES)
@@ -296,6 +319,9 @@ Ops* make_ops(const PdesConfig& c) {
       case 4: return new OpsImpl<3, 11, 6, 64, 2, 16, 8>();
       case 5: return new OpsImpl<3, 11, 6, 38, 3, 16, 8>();
       case 6: return new OpsImpl<3, 11, 6, 24, 5, 16, 8>();
+      case 9: return new OpsImpl<3, 11, 6, 32, 4, 16, 8, 5>();
+      case 10: return new OpsImpl<3, 11, 6, 32, 4, 16, 8, 6>();
+      case 11: return new OpsImpl<3, 11, 6, 32, 4, 16, 8, 3>();
       case 7: return new OpsImpl<3, 11, 6, 32, 4, 16, 4>();
       case 8: return new OpsImpl<3, 11, 6, 32, 4, 16, 5>();
       default: return new OpsImpl<3, 11, 6, 32, 4, 16, 8>();
