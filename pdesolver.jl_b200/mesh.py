@@ -129,6 +129,132 @@ def _per_dim(n, dim):
     return [int(n)] * dim if np.isscalar(n) else [int(v) for v in n]
 
 
+def _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of):
+    """Connectivity, metrics and partition lists from simplices given by global vertex ids ``gvid[ne, dim+1]``
+    and vertex coordinates ``vcoord[ne, dim+1, dim]`` (local elements first).  ``side_of(face_centroids)`` maps
+    boundary faces to (bc index array, numBC)."""
+    ne_ext = len(gel)
+    # ---- face pairing -----------------------------------------------------
+    fvtx = TRI_FACE_VTX if dim == 2 else TET_FACE_VTX
+    nfaces = dim + 1
+    fv = gvid[:, fvtx]                                          # [ne_ext, nfaces, dim]
+    key = np.sort(fv, axis=2).reshape(-1, dim)
+    el_of = np.repeat(np.arange(ne_ext), nfaces)
+    lf_of = np.tile(np.arange(nfaces), ne_ext)
+    srt = np.lexsort(tuple(key[:, d] for d in range(dim - 1, -1, -1)))
+    ks = key[srt]
+    same = np.all(ks[1:] == ks[:-1], axis=1)
+    first = np.nonzero(same)[0]                                 # pair (first, first+1)
+    paired = np.zeros(len(ks), dtype=bool)
+    paired[first] = True
+    paired[first + 1] = True
+    a, b = srt[first], srt[first + 1]
+    ea, eb = el_of[a], el_of[b]
+    swap = ea > eb
+    a, b = np.where(swap, b, a), np.where(swap, a, b)
+    eL, eR, fL, fR = el_of[a], el_of[b], lf_of[a], lf_of[b]
+    keyL = ks[first]
+
+    if dim == 2:
+        orient = np.zeros(len(eL), dtype=np.int64)
+    else:
+        vl = fv[eL, fL]                                         # [np, 3]
+        vr = fv[eR, fR]
+        orient = np.full(len(eL), -1, dtype=np.int64)
+        orient[(vr[:, 0] == vl[:, 0]) & (vr[:, 1] == vl[:, 2])] = 0
+        orient[(vr[:, 1] == vl[:, 1]) & (vr[:, 0] == vl[:, 2])] = 1
+        orient[(vr[:, 2] == vl[:, 2]) & (vr[:, 0] == vl[:, 1])] = 2
+        assert orient.min() >= 0, "inconsistent face orientation"
+
+    locL, locR = eL < nE, eR < nE
+    both = locL & locR
+    shared = locL ^ locR
+
+    # ---- element metrics ---------------------------------------------------
+    nn = op.numnodes
+    nfn = op.face.numnodes
+    vloc = vcoord[:nE]                                          # [nE, dim+1, dim]
+    A = 0.5 * (vloc[:, 1:, :] - vloc[:, :1, :]).transpose(0, 2, 1)   # dx/dxi [nE, dim, dim]
+    detA = np.linalg.det(A)
+    assert detA.min() > 0
+    Ainv = np.linalg.inv(A)                                     # dxi/dx
+    jac_e = 1.0 / detA
+    dxidx_e = Ainv * detA[:, None, None]                        # (dxi/dx)/jac
+    dxidx = np.empty((dim, dim, nn, nE), order="F")
+    dxidx[:] = dxidx_e.transpose(1, 2, 0)[:, :, None, :]
+    jac = np.empty((nn, nE), order="F")
+    jac[:] = jac_e[None, :]
+    coords = _F(np.einsum("jv,evd->dje", op.bary, vloc))
+
+    ref_n = np.asarray(op.face.normal)                          # [dim, nfaces]
+    fb = op.face.facenodes_bary                                 # [nfn, dim]
+
+    def face_normals(els, lfaces, dx_src):
+        # nrm_p = sum_k dxidx[k,p] * n_ref[k]
+        nr = np.einsum("ekp,ke->pe", dx_src[els], ref_n[:, lfaces])
+        out = np.empty((dim, nfn, len(els)), order="F")
+        out[:] = nr[:, None, :]
+        return out
+
+    # interior interfaces
+    iface = np.zeros(int(both.sum()), dtype=INTERFACE_DTYPE)
+    iface["elementL"], iface["elementR"] = eL[both], eR[both]
+    iface["faceL"], iface["faceR"], iface["orient"] = fL[both], fR[both], orient[both]
+    io = np.lexsort((iface["faceL"], iface["elementL"]))
+    iface = iface[io]
+    nrm_face = face_normals(iface["elementL"].astype(np.int64),
+                            iface["faceL"].astype(np.int64), dxidx_e)
+
+    # boundary faces: unpaired faces of local elements
+    un = srt[~paired]
+    un = un[el_of[un] < nE]
+    be, bf = el_of[un], lf_of[un]
+    bvc = vcoord[be][np.arange(len(be))[:, None], fvtx[bf]]     # [nB, dim, dim] face vertex coords
+    cen = bvc.mean(axis=1)
+    bc, numBC = side_of(cen)
+    bo = np.lexsort((bf, be, bc))
+    be, bf, bc, bvc = be[bo], bf[bo], bc[bo], bvc[bo]
+    bndry = np.zeros(len(be), dtype=BOUNDARY_DTYPE)
+    bndry["element"], bndry["face"] = be, bf
+    bndry_offsets = np.searchsorted(bc, np.arange(numBC + 1)).astype(np.int64)
+    nrm_bndry = face_normals(be, bf, dxidx_e)
+    coords_bndry = _F(np.einsum("iv,bvd->dib", fb, bvc))
+
+    mesh = Mesh(dim=dim, numEl=nE, numNodesPerElement=nn, numNodesPerFace=nfn,
+                numDofPerNode=dim + 2, coords=coords, dxidx=dxidx, jac=jac,
+                interfaces=iface, bndryfaces=bndry, bndry_offsets=bndry_offsets,
+                nrm_face=nrm_face, nrm_bndry=nrm_bndry, coords_bndry=coords_bndry,
+                sbpface=op.face, myrank=rank, commsize=nranks,
+                global_elnum=gel[:nE].copy(), elem_vtx_coords=vloc)
+
+    # ---- shared faces ------------------------------------------------------
+    if shared.any():
+        # local element is always elementL of a shared interface
+        sl = np.where(locL[shared], eL[shared], eR[shared])
+        sr = np.where(locL[shared], eR[shared], eL[shared])
+        sfl = np.where(locL[shared], fL[shared], fR[shared])
+        sfr = np.where(locL[shared], fR[shared], fL[shared])
+        so = orient[shared]
+        skey = keyL[shared]
+        peer = el_owner[sr]
+        for p in np.unique(peer):
+            m = peer == p
+            # identical ordering on both ranks: sort by global face key
+            kk = skey[m]
+            o2 = np.lexsort(tuple(kk[:, d] for d in range(dim - 1, -1, -1)))
+            bl = np.zeros(int(m.sum()), dtype=BOUNDARY_DTYPE)
+            bl["element"], bl["face"] = sl[m][o2], sfl[m][o2]
+            si = np.zeros(int(m.sum()), dtype=INTERFACE_DTYPE)
+            si["elementL"], si["elementR"] = sl[m][o2], sr[m][o2]
+            si["faceL"], si["faceR"], si["orient"] = sfl[m][o2], sfr[m][o2], so[m][o2]
+            mesh.peer_parts.append(int(p))
+            mesh.bndries_local.append(bl)
+            mesh.shared_interfaces.append(si)
+            mesh.nrm_sharedface.append(face_normals(sl[m][o2], sfl[m][o2], dxidx_e))
+            mesh.shared_element_offsets.append(int(np.nonzero(el_owner == p)[0].min()))
+    return mesh
+
+
 def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
                     domain=None, bc_sides=None, shuffle_seed=None) -> Mesh:
     """Structured simplex mesh of ``n^dim`` cells; ``n`` may also be
@@ -214,133 +340,16 @@ def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
     nE = int(is_local.sum())
     ne_ext = len(gel)
 
-    # ---- face pairing -----------------------------------------------------
-    fvtx = TRI_FACE_VTX if dim == 2 else TET_FACE_VTX
-    nfaces = dim + 1
-    fv = gvid[:, fvtx]                                          # [ne_ext, nfaces, dim]
-    key = np.sort(fv, axis=2).reshape(-1, dim)
-    el_of = np.repeat(np.arange(ne_ext), nfaces)
-    lf_of = np.tile(np.arange(nfaces), ne_ext)
-    srt = np.lexsort(tuple(key[:, d] for d in range(dim - 1, -1, -1)))
-    ks = key[srt]
-    same = np.all(ks[1:] == ks[:-1], axis=1)
-    first = np.nonzero(same)[0]                                 # pair (first, first+1)
-    paired = np.zeros(len(ks), dtype=bool)
-    paired[first] = True
-    paired[first + 1] = True
-    a, b = srt[first], srt[first + 1]
-    ea, eb = el_of[a], el_of[b]
-    swap = ea > eb
-    a, b = np.where(swap, b, a), np.where(swap, a, b)
-    eL, eR, fL, fR = el_of[a], el_of[b], lf_of[a], lf_of[b]
-    keyL = ks[first]
+    def side_of(cen):
+        side = np.full(len(cen), -1, dtype=np.int64)
+        for d in range(dim):
+            side[np.abs(cen[:, d] - domain[0]) < 1e-9 * h + 1e-12] = 2 * d
+            side[np.abs(cen[:, d] - (domain[0] + h * nv[d])) < 1e-9 * h + 1e-12] = 2 * d + 1
+        assert side.min() >= 0, "unpaired face not on the domain boundary"
+        sides = [0] * (2 * dim) if bc_sides is None else bc_sides
+        return np.asarray(sides)[side], int(max(sides)) + 1
 
-    if dim == 2:
-        orient = np.zeros(len(eL), dtype=np.int64)
-    else:
-        vl = fv[eL, fL]                                         # [np, 3]
-        vr = fv[eR, fR]
-        orient = np.full(len(eL), -1, dtype=np.int64)
-        orient[(vr[:, 0] == vl[:, 0]) & (vr[:, 1] == vl[:, 2])] = 0
-        orient[(vr[:, 1] == vl[:, 1]) & (vr[:, 0] == vl[:, 2])] = 1
-        orient[(vr[:, 2] == vl[:, 2]) & (vr[:, 0] == vl[:, 1])] = 2
-        assert orient.min() >= 0, "inconsistent face orientation"
-
-    locL, locR = eL < nE, eR < nE
-    both = locL & locR
-    shared = locL ^ locR
-
-    # ---- element metrics ---------------------------------------------------
-    nn = op.numnodes
-    nfn = op.face.numnodes
-    vloc = vcoord[:nE]                                          # [nE, dim+1, dim]
-    A = 0.5 * (vloc[:, 1:, :] - vloc[:, :1, :]).transpose(0, 2, 1)   # dx/dxi [nE, dim, dim]
-    detA = np.linalg.det(A)
-    assert detA.min() > 0
-    Ainv = np.linalg.inv(A)                                     # dxi/dx
-    jac_e = 1.0 / detA
-    dxidx_e = Ainv * detA[:, None, None]                        # (dxi/dx)/jac
-    dxidx = np.empty((dim, dim, nn, nE), order="F")
-    dxidx[:] = dxidx_e.transpose(1, 2, 0)[:, :, None, :]
-    jac = np.empty((nn, nE), order="F")
-    jac[:] = jac_e[None, :]
-    coords = _F(np.einsum("jv,evd->dje", op.bary, vloc))
-
-    ref_n = np.asarray(op.face.normal)                          # [dim, nfaces]
-    fb = op.face.facenodes_bary                                 # [nfn, dim]
-
-    def face_normals(els, lfaces, dx_src):
-        # nrm_p = sum_k dxidx[k,p] * n_ref[k]
-        nr = np.einsum("ekp,ke->pe", dx_src[els], ref_n[:, lfaces])
-        out = np.empty((dim, nfn, len(els)), order="F")
-        out[:] = nr[:, None, :]
-        return out
-
-    # interior interfaces
-    iface = np.zeros(int(both.sum()), dtype=INTERFACE_DTYPE)
-    iface["elementL"], iface["elementR"] = eL[both], eR[both]
-    iface["faceL"], iface["faceR"], iface["orient"] = fL[both], fR[both], orient[both]
-    io = np.lexsort((iface["faceL"], iface["elementL"]))
-    iface = iface[io]
-    nrm_face = face_normals(iface["elementL"].astype(np.int64),
-                            iface["faceL"].astype(np.int64), dxidx_e)
-
-    # boundary faces: unpaired faces of local elements
-    un = srt[~paired]
-    un = un[el_of[un] < nE]
-    be, bf = el_of[un], lf_of[un]
-    bvc = vcoord[be][np.arange(len(be))[:, None], fvtx[bf]]     # [nB, dim, dim] face vertex coords
-    cen = bvc.mean(axis=1)
-    side = np.full(len(be), -1, dtype=np.int64)
-    for d in range(dim):
-        side[np.abs(cen[:, d] - domain[0]) < 1e-9 * h + 1e-12] = 2 * d
-        side[np.abs(cen[:, d] - (domain[0] + h * nv[d])) < 1e-9 * h + 1e-12] = 2 * d + 1
-    assert side.min() >= 0, "unpaired face not on the domain boundary"
-    if bc_sides is None:
-        bc_sides = [0] * (2 * dim)
-    bc = np.asarray(bc_sides)[side]
-    numBC = int(max(bc_sides)) + 1
-    bo = np.lexsort((bf, be, bc))
-    be, bf, bc, bvc = be[bo], bf[bo], bc[bo], bvc[bo]
-    bndry = np.zeros(len(be), dtype=BOUNDARY_DTYPE)
-    bndry["element"], bndry["face"] = be, bf
-    bndry_offsets = np.searchsorted(bc, np.arange(numBC + 1)).astype(np.int64)
-    nrm_bndry = face_normals(be, bf, dxidx_e)
-    coords_bndry = _F(np.einsum("iv,bvd->dib", fb, bvc))
-
-    mesh = Mesh(dim=dim, numEl=nE, numNodesPerElement=nn, numNodesPerFace=nfn,
-                numDofPerNode=dim + 2, coords=coords, dxidx=dxidx, jac=jac,
-                interfaces=iface, bndryfaces=bndry, bndry_offsets=bndry_offsets,
-                nrm_face=nrm_face, nrm_bndry=nrm_bndry, coords_bndry=coords_bndry,
-                sbpface=op.face, myrank=rank, commsize=nranks,
-                global_elnum=gel[:nE].copy(), elem_vtx_coords=vloc)
-
-    # ---- shared faces ------------------------------------------------------
-    if shared.any():
-        # local element is always elementL of a shared interface
-        sl = np.where(locL[shared], eL[shared], eR[shared])
-        sr = np.where(locL[shared], eR[shared], eL[shared])
-        sfl = np.where(locL[shared], fL[shared], fR[shared])
-        sfr = np.where(locL[shared], fR[shared], fL[shared])
-        so = orient[shared]
-        skey = keyL[shared]
-        peer = el_owner[sr]
-        for p in np.unique(peer):
-            m = peer == p
-            # identical ordering on both ranks: sort by global face key
-            kk = skey[m]
-            o2 = np.lexsort(tuple(kk[:, d] for d in range(dim - 1, -1, -1)))
-            bl = np.zeros(int(m.sum()), dtype=BOUNDARY_DTYPE)
-            bl["element"], bl["face"] = sl[m][o2], sfl[m][o2]
-            si = np.zeros(int(m.sum()), dtype=INTERFACE_DTYPE)
-            si["elementL"], si["elementR"] = sl[m][o2], sr[m][o2]
-            si["faceL"], si["faceR"], si["orient"] = sfl[m][o2], sfr[m][o2], so[m][o2]
-            mesh.peer_parts.append(int(p))
-            mesh.bndries_local.append(bl)
-            mesh.shared_interfaces.append(si)
-            mesh.nrm_sharedface.append(face_normals(sl[m][o2], sfl[m][o2], dxidx_e))
-            mesh.shared_element_offsets.append(int(np.nonzero(el_owner == p)[0].min()))
-    return mesh
+    return _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of)
 
 
 def two_element_mesh(op: SBPOperator) -> Mesh:
@@ -379,3 +388,23 @@ def two_element_mesh(op: SBPOperator) -> Mesh:
                 nrm_face=nrm(np.array([0]), np.array([0])), nrm_bndry=nrm(be, bf),
                 coords_bndry=_F(np.einsum("iv,bvd->dib", fb, bvc)), sbpface=op.face,
                 elem_vtx_coords=v)
+
+
+def simplex_mesh(op: SBPOperator, vertex_coords, simplices, bc_of_face=None) -> Mesh:
+    """Mesh object for an arbitrary conforming simplex mesh: ``vertex_coords[nV, dim]``, ``simplices[nE, dim+1]``
+    (vertex ids).  Elements are re-oriented to positive volume.  ``bc_of_face(centroids) -> (bc index, numBC)``
+    classifies boundary faces (default: one BC).  Used to run the reference's own mesh fixtures
+    (tests/golden/import_smb.py converts PUMI .smb files)."""
+    dim = op.dim
+    simplices = np.array(simplices, dtype=np.int64)
+    vc = np.asarray(vertex_coords, dtype=np.float64)[:, :dim]
+    vcoord = vc[simplices]                                       # [nE, dim+1, dim]
+    A = (vcoord[:, 1:, :] - vcoord[:, :1, :]).transpose(0, 2, 1)
+    neg = np.linalg.det(A) < 0
+    simplices[neg] = simplices[neg][:, [1, 0] + list(range(2, dim + 1))]
+    vcoord = vc[simplices]
+    nE = len(simplices)
+    if bc_of_face is None:
+        def bc_of_face(cen):
+            return np.zeros(len(cen), dtype=np.int64), 1
+    return _assemble(op, dim, simplices, vcoord, np.zeros(nE, dtype=np.int64), np.arange(nE), nE, 0, 1, bc_of_face)

@@ -454,3 +454,20 @@ def test_full_size_properties(workload):
         w = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
         Jv, Jw = pd.evaldRdqProduct(mesh, op, eqn, opts, v), pd.evaldRdqProduct(mesh, op, eqn, opts, w)
         assert rel_l2(pd.evaldRdqProduct(mesh, op, eqn, opts, v - 2.0 * w), Jv - 2.0 * Jw) < 1e-12
+
+
+def test_reference_convergence_golden_gpu():
+    """test/euler/convergence/p1/conservative_dg/runtests.jl:27-37 through the CUDA path: steady isentropic vortex on
+    the reference's own meshes (tests/golden/squarevortex_*.npz), err[1] = 0.01200 x/ 1.25, slope 2.00 +- 0.1."""
+    from test_oracle_golden import _steady_vortex_error
+
+    def runner(mesh, op, opts, P, q0, h):
+        eqn = pd.EulerData(mesh, op, opts)
+        eqn.q[...] = q0
+        pd.rk4(pd.evalResidual, h, 40000 * h, mesh, op, eqn, opts, res_tol=1e-12)     # stops on the residual norm
+        assert eqn.convergence[-1] < 1e-12 and len(eqn.convergence) < 40000
+        return eqn.q.copy(order="F")
+    e1 = _steady_vortex_error(runner, "squarevortex_small", 0.02)
+    e2 = _steady_vortex_error(runner, "squarevortex_large", 0.01)
+    assert 0.01200 / 1.25 < e1 < 0.01200 * 1.25 and abs(e1 - 0.01200) < 2e-5
+    assert 1.9 < np.log(e1 / e2) / np.log(2.0) < 2.1

@@ -458,3 +458,40 @@ def test_reference_known_answers_file():
     sol = np.zeros(4)
     L.orc_isentropic_vortex(2, G, 287.058, _ptr(np.array(a["coords"])), _ptr(sol))
     assert np.allclose(sol, a["q"], atol=a["tol"])
+
+
+# --- test/euler/convergence/p1/conservative_dg/runtests.jl:1-42: the reference's integration-level golden --------
+def _steady_vortex_error(runner, name, h):
+    """Pseudo-time RK4 to the steady state of the isentropic vortex on the reference's own mesh fixture, then the
+    M-weighted L2 error against the exact solution (startup_func.jl:188-201: calcNorm(|q - q_IC|))."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    op = sbp.build_operator(2, 1)
+    mesh = pmesh.simplex_mesh(op, fx["vertex_coords"], fx["triangles"])
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC", "use_itermax": False}
+    P = oracle.Problem(mesh, op, opts)
+    q0 = P.exact_state("ICIsentropicVortex")
+    q = runner(mesh, op, opts, P, q0, h)
+    M = 1.0 / P.mass_matrix_inverse()
+    return float(np.sqrt(np.sum(M * (q - q0) ** 2)))
+
+
+def _oracle_runner(mesh, op, opts, P, q0, h):
+    q = q0
+    for _ in range(20):
+        _, q, norms = P.rk4(q, h, 2000 * h)
+        if norms[-1] < 1e-12:
+            return q
+    raise AssertionError("pseudo-time iteration did not converge")
+
+
+def test_reference_convergence_golden():
+    """The reference asserts err[1] = 0.01200 (x/ 1.25) on squarevortex_small and a convergence slope of 2.00 +- 0.1
+    between squarevortex_small and squarevortex_large (p=1 SBP-Omega DG, Roe flux, isentropicVortexBC, steady state
+    reached there by Newton).  The oracle, marched to the same steady state, must land inside those bands."""
+    e1 = _steady_vortex_error(_oracle_runner, "squarevortex_small", 0.02)
+    e2 = _steady_vortex_error(_oracle_runner, "squarevortex_large", 0.01)
+    assert 0.01200 / 1.25 < e1 < 0.01200 * 1.25
+    assert abs(e1 - 0.01200) < 2e-5           # measured 0.0120031: the golden to its printed precision
+    slope = np.log(e1 / e2) / np.log(2.0)
+    assert 1.9 < slope < 2.1
