@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdes_euler_b200.so")
+LIB_PATH = os.environ.get("PDES_LIB") or os.path.join(_HERE, "libpdes_euler_b200.so")   # PDES_LIB: kernel A/B builds
 
 PDES_OK = 0
 PDES_ERR_NEG_DENSITY = 1

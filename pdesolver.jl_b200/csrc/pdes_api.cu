@@ -96,6 +96,14 @@ struct Ops {
   virtual int resident_face_ctas() = 0;
   virtual int tile_elems() const = 0;
   virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
+  // fused face + element kernel (k_fused); families without one return 0 faces per group
+  virtual int fused_group_faces() const { return 0; }
+  virtual int fused_tile_elems() const { return 0; }
+  virtual int resident_fused_ctas() { return 0; }
+  virtual cudaError_t launch_fused(const FusedArgs& a, int mode, cudaStream_t s) {
+    (void)a; (void)mode; (void)s;
+    return cudaErrorNotSupported;
+  }
   // J*v kernels (dual numbers); cudaErrorNotSupported when the operator family has none
   virtual cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) {
     (void)fa; (void)a; (void)v; (void)out; (void)s;
@@ -103,11 +111,33 @@ struct Ops {
   }
 };
 
-template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F, int WMINB = 4>
+template <int DIM, int NN, int NFN, int E, int MINB_E, int FT, int MINB_F, int WMINB = 4, int FFT = 16, int NSUB = 4>
 struct OpsImpl : Ops {
   using Tab = OpTab<DIM, NN, NFN>;
   using Cfg = TileCfg<DIM, NN, NFN, E>;
   using FCfg = FaceCfg<DIM, NN, NFN, FT>;
+  using UCfg = FusedCfg<DIM, NN, NFN, E, FFT, NSUB>;
+  int fused_group_faces() const override { return FFT * NSUB; }
+  int fused_tile_elems() const override { return E; }
+  int resident_fused_ctas() override {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RK, MINB_E>, UCfg::T,
+                                                  UCfg::smem_bytes);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
+  }
+  cudaError_t launch_fused(const FusedArgs& a, int mode, cudaStream_t s) override {
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    const int64_t g = std::max<int64_t>(a.n_groups, (int64_t)a.n_tiles + a.lag);
+    if (g <= 0) return cudaSuccess;
+    dim3 grid((unsigned)g), block(UCfg::T);
+    if (mode == EPI_RES)
+      k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RES, MINB_E><<<grid, block, UCfg::smem_bytes, s>>>(tab, a);
+    else
+      k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RK, MINB_E><<<grid, block, UCfg::smem_bytes, s>>>(tab, a);
+    return cudaGetLastError();
+  }
   Tab tab;
   bool attr_set = false;
   bool use_tma = false;
@@ -201,6 +231,12 @@ struct OpsImpl : Ops {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RES, MINB_E>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RK, MINB_E>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UCfg::smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
     return cudaSuccess;
@@ -308,9 +344,9 @@ Ops* make_ops(const PdesConfig& c) {
   }
   if (c.volume_integral_type != 1 || c.flux_id != PDES_FLUX_ROE) return nullptr;
   const int variant = env_int("PDES_VARIANT", 0);   // tuning knob (tools/bench_variants.sh)
-  if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64, 2, 64, 2>();
-  if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32, 2, 32, 2>();
-  if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32, 2, 32, 2>();
+  if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImpl<2, 3, 2, 64, 2, 64, 2, 4, 32, 3>();
+  if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImpl<2, 6, 3, 32, 2, 32, 2, 4, 16, 3>();
+  if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImpl<3, 4, 3, 32, 2, 32, 2, 4, 16, 4>();
   if (c.dim == 3 && c.nn == 11 && c.nfn == 6) {
     switch (variant) {
       case 1: return new OpsImpl<3, 11, 6, 32, 3, 16, 8>();
@@ -375,6 +411,17 @@ struct PdesCtx {
   std::vector<double> h_nrm;        // nrm_face | nrm_bndry
   bool dx_compact = false, nrm_compact = false;   // node-independent metrics detected at upload
   int prefetch_ahead = 0, prefetch_ahead_faces = 0;
+  // k_fused schedule: plan A = interior + boundary faces with the element tiles that touch no shared face (all tiles
+  // on one GPU); plan B = the shared faces and the remaining tiles, launched once the receive has completed
+  struct FusedPlan {
+    int32_t *tile_list = nullptr, *need = nullptr;
+    int32_t n_tiles = 0, n_groups = 0, lag = 0;
+    int64_t g0 = 0, ng = 0;
+  } plan[2];
+  bool fused = false;
+  int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
+  Sched* sched = nullptr;
+  unsigned* flags = nullptr;
   // CUDA graphs of one RK4 step, one per state-buffer rotation; key = (h, norm?, res_tol, pseudo_time)
   cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr};
   double g_h = -1.0, g_tol = 0.0;
@@ -436,6 +483,10 @@ int fetch_ctl(PdesCtx* ctx) {
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->comm_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->h_ctl->err_code == 3) {
+    set_err(ctx, "k_fused: an element tile waited for face groups that never completed (scheduler time-out)");
+    return PDES_ERR_CUDA;
+  }
   if (ctx->h_ctl->err_code) {
     unsigned long long key = ctx->h_ctl->err_loc;
     int code = (int)(key >> 62) + 1;
@@ -523,6 +574,45 @@ int finalize(PdesCtx* ctx) {
       ctx->chunk_g[k] = k == nc ? nIB : g;
     }
     ctx->chunk_g[0] = 0;
+
+    // k_fused schedule (see residual_kernels.cuh): the faces an element tile integrates are a prefix of the sorted list
+    const int FPG = ctx->ops->fused_group_faces();
+    ctx->fused = FPG > 0 && nc == 1 && env_int("PDES_FUSED", 0) != 0 && env_int("PDES_ELEM_W", 0) == 0;
+    if (ctx->fused) {
+      const int E = ctx->ops->fused_tile_elems();
+      const int64_t nt = (c.nE + E - 1) / E;
+      std::vector<char> touches(nt, 0);
+      for (int64_t j = 0; j < ctx->nS; ++j) touches[sh_el[j] / E] = 1;
+      std::vector<int32_t> list[2], need[2];
+      int64_t gp = 0;
+      for (int64_t t = 0; t < nt; ++t) {
+        const int64_t e_end = std::min<int64_t>((t + 1) * E, c.nE);
+        while (gp < nIB && key(gp) < e_end) ++gp;
+        const int k = touches[t] ? 1 : 0;
+        list[k].push_back((int32_t)t);
+        need[k].push_back((int32_t)((gp + FPG - 1) / FPG));
+      }
+      const int32_t groupsB = (int32_t)((ctx->nS + FPG - 1) / FPG);
+      for (auto& v : need[1]) v = groupsB;
+      for (int k = 0; k < 2; ++k) {
+        PdesCtx::FusedPlan& pl = ctx->plan[k];
+        pl.n_tiles = (int32_t)list[k].size();
+        pl.g0 = k == 0 ? 0 : nIB;
+        pl.ng = k == 0 ? nIB : ctx->nS;
+        pl.n_groups = (int32_t)((pl.ng + FPG - 1) / FPG);
+        pl.lag = 0;
+        for (size_t i = 0; i < need[k].size(); ++i) pl.lag = std::max<int32_t>(pl.lag, need[k][i] - (int32_t)i);
+        // slack: a tile should wait for groups that are (almost surely) complete, i.e. older than one wave of CTAs
+        if (k == 0) pl.lag += env_int("PDES_LAG_SLACK", ctx->ops->resident_fused_ctas() + 64);
+        if (pl.tile_list) { cudaFree(pl.tile_list); pl.tile_list = nullptr; }
+        if (ctx->nS > 0) CUDA_TRY(ctx, dev_upload(ctx->stream, &pl.tile_list, list[k].data(), list[k].size()));
+        CUDA_TRY(ctx, dev_upload(ctx->stream, &pl.need, need[k].data(), need[k].size()));
+      }
+      const size_t nflags = (size_t)std::max(ctx->plan[0].n_groups, ctx->plan[1].n_groups) + 1;
+      CUDA_TRY(ctx, dev_upload<unsigned>(ctx->stream, &ctx->flags, nullptr, nflags));
+      Sched s0{0u, 0u, 0u, 1u};
+      CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sched, &s0, 1));
+    }
   }
   for (int64_t e = 0; e < c.nE; ++e)
     for (int f = 0; f < NF; ++f)
@@ -559,6 +649,13 @@ int finalize(PdesCtx* ctx) {
   CUDA_TRY(ctx, ctx->ops->prepare());
   ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas() / 8);   // measured optimum: ~half a wave
   ctx->prefetch_ahead_faces = env_int("PDES_PREFETCH_AHEAD_F", ctx->ops->resident_face_ctas());
+  if (ctx->fused) {
+    const int res = ctx->ops->resident_fused_ctas();
+    ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", res / 8);
+    ctx->prefetch_ahead_groups = env_int("PDES_PREFETCH_AHEAD_G", res);
+    ctx->discard_records = env_int("PDES_DISCARD", 1);
+    ctx->acquire_fence = env_int("PDES_ACQ_FENCE", 1);
+  }
   ctx->finalized = true;
   return PDES_OK;
 }
@@ -618,6 +715,29 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.prefetch_ahead = ctx->prefetch_ahead_faces;
+  if (ctx->fused) {
+    FusedArgs fu;
+    memset(&fu, 0, sizeof(fu));
+    fu.f = fa; fu.e = a; fu.sched = ctx->sched; fu.flags = ctx->flags;
+    fu.e.discard_records = ctx->discard_records;
+    fu.acquire_fence = ctx->acquire_fence;
+    fu.prefetch_ahead_groups = ctx->prefetch_ahead_groups;
+    for (int k = 0; k < 2; ++k) {
+      const PdesCtx::FusedPlan& pl = ctx->plan[k];
+      if (k == 1) {
+        if (ctx->nS == 0) break;
+        if (ctx->comm) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
+      }
+      if (pl.n_groups == 0 && pl.n_tiles == 0) continue;
+      fu.f.g0 = pl.g0; fu.f.ng = pl.ng;
+      fu.tile_list = pl.tile_list; fu.need = pl.need;
+      fu.n_tiles = pl.n_tiles; fu.n_groups = pl.n_groups; fu.lag = pl.lag;
+      CUDA_TRY(ctx, ctx->ops->launch_fused(fu, mode, ctx->stream));
+      ctx->launches++;
+    }
+    ctx->n_evals++;
+    return PDES_OK;
+  }
   const int nc = ctx->nchunks;
   cudaStream_t fs = nc > 1 ? ctx->face_stream : ctx->stream;
   if (nc > 1) {
@@ -852,7 +972,8 @@ void pdes_destroy(PdesCtx* ctx) {
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
                   ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
-                  ctx->norm_sq, ctx->norms_dev};
+                  ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
+                  ctx->plan[1].need, ctx->flags, ctx->sched};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);

@@ -26,6 +26,10 @@
 #include <stdint.h>
 #include "euler_device.cuh"
 
+#ifndef PDES_OPT
+#define PDES_OPT 0      // all three measured slower on C3 (1.101 / 1.141 / 1.129 vs 1.093 ms per RK4 step). bit 0: pipelined metrics loads in S1; bit 1: face records two faces ahead; bit 2: staged Minv
+#endif
+
 namespace pdes {
 
 // host-side bookkeeping per (element, local face): which face covers it (every element face must be claimed by
@@ -106,6 +110,7 @@ struct ElemArgs {
   int32_t scheme;              // 0: rk4 (rk4.jl:244-319), 1: lserk54 (lserk.jl:183-205)
   int32_t stage;               // 1..4 (rk4) | 1..5 (lserk54)
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
+  int32_t discard_records;     // k_fused: drop the consumed face records from L2 (discard.global.L2)
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
@@ -197,42 +202,49 @@ struct FaceCfg {
   static constexpr int FS = (pad_stride(NFN * ND, ND) + 1) & ~1;   // per-face stride of a face-state tile (even: LDS.128)
 };
 
-template <int DIM, int NN, int NFN, int FT, int MINB>
-__global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
-k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
-  using Cfg = FaceCfg<DIM, NN, NFN, FT>;
-  constexpr int ND = Cfg::ND, T = Cfg::T, FS = Cfg::FS, NF = DIM + 1, EL = NN * ND;
-  __shared__ double sL[FT * FS];
-  __shared__ double sR[FT * FS];
-  __shared__ FaceRec sRec[FT];
-  __shared__ int s_dst[2 * FT];            // (element*NF + face) of the record each side of a face writes, or -1
-  __shared__ int s_perm[NF][NN];
-  __shared__ int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
+// shared-memory working set of one face tile (aliased onto the element tile's storage by the fused kernel)
+template <int DIM, int NN, int NFN, int FT>
+struct FaceTileSmem {
+  static constexpr int FS = FaceCfg<DIM, NN, NFN, FT>::FS;
+  double sL[FT * FS];
+  double sR[FT * FS];
+  FaceRec sRec[FT];
+  int s_dst[2 * FT];            // (element*NF + face) of the record each side of a face writes, or -1
+  int s_perm[DIM + 1][NN];
+  int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
+};
 
-  if (a.ctl->stop) return;
-  const int tid = threadIdx.x;
-  const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FT;
-  const int64_t rem = a.g0 + a.ng - g0;
-  const int nf = (int)(rem < FT ? rem : FT);
+template <int DIM, int NN, int NFN, int FT, int TB>
+__device__ __forceinline__ void face_tables(const OpTab<DIM, NN, NFN>& op, FaceTileSmem<DIM, NN, NFN, FT>& sm, int tid) {
+  constexpr int NF = DIM + 1;
+  for (int idx = tid; idx < NF * NN; idx += TB) sm.s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
+  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += TB)
+    sm.s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
+}
+
+// One tile of nf <= FT faces starting at face g0, executed by a CTA of TB threads.  ga = first face of the tile whose
+// gathers are prefetched into L2 (or < 0).  The caller has filled sm.s_perm / sm.s_nbrperm (face_tables) and puts a
+// block barrier between consecutive tiles.
+template <int DIM, int NN, int NFN, int FT, int TB>
+__device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const FaceArgs& a,
+                                          FaceTileSmem<DIM, NN, NFN, FT>& sm, int64_t g0, int nf, int64_t ga, int tid) {
+  using Cfg = FaceCfg<DIM, NN, NFN, FT>;
+  constexpr int ND = Cfg::ND, FS = Cfg::FS, NF = DIM + 1, EL = NN * ND;
+  static_assert(TB >= Cfg::T, "block too small for the face tile");
+  double* sL = sm.sL;
+  double* sR = sm.sR;
+  FaceRec* sRec = sm.sRec;
+  const int64_t gend = a.g0 + a.ng;
   if (tid < nf) {
     const FaceRec r = a.faces[g0 + tid];
     sRec[tid] = r;
-    s_dst[2 * tid] = r.elL * NF + r.fL;
-    s_dst[2 * tid + 1] = r.kind == FK_INTERIOR ? r.elR * NF + r.fR : -1;
+    sm.s_dst[2 * tid] = r.elL * NF + r.fL;
+    sm.s_dst[2 * tid + 1] = r.kind == FK_INTERIOR ? r.elR * NF + r.fR : -1;
   }
   // the tile that will run on this SM slot next: fetch its records now, prefetch what they point at when done
   FaceRec nxt;
   nxt.kind = 255;
-  const int64_t ga = g0 + (int64_t)a.prefetch_ahead * FT;
-  if (a.prefetch_ahead > 0 && tid < FT && ga + tid < a.g0 + a.ng) nxt = a.faces[ga + tid];
-  if (a.prefetch_ahead > 0 && tid == 0 && ga + (int64_t)a.prefetch_ahead * FT < a.g0 + a.ng) {
-    const char* pr = reinterpret_cast<const char*>(a.faces + ga + (int64_t)a.prefetch_ahead * FT);
-#pragma unroll
-    for (int o = 0; o < FT * 16; o += 128) prefetch_l2(pr + o);
-  }
-  for (int idx = tid; idx < NF * NN; idx += T) s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
-  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += T)
-    s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
+  if (ga >= 0 && tid < FT && ga + tid < gend) nxt = a.faces[ga + tid];
   __syncthreads();
 
   // ---- A: interpolate both sides to the face nodes (variable threads) ----------------------------------
@@ -243,12 +255,12 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
     {
       const double* b = a.q + (int64_t)r.elL * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) ql[j] = __ldg(b + s_perm[r.fL][j] * ND);
+      for (int j = 0; j < NN; ++j) ql[j] = __ldg(b + sm.s_perm[r.fL][j] * ND);
     }
     if (r.kind == FK_INTERIOR) {
       const double* b = a.q + (int64_t)r.elR * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) qr[j] = __ldg(b + s_perm[r.fR][j] * ND);
+      for (int j = 0; j < NN; ++j) qr[j] = __ldg(b + sm.s_perm[r.fR][j] * ND);
     } else {
 #pragma unroll
       for (int j = 0; j < NN; ++j) qr[j] = 0.0;
@@ -265,13 +277,13 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
       }
       sL[fi * FS + i * ND + k] = s;
       // elementR's face node i coincides with elementL's face node nbrperm[i,orient] (involution)
-      if (r.kind == FK_INTERIOR) sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = t;
+      if (r.kind == FK_INTERIOR) sR[fi * FS + sm.s_nbrperm[r.orient][i] * ND + k] = t;
     }
     if (r.kind == FK_SHARED) {
       // permuteinterface! (Utils/parallel.jl:198-201): received node i of the peer is own node nbrperm[i,orient]
       const double* b = a.q_recv + (int64_t)r.aux * (NFN * ND) + k;
 #pragma unroll
-      for (int i = 0; i < NFN; ++i) sR[fi * FS + s_nbrperm[r.orient][i] * ND + k] = b[i * ND];
+      for (int i = 0; i < NFN; ++i) sR[fi * FS + sm.s_nbrperm[r.orient][i] * ND + k] = b[i * ND];
     }
   }
   __syncthreads();
@@ -309,7 +321,7 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
         roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
       }
       const double w = op.wface[i];
-      const int ir = (r.kind == FK_INTERIOR) ? s_nbrperm[r.orient][i] : i;
+      const int ir = (r.kind == FK_INTERIOR) ? sm.s_nbrperm[r.orient][i] : i;
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         const double wf = w * flux[k];
@@ -324,8 +336,8 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   constexpr int FL = NFN * ND;
   {
     const int half = tid >> 4, hl = tid & 15;
-    for (int rec = half; rec < 2 * nf; rec += T / 16) {
-      const int di = s_dst[rec];
+    for (int rec = half; rec < 2 * nf; rec += TB / 16) {
+      const int di = sm.s_dst[rec];
       if (di < 0) continue;
       const double* src = ((rec & 1) ? sR : sL) + (rec >> 1) * FS;
       double* dst = a.fluxe + (int64_t)di * FL;
@@ -348,6 +360,26 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
     }
     prefetch_l2(a.nrm + (ga + tid) * a.nrm_face_stride);
   }
+}
+
+template <int DIM, int NN, int NFN, int FT, int MINB>
+__global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
+k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  constexpr int T = FaceCfg<DIM, NN, NFN, FT>::T;
+  __shared__ FaceTileSmem<DIM, NN, NFN, FT> sm;
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FT;
+  const int64_t rem = a.g0 + a.ng - g0;
+  const int nf = (int)(rem < FT ? rem : FT);
+  const int64_t ga = a.prefetch_ahead > 0 ? g0 + (int64_t)a.prefetch_ahead * FT : -1;
+  if (a.prefetch_ahead > 0 && tid == 0 && ga + (int64_t)a.prefetch_ahead * FT < a.g0 + a.ng) {
+    const char* pr = reinterpret_cast<const char*>(a.faces + ga + (int64_t)a.prefetch_ahead * FT);
+#pragma unroll
+    for (int o = 0; o < FT * 16; o += 128) prefetch_l2(pr + o);
+  }
+  face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
+  face_tile<DIM, NN, NFN, FT, T>(op, a, sm, g0, nf, ga, tid);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -703,31 +735,29 @@ struct TileCfg {
   static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
 };
 
-template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
-__global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
-k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
+// One tile of ne <= E elements starting at element e0, executed by a CTA of TB threads.  ea = first element of the
+// tile whose inputs are prefetched into L2 (or < 0); na its size.  COHERENT: the face records were written by other
+// CTAs of the SAME launch (fused kernel): plain loads instead of the read-only path, and the consumed records are
+// dropped from L2 without a write-back (discard.global.L2), since nothing reads them again.
+template <int DIM, int NN, int NFN, int E, int MODE, int TB, bool COHERENT>
+__device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, const ElemArgs& a, unsigned char* smem_raw,
+                                             double* s_red, int64_t e0, int ne, int64_t ea, int na, int tid) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
-  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = Cfg::T, SQ = Cfg::SQ, HP = Cfg::HP;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, T = TB, SQ = Cfg::SQ, HP = Cfg::HP;
+  static_assert(TB >= Cfg::T, "block too small for the element tile");
   constexpr int EL = NN * ND;                       // doubles per element
   constexpr int FL = NFN * ND;                      // doubles per face
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sq = reinterpret_cast<double*>(smem_raw);             // [E][EL]
   double* sF = sq + E * SQ;                                     // [E][ND][DIM][NN]
-  __shared__ double s_red[T / 32];
+  auto ldrec = [](const double* p) { return COHERENT ? *p : __ldg(p); };
 
-  if (a.ctl->stop) return;
-  const int tid = threadIdx.x;
-  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
-  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
   const double gami = a.ph.gamma - 1.0;
 
   // ---- S0: q tile (asynchronous copy) + L2 prefetch of the streams of the tile this SM slot runs next --------
   async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
   cp_async_commit();
   {
-    const int64_t ea = e0 + (int64_t)a.prefetch_ahead * E;
-    if (a.prefetch_ahead > 0 && ea < a.nE) {
-      const int na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
+    if (ea >= 0) {
       const int64_t b0 = ea * EL * 8, nb = (int64_t)na * EL * 8;
       for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
         prefetch_l2(reinterpret_cast<const char*>(a.q) + b0 + o);
@@ -738,8 +768,9 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
           if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
         }
       }
-      for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NF * FL * 8; o += (int64_t)T * 128)
-        prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + ea * NF * FL * 8 + o);
+      if (!COHERENT)     // (fused kernel: the records are written into L2 shortly before they are consumed)
+        for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * NF * FL * 8; o += (int64_t)T * 128)
+          prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + ea * NF * FL * 8 + o);
       for (int64_t o = (int64_t)tid * 128; o < (int64_t)na * a.dx_el_stride * 8; o += (int64_t)T * 128)
         prefetch_l2(reinterpret_cast<const char*>(a.dxidx) + ea * a.dx_el_stride * 8 + o);
     }
@@ -755,8 +786,18 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
         if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
       }
     }
-    for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NF * FL * 8; o += (int64_t)T * 128)
-      prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + e0 * NF * FL * 8 + o);
+    if (!COHERENT)
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NF * FL * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + e0 * NF * FL * 8 + o);
+  }
+  // the metrics of this thread's first node are requested before the wait for the q tile, those of the next node
+  // before the current one is processed (they are L2 hits after the prefetch, but still ~1000 cycles away)
+  double dxn[DIM * DIM];
+  if ((PDES_OPT & 1) && tid < ne * NN) {
+    const int s = tid / NN, j = tid - s * NN;
+    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
+#pragma unroll
+    for (int m = 0; m < DIM * DIM; ++m) dxn[m] = __ldg(dx + m);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -767,10 +808,20 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
     double qn[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) qn[k] = sq[s * SQ + j * ND + k];
-    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
     double dxl[DIM * DIM];
+    if (!(PDES_OPT & 1)) {
+      const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + j * a.dx_node_stride;
 #pragma unroll
-    for (int m = 0; m < DIM * DIM; ++m) dxl[m] = __ldg(dx + m);
+      for (int m = 0; m < DIM * DIM; ++m) dxn[m] = __ldg(dx + m);
+    }
+#pragma unroll
+    for (int m = 0; m < DIM * DIM; ++m) dxl[m] = dxn[m];
+    if ((PDES_OPT & 1) && it + T < ne * NN) {
+      const int s2 = (it + T) / NN, j2 = (it + T) - s2 * NN;
+      const double* dx = a.dxidx + (e0 + s2) * a.dx_el_stride + j2 * a.dx_node_stride;
+#pragma unroll
+      for (int m = 0; m < DIM * DIM; ++m) dxn[m] = __ldg(dx + m);
+    }
     const double press = calc_pressure<DIM>(qn, gami);
     if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
       const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
@@ -795,6 +846,13 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
     }
   }
   __syncthreads();       // sF complete; nobody reads the q tile any more (it becomes the output staging tile)
+  if (MODE == EPI_RK && (PDES_OPT & 4)) {
+    // Minv[node] replicated over the ND slots of the node in the dead q tile: the owner of a row later reads and
+    // then overwrites exactly its own slots, so the multiply by Minv costs LDS instead of exposed global loads
+    const double* mb = a.minv + e0 * NN;
+    for (int idx = tid; idx < ne * EL; idx += T) cp_async8(sq + idx, mb + idx / ND);
+    cp_async_commit();
+  }
 
   // ---- S2 + S3: variable threads -------------------------------------------------------------------
   const int vp = tid / ND, vk = tid - vp * ND;
@@ -809,10 +867,15 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   // f+1 are requested before the products of face f are issued (software pipeline; they are L2 hits).
   const double* G0 = a.fluxe + (e0 + s0c) * (NF * FL) + vk;
   const double* G1 = a.fluxe + (e0 + (act0 ? s1c : 0)) * (NF * FL) + vk;
-  double g0v[NFN], g1v[NFN];
+  // records of faces 0 and 1 are requested before the volume products, face f+2 before the products of face f
+  double g0v[NFN], g1v[NFN], h0v[NFN], h1v[NFN];
   if (act0) {
 #pragma unroll
-    for (int i = 0; i < NFN; ++i) { g0v[i] = __ldg(G0 + i * ND); g1v[i] = __ldg(G1 + i * ND); }
+    for (int i = 0; i < NFN; ++i) { g0v[i] = ldrec(G0 + i * ND); g1v[i] = ldrec(G1 + i * ND); }
+    if (NF > 1 && (PDES_OPT & 2)) {
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) { h0v[i] = ldrec(G0 + (NFN + i) * ND); h1v[i] = ldrec(G1 + (NFN + i) * ND); }
+    }
     // S2: volume integral  res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j]   (weakdifferentiate!, trans=true)
     // (the loop over directions stays rolled: fully unrolled operator products overflow the instruction cache)
     const double* F0 = sF + (s0 * ND + vk) * DIM * NN;
@@ -834,7 +897,8 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   constexpr bool STAGED = (MODE == EPI_RK);
   if (STAGED) {
     // the volume-flux tile is dead: its storage receives the epilogue's streams (srcm | x_old | ksum), which are
-    // in flight while the face products run
+    // in flight while the face products run.  The Minv tile (requested before S2) has landed.
+    cp_async_wait<0>();
     __syncthreads();
     const unsigned long long pol = policy_evict_first();
     if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
@@ -849,9 +913,14 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
 #pragma unroll 1
     for (int f = 0; f < NF; ++f) {
       double n0v[NFN], n1v[NFN];
-      const int fn = f + 1 < NF ? f + 1 : f;
+      constexpr int AH = (PDES_OPT & 2) ? 2 : 1;
+      if (f + AH < NF) {
 #pragma unroll
-      for (int i = 0; i < NFN; ++i) { n0v[i] = __ldg(G0 + (fn * NFN + i) * ND); n1v[i] = __ldg(G1 + (fn * NFN + i) * ND); }
+        for (int i = 0; i < NFN; ++i) {
+          n0v[i] = ldrec(G0 + ((f + AH) * NFN + i) * ND);
+          n1v[i] = ldrec(G1 + ((f + AH) * NFN + i) * ND);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < NFN; ++i)
 #pragma unroll
@@ -861,14 +930,23 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
           acc1[u] = fma(c, g1v[i], acc1[u]);
         }
 #pragma unroll
-      for (int i = 0; i < NFN; ++i) { g0v[i] = n0v[i]; g1v[i] = n1v[i]; }
+      for (int i = 0; i < NFN; ++i) {
+        if (PDES_OPT & 2) { g0v[i] = h0v[i]; g1v[i] = h1v[i]; h0v[i] = n0v[i]; h1v[i] = n1v[i]; }
+        else { g0v[i] = n0v[i]; g1v[i] = n1v[i]; }
+      }
     }
     // pde_post_func: res_vec *= Minv (EPI_RK); staged for the coalesced epilogue
     if (MODE == EPI_RK) {
-      const double* m0 = a.minv + (e0 + s0) * NN;
-      const double* m1 = a.minv + (e0 + s1c) * NN;
 #pragma unroll
-      for (int u = 0; u < NN; ++u) { acc0[u] *= __ldg(m0 + u); acc1[u] *= __ldg(m1 + u); }
+      for (int u = 0; u < NN; ++u) {
+        if (PDES_OPT & 4) {
+          acc0[u] *= sq[s0 * SQ + u * ND + vk];
+          acc1[u] *= sq[s1c * SQ + u * ND + vk];
+        } else {
+          acc0[u] *= __ldg(a.minv + (e0 + s0) * NN + u);
+          acc1[u] *= __ldg(a.minv + (e0 + s1c) * NN + u);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < NN; ++u) sq[s0 * SQ + u * ND + vk] = acc0[u];
@@ -879,9 +957,221 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   }
   if (STAGED) cp_async_wait<0>();
   __syncthreads();
+  if (COHERENT && a.discard_records) {
+    // every thread has consumed its records: drop the tile's full 128-byte lines (tiles are line-aligned whenever
+    // E*NF*FL*8 is a multiple of 128; partial lines at the ends are left alone)
+    const uintptr_t b = reinterpret_cast<uintptr_t>(a.fluxe + e0 * (NF * FL));
+    const uintptr_t lo = (b + 127) & ~(uintptr_t)127, hi = (b + (uintptr_t)ne * NF * FL * 8) & ~(uintptr_t)127;
+    for (uintptr_t p = lo + (uintptr_t)tid * 128; p < hi; p += (uintptr_t)T * 128)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+  }
 
   // ---- S4: coalesced epilogue (source, res | fused RK4 stage, stage-1 norm partial) ----------------------------
   epilogue_tile<NN, ND, E, T, MODE, STAGED>(a, sq, ne, e0, tid, s_red, sF);
+}
+
+template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
+__global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
+k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
+  using Cfg = TileCfg<DIM, NN, NFN, E>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[Cfg::T / 32];
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
+  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
+  int64_t ea = e0 + (int64_t)a.prefetch_ahead * E;
+  int na = 0;
+  if (a.prefetch_ahead > 0 && ea < a.nE) na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
+  else ea = -1;
+  element_tile<DIM, NN, NFN, E, MODE, Cfg::T, false>(op, a, smem_raw, s_red, e0, ne, ea, na, tid);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_fused: one residual evaluation (+ RK stage) in ONE launch.
+//
+// k_face_flux is instruction-issue bound and k_element_rk is HBM-latency bound; run back to back, their times add and
+// the face records make a round trip through DRAM (2 x 171 MB of the 917 MB a C3 evaluation moves).  Here every CTA
+// draws a ticket T (atomic counter, so tickets follow the order in which CTAs really start) and runs
+//     face group T            NSUB tiles of FT faces of the face list, which is sorted by the lowest element it touches
+//     element tile T - lag    whose faces are then a PREFIX of that list: groups [0, need[T-lag]) with need[u] <= u + lag
+// so that the records an element tile integrates were written ~lag tickets earlier and are still in L2; the tile drops
+// them from L2 when it is done (discard.global.L2: no write-back).  CTAs in their face phase and CTAs in their
+// element phase share every SM, which overlaps the issue-bound and the memory-bound halves of the evaluation.
+//
+// Synchronisation: a face group publishes flags[g] = epoch (release) and advances the watermark W over the
+// leading complete groups; an element tile waits for W >= need (acquire).  Deadlock-free by construction: the
+// groups a ticket waits for have smaller tickets, i.e. they are running or done, and a face phase never waits.
+// The wait polls ctl->stop (physics error raised by another CTA) and gives up after a bounded number of polls
+// (err_code 3) instead of hanging the device.  The last CTA to finish resets the ticket / watermark counters and
+// bumps the epoch, so the launch can be replayed from a CUDA graph.
+// ------------------------------------------------------------------------------------------------------
+struct Sched {
+  unsigned ticket, watermark, finished, epoch;
+};
+
+struct FusedArgs {
+  FaceArgs f;                  // f.g0, f.ng: the face range of this launch (groups count from f.g0)
+  ElemArgs e;
+  const int32_t* tile_list;    // element tile -> tile number (first element / E); nullptr: identity
+  const int32_t* need;         // per element tile: number of leading face groups that must be complete
+  int32_t n_tiles, n_groups, lag;
+  int32_t prefetch_ahead_groups;
+  int32_t acquire_fence;       // element tiles issue fence.acq_rel.gpu after their wait (invalidates the SM's L1)
+  Sched* sched;
+  unsigned* flags;             // [n_groups]
+};
+
+template <int DIM, int NN, int NFN, int E, int FT, int NSUB>
+struct FusedCfg {
+  using TC = TileCfg<DIM, NN, NFN, E>;
+  using FC = FaceCfg<DIM, NN, NFN, FT>;
+  static constexpr int T = TC::T > FC::T ? TC::T : FC::T;
+  static constexpr size_t face_bytes = sizeof(FaceTileSmem<DIM, NN, NFN, FT>);
+  static constexpr size_t smem_bytes = TC::smem_bytes > face_bytes ? TC::smem_bytes : face_bytes;
+};
+
+// polls use relaxed loads: ld.acquire compiles to LDG.STRONG.GPU + CCTL.IVALL, and an L1 invalidation per poll starves
+// the face gathers of every CTA on the SM (measured: 10x slower).  The acquire is one fence after the poll succeeds.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_sc_gpu() { asm volatile("fence.sc.gpu;" ::: "memory"); }
+
+// One warp scans the flags of the 32 groups that follow the watermark and publishes the longest complete prefix
+// (atomicMax: every published value is a valid prefix, so concurrent scans commute).  A serial one-group-per-step
+// advance costs two dependent L2 round trips per group (~0.5 us x 5672 groups: measured 2.7 ms per evaluation).
+// Returns the watermark this warp knows of (warp-uniform).
+__device__ __forceinline__ unsigned advance_watermark(Sched* sched, const unsigned* flags, int n_groups, unsigned epoch,
+                                                     int lane) {
+  unsigned w = __shfl_sync(0xffffffffu, lane == 0 ? ld_relaxed_u32(&sched->watermark) : 0u, 0);
+  while (w < (unsigned)n_groups) {
+    const bool set = w + lane < (unsigned)n_groups && ld_relaxed_u32(flags + w + lane) == epoch;
+    const unsigned m = __ballot_sync(0xffffffffu, set);
+    const int lead = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+    if (lead == 0) break;
+    if (lane == 0) {
+      fence_acq_rel_gpu();       // relay: the flag reads synchronise with the groups' releases, the max republishes them
+      atomicMax(&sched->watermark, w + lead);
+    }
+    w += lead;
+    if (lead < 32) break;
+  }
+  return w;
+}
+
+template <int DIM, int NN, int NFN, int E, int FT, int NSUB, int MODE, int MINB>
+__global__ void __launch_bounds__((FusedCfg<DIM, NN, NFN, E, FT, NSUB>::T), MINB)
+k_fused(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FusedArgs a) {
+  using Cfg = FusedCfg<DIM, NN, NFN, E, FT, NSUB>;
+  constexpr int T = Cfg::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[T / 32];
+  __shared__ unsigned s_ctl[3];      // ticket, epoch, stop
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_ctl[2] = (unsigned)*reinterpret_cast<const volatile int32_t*>(&a.e.ctl->stop);
+    s_ctl[1] = *reinterpret_cast<const volatile unsigned*>(&a.sched->epoch);
+    s_ctl[0] = atomicAdd(&a.sched->ticket, 1u);
+  }
+  __syncthreads();
+  const int ticket = (int)s_ctl[0];
+  const unsigned epoch = s_ctl[1];
+  bool live = s_ctl[2] == 0;
+
+  // ---- face group ---------------------------------------------------------------------------------------
+  if (live && ticket < a.n_groups) {
+    auto& sm = *reinterpret_cast<FaceTileSmem<DIM, NN, NFN, FT>*>(smem_raw);
+    face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
+    const int64_t gend = a.f.g0 + a.f.ng;
+    const int64_t gg = a.f.g0 + (int64_t)ticket * (NSUB * FT);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const int64_t g0 = gg + sub * FT;
+      if (g0 >= gend) break;
+      const int nf = (int)((gend - g0) < FT ? (gend - g0) : FT);
+      const int64_t ga = a.prefetch_ahead_groups > 0 ? g0 + (int64_t)a.prefetch_ahead_groups * (NSUB * FT) : -1;
+      face_tile<DIM, NN, NFN, FT, T>(op, a.f, sm, g0, nf, ga, tid);
+      __syncthreads();
+    }
+    // every thread's records are written (barrier above): publish the group, then advance the watermark over the
+    // leading complete groups (fence.sc between the flag store and the scan: of two groups that complete
+    // concurrently at least one sees the other's flag; waiting tiles run the same scan, so progress never
+    // depends on who wins)
+    if (tid < 32) {
+      if (tid == 0) {
+        st_release_u32(a.flags + ticket, epoch);
+        fence_sc_gpu();
+      }
+      __syncwarp();
+      advance_watermark(a.sched, a.flags, a.n_groups, epoch, tid);
+    }
+  }
+
+  // ---- element tile ---------------------------------------------------------------------------------------
+  const int u = ticket - a.lag;
+  if (live && u >= 0 && u < a.n_tiles) {
+    if (tid < 32) {
+      const unsigned need = (unsigned)a.need[u];
+      unsigned ok = 1, spins = 0;
+      unsigned w = __shfl_sync(0xffffffffu, tid == 0 ? ld_relaxed_u32(&a.sched->watermark) : 0u, 0);
+      while (w < need) {
+        w = advance_watermark(a.sched, a.flags, a.n_groups, epoch, tid);
+        if (w >= need) break;
+        __nanosleep(128);
+        int stop = 0;
+        if (tid == 0) stop = *reinterpret_cast<const volatile int32_t*>(&a.e.ctl->stop);
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (stop) { ok = 0; break; }
+        if (++spins > (1u << 22)) {          // ~1 s: never reached unless the schedule is broken
+          if (tid == 0) {
+            atomicExch(&a.e.ctl->err_code, 3);
+            atomicExch(&a.e.ctl->stop, 1);
+          }
+          ok = 0;
+          break;
+        }
+      }
+      if (tid == 0) {
+        if (a.acquire_fence) fence_acq_rel_gpu();
+        s_ctl[2] = ok ? 0u : 1u;
+      }
+    }
+    __syncthreads();       // also separates the face phase's shared-memory use from the element tile's
+    live = s_ctl[2] == 0;
+    if (live) {
+      const int64_t tile = a.tile_list ? a.tile_list[u] : u;
+      const int64_t e0 = tile * E;
+      const int ne = (int)((a.e.nE - e0) < E ? (a.e.nE - e0) : E);
+      int64_t ea = -1;
+      int na = 0;
+      const int ua = u + a.e.prefetch_ahead;
+      if (a.e.prefetch_ahead > 0 && ua < a.n_tiles) {
+        ea = (a.tile_list ? (int64_t)a.tile_list[ua] : (int64_t)ua) * E;
+        na = (int)((a.e.nE - ea) < E ? (a.e.nE - ea) : E);
+      }
+      element_tile<DIM, NN, NFN, E, MODE, T, true>(op, a.e, smem_raw, s_red, e0, ne, ea, na, tid);
+    }
+  }
+
+  // ---- the last CTA re-arms the scheduler ---------------------------------------------------------------------
+  if (tid == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&a.sched->finished, 1u);
+    if (done == gridDim.x - 1) {
+      a.sched->ticket = 0;
+      a.sched->watermark = 0;
+      a.sched->finished = 0;
+      __threadfence();
+      a.sched->epoch = epoch + 1;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------

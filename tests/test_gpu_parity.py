@@ -471,3 +471,25 @@ def test_reference_convergence_golden_gpu():
     e2 = _steady_vortex_error(runner, "squarevortex_large", 0.01)
     assert 0.01200 / 1.25 < e1 < 0.01200 * 1.25 and abs(e1 - 0.01200) < 2e-5
     assert 1.9 < np.log(e1 / e2) / np.log(2.0) < 2.1
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 20), ("2d_p2_roe", 9), ("3d_p1_roe_src", 6), ("c3_3d_p2_roe_src", 9)])
+def test_fused_kernel_bitwise_equals_split(case, n, monkeypatch):
+    """k_fused (PDES_FUSED=1: face groups + lagged element tiles in one launch, records handed over through L2)
+    runs the same tile bodies as k_face_flux + k_element_rk: residual and RK4 trajectory must be bit-identical,
+    and one evaluation is one launch."""
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("PDES_FUSED", fused)
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=11)
+        eqn.q[...] = q0
+        n0 = eqn.kernel_launch_count()
+        pd.evalResidual(mesh, op, eqn, opts)
+        launches = eqn.kernel_launch_count() - n0
+        res = eqn.res.copy(order="F")
+        pd.rk4(pd.evalResidual, 1e-4, 6e-4, mesh, op, eqn, opts)
+        out[fused] = (launches, res, eqn.q.copy(order="F"), list(eqn.convergence))
+    assert out["0"][0] == 2 and out["1"][0] == 1
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert np.array_equal(out["0"][2], out["1"][2])
+    assert out["0"][3] == out["1"][3]
