@@ -152,6 +152,33 @@ int pdes_sync(PdesCtx *ctx);
  * applyLinearOperator NonlinearSolvers/newton_setup.jl:632-662); evaluated here on dual numbers, exact to round-off. */
 int pdes_eval_jvp(PdesCtx *ctx, const double *v, double *out);
 
+/* Matrix-free Newton-Krylov on the resident q (configuration 5): the reference's
+ * newton()/newtonInner (NonlinearSolvers/newton.jl:54-304) with jac_type=4 -- dR/dq * delta_q = -R(q) solved by
+ * restarted GMRES on the complex-step product (here: pdes_eval_jvp's dual-number product), update
+ * q += step_fac*delta_q, convergence tests of checkConvergence (newton.jl:402-445) on the strong-residual norm
+ * sqrt(sum Minv res^2) (physicsRhs, jacobian/residual_evaluation.jl:64-88).  Linear-solver defaults:
+ * krylov_reltol 1e-2, abstol 1e-50, dtol 1e5, itermax 1000 (read_input.jl:493-496), GMRES restart 30
+ * (read_input.jl:569), no preconditioner.  The Krylov basis and all reductions stay on the device. */
+typedef struct PdesNewtonOpts {
+  int64_t itermax;          /* Newton iterations (opts["itermax"]) */
+  double res_abstol, res_reltol, step_tol, step_fac;
+  double krylov_reltol, krylov_abstol, krylov_dtol;
+  int64_t krylov_itermax;
+  int32_t krylov_restart;
+} PdesNewtonOpts;
+typedef struct PdesNewtonResult {
+  int32_t converged;        /* 1: a checkConvergence test passed */
+  int32_t krylov_reason;    /* last linear solve: 1 rtol, 2 abstol, 3 breakdown (exact), -1 itermax, -2 dtol */
+  int64_t newton_iters, krylov_iters, residual_evals;
+  double res_norm, res_norm_rel, step_norm;
+} PdesNewtonResult;
+/* res_norms_out[itermax+1]: recordResNorm history (entry 0 = initial residual); step_norms_out[itermax] */
+int pdes_newton_krylov(PdesCtx *ctx, const PdesNewtonOpts *o, double *res_norms_out, double *step_norms_out,
+                       PdesNewtonResult *result);
+/* One linear solve dR/dq(q) x = b with the same GMRES (x0 = 0); b, x host arrays [nd,nn,nE]. */
+int pdes_gmres(PdesCtx *ctx, const double *b, double *x, double reltol, double abstol, double dtol,
+               int64_t itermax, int32_t restart, int64_t *iters_out, double *rnorm_out, int32_t *reason_out);
+
 /* rk4 (rk4.jl:144-344) on the resident q.  itermax < 0: use_itermax=false.
  * norms_out[norms_cap] receives the stage-1 norm of every executed step (the
  * convergence.dat column); nsteps_out the number of executed step heads;

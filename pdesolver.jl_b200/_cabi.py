@@ -32,6 +32,7 @@ EXPORTS = [
     "pdes_res_dev", "pdes_eval_residual", "pdes_eval_residual_async", "pdes_sync", "pdes_rk4",
     "pdes_rk4_steps_async", "pdes_get_minv", "pdes_get_timings", "pdes_kernel_launch_count",
     "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp", "pdes_lserk54",
+    "pdes_newton_krylov", "pdes_gmres",
 ]
 
 
@@ -49,6 +50,19 @@ class PdesTimings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("t_send", "t_dataprep", "t_volume", "t_face", "t_sharedface",
                                           "t_source", "t_func", "t_timemarch", "t_wait", "t_allreduce")] + \
                [("n_residual_evals", C.c_int64), ("n_kernel_launches", C.c_int64)]
+
+
+class PdesNewtonOpts(C.Structure):
+    _fields_ = [("itermax", C.c_int64)] + \
+               [(n, C.c_double) for n in ("res_abstol", "res_reltol", "step_tol", "step_fac", "krylov_reltol",
+                                          "krylov_abstol", "krylov_dtol")] + \
+               [("krylov_itermax", C.c_int64), ("krylov_restart", C.c_int32)]
+
+
+class PdesNewtonResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("krylov_reason", C.c_int32)] + \
+               [(n, C.c_int64) for n in ("newton_iters", "krylov_iters", "residual_evals")] + \
+               [(n, C.c_double) for n in ("res_norm", "res_norm_rel", "step_norm")]
 
 
 _lib = None
@@ -96,6 +110,8 @@ def lib():
         L.pdes_lserk54.argtypes = [p, d, d, i64, d, i32, C.POINTER(d), p, i64, C.POINTER(i64)]
         L.pdes_rk4_steps_async.argtypes = [p, d, i64]
         L.pdes_get_timings.argtypes = [p, C.POINTER(PdesTimings)]
+        L.pdes_newton_krylov.argtypes = [p, C.POINTER(PdesNewtonOpts), p, p, C.POINTER(PdesNewtonResult)]
+        L.pdes_gmres.argtypes = [p, p, p, d, d, d, i64, i32, C.POINTER(i64), C.POINTER(d), C.POINTER(i32)]
         L.pdes_kernel_launch_count.argtypes = [p]
         L.pdes_kernel_launch_count.restype = i64
         _lib = L

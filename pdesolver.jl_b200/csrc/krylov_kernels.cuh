@@ -1,0 +1,111 @@
+// Device-resident vector kernels of the matrix-free Newton-Krylov solver (configuration 5).
+//
+// The reference solves dR/dq * delta_q = -R(q) with PETSc's GMRES(30) on a MatShell whose product is the complex-step
+// residual (NonlinearSolvers/newton.jl:137-304, newton_setup.jl:632-662, linear solver defaults
+// input/read_input.jl:493-496, 560-570).  Here the Krylov basis, the Newton update and every reduction stay in HBM;
+// per GMRES iteration the host reads back one small vector (the Hessenberg column) to update its Givens rotations.
+//
+// All reductions are two-pass and deterministic: per-CTA partials, then one CTA per result sums them in a fixed order.
+#pragma once
+#include <stdint.h>
+
+namespace pdes {
+
+constexpr int KRY_T = 256;     // threads per CTA of the vector kernels
+constexpr int KRY_VB = 8;      // basis vectors per CTA row of k_multi_dot
+
+// partials[i * gridDim.x + blockIdx.x] = sum over this CTA's dofs of V_i[idx] * w[idx],  i in [8*blockIdx.y, +8)
+__global__ void __launch_bounds__(KRY_T)
+k_multi_dot(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ w, int64_t n,
+            double* __restrict__ partials) {
+  const int i0 = blockIdx.y * KRY_VB;
+  double acc[KRY_VB];
+#pragma unroll
+  for (int u = 0; u < KRY_VB; ++u) acc[u] = 0.0;
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T) {
+    const double wv = w[idx];
+#pragma unroll
+    for (int u = 0; u < KRY_VB; ++u)
+      if (i0 + u < nv) acc[u] = fma(V[(int64_t)(i0 + u) * ld + idx], wv, acc[u]);
+  }
+  __shared__ double sh[KRY_VB][KRY_T / 32];
+#pragma unroll
+  for (int u = 0; u < KRY_VB; ++u) {
+    double s = acc[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[u][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < KRY_VB && i0 + threadIdx.x < nv) {
+    double s = 0.0;
+    for (int wp = 0; wp < KRY_T / 32; ++wp) s += sh[threadIdx.x][wp];
+    partials[(int64_t)(i0 + threadIdx.x) * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// sum_j Minv[node(j)] * r[j]^2  (calcNorm with strongres=true, Utils/Utils.jl:427-449) as CTA partials (row 0)
+__global__ void __launch_bounds__(KRY_T)
+k_strong_norm_partials(const double* __restrict__ r, const double* __restrict__ minv, int nd, int64_t n,
+                       double* __restrict__ partials) {
+  double acc = 0.0;
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T) {
+    const double v = r[idx];
+    acc = fma(v * v, minv[idx / nd], acc);
+  }
+  __shared__ double sh[KRY_T / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wp = 0; wp < KRY_T / 32; ++wp) s += sh[wp];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// out[i] = sum_b partials[i * B + b]   (one CTA per result, fixed summation order)
+__global__ void __launch_bounds__(KRY_T)
+k_reduce_rows(const double* __restrict__ partials, int B, double* __restrict__ out) {
+  __shared__ double sh[KRY_T];
+  const double* p = partials + (int64_t)blockIdx.x * B;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < B; b += KRY_T) s += p[b];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = KRY_T / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// w -= sum_i h[i] V_i   (Gram-Schmidt projection; h lives on the device: no host round trip between the dot and the update)
+__global__ void __launch_bounds__(KRY_T)
+k_multi_axpy(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ h, double sign,
+             double* __restrict__ w, int64_t n) {
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T) {
+    double s = 0.0;
+    for (int i = 0; i < nv; ++i) s = fma(h[i], V[(int64_t)i * ld + idx], s);
+    w[idx] = fma(sign, s, w[idx]);
+  }
+}
+
+// dst = src / sqrt(*norm_sq)   (next basis vector; a zero norm leaves zeros: happy breakdown is detected on the host)
+__global__ void __launch_bounds__(KRY_T)
+k_normalize(const double* __restrict__ src, const double* __restrict__ norm_sq, double* __restrict__ dst, int64_t n) {
+  const double nv = *norm_sq;
+  const double s = nv > 0.0 ? 1.0 / sqrt(nv) : 0.0;
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T)
+    dst[idx] = s * src[idx];
+}
+
+// y = a*x + b*y  (b = 0: y = a*x without reading y)
+__global__ void __launch_bounds__(KRY_T)
+k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n) {
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T)
+    y[idx] = b == 0.0 ? a * x[idx] : fma(a, x[idx], b * y[idx]);
+}
+
+}  // namespace pdes

@@ -22,6 +22,7 @@
 #include "residual_kernels.cuh"
 #include "es_kernels.cuh"
 #include "jvp_kernels.cuh"
+#include "krylov_kernels.cuh"
 
 using namespace pdes;
 
@@ -422,6 +423,12 @@ struct PdesCtx {
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
   Sched* sched = nullptr;
   unsigned* flags = nullptr;
+  // Newton-Krylov workspace (allocated on first use): basis V[(restart+1)][ndof], work vectors, reduction scratch
+  struct Krylov {
+    int restart = 0, nblk = 0;
+    double *V = nullptr, *w = nullptr, *b = nullptr, *x = nullptr, *partials = nullptr, *hdev = nullptr;
+    double* hhost = nullptr;     // pinned: [3*(restart+2)]
+  } kry;
   // CUDA graphs of one RK4 step, one per state-buffer rotation; key = (h, norm?, res_tol, pseudo_time)
   cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr};
   double g_h = -1.0, g_tol = 0.0;
@@ -883,6 +890,28 @@ int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int 
   return PDES_OK;
 }
 
+// out = dR/dq(q) * v on device vectors (q = the resident state)
+int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev) {
+  const PdesConfig& c = ctx->cfg;
+  ElemArgs a;
+  fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
+  FaceArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
+  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
+  fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
+  fa.g0 = 0; fa.ng = c.nF + c.nB;
+  cudaError_t e = ctx->ops->launch_jvp(fa, a, vdev, odev, ctx->stream);
+  if (e == cudaErrorNotSupported) {
+    set_err(ctx, "pdes_eval_jvp is implemented for dense-face operators with the Roe flux only");
+    return PDES_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(ctx, e);
+  ctx->launches += 2;
+  return PDES_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -973,8 +1002,10 @@ void pdes_destroy(PdesCtx* ctx) {
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
                   ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
-                  ctx->plan[1].need, ctx->flags, ctx->sched};
+                  ctx->plan[1].need, ctx->flags, ctx->sched, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
+                  ctx->kry.partials, ctx->kry.hdev};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
   if (ctx->ev_recv) cudaEventDestroy(ctx->ev_recv);
@@ -1295,26 +1326,11 @@ int pdes_eval_jvp(PdesCtx* ctx, const double* v, double* out) {
     return PDES_ERR_UNSUPPORTED;
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
-  const PdesConfig& c = ctx->cfg;
   double* vdev = ctx->qbuf[(ctx->cur + 1) % 3];     // RK4 scratch buffers double as (v, out) storage
   double* odev = ctx->qbuf[(ctx->cur + 2) % 3];
   CUDA_TRY(ctx, cudaMemcpyAsync(vdev, v, sizeof(double) * ctx->ndof, cudaMemcpyHostToDevice, ctx->stream));
-  ElemArgs a;
-  fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
-  FaceArgs fa;
-  memset(&fa, 0, sizeof(fa));
-  fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
-  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
-  fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
-  fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
-  fa.g0 = 0; fa.ng = c.nF + c.nB;
-  cudaError_t e = ctx->ops->launch_jvp(fa, a, vdev, odev, ctx->stream);
-  if (e == cudaErrorNotSupported) {
-    set_err(ctx, "pdes_eval_jvp is implemented for dense-face operators with the Roe flux only");
-    return PDES_ERR_UNSUPPORTED;
-  }
-  CUDA_TRY(ctx, e);
-  ctx->launches += 2;
+  rc = enqueue_jvp(ctx, vdev, odev);
+  if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(out, odev, sizeof(double) * ctx->ndof, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return PDES_OK;
@@ -1455,6 +1471,266 @@ int pdes_lserk54(PdesCtx* ctx, double h, double t_max, int64_t itermax, double r
   if (ctx->h_ctl->stop) reset_ctl(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return status;
+}
+
+// ---- matrix-free Newton-Krylov (configuration 5) -------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+int kry_alloc(PdesCtx* ctx, int restart) {
+  PdesCtx::Krylov& k = ctx->kry;
+  if (k.restart >= restart && k.V) return PDES_OK;
+  void* old[] = {k.V, k.w, k.b, k.x, k.partials, k.hdev};
+  for (void* p : old) if (p) cudaFree(p);
+  if (k.hhost) cudaFreeHost(k.hhost);
+  k = PdesCtx::Krylov();
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n = ctx->ndof;
+  k.nblk = (int)std::max<int64_t>(1, std::min<int64_t>((n + KRY_T - 1) / KRY_T, (int64_t)sms * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.V, sizeof(double) * (size_t)(restart + 1) * n));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.w, sizeof(double) * n));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.b, sizeof(double) * n));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.x, sizeof(double) * n));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.partials, sizeof(double) * (size_t)(restart + 2) * k.nblk));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.hdev, sizeof(double) * 3 * (size_t)(restart + 2)));
+  CUDA_TRY(ctx, cudaMallocHost((void**)&k.hhost, sizeof(double) * 3 * (size_t)(restart + 2)));
+  k.restart = restart;
+  return PDES_OK;
+}
+
+// out[0..nv) = V[0..nv)^T w  (device results)
+int kry_dots(PdesCtx* ctx, const double* V, int nv, const double* w, double* out) {
+  PdesCtx::Krylov& k = ctx->kry;
+  dim3 grid(k.nblk, (nv + KRY_VB - 1) / KRY_VB);
+  k_multi_dot<<<grid, KRY_T, 0, ctx->stream>>>(V, ctx->ndof, nv, w, ctx->ndof, k.partials);
+  k_reduce_rows<<<nv, KRY_T, 0, ctx->stream>>>(k.partials, k.nblk, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  return PDES_OK;
+}
+
+int kry_fetch(PdesCtx* ctx, int count) {
+  PdesCtx::Krylov& k = ctx->kry;
+  CUDA_TRY(ctx, cudaMemcpyAsync(k.hhost, k.hdev, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+// Restarted GMRES on device vectors: solves dR/dq(q) x = b, x0 = 0; classical Gram-Schmidt applied twice (CGS2): two
+// batched dot kernels instead of j+1 dependent ones.  Convergence as PETSc's default test: rnorm <= max(reltol*|b|,
+// abstol); divergence when rnorm >= dtol*|b|.  reason: 1 rtol, 2 abstol, 3 exact breakdown, -1 itermax, -2 dtol.
+int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double abstol, double dtol, int64_t itermax,
+              int restart, int64_t* iters_out, double* rnorm_out, int* reason_out) {
+  int rc = kry_alloc(ctx, restart);
+  if (rc) return rc;
+  PdesCtx::Krylov& k = ctx->kry;
+  const int64_t n = ctx->ndof;
+  const int m = restart, S = restart + 2;
+  double* h1 = k.hdev;           // first projection coefficients
+  double* h2 = k.hdev + S;       // second pass
+  double* nq = k.hdev + 2 * S;   // squared norms
+  const int nb = k.nblk;
+  cudaStream_t st = ctx->stream;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m);
+  CUDA_TRY(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+  rc = kry_dots(ctx, b, 1, b, nq);
+  if (rc) return rc;
+  rc = kry_fetch(ctx, 3 * S);
+  if (rc) return rc;
+  const double bnorm = sqrt(k.hhost[2 * S]);
+  int64_t its = 0;
+  int reason = 0;
+  double rnorm = bnorm;
+  if (bnorm == 0.0) reason = 3;
+  const double tol = std::max(reltol * bnorm, abstol);
+  bool first = true;
+  while (!reason) {
+    // r = b - J x  (x = 0 in the first cycle)
+    if (first) {
+      k_axpby<<<nb, KRY_T, 0, st>>>(1.0, b, 0.0, k.w, n);
+    } else {
+      rc = enqueue_jvp(ctx, x, k.w);
+      if (rc) return rc;
+      k_axpby<<<nb, KRY_T, 0, st>>>(1.0, b, -1.0, k.w, n);
+    }
+    ctx->launches++;
+    rc = kry_dots(ctx, k.w, 1, k.w, nq);
+    if (rc) return rc;
+    k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V, n);
+    ctx->launches++;
+    rc = kry_fetch(ctx, 3 * S);
+    if (rc) return rc;
+    const double beta = sqrt(k.hhost[2 * S]);
+    rnorm = beta;
+    if (!first && beta <= tol) { reason = beta <= reltol * bnorm ? 1 : 2; break; }
+    first = false;
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int j = 0;
+    for (; j < m && !reason; ++j) {
+      rc = enqueue_jvp(ctx, k.V + (size_t)j * n, k.w);
+      if (rc) return rc;
+      rc = kry_dots(ctx, k.V, j + 1, k.w, h1);
+      if (rc) return rc;
+      k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, j + 1, h1, -1.0, k.w, n);
+      rc = kry_dots(ctx, k.V, j + 1, k.w, h2);
+      if (rc) return rc;
+      k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, j + 1, h2, -1.0, k.w, n);
+      rc = kry_dots(ctx, k.w, 1, k.w, nq);
+      if (rc) return rc;
+      k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V + (size_t)(j + 1) * n, n);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 3;
+      rc = kry_fetch(ctx, 3 * S);
+      if (rc) return rc;
+      for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = k.hhost[i] + k.hhost[S + i];
+      const double hn = sqrt(k.hhost[2 * S]);
+      H[(size_t)(j + 1) * m + j] = hn;
+      // previous Givens rotations, then the new one
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
+        H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
+        H[(size_t)i * m + j] = t;
+      }
+      const double a0 = H[(size_t)j * m + j], a1 = hn, d = hypot(a0, a1);
+      if (d == 0.0) { cs[j] = 1.0; sn[j] = 0.0; }
+      else { cs[j] = a0 / d; sn[j] = a1 / d; }
+      H[(size_t)j * m + j] = d;
+      H[(size_t)(j + 1) * m + j] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      rnorm = fabs(g[j + 1]);
+      ++its;
+      if (rnorm <= reltol * bnorm) reason = 1;
+      else if (rnorm <= abstol) reason = 2;
+      else if (hn == 0.0) reason = 3;
+      else if (rnorm >= dtol * bnorm) reason = -2;
+      else if (its >= itermax) reason = -1;
+    }
+    // x += V y with H y = g (back substitution over the j columns built in this cycle)
+    const int jj = j;
+    for (int i = jj - 1; i >= 0; --i) {
+      double sacc = g[i];
+      for (int c2 = i + 1; c2 < jj; ++c2) sacc -= H[(size_t)i * m + c2] * y[c2];
+      y[i] = H[(size_t)i * m + i] != 0.0 ? sacc / H[(size_t)i * m + i] : 0.0;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(h1, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
+    k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj, h1, 1.0, x, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));     // y is a host temporary
+    ctx->launches++;
+  }
+  *iters_out = its;
+  *rnorm_out = rnorm;
+  *reason_out = reason;
+  return PDES_OK;
+}
+
+// physicsRhs (jacobian/residual_evaluation.jl:64-88): res = R(q) on the device, returns calcNorm(strongres=true)
+int newton_rhs(PdesCtx* ctx, double* norm_out) {
+  int rc = pdes_eval_residual_async(ctx, 0.0);
+  if (rc) return rc;
+  PdesCtx::Krylov& k = ctx->kry;
+  k_strong_norm_partials<<<k.nblk, KRY_T, 0, ctx->stream>>>(ctx->res, ctx->minv, ctx->nd, ctx->ndof, k.partials);
+  k_reduce_rows<<<1, KRY_T, 0, ctx->stream>>>(k.partials, k.nblk, k.hdev);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaMemcpyAsync(k.hhost, k.hdev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = pdes_sync(ctx);                     // also turns a negative density / pressure into the reference's exception
+  if (rc) return rc;
+  *norm_out = sqrt(k.hhost[0]);
+  return PDES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pdes_gmres(PdesCtx* ctx, const double* b, double* x, double reltol, double abstol, double dtol, int64_t itermax,
+               int32_t restart, int64_t* iters_out, double* rnorm_out, int32_t* reason_out) {
+  if (!ctx || !b || !x || !iters_out || !rnorm_out || !reason_out) return usage(ctx, "pdes_gmres: null argument");
+  if (restart < 1 || itermax < 1) return usage(ctx, "pdes_gmres: restart and itermax must be positive");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (ctx->nS > 0) { set_err(ctx, "pdes_gmres is not implemented for partitioned meshes"); return PDES_ERR_UNSUPPORTED; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  rc = kry_alloc(ctx, restart);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kry.b, b, sizeof(double) * ctx->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  int reason = 0;
+  rc = gmres_dev(ctx, ctx->kry.b, ctx->kry.x, reltol, abstol, dtol, itermax, restart, iters_out, rnorm_out, &reason);
+  if (rc) return rc;
+  *reason_out = reason;
+  CUDA_TRY(ctx, cudaMemcpyAsync(x, ctx->kry.x, sizeof(double) * ctx->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_newton_krylov(PdesCtx* ctx, const PdesNewtonOpts* o, double* res_norms_out, double* step_norms_out,
+                       PdesNewtonResult* result) {
+  if (!ctx || !o || !result) return usage(ctx, "pdes_newton_krylov: null argument");
+  if (o->krylov_restart < 1 || o->krylov_itermax < 1 || o->itermax < 0) return usage(ctx, "pdes_newton_krylov: bad options");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (ctx->nS > 0) { set_err(ctx, "pdes_newton_krylov is not implemented for partitioned meshes"); return PDES_ERR_UNSUPPORTED; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  rc = kry_alloc(ctx, o->krylov_restart);
+  if (rc) return rc;
+  PdesCtx::Krylov& k = ctx->kry;
+  const int64_t n = ctx->ndof;
+  memset(result, 0, sizeof(*result));
+  double res_norm = 0.0, step_norm = 0.0;
+  rc = newton_rhs(ctx, &res_norm);
+  if (rc) return rc;
+  result->residual_evals = 1;
+  if (res_norms_out) res_norms_out[0] = res_norm;
+  const double res_norm_rel = res_norm;                      // set_rel_norm: the first residual (newton.jl:198-200)
+  auto converged = [&](int64_t itr) {                        // checkConvergence (newton.jl:402-445)
+    bool c = res_norm < o->res_abstol;
+    if (res_norm / res_norm_rel < o->res_reltol) c = true;
+    if (step_norm <= o->step_tol && itr > 0) c = true;
+    return c;
+  };
+  bool conv = converged(0);
+  int64_t itr = 0;
+  while (!conv && itr < o->itermax) {
+    ++itr;
+    // delta_q: J delta_q = -res
+    k_axpby<<<k.nblk, KRY_T, 0, ctx->stream>>>(-1.0, ctx->res, 0.0, k.b, n);
+    ctx->launches++;
+    int64_t kits = 0;
+    double krn = 0.0;
+    int reason = 0;
+    rc = gmres_dev(ctx, k.b, k.x, o->krylov_reltol, o->krylov_abstol, o->krylov_dtol, o->krylov_itermax,
+                   o->krylov_restart, &kits, &krn, &reason);
+    if (rc) return rc;
+    result->krylov_iters += kits;
+    result->krylov_reason = reason;
+    // step_norm = norm(delta_q_vec) (plain 2-norm, newton.jl:237), q += step_fac * delta_q
+    rc = kry_dots(ctx, k.x, 1, k.x, k.hdev);
+    if (rc) return rc;
+    k_axpby<<<k.nblk, KRY_T, 0, ctx->stream>>>(o->step_fac, k.x, 1.0, ctx->qbuf[ctx->cur], n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    rc = kry_fetch(ctx, 1);
+    if (rc) return rc;
+    step_norm = sqrt(k.hhost[0]);
+    if (step_norms_out) step_norms_out[itr - 1] = step_norm;
+    rc = newton_rhs(ctx, &res_norm);
+    if (rc) return rc;
+    result->residual_evals++;
+    if (res_norms_out) res_norms_out[itr] = res_norm;
+    conv = converged(itr);
+  }
+  result->converged = conv ? 1 : 0;
+  result->newton_iters = itr;
+  result->res_norm = res_norm;
+  result->res_norm_rel = res_norm_rel;
+  result->step_norm = step_norm;
+  return PDES_OK;
 }
 
 int pdes_get_minv(PdesCtx* ctx, double* Minv) {

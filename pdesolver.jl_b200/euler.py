@@ -249,6 +249,66 @@ def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=Fa
     return t_out.value
 
 
+def _krylov_opts(opts):
+    """Linear-solver defaults of the input system (input/read_input.jl:493-496, 560-570: GMRES restart 30)."""
+    return dict(reltol=float(opts.get("krylov_reltol", 1e-2)), abstol=float(opts.get("krylov_abstol", 1e-50)),
+                dtol=float(opts.get("krylov_dtol", 1e5)), itermax=int(opts.get("krylov_itermax", 1000)),
+                restart=int(opts.get("krylov_restart", 30)))
+
+
+def linearSolve(mesh, sbp, eqn: EulerData, opts, b, x=None):
+    """``linearSolve(ls, b, x)`` (linearsolvers) for the matrix-free operator of jac_type 4: solves
+    ``dR/dq(eqn.q) x = b`` by restarted GMRES on the device (no preconditioner), zero initial guess.
+    Returns ``x``; iteration count, final residual norm and PETSc-style reason are left in ``eqn.krylov_info``."""
+    b = np.asfortranarray(np.asarray(b, dtype=np.float64).reshape(eqn.q.shape, order="F"))
+    if x is None:
+        x = np.zeros_like(eqn.q, order="F")
+    k = _krylov_opts(opts)
+    L, ctx = eqn._L, eqn._ctx
+    its, rn, reason = C.c_int64(0), C.c_double(0.0), C.c_int32(0)
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_gmres(ctx, _ptr(b), _ptr(x), k["reltol"], k["abstol"], k["dtol"], k["itermax"], k["restart"],
+                            C.byref(its), C.byref(rn), C.byref(reason)))
+    eqn.krylov_info = {"iterations": its.value, "rnorm": rn.value, "reason": reason.value}
+    return x
+
+
+def newton(func, mesh, sbp, eqn: EulerData, opts, pmesh=None, t=0.0):
+    """``newton(func, mesh, sbp, eqn, opts, pmesh=mesh, t=0.0)`` (NonlinearSolvers/newton.jl:54-74) for the
+    matrix-free configuration (``jac_type = 4``: Jacobian-vector products of the residual, Krylov linear solves;
+    BASELINE.json configuration 5).  Newton's method on ``R(q) = 0`` starting from ``eqn.q``: ``dR/dq dq = -R(q)`` by
+    GMRES on the device, ``q += dq``, until ``res_abstol`` / ``res_reltol`` (relative to the first residual) /
+    ``step_tol`` or ``itermax`` (newtonInner, newton.jl:137-304; checkConvergence :402-445).  The residual-norm and
+    step-norm histories are left in ``eqn.convergence`` / ``eqn.step_norms``; ``eqn.newton_info`` holds the counts.
+    Returns None like the reference."""
+    if func is not evalResidual:
+        raise PDESolverError("newton: func must be pdesolver_jl_b200.evalResidual (device-resident residual)")
+    jac_type = int(opts.get("jac_type", 4))
+    if jac_type != 4:
+        raise PDESolverError("newton: only the matrix-free Jacobian (jac_type = 4) is implemented on the device")
+    from ._cabi import PdesNewtonOpts, PdesNewtonResult
+    k = _krylov_opts(opts)
+    o = PdesNewtonOpts(itermax=int(opts.get("itermax", 10)), res_abstol=float(opts.get("res_abstol", 1e-6)),
+                       res_reltol=float(opts.get("res_reltol", 1e-6)), step_tol=float(opts.get("step_tol", 0.0)),
+                       step_fac=1.0, krylov_reltol=k["reltol"], krylov_abstol=k["abstol"], krylov_dtol=k["dtol"],
+                       krylov_itermax=k["itermax"], krylov_restart=k["restart"])
+    res_norms = np.zeros(o.itermax + 1)
+    step_norms = np.zeros(max(o.itermax, 1))
+    r = PdesNewtonResult()
+    L, ctx = eqn._L, eqn._ctx
+    eqn.params.t = t
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_newton_krylov(ctx, C.byref(o), _ptr(res_norms), _ptr(step_norms), C.byref(r)))
+    eqn._check(L.pdes_get_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_get_res(ctx, _ptr(eqn.res)))
+    eqn.convergence = res_norms[:r.newton_iters + 1].copy()
+    eqn.step_norms = step_norms[:r.newton_iters].copy()
+    eqn.newton_info = {"converged": bool(r.converged), "newton_iters": r.newton_iters, "krylov_iters": r.krylov_iters,
+                       "residual_evals": r.residual_evals, "krylov_reason": r.krylov_reason,
+                       "res_norm": r.res_norm, "res_norm_rel": r.res_norm_rel, "step_norm": r.step_norm}
+    return None
+
+
 def createObjects(mesh, sbp, opts, device=0):
     """Synthetic-mesh analogue of ``createObjects`` (solver/euler/startup_func.jl:45-66):
     returns ``(mesh, sbp, eqn, opts)`` with the device context initialised."""

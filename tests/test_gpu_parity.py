@@ -493,3 +493,73 @@ def test_fused_kernel_bitwise_equals_split(case, n, monkeypatch):
     assert np.array_equal(out["0"][1], out["1"][1])
     assert np.array_equal(out["0"][2], out["1"][2])
     assert out["0"][3] == out["1"][3]
+
+
+def test_gmres_solves_jacobian_system():
+    """pdes_gmres (the linear solve of the matrix-free Newton path, newton_setup.jl:632-662 +
+    PETSc GMRES defaults read_input.jl:493-496, 560-570): x must satisfy dR/dq x = b, checked against a dense
+    solve with the Jacobian assembled column by column from evaldRdqProduct."""
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 3, shuffle_seed=4)
+    eqn.q[...] = q0
+    n = q0.size
+    J = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        J[:, j] = pd.evaldRdqProduct(mesh, op, eqn, opts, e.reshape(q0.shape, order="F")).ravel(order="F")
+    rng = np.random.RandomState(7)
+    b = rng.standard_normal(n)
+    opts.update({"krylov_reltol": 1e-11, "krylov_itermax": 5 * n, "krylov_restart": n})     # full GMRES
+    x = pd.linearSolve(mesh, op, eqn, opts, b.reshape(q0.shape, order="F")).ravel(order="F")
+    info = eqn.krylov_info
+    assert info["reason"] == 1 and info["iterations"] <= n
+    assert np.linalg.norm(J @ x - b) / np.linalg.norm(b) < 1e-10
+    assert rel_l2(x, np.linalg.solve(J, b)) < 1e-8
+    # restarted GMRES(30), loose tolerance (the reference's defaults): the residual test must hold for the true residual
+    opts.update({"krylov_reltol": 1e-2, "krylov_itermax": 1000, "krylov_restart": 30})
+    x = pd.linearSolve(mesh, op, eqn, opts, b.reshape(q0.shape, order="F")).ravel(order="F")
+    assert eqn.krylov_info["reason"] == 1
+    assert np.linalg.norm(J @ x - b) / np.linalg.norm(b) < 1.05e-2
+    # zero right-hand side: exact breakdown, x = 0
+    x = pd.linearSolve(mesh, op, eqn, opts, np.zeros_like(q0))
+    assert eqn.krylov_info["reason"] == 3 and not x.any()
+
+
+def test_newton_krylov_reference_convergence_golden():
+    """The reference reaches the steady isentropic vortex of test/euler/convergence/p1/conservative_dg with Newton's
+    method (runtests.jl:1-42: err[1] = 0.01200 x/ 1.25, slope 2.00 +- 0.1).  Same meshes, Newton-Krylov on the device
+    (newton.jl:54-304 semantics, matrix-free): quadratic convergence to res_abstol and the golden error."""
+    from test_oracle_golden import _steady_vortex_error
+    hist = {}
+
+    def runner(mesh, op, opts, P, q0, h):
+        opts = dict(opts, jac_type=4, itermax=20, res_abstol=1e-11, res_reltol=1e-30, krylov_reltol=1e-6,
+                    krylov_itermax=4000, krylov_restart=200)
+        eqn = pd.EulerData(mesh, op, opts)
+        eqn.q[...] = q0
+        pd.newton(pd.evalResidual, mesh, op, eqn, opts)
+        assert eqn.newton_info["converged"] and eqn.convergence[-1] < 1e-11
+        assert eqn.newton_info["newton_iters"] <= 8            # Newton, not a fixed-point crawl
+        hist[mesh.numEl] = eqn.convergence
+        # the residual the solver leaves in eqn.res is the one of the final q
+        res = eqn.res.copy(order="F")
+        pd.evalResidual(mesh, op, eqn, opts)
+        assert np.array_equal(res, eqn.res)
+        return eqn.q.copy(order="F")
+    e1 = _steady_vortex_error(runner, "squarevortex_small", 0.02)
+    e2 = _steady_vortex_error(runner, "squarevortex_large", 0.01)
+    assert 0.01200 / 1.25 < e1 < 0.01200 * 1.25 and abs(e1 - 0.01200) < 2e-5
+    assert 1.9 < np.log(e1 / e2) / np.log(2.0) < 2.1
+
+
+def test_newton_option_errors():
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 3)
+    with pytest.raises(pd.PDESolverError):
+        pd.newton(pd.evalResidual, mesh, op, eqn, dict(opts, jac_type=2))
+    with pytest.raises(pd.PDESolverError):
+        pd.newton(lambda *a: None, mesh, op, eqn, opts)
+    # initial condition already satisfies res_abstol: no iteration (newton.jl:205-210)
+    eqn.q[...] = q0
+    pd.newton(pd.evalResidual, mesh, op, eqn, dict(opts, res_abstol=1e30))
+    assert eqn.newton_info["newton_iters"] == 0 and eqn.newton_info["converged"] and len(eqn.convergence) == 1
+    assert np.array_equal(eqn.q, q0)
