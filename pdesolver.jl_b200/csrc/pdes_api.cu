@@ -404,7 +404,7 @@ struct PdesCtx {
   int cur = 0;
   double *ksum = nullptr, *res = nullptr;
   // mesh
-  double *dxidx = nullptr, *minv = nullptr, *srcw = nullptr, *coords_bndry = nullptr, *w_dev = nullptr;
+  double *dxidx = nullptr, *minv = nullptr, *mass = nullptr, *srcw = nullptr, *coords_bndry = nullptr, *w_dev = nullptr;
   FaceRec* faces = nullptr;
   double *nrm_all = nullptr, *fluxe = nullptr, *srcm = nullptr;
   std::vector<EFace> h_efaces;      // interior + boundary part (shared faces added by finalize)
@@ -672,7 +672,7 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->q = q; a->dxidx = ctx->dxidx; a->fluxe = ctx->fluxe;
   a->srcw = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcw : nullptr;
   a->srcm = ctx->cfg.src_id == PDES_SRC_EXP ? ctx->srcm : nullptr;
-  a->minv = ctx->minv; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
+  a->minv = ctx->minv; a->mass = ctx->mass; a->nE = ctx->cfg.nE; a->ctl = ctx->ctl; a->ph = phys_of(ctx->cfg);
   a->norm_partials = ctx->norm_partials;
   a->e_begin = 0;
   const int dd = ctx->cfg.dim * ctx->cfg.dim;
@@ -1002,7 +1002,7 @@ void pdes_destroy(PdesCtx* ctx) {
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
                   ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
-                  ctx->plan[1].need, ctx->flags, ctx->sched, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
+                  ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
                   ctx->kry.partials, ctx->kry.hdev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
@@ -1134,8 +1134,9 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
   double* jac_dev = nullptr;
   CUDA_TRY(ctx, dev_upload(ctx->stream, &jac_dev, jac, nnE));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->minv, nullptr, nnE));
+  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->mass, nullptr, nnE));
   unsigned nb = (unsigned)((nnE + 255) / 256);
-  k_minv<<<nb, 256, 0, ctx->stream>>>(jac_dev, ctx->w_dev, c.nn, c.nE, ctx->minv);
+  k_minv<<<nb, 256, 0, ctx->stream>>>(jac_dev, ctx->w_dev, c.nn, c.nE, ctx->minv, ctx->mass);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   if (c.src_id == PDES_SRC_EXP) {

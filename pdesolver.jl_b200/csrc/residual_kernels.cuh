@@ -30,6 +30,11 @@
 #define PDES_OPT 0      // all three measured slower on C3 (1.101 / 1.141 / 1.129 vs 1.093 ms per RK4 step). bit 0: pipelined metrics loads in S1; bit 1: face records two faces ahead; bit 2: staged Minv
 #endif
 
+#ifndef PDES_SKEL
+#define PDES_SKEL 0     // measurement builds only (results are meaningless): bit 0 drops the operator / Roe arithmetic,
+#endif                  // 1: no face-record loads (element), 2: no volume-flux tile (element), 3: no L2 prefetches,
+                        // 4: no element gathers (face), 5: no record stores (face), 6: no epilogue streams (element)
+
 namespace pdes {
 
 // host-side bookkeeping per (element, local face): which face covers it (every element face must be claimed by
@@ -100,6 +105,7 @@ struct ElemArgs {
   double* res;                 // EPI_RES: [ND,NN,nE]
   // EPI_RK (rk4.jl:244-319): k = Minv*res; q_next = x_old + ah*k; ksum updated; last stage: x_new
   const double* minv;          // [NN,nE]  1/(w_j/jac_j)   (mass_matrix.jl:20-44)
+  const double* mass;          // [NN,nE]  w_j/jac_j = eqn.M: the weight of calcNorm (Utils.jl:427-449)
   const double* x_old;
   double* ksum;
   double* q_next;
@@ -116,7 +122,9 @@ struct ElemArgs {
   PhysPar ph;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  if (!(PDES_SKEL & 8)) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // Ampere-style asynchronous global->shared copies (LDGSTS): issued at the top of a tile, consumed stages later
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -255,12 +263,12 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
     {
       const double* b = a.q + (int64_t)r.elL * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) ql[j] = __ldg(b + sm.s_perm[r.fL][j] * ND);
+      for (int j = 0; j < NN; ++j) ql[j] = (PDES_SKEL & 16) ? 1.0 + j : __ldg(b + sm.s_perm[r.fL][j] * ND);
     }
     if (r.kind == FK_INTERIOR) {
       const double* b = a.q + (int64_t)r.elR * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) qr[j] = __ldg(b + sm.s_perm[r.fR][j] * ND);
+      for (int j = 0; j < NN; ++j) qr[j] = (PDES_SKEL & 16) ? 2.0 + j : __ldg(b + sm.s_perm[r.fR][j] * ND);
     } else {
 #pragma unroll
       for (int j = 0; j < NN; ++j) qr[j] = 0.0;
@@ -269,12 +277,17 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
 #pragma unroll
     for (int i = 0; i < NFN; ++i) {
       double s = 0.0, t = 0.0;
+#if (PDES_SKEL & 1)
+#pragma unroll
+      for (int j = i; j < NN; j += NFN) { s += ql[j]; t += qr[j]; }
+#else
 #pragma unroll
       for (int j = 0; j < NN; ++j) {
         const double c = op.interp[j][i];
         s = fma(c, ql[j], s);
         t = fma(c, qr[j], t);
       }
+#endif
       sL[fi * FS + i * ND + k] = s;
       // elementR's face node i coincides with elementL's face node nbrperm[i,orient] (involution)
       if (r.kind == FK_INTERIOR) sR[fi * FS + sm.s_nbrperm[r.orient][i] * ND + k] = t;
@@ -318,7 +331,12 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
 #pragma unroll
         for (int k = 0; k < ND; ++k) flux[k] = fb[k];
       } else {
+#if (PDES_SKEL & 1)
+#pragma unroll
+        for (int k = 0; k < ND; ++k) flux[k] = qL[k] + qR[k] * nrm[k % DIM];
+#else
         roe_flux<DIM>(qL, qR, nrm, a.ph.gamma, flux);
+#endif
       }
       const double w = op.wface[i];
       const int ir = (r.kind == FK_INTERIOR) ? sm.s_nbrperm[r.orient][i] : i;
@@ -336,7 +354,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
   constexpr int FL = NFN * ND;
   {
     const int half = tid >> 4, hl = tid & 15;
-    for (int rec = half; rec < 2 * nf; rec += TB / 16) {
+    for (int rec = half; rec < ((PDES_SKEL & 32) ? (int)(sL[0] == 12345.678) : 2 * nf); rec += TB / 16) {
       const int di = sm.s_dst[rec];
       if (di < 0) continue;
       const double* src = ((rec & 1) ? sR : sL) + (rec >> 1) * FS;
@@ -365,6 +383,8 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
 template <int DIM, int NN, int NFN, int FT, int MINB>
 __global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
 k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  // one CTA per tile: a persistent loop over tiles was measured (no gain, and under the 80-register cap the loop
+  // state spills: 1.134 vs 1.093 ms per RK4 step on C3)
   constexpr int T = FaceCfg<DIM, NN, NFN, FT>::T;
   __shared__ FaceTileSmem<DIM, NN, NFN, FT> sm;
   if (a.ctl->stop) return;
@@ -666,13 +686,11 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         const double2 k = make_double2(v[u].x + sv[u].x, v[u].y + sv[u].y);
         double2 o1 = k, o2 = k;
         if (MODE == EPI_RK && a.stage == 1) {
-          // calcNorm: sum res*M*res (Utils.jl:427-449), M = 1/Minv of the dof's node
-          const int sa = (2 * i2) / EL, ra = (2 * i2) - sa * EL;
-          nrm2 += k.x * k.x / __ldg(a.minv + (e0 + sa) * NN + ra / ND);
-          if (two[u]) {
-            const int sb = (2 * i2 + 1) / EL, rb = (2 * i2 + 1) - sb * EL;
-            nrm2 += k.y * k.y / __ldg(a.minv + (e0 + sb) * NN + rb / ND);
-          }
+          // calcNorm: sum res*M*res (Utils.jl:427-449); the tile's nodes are contiguous in M: node = dof / ND
+          // (a multiplication by the stored M as in the reference: an FP64 division per dof cost 25 us per step)
+          const double* mt = a.mass + e0 * NN;
+          nrm2 = fma(k.x * __ldg(mt + (2 * i2) / ND), k.x, nrm2);
+          if (two[u]) nrm2 = fma(k.y * __ldg(mt + (2 * i2 + 1) / ND), k.y, nrm2);
         }
         if (MODE == EPI_RK && a.scheme == 1) {
           // lserk54: dq = a_s*dq + delta_t*res ; q += b_s*dq
@@ -749,7 +767,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
   constexpr int FL = NFN * ND;                      // doubles per face
   double* sq = reinterpret_cast<double*>(smem_raw);             // [E][EL]
   double* sF = sq + E * SQ;                                     // [E][ND][DIM][NN]
-  auto ldrec = [](const double* p) { return COHERENT ? *p : __ldg(p); };
+  auto ldrec = [](const double* p) { return (PDES_SKEL & 2) ? 1.0 : (COHERENT ? *p : __ldg(p)); };
 
   const double gami = a.ph.gamma - 1.0;
 
@@ -823,7 +841,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
       for (int m = 0; m < DIM * DIM; ++m) dxn[m] = __ldg(dx + m);
     }
     const double press = calc_pressure<DIM>(qn, gami);
-    if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
+    if (!PDES_SKEL && ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0)))) {
       const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
       const unsigned long long loc = ((unsigned long long)(e0 + s) << 8) | (unsigned)j;
       // density errors win over pressure errors (checkDensity runs first), lowest location wins
@@ -884,13 +902,17 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
     for (int d = 0; d < DIM; ++d) {
 #pragma unroll
       for (int j = 0; j < NN; ++j) {
-        const double f0 = F0[d * NN + j], f1 = F1[d * NN + j];
+        const double f0 = (PDES_SKEL & 4) ? 1.0 : F0[d * NN + j], f1 = (PDES_SKEL & 4) ? 1.0 : F1[d * NN + j];
+#if (PDES_SKEL & 1)
+        acc0[j] += f0; acc1[j] += f1;
+#else
 #pragma unroll
         for (int u = 0; u < NN; ++u) {
           const double c = op.Qt[d * NN + j][u];
           acc0[u] = fma(c, f0, acc0[u]);
           acc1[u] = fma(c, f1, acc1[u]);
         }
+#endif
       }
     }
   }
@@ -901,10 +923,12 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
     cp_async_wait<0>();
     __syncthreads();
     const unsigned long long pol = policy_evict_first();
+    if (!(PDES_SKEL & 64)) {
     if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
     if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);   // x_old == q of this stage
     else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
     if (a.stage > 1) async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
+    }
     cp_async_commit();
   }
   if (act0) {
@@ -921,6 +945,10 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
           n1v[i] = ldrec(G1 + ((f + AH) * NFN + i) * ND);
         }
       }
+#if (PDES_SKEL & 1)
+#pragma unroll
+      for (int i = 0; i < NFN; ++i) { acc0[i] += g0v[i]; acc1[i] += g1v[i]; }
+#else
 #pragma unroll
       for (int i = 0; i < NFN; ++i)
 #pragma unroll
@@ -929,6 +957,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
           acc0[u] = fma(c, g0v[i], acc0[u]);
           acc1[u] = fma(c, g1v[i], acc1[u]);
         }
+#endif
 #pragma unroll
       for (int i = 0; i < NFN; ++i) {
         if (PDES_OPT & 2) { g0v[i] = h0v[i]; g1v[i] = h1v[i]; h0v[i] = n0v[i]; h1v[i] = n1v[i]; }
@@ -1422,10 +1451,12 @@ __global__ void k_srcm(const double* __restrict__ srcw, const double* __restrict
 }
 
 __global__ void k_minv(const double* __restrict__ jac, const double* __restrict__ w, int nn, int64_t nE,
-                       double* __restrict__ minv) {
+                       double* __restrict__ minv, double* __restrict__ mass) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nE * nn) return;
-  minv[t] = 1.0 / (w[t % nn] / jac[t]);
+  const double m = w[t % nn] / jac[t];
+  mass[t] = m;
+  minv[t] = 1.0 / m;
 }
 
 }  // namespace pdes
