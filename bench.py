@@ -120,7 +120,8 @@ def build_problem(wl, rank, nranks):
     if nranks > 1 and wl["dim"] == 2:
         parts = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
     n = tuple(wl["n"] * p for p in parts)
-    mesh = pd.structured_mesh(op, n, parts=parts, rank=rank)
+    # 2D: the reference's benchmark meshes cut every square along the "\\" diagonal (tests/test_smb.py)
+    mesh = pd.structured_mesh(op, n, parts=parts, rank=rank, diagonal="\\")
     opts = dict(wl["opts"])
     opts["use_itermax"] = False
     params = pd.ParamType(opts)
@@ -137,7 +138,7 @@ def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
     from pdesolver_jl_b200 import ic
     op = pd.build_operator(wl["dim"], wl["p"], wl.get("kind", "omega"))
     n = sample_cells or wl.get("cpu_cells", wl["n"])
-    mesh = pd.structured_mesh(op, n)
+    mesh = pd.structured_mesh(op, n, diagonal="\\")
     opts = dict(wl["opts"])
     P = oracle.Problem(mesh, op, opts)
     q0 = perturbed(ic.ICDict[wl["ic"]](mesh.coords, pd.ParamType(opts)))

@@ -256,7 +256,7 @@ def _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of):
 
 
 def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
-                    domain=None, bc_sides=None, shuffle_seed=None) -> Mesh:
+                    domain=None, bc_sides=None, shuffle_seed=None, diagonal="/") -> Mesh:
     """Structured simplex mesh of ``n^dim`` cells; ``n`` may also be
     one cell count per dimension (the cell size then stays ``(domain[1]-domain[0])/n[0]``
     in every direction, i.e. the box grows: used for weak-scaling runs).
@@ -264,6 +264,9 @@ def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
     parts: block partition (px,py[,pz]); ``rank`` selects the local block.
     bc_sides: optional list, one BC index per geometric side
     (xmin,xmax,ymin,ymax[,zmin,zmax]); default: all sides in BC 0.
+    diagonal (2D): "/" cuts every square from (x0,y0) to (x1,y1); "\\" from (x1,y0) to (x0,y1), which is the
+    triangulation of the reference's ``square_benchmarksmall`` (perf/input_vals_2d_rk4.jl; verified against the
+    .smb fixture in tests/test_smb.py).  The 3D Kuhn split already equals ``cube_benchmarksmall``.
     shuffle_seed: if given, apply a pseudo-random even permutation (keyed on the
     global element number, so it is partition independent) to every element's
     vertex list; this exercises every faceL/faceR/orient combination, which the
@@ -307,6 +310,10 @@ def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
     if dim == 2:
         # A = (v00, v10, v11), B = (v00, v11, v01): same diagonal everywhere
         simp = np.array([[[0, 0], [1, 0], [1, 1]], [[0, 0], [1, 1], [0, 1]]])
+        if diagonal == "\\":
+            simp = np.array([[[0, 0], [1, 0], [0, 1]], [[1, 0], [1, 1], [0, 1]]])
+        elif diagonal != "/":
+            raise ValueError("diagonal must be '/' or '\\'")
     else:
         simp = _kuhn_tets()
     ns = simp.shape[0]

@@ -563,3 +563,25 @@ def test_newton_option_errors():
     pd.newton(pd.evalResidual, mesh, op, eqn, dict(opts, res_abstol=1e30))
     assert eqn.newton_info["newton_iters"] == 0 and eqn.newton_info["converged"] and len(eqn.convergence) == 1
     assert np.array_equal(eqn.q, q0)
+
+
+@pytest.mark.parametrize("name,dim,p,ic,extra,h", [
+    ("square_benchmarksmall", 2, 1, "ICIsentropicVortex", {"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}, 1e-3),
+    ("cube_benchmarksmall", 3, 2, "ICExp", {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}, 5e-5)])
+def test_reference_benchmark_meshes(name, dim, p, ic, extra, h):
+    """perf/input_vals_2d_rk4.jl and perf/input_vals_3d_rk4.jl (BASELINE.json configurations 1 and 3) on the reference's
+    own PUMI meshes (fixtures imported by tests/golden/import_smb.py): residual and RK4 trajectory against the oracle."""
+    from test_smb import fixture_mesh
+    op = pd.build_operator(dim, p)
+    mesh = fixture_mesh(op, name)
+    opts = dict(extra, use_itermax=False)
+    orc = oracle.Problem(mesh, op, opts)
+    q0 = perturbed(orc.exact_state(ic))
+    eqn = pd.EulerData(mesh, op, opts)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+    t = pd.rk4(pd.evalResidual, h, 8 * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 8 * h)
+    assert t == t_ref and rel_l2(eqn.q, q_ref) < RK_TOL
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
