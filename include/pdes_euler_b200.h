@@ -195,6 +195,12 @@ int pdes_lserk54(PdesCtx *ctx, double h, double t_max, int64_t itermax, double r
 /* n plain RK4 steps, no host sync inside (bench inner loop; CUDA-graph replay) */
 int pdes_rk4_steps_async(PdesCtx *ctx, double h, int64_t nsteps);
 
+/* Functionals of majorIterationCallback (solver/euler/euler.jl:330-407) for the resident q, reduced on the device after
+ * one residual evaluation: out[0] calcEntropyIntegral, out[1] contractResEntropyVars (w^T R), out[2] calcKineticEnergy,
+ * out[3] calcKineticEnergydt (solver/euler/entropy_flux.jl:141-186, 414-485), out[4] mesh.volume (sum of M),
+ * out[5..5+nd) integrateQ (entropy_flux.jl:231-247).  Per mesh part: the Allreduce over ranks stays with the host. */
+int pdes_diagnostics(PdesCtx *ctx, double *out);
+
 /* eqn.Minv[nd,nn,nE] as the reference computes it (mass_matrix.jl:20-44) */
 int pdes_get_minv(PdesCtx *ctx, double *Minv);
 int pdes_get_timings(PdesCtx *ctx, PdesTimings *out);

@@ -32,7 +32,7 @@ EXPORTS = [
     "pdes_res_dev", "pdes_eval_residual", "pdes_eval_residual_async", "pdes_sync", "pdes_rk4",
     "pdes_rk4_steps_async", "pdes_get_minv", "pdes_get_timings", "pdes_kernel_launch_count",
     "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp", "pdes_lserk54",
-    "pdes_newton_krylov", "pdes_gmres",
+    "pdes_newton_krylov", "pdes_gmres", "pdes_diagnostics",
 ]
 
 
@@ -92,7 +92,7 @@ def lib():
         L.pdes_set_comm.argtypes = [p, p, i32, i32]
         L.pdes_pack_send.argtypes = [p, i32, p]
         L.pdes_inject_recv.argtypes = [p, i32, p]
-        for n in ("pdes_set_q", "pdes_get_q", "pdes_get_res", "pdes_get_minv", "pdes_set_q_dev"):
+        for n in ("pdes_set_q", "pdes_get_q", "pdes_get_res", "pdes_get_minv", "pdes_set_q_dev", "pdes_diagnostics"):
             getattr(L, n).argtypes = [p, p]
         L.pdes_q_dev.argtypes = [p]
         L.pdes_q_dev.restype = p

@@ -23,6 +23,7 @@
 #include "es_kernels.cuh"
 #include "jvp_kernels.cuh"
 #include "krylov_kernels.cuh"
+#include "diag_kernels.cuh"
 
 using namespace pdes;
 
@@ -423,6 +424,8 @@ struct PdesCtx {
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
   Sched* sched = nullptr;
   unsigned* flags = nullptr;
+  double* diag_buf = nullptr;
+  int diag_B = 0;
   // Newton-Krylov workspace (allocated on first use): basis V[(restart+1)][ndof], work vectors, reduction scratch
   struct Krylov {
     int restart = 0, nblk = 0;
@@ -1002,7 +1005,7 @@ void pdes_destroy(PdesCtx* ctx) {
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
                   ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
-                  ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
+                  ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
                   ctx->kry.partials, ctx->kry.hdev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
@@ -1731,6 +1734,42 @@ int pdes_newton_krylov(PdesCtx* ctx, const PdesNewtonOpts* o, double* res_norms_
   result->res_norm = res_norm;
   result->res_norm_rel = res_norm_rel;
   result->step_norm = step_norm;
+  return PDES_OK;
+}
+
+// majorIterationCallback functionals (euler.jl:330-407) of the resident q: evaluates R(q) and reduces on the device.
+// out[0..5+nd): entropy integral, w^T R, kinetic energy, d(kinetic energy)/dt, volume, integral of q[0..nd)
+int pdes_diagnostics(PdesCtx* ctx, double* out) {
+  if (!ctx || !out) return usage(ctx, "pdes_diagnostics: null argument");
+  int rc = pdes_eval_residual_async(ctx, 0.0);
+  if (rc) return rc;
+  const int nv = 5 + ctx->nd;
+  const int64_t n_nodes = (int64_t)ctx->cfg.nn * ctx->cfg.nE;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int B = (int)std::max<int64_t>(1, std::min<int64_t>((n_nodes + DIAG_T - 1) / DIAG_T, (int64_t)sms * 4));
+  if (!ctx->diag_buf || ctx->diag_B != B) {
+    if (ctx->diag_buf) cudaFree(ctx->diag_buf);
+    ctx->diag_buf = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->diag_buf, sizeof(double) * (size_t)nv * (B + 1)));
+    ctx->diag_B = B;
+  }
+  double* partials = ctx->diag_buf;
+  double* sums = ctx->diag_buf + (size_t)nv * B;
+  if (ctx->cfg.dim == 2)
+    k_diag_partials<2><<<B, DIAG_T, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->res, ctx->mass, n_nodes, ctx->cfg.gamma, partials);
+  else
+    k_diag_partials<3><<<B, DIAG_T, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->res, ctx->mass, n_nodes, ctx->cfg.gamma, partials);
+  k_reduce_rows<<<nv, KRY_T, 0, ctx->stream>>>(partials, B, sums);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, sums, sizeof(double) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = pdes_sync(ctx);
+  if (rc) return rc;
+  const double volume = out[4];
+  out[2] = 0.5 * out[2] / volume;
+  out[3] = out[3] / volume;
   return PDES_OK;
 }
 

@@ -249,6 +249,44 @@ def rk4(f, h, t_max, mesh, sbp, eqn: EulerData, opts, res_tol=-1.0, real_time=Fa
     return t_out.value
 
 
+def diagnostics(mesh, sbp, eqn: EulerData, opts):
+    """The functionals ``majorIterationCallback`` logs (solver/euler/euler.jl:330-407) for ``eqn.q``, evaluated on the
+    device in one reduction pass after one residual evaluation: ``calcEntropyIntegral``, ``contractResEntropyVars``
+    (``w^T R``), ``calcKineticEnergy``, ``calcKineticEnergydt`` (solver/euler/entropy_flux.jl:141-186, 414-485),
+    ``volume`` and ``integrateQ`` (:231-247).  ``eqn.res`` is left holding R(q) on the device side only."""
+    out = np.zeros(5 + eqn.q.shape[0])
+    L, ctx = eqn._L, eqn._ctx
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_diagnostics(ctx, _ptr(out)))
+    return {"entropy_integral": out[0], "wT_res": out[1], "kinetic_energy": out[2], "kinetic_energy_dt": out[3],
+            "volume": out[4], "integral_q": out[5:].copy()}
+
+
+def calcEntropyIntegral(mesh, sbp, eqn: EulerData, opts, q_vec=None):
+    """solver/euler/entropy_flux.jl:141-157"""
+    return diagnostics(mesh, sbp, eqn, opts)["entropy_integral"]
+
+
+def contractResEntropyVars(mesh, sbp, eqn: EulerData, opts, q_vec=None, res_vec=None):
+    """solver/euler/entropy_flux.jl:164-186 with res_vec = the weak residual of eqn.q"""
+    return diagnostics(mesh, sbp, eqn, opts)["wT_res"]
+
+
+def integrateQ(mesh, sbp, eqn: EulerData, opts, q_vec=None):
+    """solver/euler/entropy_flux.jl:231-247"""
+    return diagnostics(mesh, sbp, eqn, opts)["integral_q"]
+
+
+def calcKineticEnergy(mesh, sbp, eqn: EulerData, opts, q_vec=None):
+    """solver/euler/entropy_flux.jl:414-440"""
+    return diagnostics(mesh, sbp, eqn, opts)["kinetic_energy"]
+
+
+def calcKineticEnergydt(mesh, sbp, eqn: EulerData, opts, q_vec=None, res_vec=None):
+    """solver/euler/entropy_flux.jl:456-485 with res_vec = Minv R(eqn.q)"""
+    return diagnostics(mesh, sbp, eqn, opts)["kinetic_energy_dt"]
+
+
 def _krylov_opts(opts):
     """Linear-solver defaults of the input system (input/read_input.jl:493-496, 560-570: GMRES restart 30)."""
     return dict(reltol=float(opts.get("krylov_reltol", 1e-2)), abstol=float(opts.get("krylov_abstol", 1e-50)),

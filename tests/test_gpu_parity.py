@@ -585,3 +585,40 @@ def test_reference_benchmark_meshes(name, dim, p, ic, extra, h):
     t_ref, q_ref, norms_ref = orc.rk4(q0, h, 8 * h)
     assert t == t_ref and rel_l2(eqn.q, q_ref) < RK_TOL
     assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 7), ("c3_3d_p2_roe_src", 3), ("c2_2d_p2_es", 6)])
+def test_device_diagnostics(case, n):
+    """the functionals of majorIterationCallback (euler.jl:330-407), reduced on the device, against
+    their definitions (entropy_flux.jl:141-186, 231-247, 414-485) evaluated with numpy on the oracle's residual."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=9)
+    eqn.q[...] = q0
+    d = pd.diagnostics(mesh, op, eqn, opts)
+    g, g1 = 1.4, 0.4
+    R = orc.eval_residual(q0)
+    M = 1.0 / orc.mass_matrix_inverse()            # [nd, nn, nE], equal over the variables of a node
+    Mn = M[0]
+    dim = op.dim
+    rho, mom, E = q0[0], q0[1:1 + dim], q0[dim + 1]
+    k1 = 0.5 * (mom ** 2).sum(axis=0) / rho
+    rho_int = E - k1
+    p = g1 * rho_int
+    U = -rho * (np.log(p) - g * np.log(rho)) / g1
+    assert abs(d["entropy_integral"] - (U * Mn).sum()) <= 1e-12 * abs((U * Mn).sum())
+    s = np.log(g1 * rho_int / rho ** g)
+    w = np.concatenate([((rho_int * (g + 1 - s) - E) / rho_int)[None], mom / rho_int, (-rho / rho_int)[None]]) / g1
+    wr = (w * R).sum()
+    assert abs(d["wT_res"] - wr) <= 1e-11 * np.abs(w * R).sum()
+    vol = Mn.sum()
+    assert abs(d["volume"] - vol) <= 1e-13 * vol
+    v = mom / rho
+    ke = 0.5 * (Mn * rho * (v ** 2).sum(axis=0)).sum() / vol
+    assert abs(d["kinetic_energy"] - ke) <= 1e-12 * ke
+    dqdt = R / M
+    kedt = (Mn * (v * (dqdt[1:1 + dim] - dqdt[0] * v)).sum(axis=0)).sum() / vol
+    assert abs(d["kinetic_energy_dt"] - kedt) <= 1e-11 * (Mn * np.abs(v * (dqdt[1:1 + dim] - dqdt[0] * v)).sum(axis=0)).sum() / vol
+    assert np.allclose(d["integral_q"], (M * q0).sum(axis=(1, 2)), rtol=1e-12, atol=0)
+    # the named wrappers return the same numbers
+    assert pd.calcEntropyIntegral(mesh, op, eqn, opts) == d["entropy_integral"]
+    assert pd.calcKineticEnergy(mesh, op, eqn, opts) == d["kinetic_energy"]
+    assert np.array_equal(pd.integrateQ(mesh, op, eqn, opts), d["integral_q"])
