@@ -43,6 +43,9 @@ enum {
   PDES_ERR_UNSUPPORTED = -3,  /* euler.jl:653,796,855,863 ErrorException for option combos */
   PDES_ERR_COMM = -4
 };
+/* faceElementIntegrals.jl:735-741 FaceElementDict (face_integral_type 2; the Lax-Wendroff kernels are unsupported) */
+enum { PDES_FEI_EC = 1, PDES_FEI_ELF_PENALTY = 2, PDES_FEI_ESLF = 3 };
+
 
 /* FluxDict names (src/solver/euler/flux.jl) -> ids */
 enum { PDES_FLUX_ROE = 1, PDES_FLUX_IR = 2, PDES_FLUX_IRSLF = 3, PDES_FLUX_STANDARD = 4 };
@@ -69,13 +72,13 @@ typedef struct {
   int32_t numBC;                /* mesh.numBC                                       */
   int32_t npeers;               /* mesh.npeers                                      */
   int32_t volume_integral_type; /* opts["volume_integral_type"]: 1 | 2              */
-  int32_t face_integral_type;   /* opts["face_integral_type"]: 1                    */
+  int32_t face_integral_type;   /* opts["face_integral_type"]: 1 | 2 (face-element)  */
   int32_t flux_id;              /* opts["Flux_name"]                                */
   int32_t volume_flux_id;       /* opts["Volume_flux_name"] (type 2 only)           */
   int32_t src_id;               /* opts["SRCname"]                                  */
   int32_t check_density;        /* opts["check_density"]                            */
   int32_t check_pressure;       /* opts["check_pressure"]                           */
-  int32_t reserved;
+  int32_t face_element_id;      /* opts["FaceElementIntegral_name"] (type 2 only): PDES_FEI_* */
   double gamma, R;              /* params.gamma, params.R   (types.jl:241-244)      */
   double Ma, aoa;               /* params.Ma, params.aoa [rad] (types.jl:246-247)   */
   double rho_free, E_free;      /* params.rho_free, params.E_free (types.jl:249-252)*/

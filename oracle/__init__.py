@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 FLUX_IDS = {"RoeFlux": 1, "IRFlux": 2, "IRSLFFlux": 3, "StandardFlux": 4}
 BC_IDS = {"isentropicVortexBC": 1, "ExpBC": 2, "FreeStreamBC": 3, "noPenetrationBC": 4}
 SRC_IDS = {"SRC0": 0, "SRCExp": 1}
+FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3}
 
 
 def build(force=False):
@@ -32,7 +33,7 @@ class OrcProblem(C.Structure):
                [(n, C.c_int64) for n in ("nE", "nF", "nB")] + \
                [(n, C.c_int32) for n in ("numBC", "flux_id", "volume_flux_id",
                                          "volume_integral_type", "src_id", "check_density",
-                                         "check_pressure", "pad0")] + \
+                                         "check_pressure", "face_element_id")] + \
                [(n, C.c_double) for n in ("gamma", "R", "Ma", "aoa", "rho_free", "E_free")] + \
                [(n, C.c_void_p) for n in ("Q", "w", "interp", "wface", "perm", "nbrperm", "dxidx",
                                           "jac", "coords", "nrm_face", "nrm_bndry", "coords_bndry",
@@ -125,6 +126,8 @@ class Problem:
         P.src_id = SRC_IDS[opts.get("SRCname", "SRC0")]
         P.check_density = int(opts.get("check_density", True))
         P.check_pressure = int(opts.get("check_pressure", True))
+        P.face_element_id = (FEI_IDS[opts.get("FaceElementIntegral_name", "ESLFFaceIntegral")]
+                             if int(opts.get("face_integral_type", 1)) == 2 else 0)
         g = opts.get("gamma", 1.4)
         P.gamma, P.R = g, opts.get("R", 287.058)
         Ma = opts.get("Ma", -1.0)

@@ -36,12 +36,15 @@ enum { ORC_FLUX_ROE = 1, ORC_FLUX_IR = 2, ORC_FLUX_IRSLF = 3, ORC_FLUX_STANDARD 
 enum { ORC_BC_ISENTROPIC_VORTEX = 1, ORC_BC_EXP = 2, ORC_BC_FREESTREAM = 3,
        ORC_BC_NOPENETRATION = 4 };
 enum { ORC_SRC_NONE = 0, ORC_SRC_EXP = 1 };
+/* faceElementIntegrals.jl:735-741 FaceElementDict (the Lax-Wendroff kernels are not restated) */
+enum { ORC_FEI_EC = 1, ORC_FEI_ELF_PENALTY = 2, ORC_FEI_ESLF = 3 };
 
 typedef struct {
   int32_t dim, nd, nn, nfn, ss, nfaces, norient, sparse_face;
   int64_t nE, nF, nB;
   int32_t numBC, flux_id, volume_flux_id, volume_integral_type, src_id;
-  int32_t check_density, check_pressure, pad0;
+  int32_t check_density, check_pressure;
+  int32_t face_element_id;   /* 0: face_integral_type 1; else face_integral_type 2 with this FaceElementIntegralType */
   double gamma, R, Ma, aoa, rho_free, E_free;
   const double *Q, *w, *interp, *wface;
   const int64_t *perm, *nbrperm;
@@ -748,6 +751,107 @@ static void calc_volume_integrals_split_linear(const OrcProblem *P, const double
       }
 }
 
+
+/* conversion.jl:225-259 convertToConservativeFromIR_ */
+void orc_convert_from_ir(int dim, double gamma, const double *qe, double *qc) {
+  double gamma_1 = gamma - 1.0, k1 = 0.0;
+  for (int d = 0; d < dim; ++d) k1 += qe[1 + d] * qe[1 + d];
+  k1 = 0.5 * gamma_1 * k1 / qe[dim + 1];
+  double s = gamma - gamma_1 * qe[0] + k1;
+  double rho_int = exp(-s / gamma_1) * pow(gamma_1 / pow(-gamma_1 * qe[dim + 1], gamma), 1 / gamma_1);
+  rho_int *= gamma_1;
+  qc[0] = -qe[dim + 1] * rho_int;
+  for (int d = 0; d < dim; ++d) qc[1 + d] = qe[1 + d] * rho_int;
+  qc[dim + 1] = (1.0 - k1) * rho_int / gamma_1;
+}
+
+/* faceElementIntegrals.jl:58-117 calcECFaceIntegral (DenseFace): two-point fluxes between every stencil node of
+ * elementL and every stencil node of elementR in the Cartesian directions (nrmD = I), weighted by
+ * E_ij^d = sum_k interp[i,k] interp[j,nbrperm[k]] wface[k] nrm[d,k].  resL/resR: [nd, nn] element blocks. */
+static void calc_ec_face_integral(const OrcProblem *P, const OrcInterface *f, const double *qL, const double *qR,
+                                  const double *nrm_xy, double *resL, double *resR) {
+  int nd = P->nd, dim = P->dim, ss = P->ss, nfn = P->nfn;
+  double nrmD[9] = {0}, fluxD[ORC_MAXD * 3];
+  for (int d = 0; d < dim; ++d) nrmD[d + dim * d] = 1.0;
+  if (P->flux_id != ORC_FLUX_IR) { fprintf(stderr, "oracle: the face-element integrals use IRFlux\n"); abort(); }
+  for (int i = 0; i < ss; ++i) {
+    int p_i = (int)P->perm[i + ss * f->faceL];
+    for (int j = 0; j < ss; ++j) {
+      int p_j = (int)P->perm[j + ss * f->faceR];
+      orc_ir_flux(dim, P->gamma, qL + nd * p_i, qR + nd * p_j, nrmD, dim, fluxD);
+      for (int d = 0; d < dim; ++d) {
+        double Eij = 0.0;
+        for (int k = 0; k < nfn; ++k) {
+          int kR = (int)P->nbrperm[k + nfn * f->orient];
+          Eij += P->interp[i + ss * k] * P->interp[j + ss * kR] * P->wface[k] * nrm_xy[d + dim * k];
+        }
+        for (int p = 0; p < nd; ++p) {
+          resL[p + nd * p_i] -= Eij * fluxD[p + nd * d];
+          resR[p + nd * p_j] += Eij * fluxD[p + nd * d];
+        }
+      }
+    }
+  }
+}
+
+/* faceElementIntegrals.jl:209-290 calcEntropyPenaltyIntegral (DenseFace) with the LFKernel (:455-468):
+ * the entropy variables are interpolated to the face, the penalty lambda_max A0(q_avg) (wL - wR) wface is
+ * interpolated back */
+static void calc_entropy_penalty_integral(const OrcProblem *P, const OrcInterface *f, const double *qL,
+                                          const double *qR, const double *nrm_face, double *resL, double *resR) {
+  int nd = P->nd, dim = P->dim, ss = P->ss, nfn = P->nfn;
+  double wL[ORC_MAXD * 32], wR[ORC_MAXD * 32];
+  for (int i = 0; i < ss; ++i) {
+    orc_convert_to_ir(dim, P->gamma, qL + nd * (int)P->perm[i + ss * f->faceL], wL + nd * i);
+    orc_convert_to_ir(dim, P->gamma, qR + nd * (int)P->perm[i + ss * f->faceR], wR + nd * i);
+  }
+  for (int i = 0; i < nfn; ++i) {
+    int ni = (int)P->nbrperm[i + nfn * f->orient];
+    const double *dir = nrm_face + dim * i;
+    double wL_i[ORC_MAXD] = {0}, wR_i[ORC_MAXD] = {0}, qL_i[ORC_MAXD], qR_i[ORC_MAXD], q_avg[ORC_MAXD],
+           delta_w[ORC_MAXD], flux[ORC_MAXD], A0[ORC_MAXD * ORC_MAXD];
+    for (int j = 0; j < ss; ++j) {
+      double interpL = P->interp[j + ss * i], interpR = P->interp[j + ss * ni];
+      for (int k = 0; k < nd; ++k) { wL_i[k] += interpL * wL[k + nd * j]; wR_i[k] += interpR * wR[k + nd * j]; }
+    }
+    orc_convert_from_ir(dim, P->gamma, wL_i, qL_i);
+    orc_convert_from_ir(dim, P->gamma, wR_i, qR_i);
+    for (int j = 0; j < nd; ++j) { q_avg[j] = 0.5 * (qL_i[j] + qR_i[j]); delta_w[j] = wL_i[j] - wR_i[j]; }
+    /* applyEntropyKernel(LFKernel): lambda_max * A0 * delta_w */
+    orc_ira0(dim, P->gamma, q_avg, A0);
+    double lambda_max = orc_lambda_max(dim, P->gamma, q_avg, dir);
+    for (int r = 0; r < nd; ++r) {
+      double s = 0.0;
+      for (int c = 0; c < nd; ++c) s += A0[r + nd * c] * delta_w[c];
+      flux[r] = s * lambda_max;
+    }
+    for (int j = 0; j < nd; ++j) flux[j] *= P->wface[i];
+    for (int j = 0; j < ss; ++j) {
+      int j_pL = (int)P->perm[j + ss * f->faceL], j_pR = (int)P->perm[j + ss * f->faceR];
+      for (int p = 0; p < nd; ++p) {
+        resL[p + nd * j_pL] -= P->interp[j + ss * i] * flux[p];
+        resR[p + nd * j_pR] += P->interp[j + ss * ni] * flux[p];
+      }
+    }
+  }
+}
+
+/* flux.jl:132-160 getFaceElementIntegral + the functors of faceElementIntegrals.jl:586-655 */
+static void face_element_integrals(const OrcProblem *P, const double *q, double *res) {
+  int nd = P->nd, nn = P->nn, dim = P->dim, nfn = P->nfn;
+  if (P->ss > 32) { fprintf(stderr, "oracle: stencil too large\n"); abort(); }
+  for (int64_t i = 0; i < P->nF; ++i) {
+    const OrcInterface *f = &P->ifaces[i];
+    const double *qL = q + (int64_t)nd * nn * f->elementL, *qR = q + (int64_t)nd * nn * f->elementR;
+    double *resL = res + (int64_t)nd * nn * f->elementL, *resR = res + (int64_t)nd * nn * f->elementR;
+    const double *nrm = P->nrm_face + (int64_t)dim * nfn * i;
+    if (P->face_element_id == ORC_FEI_EC || P->face_element_id == ORC_FEI_ESLF)
+      calc_ec_face_integral(P, f, qL, qR, nrm, resL, resR);
+    if (P->face_element_id == ORC_FEI_ELF_PENALTY || P->face_element_id == ORC_FEI_ESLF)
+      calc_entropy_penalty_integral(P, f, qL, qR, nrm, resL, resR);
+  }
+}
+
 /* source.jl:27-47 applySourceTerm */
 static void apply_source_term(const OrcProblem *P, double *res) {
   int nd = P->nd, nn = P->nn, dim = P->dim;
@@ -805,8 +909,10 @@ int orc_eval_residual(const OrcProblem *P, const double *q, double *res, double 
   if (status) { work_free(&W); return status; }
   if (precompute) {
     get_euler_flux(P, q, W.flux_parametric);            /* runs even for split form (Appendix E.3) */
-    interpolate_face(P, q, W.q_face);
-    calc_face_flux(P, W.q_face, W.flux_face);
+    if (!P->face_element_id) {
+      interpolate_face(P, q, W.q_face);
+      calc_face_flux(P, W.q_face, W.flux_face);
+    }
   }
   interpolate_boundary(P, q, W.q_bndry);
   get_bc_fluxes(P, W.q_bndry, W.bndryflux);
@@ -823,7 +929,10 @@ int orc_eval_residual(const OrcProblem *P, const double *q, double *res, double 
   /* evalBoundaryIntegrals euler.jl:669-690 */
   boundary_integrate(P, W.bndryflux, res);
   /* evalFaceIntegrals euler.jl:770-802 */
-  if (precompute) interior_face_integrate(P, W.flux_face, res);
+  if (P->face_element_id) {                              /* face_integral_type == 2 (euler.jl:783-793) */
+    if (npeers) { fprintf(stderr, "oracle: face-element integrals on partitioned meshes are not restated\n"); abort(); }
+    face_element_integrals(P, q, res);
+  } else if (precompute) interior_face_integrate(P, W.flux_face, res);
   else calc_face_integral_nopre(P, q, res);
   /* evalSharedFaceIntegrals euler.jl:843-867 */
   for (int p = 0; p < npeers; ++p) shared_face_integrals(P, &peers[p], res);
@@ -849,7 +958,8 @@ void orc_volume_integrals(const OrcProblem *P, const double *q, double *res, int
 void orc_euler_flux_parametric(const OrcProblem *P, const double *q, double *fp) { get_euler_flux(P, q, fp); }
 void orc_face_integrals(const OrcProblem *P, const double *q, double *res, int precompute) {
   OrcWork W = work_alloc(P);
-  if (precompute) {
+  if (P->face_element_id) face_element_integrals(P, q, res);
+  else if (precompute) {
     interpolate_face(P, q, W.q_face);
     calc_face_flux(P, W.q_face, W.flux_face);
     interior_face_integrate(P, W.flux_face, res);

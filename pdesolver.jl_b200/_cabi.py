@@ -24,6 +24,7 @@ PDES_ERR_COMM = -4
 FLUX_IDS = {"RoeFlux": 1, "IRFlux": 2, "IRSLFFlux": 3, "StandardFlux": 4}
 BC_IDS = {"isentropicVortexBC": 1, "ExpBC": 2, "FreeStreamBC": 3, "noPenetrationBC": 4}
 SRC_IDS = {"SRC0": 0, "SRCExp": 1}
+FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3}
 
 EXPORTS = [
     "pdes_create", "pdes_destroy", "pdes_last_error", "pdes_last_error_location",
@@ -42,7 +43,7 @@ class PdesConfig(C.Structure):
                [(n, C.c_int64) for n in ("nE", "nF", "nB")] + \
                [(n, C.c_int32) for n in ("numBC", "npeers", "volume_integral_type",
                                          "face_integral_type", "flux_id", "volume_flux_id", "src_id",
-                                         "check_density", "check_pressure", "reserved")] + \
+                                         "check_density", "check_pressure", "face_element_id")] + \
                [(n, C.c_double) for n in ("gamma", "R", "Ma", "aoa", "rho_free", "E_free")]
 
 

@@ -101,6 +101,158 @@ __global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> 
   q_send[t] = q[((int64_t)sh_el[j] * NN + op.perm[sh_face[j]][i]) * ND + k];
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// k_face_element: face_integral_type = 2 for dense-face (SBP-Omega) operators:
+// getFaceElementIntegral (flux.jl:132-160) with the functors ECFaceIntegral / ELFPenaltyFaceIntegral /
+// ESLFFaceIntegral (faceElementIntegrals.jl:586-655):
+//   calcECFaceIntegral (:58-117)           nn x nn two-point Ismail-Roe fluxes in the Cartesian directions between the
+//                                          stencil nodes of the two elements, weighted by
+//                                          E_ij^d = sum_k interp[i,k] interp[j,nbrperm[k]] wface[k] nrm[d,k]
+//   calcEntropyPenaltyIntegral (:209-290)  entropy variables interpolated to the face, LFKernel (:455-468), interpolated back
+// Boundary faces keep the standard boundary integral (Dirichlet state + Roe, bc.jl:251-284; boundaryintegrate!).
+// One CTA per face.  The result is one record per (element, local face) holding the contribution to EVERY volume node
+// of the element ([nd, nn], element node order), which k_element_split<..., DENSEREC> adds: atomic-free, deterministic.
+// ------------------------------------------------------------------------------------------------------
+enum FaceElementId { FEI_EC = 1, FEI_ELF_PENALTY = 2, FEI_ESLF = 3 };
+
+template <int DIM, int NN, int NFN>
+__global__ void __launch_bounds__(128)
+k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a, int fei) {
+  constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, T = 128;
+  __shared__ double sq[2][NN][ND];          // states at the stencil nodes (stencil order) of elementL / elementR
+  __shared__ IRNode<DIM> sZ[2][NN];
+  __shared__ double sw[2][NN][ND];          // IR entropy variables
+  __shared__ double sG[NN * NN][ND];        // sum_d E_ij^d F_d(q_i, q_j)
+  __shared__ double sc[DIM][NFN];           // wface[k] * nrm[d,k]
+  __shared__ double spen[NFN][ND];          // wface-weighted flux at the face nodes
+  __shared__ double srec[2][NN][ND];
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t g = a.g0 + blockIdx.x;
+  const FaceRec r = a.faces[g];
+  const bool interior = r.kind == FK_INTERIOR;
+  for (int idx = tid; idx < NN * ND; idx += T) {
+    const int j = idx / ND, k = idx - j * ND;
+    sq[0][j][k] = __ldg(a.q + (int64_t)r.elL * EL + op.perm[r.fL][j] * ND + k);
+    sq[1][j][k] = interior ? __ldg(a.q + (int64_t)r.elR * EL + op.perm[r.fR][j] * ND + k) : 0.0;
+    srec[0][j][k] = 0.0;
+    srec[1][j][k] = 0.0;
+  }
+  for (int idx = tid; idx < DIM * NFN; idx += T) {
+    const int d = idx / NFN, k = idx - d * NFN;
+    sc[d][k] = op.wface[k] * __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
+  }
+  __syncthreads();
+  const int* nbr = op.nbrperm[interior ? r.orient : 0];
+
+  if (!interior) {
+    // interpolateBoundary + BC functor + boundaryintegrate! (bc.jl:162-175, 251-284; euler.jl:669-690)
+    if (tid < NFN) {
+      const int k = tid;
+      double qb[ND], xb[DIM], nb_[DIM], fb[ND];
+#pragma unroll
+      for (int p = 0; p < ND; ++p) qb[p] = 0.0;
+      for (int j = 0; j < NN; ++j) {
+        const double c = op.interp[j][k];
+#pragma unroll
+        for (int p = 0; p < ND; ++p) qb[p] = fma(c, sq[0][j][p], qb[p]);
+      }
+      const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + k) * DIM;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d); }
+      bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+      for (int p = 0; p < ND; ++p) spen[k][p] = op.wface[k] * fb[p];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NN * ND; idx += T) {
+      const int j = idx / ND, p = idx - j * ND;
+      double s = 0.0;
+      for (int k = 0; k < NFN; ++k) s = fma(op.interp[j][k], spen[k][p], s);
+      srec[0][j][p] = -s;
+    }
+    __syncthreads();
+  } else {
+    if (fei == FEI_EC || fei == FEI_ESLF) {
+      for (int idx = tid; idx < 2 * NN; idx += T) sZ[idx / NN][idx % NN] = ir_node<DIM>(sq[idx / NN][idx % NN], a.ph.gamma - 1.0);
+      __syncthreads();
+      for (int pr = tid; pr < NN * NN; pr += T) {
+        const int i = pr / NN, j = pr - i * NN;
+        double dirs[DIM][DIM], F[DIM][ND];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+          for (int e = 0; e < DIM; ++e) dirs[d][e] = d == e ? 1.0 : 0.0;
+        ir_flux<DIM, DIM>(sZ[0][i], sZ[1][j], dirs, a.ph.gamma, F);
+        double gsum[ND];
+#pragma unroll
+        for (int p = 0; p < ND; ++p) gsum[p] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          double Eij = 0.0;
+          for (int k = 0; k < NFN; ++k) Eij = fma(op.interp[i][k] * op.interp[j][nbr[k]], sc[d][k], Eij);
+#pragma unroll
+          for (int p = 0; p < ND; ++p) gsum[p] = fma(Eij, F[d][p], gsum[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < ND; ++p) sG[pr][p] = gsum[p];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < NN * ND; idx += T) {
+        const int i = idx / ND, p = idx - i * ND;
+        double sl = 0.0, sr = 0.0;
+        for (int j = 0; j < NN; ++j) { sl += sG[i * NN + j][p]; sr += sG[j * NN + i][p]; }
+        srec[0][i][p] = -sl;
+        srec[1][i][p] = sr;
+      }
+      __syncthreads();
+    }
+    if (fei == FEI_ELF_PENALTY || fei == FEI_ESLF) {
+      for (int idx = tid; idx < 2 * NN; idx += T) convert_to_ir<DIM>(sq[idx / NN][idx % NN], a.ph.gamma, sw[idx / NN][idx % NN]);
+      __syncthreads();
+      if (tid < NFN) {
+        const int k = tid, nk = nbr[k];
+        double wL[ND], wR[ND], qL[ND], qR[ND], qa[ND], dw[ND], fl[ND], nrm[DIM];
+#pragma unroll
+        for (int p = 0; p < ND; ++p) { wL[p] = 0.0; wR[p] = 0.0; }
+        for (int j = 0; j < NN; ++j) {
+          const double cL = op.interp[j][k], cR = op.interp[j][nk];
+#pragma unroll
+          for (int p = 0; p < ND; ++p) { wL[p] += cL * sw[0][j][p]; wR[p] += cR * sw[1][j][p]; }
+        }
+        convert_from_ir<DIM>(wL, a.ph.gamma, qL);
+        convert_from_ir<DIM>(wR, a.ph.gamma, qR);
+#pragma unroll
+        for (int p = 0; p < ND; ++p) { qa[p] = 0.5 * (qL[p] + qR[p]); dw[p] = wL[p] - wR[p]; }
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
+        lf_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
+#pragma unroll
+        for (int p = 0; p < ND; ++p) spen[k][p] = fl[p] * op.wface[k];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < NN * ND; idx += T) {
+        const int j = idx / ND, p = idx - j * ND;
+        double sl = srec[0][j][p], sr = srec[1][j][p];
+        for (int k = 0; k < NFN; ++k) {
+          sl -= op.interp[j][k] * spen[k][p];
+          sr += op.interp[j][nbr[k]] * spen[k][p];
+        }
+        srec[0][j][p] = sl;
+        srec[1][j][p] = sr;
+      }
+      __syncthreads();
+    }
+  }
+  // records in element node order: stencil node j of face f is volume node perm[f][j]
+  for (int idx = tid; idx < NN * ND; idx += T) {
+    const int j = idx / ND, p = idx - j * ND;
+    a.fluxe[((int64_t)r.elL * NF + r.fL) * EL + op.perm[r.fL][j] * ND + p] = srec[0][j][p];
+    if (interior) a.fluxe[((int64_t)r.elR * NF + r.fR) * EL + op.perm[r.fR][j] * ND + p] = srec[1][j][p];
+  }
+}
+
 template <int DIM, int NN, int NFN, int E>
 struct SplitCfg {
   static constexpr int ND = DIM + 2, NF = DIM + 1;
@@ -117,7 +269,7 @@ struct SplitCfg {
   static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
 };
 
-template <int DIM, int NN, int NFN, int E, int MODE>
+template <int DIM, int NN, int NFN, int E, int MODE, bool DENSEREC = false>
 __global__ void __launch_bounds__((SplitCfg<DIM, NN, NFN, E>::T), 2)
 k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = SplitCfg<DIM, NN, NFN, E>;
@@ -216,11 +368,18 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
 #pragma unroll
       for (int d = 0; d < DIM; ++d) acc = fma(-Sc[d * NN * NN + m], Fc[d * ND * PS + pi], acc);
     }
-    const double* G = a.fluxe + (e0 + s) * (NF * FL);
+    if (DENSEREC) {
+      // face-element integrals (k_face_element): one [nd, nn] record per local face
+      const double* G = a.fluxe + (e0 + s) * (NF * EL) + r;
 #pragma unroll
-    for (int u = 0; u < DIM; ++u) {
-      const int slot = op.inv[i][u];
-      if (slot >= 0) acc += __ldg(G + slot * ND + c);
+      for (int f = 0; f < NF; ++f) acc += __ldg(G + f * EL);
+    } else {
+      const double* G = a.fluxe + (e0 + s) * (NF * FL);
+#pragma unroll
+      for (int u = 0; u < DIM; ++u) {
+        const int slot = op.inv[i][u];
+        if (slot >= 0) acc += __ldg(G + slot * ND + c);
+      }
     }
     if (MODE == EPI_RK) acc *= __ldg(a.minv + (e0 + s) * NN + i);
     sq[it] = acc;

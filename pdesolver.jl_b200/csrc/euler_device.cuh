@@ -293,6 +293,60 @@ __device__ __forceinline__ void irslf_flux(const double* qL, const double* qR, c
   for (int i = 0; i < ND; ++i) F[i] = Fi[0][i] + out[i] * lambda_max;
 }
 
+
+// conversion.jl:225-259 convertToConservativeFromIR_
+template <int DIM>
+__device__ __forceinline__ void convert_from_ir(const double* qe, double gamma, double* qc) {
+  const double gamma_1 = gamma - 1.0;
+  double k1 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) k1 += qe[1 + d] * qe[1 + d];
+  k1 = 0.5 * gamma_1 * k1 / qe[DIM + 1];
+  const double s = gamma - gamma_1 * qe[0] + k1;
+  double rho_int = exp(-s / gamma_1) * pow(gamma_1 / pow(-gamma_1 * qe[DIM + 1], gamma), 1.0 / gamma_1);
+  rho_int *= gamma_1;
+  qc[0] = -qe[DIM + 1] * rho_int;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) qc[1 + d] = qe[1 + d] * rho_int;
+  qc[DIM + 1] = (1.0 - k1) * rho_int / gamma_1;
+}
+
+// applyEntropyKernel(LFKernel) (faceElementIntegrals.jl:455-468): out = lambda_max(q_avg, n) * A0(q_avg) * delta_w
+// (getIRA0 IR_stab.jl:15-110, getLambdaMax euler_funcs.jl:1887-1913 with absvalue3)
+template <int DIM>
+__device__ __forceinline__ void lf_entropy_kernel(const double* qa, const double* dw, const double* n, double gamma,
+                                                  double* out) {
+  const double gami = gamma - 1.0;
+  const double p = calc_pressure<DIM>(qa, gami);
+  const double rho = qa[0], rhoe = qa[DIM + 1], rhoinv = 1.0 / rho;
+  const double h = (rhoe + p) * rhoinv, a2 = gamma * p * rhoinv;
+  out[0] = rho * dw[0] + rhoe * dw[DIM + 1];
+  out[DIM + 1] = rhoe * dw[0] + (rho * h * h - a2 * p / gami) * dw[DIM + 1];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    out[0] += qa[1 + c] * dw[1 + c];
+    out[DIM + 1] += qa[1 + c] * h * dw[1 + c];
+    double r = qa[1 + c] * dw[0] + h * qa[1 + c] * dw[DIM + 1];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double a = qa[1 + d] * qa[1 + c] * rhoinv;
+      if (d == c) a += p;
+      r += a * dw[1 + d];
+    }
+    out[1 + c] = r;
+  }
+  double Un = 0.0, dA = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { Un += n[d] * qa[1 + d] * rhoinv; dA += n[d] * n[d]; }
+  dA = sqrt(dA);
+  const double delta = 1e-7;
+  const double v1 = fabs(Un);
+  const double aUn = v1 > delta ? v1 : ((Un * Un) / delta + delta) / 2;
+  const double lambda_max = aUn + dA * sqrt(a2);
+#pragma unroll
+  for (int i = 0; i < DIM + 2; ++i) out[i] *= lambda_max;
+}
+
 template <int DIM>
 __device__ __forceinline__ void ir_flux_single(const double* qL, const double* qR, const double* n, double gamma, double* F) {
   constexpr int ND = DIM + 2;

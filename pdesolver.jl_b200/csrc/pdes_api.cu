@@ -97,6 +97,7 @@ struct Ops {
   virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
   virtual int resident_face_ctas() = 0;
   virtual int tile_elems() const = 0;
+  virtual int record_doubles() const { return 0; }   // doubles per (element, local face) record; 0: nd * nfn
   virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
   // fused face + element kernel (k_fused); families without one return 0 faces per group
   virtual int fused_group_faces() const { return 0; }
@@ -336,12 +337,86 @@ struct OpsImplS : Ops {
   }
 };
 
+// SBP-Omega (dense face) operators with the entropy-stable scheme of face_integral_type = 2: split-form volume
+// integrals (k_element_split, dense records) + face-element integrals (k_face_element)
+template <int DIM, int NN, int NFN, int E>
+struct OpsImplE : Ops {
+  using Tab = OpTab<DIM, NN, NFN>;
+  using TabS = OpTabS<DIM, NN, NFN>;
+  using Cfg = SplitCfg<DIM, NN, NFN, E>;
+  Tab tab;
+  TabS tabs;
+  int fei = FEI_ESLF;
+  bool attr_set = false;
+  void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
+                    const int64_t* nbrperm, const double* wface, int base) override {
+    memset(&tab, 0, sizeof(tab));
+    memset(&tabs, 0, sizeof(tabs));
+    fei = c.face_element_id;
+    const int ss = c.ss;
+    for (int d = 0; d < DIM; ++d)
+      for (int i = 0; i < NN; ++i)
+        for (int m = 0; m < NN; ++m) tabs.S2[d][i][m] = Q[i + NN * (m + NN * d)] - Q[m + NN * (i + NN * d)];
+    for (int f = 0; f < DIM + 1; ++f)
+      for (int j = 0; j < NN; ++j) tab.perm[f][j] = j < ss ? (int)(perm[j + (int64_t)ss * f] - base) : 0;
+    for (int j = 0; j < NN; ++j)
+      for (int i = 0; i < NFN; ++i) tab.interp[j][i] = j < ss ? interp[j + ss * i] : 0.0;
+    for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
+    for (int o = 0; o < Tab::NOR; ++o)
+      for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
+    (void)w;
+  }
+  int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
+  int tile_elems() const override { return E; }
+  int resident_element_ctas() override { return 0; }
+  int resident_face_ctas() override { return 0; }
+  int record_doubles() const override { return NN * (DIM + 2); }
+  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+    if (a.ng <= 0) return cudaSuccess;
+    k_face_element<DIM, NN, NFN><<<(unsigned)a.ng, 128, 0, s>>>(tab, a, fei);
+    return cudaGetLastError();
+  }
+  cudaError_t prepare() override {
+    if (attr_set) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RES, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+    return cudaSuccess;
+  }
+  cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    if (a.nE <= a.e_begin) return cudaSuccess;
+    dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
+    if (mode == EPI_RES) k_element_split<DIM, NN, NFN, E, EPI_RES, true><<<grid, block, Cfg::smem_bytes, s>>>(tabs, a);
+    else k_element_split<DIM, NN, NFN, E, EPI_RK, true><<<grid, block, Cfg::smem_bytes, s>>>(tabs, a);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_pack(const double*, const int32_t*, const uint8_t*, int64_t nS, double*, const Ctl*, cudaStream_t) override {
+    return nS <= 0 ? cudaSuccess : cudaErrorNotSupported;
+  }
+};
+
 Ops* make_ops(const PdesConfig& c) {
   if (c.sparse_face) {
     // entropy-stable configuration: diag-E operator, split-form IR volume flux, Roe / IR / IRSLF interface flux
     if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR) return nullptr;
+    if (c.face_integral_type != 1) return nullptr;      // diagonal-E operators keep face_integral_type 1 (read_input.jl:742-755)
     if (c.flux_id != PDES_FLUX_ROE && c.flux_id != PDES_FLUX_IR && c.flux_id != PDES_FLUX_IRSLF) return nullptr;
     if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 16>();
+    return nullptr;
+  }
+  if (c.face_integral_type == 2) {
+    // entropy-stable scheme on SBP-Omega operators: split-form IR volume flux + face-element integrals with the IR flux
+    if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR || c.flux_id != PDES_FLUX_IR) return nullptr;
+    if (c.face_element_id < PDES_FEI_EC || c.face_element_id > PDES_FEI_ESLF) return nullptr;
+    if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImplE<2, 3, 2, 32>();
+    if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImplE<2, 6, 3, 32>();
+    if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImplE<3, 4, 3, 32>();
+    if (c.dim == 3 && c.nn == 11 && c.nfn == 6) return new OpsImplE<3, 11, 6, 8>();
     return nullptr;
   }
   if (c.volume_integral_type != 1 || c.flux_id != PDES_FLUX_ROE) return nullptr;
@@ -646,7 +721,10 @@ int finalize(PdesCtx* ctx) {
       CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->nrm_all, nrm.data(), nrm.size()));
     }
   }
-  CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxe, nullptr, (size_t)c.nE * NF * c.nfn * ctx->nd + 2));
+  {
+    const size_t rec = ctx->ops->record_doubles() ? (size_t)ctx->ops->record_doubles() : (size_t)c.nfn * ctx->nd;
+    CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->fluxe, nullptr, (size_t)c.nE * NF * rec + 2));
+  }
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_el, sh_el.data(), sh_el.size()));
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sh_face, sh_face.data(), sh_face.size()));
   size_t nsend = (size_t)ctx->nS * c.nfn * ctx->nd;
@@ -945,8 +1023,13 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
     return PDES_ERR_CUDA;
   }
   if (cfg->dim != 2 && cfg->dim != 3) return usage(nullptr, "pdes_create: dim must be 2 or 3");
-  if (cfg->face_integral_type != 1) {
-    set_err(nullptr, "face_integral_type %d is not supported (type 1 only)", cfg->face_integral_type);
+  if (cfg->face_integral_type != 1 && cfg->face_integral_type != 2) {
+    // euler.jl:796: ErrorException("Unsupported face integral type")
+    set_err(nullptr, "Unsupported face integral type = %d", cfg->face_integral_type);
+    return PDES_ERR_UNSUPPORTED;
+  }
+  if (cfg->face_integral_type == 2 && cfg->npeers > 0) {
+    set_err(nullptr, "face_integral_type 2 needs the element-data halo (parallel_data = element), which is not implemented");
     return PDES_ERR_UNSUPPORTED;
   }
   if (cfg->nE <= 0 || cfg->nE * (cfg->dim + 1) > 0x7fffff00ll)

@@ -22,7 +22,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import BC_IDS, FLUX_IDS, SRC_IDS
+from ._cabi import BC_IDS, FEI_IDS, FLUX_IDS, SRC_IDS
 
 
 class PDESolverError(RuntimeError):
@@ -117,6 +117,8 @@ class EulerData:
             cfg.flux_id = FLUX_IDS[opts.get("Flux_name", "RoeFlux")]
             cfg.volume_flux_id = FLUX_IDS[opts.get("Volume_flux_name", "StandardFlux")]
             cfg.src_id = SRC_IDS[opts.get("SRCname", "SRC0")]
+            if cfg.face_integral_type == 2:      # default functor: input/read_input.jl:185
+                cfg.face_element_id = FEI_IDS[opts.get("FaceElementIntegral_name", "ESLFFaceIntegral")]
             bc = [BC_IDS[opts.get(f"BC{i + 1}_name", "isentropicVortexBC")] for i in range(mesh.numBC)]
         except KeyError as e:
             raise PDESolverError(f"unsupported functor name {e}") from None

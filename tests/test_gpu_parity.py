@@ -622,3 +622,44 @@ def test_device_diagnostics(case, n):
     assert pd.calcEntropyIntegral(mesh, op, eqn, opts) == d["entropy_integral"]
     assert pd.calcKineticEnergy(mesh, op, eqn, opts) == d["kinetic_energy"]
     assert np.array_equal(pd.integrateQ(mesh, op, eqn, opts), d["integral_q"])
+
+
+ES2 = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2, "face_integral_type": 2}
+
+
+@pytest.mark.parametrize("dim,p,n", [(2, 1, 7), (2, 2, 5), (3, 1, 3), (3, 2, 2)])
+@pytest.mark.parametrize("name", ["ECFaceIntegral", "ELFPenaltyFaceIntegral", "ESLFFaceIntegral"])
+def test_face_element_integrals(dim, p, n, name):
+    """face_integral_type = 2 on SBP-Omega operators (getFaceElementIntegral flux.jl:132-160,
+    calcECFaceIntegral / calcEntropyPenaltyIntegral faceElementIntegrals.jl:58-117, 209-290) + split-form volume
+    integrals, against the oracle (pinned on the reference's identities in tests/test_oracle_ess.py)."""
+    op = pd.build_operator(dim, p)
+    mesh = pd.structured_mesh(op, n, shuffle_seed=8)
+    ic, bc = ("ICIsentropicVortex", "isentropicVortexBC") if dim == 2 else ("ICExp", "ExpBC")
+    opts = dict(ES2, FaceElementIntegral_name=name, BC1_name=bc, use_itermax=False)
+    orc = oracle.Problem(mesh, op, opts)
+    q0 = perturbed(orc.exact_state(ic), amp=1e-2)
+    eqn = pd.EulerData(mesh, op, opts)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+    if name == "ESLFFaceIntegral":
+        h = 1e-3 if dim == 2 else 1e-4
+        t = pd.rk4(pd.evalResidual, h, 6 * h, mesh, op, eqn, opts)
+        t_ref, q_ref, norms_ref = orc.rk4(q0, h, 6 * h)
+        assert t == t_ref and rel_l2(eqn.q, q_ref) < RK_TOL
+        assert np.allclose(eqn.convergence, norms_ref, rtol=1e-10, atol=0)
+
+
+def test_face_element_option_errors():
+    op = pd.build_operator(2, 1)
+    mesh = pd.structured_mesh(op, 2)
+    with pytest.raises(pd.PDESolverError):          # euler.jl:796 "Unsupported face integral type"
+        pd.EulerData(mesh, op, dict(ES2, face_integral_type=3, BC1_name="isentropicVortexBC"))
+    with pytest.raises(pd.PDESolverError):          # the Lax-Wendroff kernels are not implemented
+        pd.EulerData(mesh, op, dict(ES2, FaceElementIntegral_name="ESLW2FaceIntegral", BC1_name="isentropicVortexBC"))
+    with pytest.raises(pd.PDESolverError):          # face-element integrals need the two-point IR flux
+        pd.EulerData(mesh, op, dict(ES2, Flux_name="RoeFlux", BC1_name="isentropicVortexBC"))
+    ope = pd.build_operator(2, 2, "diage")          # diagonal-E keeps face_integral_type 1 (read_input.jl:742-755)
+    with pytest.raises(pd.PDESolverError):
+        pd.EulerData(pd.structured_mesh(ope, 2), ope, dict(ES2, BC1_name="isentropicVortexBC"))
