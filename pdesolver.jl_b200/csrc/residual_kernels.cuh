@@ -27,7 +27,7 @@
 #include "euler_device.cuh"
 
 #ifndef PDES_OPT
-#define PDES_OPT 0      // all three measured slower on C3 (1.101 / 1.141 / 1.129 vs 1.093 ms per RK4 step). bit 0: pipelined metrics loads in S1; bit 1: face records two faces ahead; bit 2: staged Minv
+#define PDES_OPT 0      // all three measured slower on C3 (1.101 / 1.141 / 1.129 vs 1.093 ms per RK4 step); bit 3: face normals requested at the top of the tile. bit 0: pipelined metrics loads in S1; bit 1: face records two faces ahead; bit 2: staged Minv
 #endif
 
 #ifndef PDES_SKEL
@@ -253,6 +253,15 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
   FaceRec nxt;
   nxt.kind = 255;
   if (ga >= 0 && tid < FT && ga + tid < gend) nxt = a.faces[ga + tid];
+#if (PDES_OPT & 8)
+  // the normal of this thread's face node depends on the face number only: requested here, consumed in stage B
+  double nrm_early[DIM];
+  if (tid < nf * NFN) {
+    const double* np_ = a.nrm + (g0 + tid / NFN) * a.nrm_face_stride + (tid % NFN) * a.nrm_node_stride;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) nrm_early[d] = __ldg(np_ + d);
+  }
+#endif
   __syncthreads();
 
   // ---- A: interpolate both sides to the face nodes (variable threads) ----------------------------------
@@ -311,9 +320,14 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
     const int64_t g = g0 + fi;
     double nrm[DIM], qL[ND], qR[ND], flux[ND];
     if (nact) {
+#if (PDES_OPT & 8)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) nrm[d] = nrm_early[d];
+#else
       const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
+#endif
 #pragma unroll
       for (int k = 0; k < ND; ++k) { qL[k] = sL[fi * FS + i * ND + k]; qR[k] = sR[fi * FS + i * ND + k]; }
     }

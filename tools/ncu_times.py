@@ -22,6 +22,9 @@ for (i, k), v in d.items():
 out = []
 for g, vs in grp.items():
     t = sum(v["gpu__time_duration.sum"] for v in vs) / len(vs) / 1e3
-    b = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in vs) / len(vs) / 1e6
-    out.append("%s %.1f us %.0f MB" % (g, t, b))
+    if "dram__bytes_read.sum" in vs[0]:
+        b = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in vs) / len(vs) / 1e6
+        out.append("%s %.1f us %.0f MB (%d launches)" % (g, t, b, len(vs)))
+    else:
+        out.append("%s %.1f us (%d launches)" % (g, t, len(vs)))
 print(sys.argv[1].split("/")[-1], " | ".join(out))
