@@ -223,6 +223,30 @@ struct OpsImpl : Ops {
       k_face_flux_tma<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
       return cudaGetLastError();
     }
+    static const int face_w = env_int("PDES_FACE_W", 0);
+    if (face_w > 0) {
+      // warp-autonomous tiles: FW faces per warp so that FW * max(nd, nfn) <= 32
+      constexpr int PER = (DIM + 2) > NFN ? (DIM + 2) : NFN;
+      constexpr int FW = 32 / PER, WPC = 4;
+      const int64_t nt = (a.ng + FW - 1) / FW;
+      dim3 gridw((unsigned)((nt + WPC - 1) / WPC)), blockw(32 * WPC);
+      if (face_w == 1) k_face_flux_w<DIM, NN, NFN, FW, WPC, 4><<<gridw, blockw, 0, s>>>(tab, a);
+      else k_face_flux_w<DIM, NN, NFN, FW, WPC, 6><<<gridw, blockw, 0, s>>>(tab, a);
+      return cudaGetLastError();
+    }
+    static const int face_p = env_int("PDES_FACE_P", 0);
+    if (face_p > 0) {
+      // persistent tiles with the next tile's records carried in registers; PDES_FACE_P = CTAs per SM (register cap)
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int per_sm = face_p >= 8 ? 8 : (face_p >= 6 ? 6 : 5);
+      dim3 gridp((unsigned)std::min<int64_t>(ntiles, (int64_t)per_sm * sms)), blockp(FCfg::T);
+      if (per_sm == 8) k_face_flux_p<DIM, NN, NFN, FT, 8><<<gridp, blockp, 0, s>>>(tab, a);
+      else if (per_sm == 6) k_face_flux_p<DIM, NN, NFN, FT, 6><<<gridp, blockp, 0, s>>>(tab, a);
+      else k_face_flux_p<DIM, NN, NFN, FT, 5><<<gridp, blockp, 0, s>>>(tab, a);
+      return cudaGetLastError();
+    }
     dim3 grid((unsigned)ntiles), block(FCfg::T);
     k_face_flux<DIM, NN, NFN, FT, MINB_F><<<grid, block, 0, s>>>(tab, a);
     return cudaGetLastError();

@@ -233,9 +233,17 @@ __device__ __forceinline__ void face_tables(const OpTab<DIM, NN, NFN>& op, FaceT
 // One tile of nf <= FT faces starting at face g0, executed by a CTA of TB threads.  ga = first face of the tile whose
 // gathers are prefetched into L2 (or < 0).  The caller has filled sm.s_perm / sm.s_nbrperm (face_tables) and puts a
 // block barrier between consecutive tiles.
-template <int DIM, int NN, int NFN, int FT, int TB>
+// barrier of the threads that share a face tile: the CTA, or one warp (k_face_flux_w: TB = 32)
+template <bool WARPSYNC>
+__device__ __forceinline__ void tile_sync() {
+  if (WARPSYNC) __syncwarp();
+  else __syncthreads();
+}
+
+template <int DIM, int NN, int NFN, int FT, int TB, bool WARPSYNC = false, bool PRELOADED = false>
 __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const FaceArgs& a,
-                                          FaceTileSmem<DIM, NN, NFN, FT>& sm, int64_t g0, int nf, int64_t ga, int tid) {
+                                          FaceTileSmem<DIM, NN, NFN, FT>& sm, int64_t g0, int nf, int64_t ga, int tid,
+                                          FaceRec* carry = nullptr) {
   using Cfg = FaceCfg<DIM, NN, NFN, FT>;
   constexpr int ND = Cfg::ND, FS = Cfg::FS, NF = DIM + 1, EL = NN * ND;
   static_assert(TB >= Cfg::T, "block too small for the face tile");
@@ -244,7 +252,8 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
   FaceRec* sRec = sm.sRec;
   const int64_t gend = a.g0 + a.ng;
   if (tid < nf) {
-    const FaceRec r = a.faces[g0 + tid];
+    // PRELOADED (persistent kernel): this tile's record was fetched while the previous tile ran
+    const FaceRec r = PRELOADED ? *carry : a.faces[g0 + tid];
     sRec[tid] = r;
     sm.s_dst[2 * tid] = r.elL * NF + r.fL;
     sm.s_dst[2 * tid + 1] = r.kind == FK_INTERIOR ? r.elR * NF + r.fR : -1;
@@ -262,7 +271,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
     for (int d = 0; d < DIM; ++d) nrm_early[d] = __ldg(np_ + d);
   }
 #endif
-  __syncthreads();
+  tile_sync<WARPSYNC>();
 
   // ---- A: interpolate both sides to the face nodes (variable threads) ----------------------------------
   if (tid < nf * ND) {
@@ -308,7 +317,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
       for (int i = 0; i < NFN; ++i) sR[fi * FS + sm.s_nbrperm[r.orient][i] * ND + k] = b[i * ND];
     }
   }
-  __syncthreads();
+  tile_sync<WARPSYNC>();
 
   // ---- B: numerical flux at every face node (node threads) ------------------------------------------------
   // results overwrite the face-state tiles: sL <- -w f* in elementL's node order, sR <- +w f* in elementR's
@@ -331,7 +340,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
 #pragma unroll
       for (int k = 0; k < ND; ++k) { qL[k] = sL[fi * FS + i * ND + k]; qR[k] = sR[fi * FS + i * ND + k]; }
     }
-    __syncthreads();       // every node thread holds its inputs: the tiles may be overwritten
+    tile_sync<WARPSYNC>();       // every node thread holds its inputs: the tiles may be overwritten
     if (nact) {
       if (r.kind == FK_BOUNDARY) {
         // separate copies so that only this (rare) path touches local memory
@@ -362,7 +371,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
       }
     }
   }
-  __syncthreads();
+  tile_sync<WARPSYNC>();
 
   // ---- C: store one record per (element, local face): 8*ND*NFN contiguous bytes each, half a warp per record ---
   constexpr int FL = NFN * ND;
@@ -392,6 +401,7 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
     }
     prefetch_l2(a.nrm + (ga + tid) * a.nrm_face_stride);
   }
+  if (PRELOADED) *carry = nxt;
 }
 
 template <int DIM, int NN, int NFN, int FT, int MINB>
@@ -414,6 +424,56 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   }
   face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
   face_tile<DIM, NN, NFN, FT, T>(op, a, sm, g0, nf, ga, tid);
+}
+
+// k_face_flux_p (PDES_FACE_P=1): persistent form of k_face_flux.  One wave of CTAs strides over the tiles; the
+// records of a CTA's NEXT tile are fetched at the top of the current tile and carried in registers, so the dependent
+// latency at the head of every tile (FaceRec fetch -> barrier -> gathers: 27 % of k_face_flux's stall samples,
+// profiles/r1_end_face_flux_c3.txt region [0,159)) is paid once per CTA instead of once per tile, and the same
+// records drive the L2 prefetch of the next tile's gathers.
+template <int DIM, int NN, int NFN, int FT, int MINB>
+__global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
+k_face_flux_p(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  constexpr int T = FaceCfg<DIM, NN, NFN, FT>::T;
+  __shared__ FaceTileSmem<DIM, NN, NFN, FT> sm;
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int ntiles = (int)((a.ng + FT - 1) / FT);
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
+  FaceRec carry;
+  carry.kind = 255;
+  if (tid < FT && (int64_t)tile * FT + tid < a.ng) carry = a.faces[a.g0 + (int64_t)tile * FT + tid];
+  const int stride = gridDim.x;
+#pragma unroll 1
+  for (; tile < ntiles; tile += stride) {
+    const int64_t g0 = a.g0 + (int64_t)tile * FT;
+    const int64_t rem = a.g0 + a.ng - g0;
+    const int nf = (int)(rem < FT ? rem : FT);
+    const int64_t ga = tile + stride < ntiles ? g0 + (int64_t)stride * FT : -1;
+    face_tile<DIM, NN, NFN, FT, T, false, true>(op, a, sm, g0, nf, ga, tid, &carry);
+    __syncthreads();
+  }
+}
+
+// k_face_flux_w (PDES_FACE_W=1): warp-autonomous form of k_face_flux.  Every warp owns FT = 5 faces (25 variable lanes,
+// 30 node lanes) with its own shared-memory tile and only warp-level barriers, so the warps of a CTA drift apart and
+// one warp's gathers overlap another's arithmetic (block barriers are ~25 % of k_face_flux's stall samples).
+template <int DIM, int NN, int NFN, int FT, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB)
+k_face_flux_w(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
+  static_assert(FaceCfg<DIM, NN, NFN, FT>::T == 32, "one warp per tile");
+  __shared__ FaceTileSmem<DIM, NN, NFN, FT> sm[WPC];
+  if (a.ctl->stop) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t g0 = a.g0 + ((int64_t)blockIdx.x * WPC + warp) * FT;
+  const int64_t rem = a.g0 + a.ng - g0;
+  if (rem <= 0) return;
+  const int nf = (int)(rem < FT ? rem : FT);
+  const int64_t ga = a.prefetch_ahead > 0 ? g0 + (int64_t)a.prefetch_ahead * FT : -1;
+  face_tables<DIM, NN, NFN, FT, 32>(op, sm[warp], lane);
+  face_tile<DIM, NN, NFN, FT, 32, true>(op, a, sm[warp], g0, nf, ga, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -663,3 +663,29 @@ def test_face_element_option_errors():
     ope = pd.build_operator(2, 2, "diage")          # diagonal-E keeps face_integral_type 1 (read_input.jl:742-755)
     with pytest.raises(pd.PDESolverError):
         pd.EulerData(pd.structured_mesh(ope, 2), ope, dict(ES2, BC1_name="isentropicVortexBC"))
+
+
+def test_face_kernel_variants_bitwise_equal():
+    """The opt-in forms of k_face_flux (PDES_FACE_W: warp-autonomous tiles; PDES_FACE_P: persistent tiles with the next
+    tile's records carried in registers) run the same tile body: bit-identical residuals.  The switches are read once
+    per process, so each variant runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_gpu_parity as t, pdesolver_jl_b200 as pd\n"
+            "h = hashlib.sha256()\n"
+            "for case, n in (('c3_3d_p2_roe_src', 7), ('c1_2d_p1_roe', 15), ('2d_p2_roe', 8), ('3d_p1_roe_src', 5)):\n"
+            "    op, mesh, opts, orc, q0, eqn = t.setup(case, n, shuffle_seed=5)\n"
+            "    eqn.q[...] = q0\n"
+            "    pd.evalResidual(mesh, op, eqn, opts)\n"
+            "    h.update(np.ascontiguousarray(eqn.res).tobytes())\n"
+            "print('DIGEST', h.hexdigest())\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                   os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("base", {}), ("warp", {"PDES_FACE_W": "2"}), ("persistent", {"PDES_FACE_P": "8"})):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        digests[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert digests["warp"] == digests["base"] and digests["persistent"] == digests["base"]
