@@ -358,6 +358,23 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
   for (int it = tid; it < ne * EL; it += T) {
     const int s = it / EL, r = it - s * EL;
     const int i = r / ND, c = r - i * ND;
+    // the face records and Minv are requested before the pair-flux gather (they were the top stall of this kernel:
+    // profiles/r1_es_element_split.txt, long scoreboard at the add that consumed them)
+    double grec[DENSEREC ? NF : DIM];
+    if (DENSEREC) {
+      // face-element integrals (k_face_element): one [nd, nn] record per local face
+      const double* G = a.fluxe + (e0 + s) * (NF * EL) + r;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) grec[f] = __ldg(G + f * EL);
+    } else {
+      const double* G = a.fluxe + (e0 + s) * (NF * FL);
+#pragma unroll
+      for (int u = 0; u < DIM; ++u) {
+        const int slot = op.inv[i][u];
+        grec[u] = slot >= 0 ? __ldg(G + slot * ND + c) : 0.0;
+      }
+    }
+    const double mv = MODE == EPI_RK ? __ldg(a.minv + (e0 + s) * NN + i) : 1.0;
     double acc = 0.0;
     const double* Fc = sFp + c * PS + s * NP;
     const double* Sc = sS2 + i * NN;
@@ -368,20 +385,9 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
 #pragma unroll
       for (int d = 0; d < DIM; ++d) acc = fma(-Sc[d * NN * NN + m], Fc[d * ND * PS + pi], acc);
     }
-    if (DENSEREC) {
-      // face-element integrals (k_face_element): one [nd, nn] record per local face
-      const double* G = a.fluxe + (e0 + s) * (NF * EL) + r;
 #pragma unroll
-      for (int f = 0; f < NF; ++f) acc += __ldg(G + f * EL);
-    } else {
-      const double* G = a.fluxe + (e0 + s) * (NF * FL);
-#pragma unroll
-      for (int u = 0; u < DIM; ++u) {
-        const int slot = op.inv[i][u];
-        if (slot >= 0) acc += __ldg(G + slot * ND + c);
-      }
-    }
-    if (MODE == EPI_RK) acc *= __ldg(a.minv + (e0 + s) * NN + i);
+    for (int u = 0; u < (DENSEREC ? NF : DIM); ++u) acc += grec[u];
+    if (MODE == EPI_RK) acc *= mv;
     sq[it] = acc;
   }
   __syncthreads();
