@@ -127,6 +127,10 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   __shared__ double sc[DIM][NFN];           // wface[k] * nrm[d,k]
   __shared__ double spen[NFN][ND];          // wface-weighted flux at the face nodes
   __shared__ double srec[2][NN][ND];
+  // operator coefficients indexed by a per-thread (i, j): from shared memory (a constant-bank load with a divergent
+  // index is replayed once per distinct address)
+  __shared__ double sA[NN][NFN];            // interp[i][k]
+  __shared__ double sB[NN][DIM][NFN];       // interp[j][nbrperm[k]] * wface[k] * nrm[d,k]
   if (a.ctl->stop) return;
   const int tid = threadIdx.x;
   const int64_t g = a.g0 + blockIdx.x;
@@ -145,6 +149,13 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   }
   __syncthreads();
   const int* nbr = op.nbrperm[interior ? r.orient : 0];
+  if (interior) {
+    for (int idx = tid; idx < NN * NFN; idx += T) sA[idx / NFN][idx % NFN] = op.interp[idx / NFN][idx % NFN];
+    for (int idx = tid; idx < NN * DIM * NFN; idx += T) {
+      const int j = idx / (DIM * NFN), d = (idx / NFN) % DIM, k = idx % NFN;
+      sB[j][d][k] = op.interp[j][nbr[k]] * sc[d][k];
+    }
+  }
 
   if (!interior) {
     // interpolateBoundary + BC functor + boundaryintegrate! (bc.jl:162-175, 251-284; euler.jl:669-690)
@@ -191,7 +202,8 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
           double Eij = 0.0;
-          for (int k = 0; k < NFN; ++k) Eij = fma(op.interp[i][k] * op.interp[j][nbr[k]], sc[d][k], Eij);
+#pragma unroll
+          for (int k = 0; k < NFN; ++k) Eij = fma(sA[i][k], sB[j][d][k], Eij);
 #pragma unroll
           for (int p = 0; p < ND; ++p) gsum[p] = fma(Eij, F[d][p], gsum[p]);
         }
@@ -217,7 +229,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
         for (int p = 0; p < ND; ++p) { wL[p] = 0.0; wR[p] = 0.0; }
         for (int j = 0; j < NN; ++j) {
-          const double cL = op.interp[j][k], cR = op.interp[j][nk];
+          const double cL = sA[j][k], cR = sA[j][nk];
 #pragma unroll
           for (int p = 0; p < ND; ++p) { wL[p] += cL * sw[0][j][p]; wR[p] += cR * sw[1][j][p]; }
         }
@@ -236,8 +248,8 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
         const int j = idx / ND, p = idx - j * ND;
         double sl = srec[0][j][p], sr = srec[1][j][p];
         for (int k = 0; k < NFN; ++k) {
-          sl -= op.interp[j][k] * spen[k][p];
-          sr += op.interp[j][nbr[k]] * spen[k][p];
+          sl -= sA[j][k] * spen[k][p];
+          sr += sA[j][nbr[k]] * spen[k][p];
         }
         srec[0][j][p] = sl;
         srec[1][j][p] = sr;
