@@ -50,7 +50,8 @@ enum { PDES_FEI_EC = 1, PDES_FEI_ELF_PENALTY = 2, PDES_FEI_ESLF = 3 };
 /* FluxDict names (src/solver/euler/flux.jl) -> ids */
 enum { PDES_FLUX_ROE = 1, PDES_FLUX_IR = 2, PDES_FLUX_IRSLF = 3, PDES_FLUX_STANDARD = 4 };
 /* BCDict names (src/solver/euler/bc.jl:2342-2369) -> ids */
-enum { PDES_BC_ISENTROPIC_VORTEX = 1, PDES_BC_EXP = 2, PDES_BC_FREESTREAM = 3, PDES_BC_NOPENETRATION = 4 };
+enum { PDES_BC_ISENTROPIC_VORTEX = 1, PDES_BC_EXP = 2, PDES_BC_FREESTREAM = 3, PDES_BC_NOPENETRATION = 4,
+       PDES_BC_RHO1E2U3 = 5, PDES_BC_ALLONES = 6, PDES_BC_ZEROFLUX = 7, PDES_BC_NOPENETRATION_ES = 8 };
 /* SRCDict names (src/solver/euler/source.jl) -> ids */
 enum { PDES_SRC_NONE = 0, PDES_SRC_EXP = 1 };
 

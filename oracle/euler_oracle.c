@@ -34,7 +34,8 @@ typedef struct { uint32_t element; uint8_t face, pad[3]; } OrcBoundary;
 
 enum { ORC_FLUX_ROE = 1, ORC_FLUX_IR = 2, ORC_FLUX_IRSLF = 3, ORC_FLUX_STANDARD = 4 };
 enum { ORC_BC_ISENTROPIC_VORTEX = 1, ORC_BC_EXP = 2, ORC_BC_FREESTREAM = 3,
-       ORC_BC_NOPENETRATION = 4 };
+       ORC_BC_NOPENETRATION = 4, ORC_BC_RHO1E2U3 = 5, ORC_BC_ALLONES = 6, ORC_BC_ZEROFLUX = 7,
+       ORC_BC_NOPENETRATION_ES = 8 };
 enum { ORC_SRC_NONE = 0, ORC_SRC_EXP = 1 };
 /* faceElementIntegrals.jl:735-741 FaceElementDict (the Lax-Wendroff kernels are not restated) */
 enum { ORC_FEI_EC = 1, ORC_FEI_ELF_PENALTY = 2, ORC_FEI_ESLF = 3 };
@@ -459,6 +460,35 @@ void orc_bc_flux(const OrcProblem *P, int bc_id, const double *q, const double *
       for (int i = 0; i < nd; ++i) qg[i] = q[i];
       for (int d = 0; d < dim; ++d) qg[1 + d] -= n[d] * Unrm;
       orc_euler_flux(dim, P->gamma, qg, nrm, flux);
+      break;
+    }
+    case ORC_BC_RHO1E2U3:      /* bc.jl:1454-1537, calcRho1Energy2U3 common_funcs.jl:754-779 */
+      qg[0] = 1.0;
+      for (int d = 0; d < dim; ++d) qg[1 + d] = 0.35355;
+      qg[dim + 1] = 2.0;
+      orc_roe_solver(dim, P->gamma, q, qg, nrm, flux);
+      break;
+    case ORC_BC_ALLONES:       /* bc.jl:1702-1722, calcOnes common_funcs.jl:647-654 */
+      for (int i = 0; i < nd; ++i) qg[i] = 1.0;
+      orc_roe_solver(dim, P->gamma, q, qg, nrm, flux);
+      break;
+    case ORC_BC_ZEROFLUX:      /* bc.jl:2140-2152 */
+      for (int i = 0; i < nd; ++i) flux[i] = 0.0;
+      break;
+    case ORC_BC_NOPENETRATION_ES: {
+      /* bc.jl:767-793: reflected state (getDirichletState :860-918) + calcLFFlux (bc_solvers.jl:428-446) with
+       * getLambdaMaxSimple (IR_stab.jl:310-325) */
+      double n[3], nn2 = 0.0, Unrm = 0.0, fluxL[ORC_MAXD], fluxR[ORC_MAXD], q_avg[ORC_MAXD];
+      for (int d = 0; d < dim; ++d) nn2 += nrm[d] * nrm[d];
+      double fac = 1.0 / sqrt(nn2);
+      for (int d = 0; d < dim; ++d) { n[d] = nrm[d] * fac; Unrm += n[d] * q[1 + d]; }
+      for (int i = 0; i < nd; ++i) qg[i] = q[i];
+      for (int d = 0; d < dim; ++d) qg[1 + d] = -2 * Unrm * n[d] + q[1 + d];
+      orc_euler_flux(dim, P->gamma, q, nrm, fluxL);
+      orc_euler_flux(dim, P->gamma, qg, nrm, fluxR);
+      for (int i = 0; i < nd; ++i) q_avg[i] = 0.5 * (q[i] + qg[i]);
+      double lambda_max = orc_lambda_max(dim, P->gamma, q_avg, nrm);
+      for (int i = 0; i < nd; ++i) flux[i] = 0.5 * (fluxL[i] + fluxR[i] - lambda_max * (qg[i] - q[i]));
       break;
     }
     default: fprintf(stderr, "oracle: unsupported BC id %d\n", bc_id); abort();

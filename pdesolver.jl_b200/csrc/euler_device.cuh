@@ -63,6 +63,16 @@ __device__ __forceinline__ Dual fast_rsqrt(Dual x) {
 }
 __device__ __forceinline__ Dual absv(Dual x) { return x.v < 0.0 ? -x : x; }
 __device__ __forceinline__ Dual maxv(Dual a, Dual b) { return a.v > b.v ? a : b; }
+// Utils/complexify.jl:157-172 absvalue3: smooth |x| (delta = 1e-7), on the value and its tangent
+__device__ __forceinline__ double absvalue3(double x) {
+  const double delta = 1e-7, v1 = fabs(x);
+  return v1 > delta ? v1 : ((x * x) / delta + delta) / 2;
+}
+__device__ __forceinline__ Dual absvalue3(Dual x) {
+  const double delta = 1e-7, v1 = fabs(x.v);
+  if (v1 > delta) return x.v < 0.0 ? -x : x;
+  return Dual(((x.v * x.v) / delta + delta) / 2, x.v * x.d / delta);
+}
 
 // euler_funcs.jl:856-863 / 897-903 calcPressure
 template <int DIM, typename T>

@@ -31,10 +31,26 @@ __device__ inline void bc_flux_dual(int bc, const Dual* q, const double* x, cons
     euler_flux<DIM, Dual>(qg, n, ph.gamma - 1.0, flux);
     return;
   }
+  if (bc == 7) {  // ZeroFluxBC
+#pragma unroll
+    for (int i = 0; i < ND; ++i) flux[i] = Dual(0.0);
+    return;
+  }
+  if (bc == 8) {  // noPenetrationESBC
+    noslip_es_flux<DIM, Dual>(q, n, ph.gamma, flux);
+    return;
+  }
   double qd[ND];
   if (bc == 1) isentropic_vortex<DIM>(x, ph.gamma, ph.R, qd);
   else if (bc == 2) calc_exp<DIM>(x, ph.gamma, qd);
-  else free_stream<DIM>(ph.rho_free, ph.E_free, ph.Ma, ph.aoa, qd);
+  else if (bc == 5) {
+    qd[0] = 1.0; qd[DIM + 1] = 2.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qd[1 + d] = 0.35355;
+  } else if (bc == 6) {
+#pragma unroll
+    for (int i = 0; i < ND; ++i) qd[i] = 1.0;
+  } else free_stream<DIM>(ph.rho_free, ph.E_free, ph.Ma, ph.aoa, qd);
 #pragma unroll
   for (int i = 0; i < ND; ++i) qg[i] = Dual(qd[i]);      // the Dirichlet state does not depend on q
   roe_flux<DIM, Dual>(q, qg, n, ph.gamma, flux);

@@ -1195,7 +1195,7 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
   }
   std::vector<char> bseen((size_t)c.nB, 0);
   for (int i = 0; i < c.numBC; ++i) {
-    if (bc_ids[i] < 1 || bc_ids[i] > 4) {
+    if (bc_ids[i] < PDES_BC_ISENTROPIC_VORTEX || bc_ids[i] > PDES_BC_NOPENETRATION_ES) {
       set_err(ctx, "BC id %d is not supported", bc_ids[i]);
       return PDES_ERR_UNSUPPORTED;
     }

@@ -172,6 +172,41 @@ __host__ __device__ constexpr int pad_stride(int n, int nd) {
   return m;
 }
 
+// noPenetrationESBC (bc.jl:767-793): qg = q with the normal momentum negated (getDirichletState :860-918), flux =
+// calcLFFlux(q, qg) = (F(q) + F(qg) - lambda_max (qg - q)) / 2 with lambda_max = getLambdaMax at the average state
+// (bc_solvers.jl:428-446, IR_stab.jl:310-325, euler_funcs.jl:1887-1913 with absvalue3).  T = double | Dual.
+template <int DIM, typename T>
+__device__ __forceinline__ void noslip_es_flux(const T* q, const double* n, double gamma, T* flux) {
+  constexpr int ND = DIM + 2;
+  double nn2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) nn2 += n[d] * n[d];
+  const double dA = ::sqrt(nn2), fac = 1.0 / dA;
+  double nh[DIM];
+  T Unrm = T(0.0);
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { nh[d] = n[d] * fac; Unrm += T(nh[d]) * q[1 + d]; }
+  T qg[ND], fL[ND], fR[ND], qa[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) qg[i] = q[i];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) qg[1 + d] = T(-2.0 * nh[d]) * Unrm + q[1 + d];
+  euler_flux<DIM, T>(q, n, gamma - 1.0, fL);
+  euler_flux<DIM, T>(qg, n, gamma - 1.0, fR);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) qa[i] = T(0.5) * (q[i] + qg[i]);
+  const T p = calc_pressure<DIM, T>(qa, gamma - 1.0);
+  const T rinv = T(1.0) / qa[0];
+  T Un = T(0.0);
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) Un += T(n[d]) * qa[1 + d] * rinv;
+  const T a2 = T(gamma) * p * rinv;
+  const T a = a2 * fast_rsqrt(a2);                       // sqrt(a2)
+  const T lam = absvalue3(Un) + T(dA) * a;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) flux[i] = T(0.5) * (fL[i] + fR[i] - lam * (qg[i] - q[i]));
+}
+
 // boundary-condition functors (bc.jl:554-567, 1756-1768, 1573-1587, 717-765): Dirichlet state + Roe, or
 // Euler flux of the wall-projected state
 template <int DIM>
@@ -193,9 +228,25 @@ __device__ __noinline__ void bc_flux(int bc, const double* q, const double* x, c
     euler_flux<DIM>(qg, n, ph.gamma - 1.0, flux);
     return;
   }
+  if (bc == 7) {  // ZeroFluxBC (bc.jl:2140-2152)
+#pragma unroll
+    for (int i = 0; i < ND; ++i) flux[i] = 0.0;
+    return;
+  }
+  if (bc == 8) {  // noPenetrationESBC (bc.jl:767-793, 860-918): reflected state + calcLFFlux (bc_solvers.jl:428-446)
+    noslip_es_flux<DIM, double>(q, n, ph.gamma, flux);
+    return;
+  }
   if (bc == 1) isentropic_vortex<DIM>(x, ph.gamma, ph.R, qg);
   else if (bc == 2) calc_exp<DIM>(x, ph.gamma, qg);
-  else free_stream<DIM>(ph.rho_free, ph.E_free, ph.Ma, ph.aoa, qg);
+  else if (bc == 5) {  // Rho1E2U3BC (bc.jl:1454-1537, calcRho1Energy2U3 common_funcs.jl:754-779)
+    qg[0] = 1.0; qg[DIM + 1] = 2.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qg[1 + d] = 0.35355;
+  } else if (bc == 6) {  // allOnesBC (bc.jl:1702-1722)
+#pragma unroll
+    for (int i = 0; i < ND; ++i) qg[i] = 1.0;
+  } else free_stream<DIM>(ph.rho_free, ph.E_free, ph.Ma, ph.aoa, qg);
   roe_flux<DIM>(q, qg, n, ph.gamma, flux);
 }
 

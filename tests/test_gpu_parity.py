@@ -54,7 +54,8 @@ def test_residual_ragged_tile_sizes():
         assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
 
 
-@pytest.mark.parametrize("bc", ["FreeStreamBC", "noPenetrationBC", "isentropicVortexBC", "ExpBC"])
+@pytest.mark.parametrize("bc", ["FreeStreamBC", "noPenetrationBC", "isentropicVortexBC", "ExpBC", "Rho1E2U3BC", "allOnesBC",
+                                "ZeroFluxBC", "noPenetrationESBC"])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_boundary_conditions(bc, dim):
     case = "c1_2d_p1_roe" if dim == 2 else "3d_p1_roe_src"
@@ -689,3 +690,17 @@ def test_face_kernel_variants_bitwise_equal():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         digests[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert digests["warp"] == digests["base"] and digests["persistent"] == digests["base"]
+
+
+@pytest.mark.parametrize("bc", ["noPenetrationESBC", "Rho1E2U3BC", "ZeroFluxBC"])
+def test_jvp_with_more_boundary_functors(bc):
+    """The dual-number J*v through the boundary functors added beyond the four scoped ones (bc.jl:767-793, 1454-1537,
+    2140-2152), against central differences of the oracle residual."""
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 5, shuffle_seed=2, extra={"BC1_name": bc})
+    rng = np.random.RandomState(3)
+    v = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+    eqn.q[...] = q0
+    Jv = pd.evaldRdqProduct(mesh, op, eqn, opts, v)
+    eps = 1e-6
+    fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
+    assert rel_l2(Jv, fd) < 1e-8

@@ -495,3 +495,74 @@ def test_reference_convergence_golden():
     assert abs(e1 - 0.01200) < 2e-5           # measured 0.0120031: the golden to its printed precision
     slope = np.log(e1 / e2) / np.log(2.0)
     assert 1.9 < slope < 2.1
+
+
+# --- boundary functors beyond the four of the named configurations (bc.jl:767-793, 1454-1537, 1702-1722, 2140-2152) ------
+def _bc_flux(P, bc_id, q, nrm, coords=None):
+    dim = len(nrm)
+    flux = np.zeros(dim + 2)
+    x = np.zeros(dim) if coords is None else np.ascontiguousarray(coords, dtype=np.float64)
+    oracle.lib().orc_bc_flux(P.ref(), int(bc_id), _ptr(np.ascontiguousarray(q)), _ptr(x),
+                             _ptr(np.ascontiguousarray(nrm, dtype=np.float64)), _ptr(flux))
+    return flux
+
+
+def _random_states(dim, n, seed, vscale=0.6):
+    rng = np.random.RandomState(seed)
+    rho = 0.5 + rng.rand(n)
+    vel = rng.standard_normal((n, dim)) * vscale
+    p = 0.5 + rng.rand(n)
+    E = p / 0.4 + 0.5 * rho * (vel ** 2).sum(axis=1)
+    return np.column_stack([rho, rho[:, None] * vel, E])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_no_penetration_es_bc_is_entropy_stable(dim):
+    """test_ESSBC (test/euler/test_ESS.jl:748-779): psi_n - w^T f <= 1e-12 with the IR entropy variables, psi = momentum,
+    on subsonic states like the vortex the reference evaluates it on (the Lax-Friedrichs speed is taken at the average of
+    q and its reflection, whose normal velocity is zero, so the bound needs a subsonic wall-normal velocity)."""
+    op = sbp.build_operator(dim, 1)
+    P = oracle.Problem(pmesh.structured_mesh(op, 1), op, {"BC1_name": "noPenetrationESBC"})
+    rng = np.random.RandomState(11)
+    L = oracle.lib()
+    for q in _random_states(dim, 200, 5, vscale=0.25):
+        n = rng.standard_normal(dim)
+        n /= np.linalg.norm(n)
+        f = _bc_flux(P, oracle.BC_IDS["noPenetrationESBC"], q, n)
+        w = np.zeros(dim + 2)
+        L.orc_convert_to_ir(dim, 1.4, _ptr(np.ascontiguousarray(q)), _ptr(w))
+        assert (q[1:1 + dim] * n).sum() - w @ f <= 1e-12
+        # for a state that already satisfies the wall condition the flux is the pressure force only (qg == q: the
+        # Lax-Friedrichs dissipation vanishes)
+        qt = q.copy()
+        qt[1:1 + dim] -= (qt[1:1 + dim] @ n) * n
+        ft = _bc_flux(P, oracle.BC_IDS["noPenetrationESBC"], qt, n)
+        pt = 0.4 * (qt[dim + 1] - 0.5 * (qt[1:1 + dim] ** 2).sum() / qt[0])
+        assert np.allclose(ft, np.concatenate([[0.0], pt * n, [0.0]]), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_constant_state_and_zero_flux_bcs(dim):
+    op = sbp.build_operator(dim, 1)
+    P = oracle.Problem(pmesh.structured_mesh(op, 1), op, {"BC1_name": "Rho1E2U3BC"})
+    L = oracle.lib()
+    rng = np.random.RandomState(2)
+    for q in _random_states(dim, 20, 9):
+        n = rng.standard_normal(dim)
+        for name, qg in (("Rho1E2U3BC", np.array([1.0] + [0.35355] * dim + [2.0])), ("allOnesBC", np.ones(dim + 2))):
+            ref = np.zeros(dim + 2)
+            L.orc_roe_solver(dim, 1.4, _ptr(np.ascontiguousarray(q)), _ptr(qg), _ptr(n), _ptr(ref))
+            assert np.array_equal(_bc_flux(P, oracle.BC_IDS[name], q, n), ref)
+        assert not _bc_flux(P, oracle.BC_IDS["ZeroFluxBC"], q, n).any()
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_rho1e2u3_uniform_state_zero_residual(dim, p):
+    """test/euler/test_dg.jl:70-84: the uniform Rho1E2U3 state with Rho1E2U3BC on every boundary gives a zero residual."""
+    op = sbp.build_operator(dim, p)
+    mesh = pmesh.structured_mesh(op, 3, shuffle_seed=4)
+    P = oracle.Problem(mesh, op, {"Flux_name": "RoeFlux", "BC1_name": "Rho1E2U3BC"})
+    q = np.zeros(P.shape, order="F")
+    q[0], q[dim + 1] = 1.0, 2.0
+    q[1:1 + dim] = 0.35355
+    assert np.abs(P.eval_residual(q)).max() < 1e-13
