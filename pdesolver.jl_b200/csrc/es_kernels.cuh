@@ -64,7 +64,7 @@ k_face_flux_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid
     for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = nrm[d]; }
 #pragma unroll
     for (int k = 0; k < ND; ++k) qb[k] = qL[k];
-    bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+    bc_flux_any<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
 #pragma unroll
     for (int k = 0; k < ND; ++k) flux[k] = fb[k];
   } else {
@@ -172,7 +172,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
       const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + k) * DIM;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d); }
-      bc_flux<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+      bc_flux_any<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
 #pragma unroll
       for (int p = 0; p < ND; ++p) spen[k][p] = op.wface[k] * fb[p];
     }

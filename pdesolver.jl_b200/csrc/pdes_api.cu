@@ -209,6 +209,12 @@ struct OpsImpl : Ops {
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
     if (a.ng <= 0) return cudaSuccess;
     const int64_t ntiles = (a.ng + FT - 1) / FT;
+    if (a.ext_bc) {
+      // a boundary functor outside the four scoped ones is in use: the instantiation with the extended dispatch
+      dim3 gridx((unsigned)ntiles), blockx(FCfg::T);
+      k_face_flux<DIM, NN, NFN, FT, MINB_F, true><<<gridx, blockx, 0, s>>>(tab, a);
+      return cudaGetLastError();
+    }
     if constexpr (FaceTmaCfg<DIM, NN, NFN, FT>::FITS) if (use_tma) {
       // persistent CTAs (one wave), elements staged by the bulk-copy engine one tile ahead
       if (tma_grid < 0) {
@@ -519,7 +525,7 @@ struct PdesCtx {
     int32_t n_tiles = 0, n_groups = 0, lag = 0;
     int64_t g0 = 0, ng = 0;
   } plan[2];
-  bool fused = false;
+  bool fused = false, has_ext_bc = false;
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
   Sched* sched = nullptr;
   unsigned* flags = nullptr;
@@ -686,7 +692,7 @@ int finalize(PdesCtx* ctx) {
 
     // k_fused schedule (see residual_kernels.cuh): the faces an element tile integrates are a prefix of the sorted list
     const int FPG = ctx->ops->fused_group_faces();
-    ctx->fused = FPG > 0 && nc == 1 && env_int("PDES_FUSED", 0) != 0 && env_int("PDES_ELEM_W", 0) == 0;
+    ctx->fused = FPG > 0 && nc == 1 && !ctx->has_ext_bc && env_int("PDES_FUSED", 0) != 0 && env_int("PDES_ELEM_W", 0) == 0;
     if (ctx->fused) {
       const int E = ctx->ops->fused_tile_elems();
       const int64_t nt = (c.nE + E - 1) / E;
@@ -827,6 +833,7 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.prefetch_ahead = ctx->prefetch_ahead_faces;
+  fa.ext_bc = ctx->has_ext_bc ? 1 : 0;
   if (ctx->fused) {
     FusedArgs fu;
     memset(&fu, 0, sizeof(fu));
@@ -1194,7 +1201,9 @@ int pdes_set_mesh(PdesCtx* ctx, const double* dxidx, const double* jac, const do
     fr.kind = FK_INTERIOR;
   }
   std::vector<char> bseen((size_t)c.nB, 0);
+  ctx->has_ext_bc = false;
   for (int i = 0; i < c.numBC; ++i) {
+    if (bc_ids[i] >= PDES_BC_RHO1E2U3) ctx->has_ext_bc = true;
     if (bc_ids[i] < PDES_BC_ISENTROPIC_VORTEX || bc_ids[i] > PDES_BC_NOPENETRATION_ES) {
       set_err(ctx, "BC id %d is not supported", bc_ids[i]);
       return PDES_ERR_UNSUPPORTED;
