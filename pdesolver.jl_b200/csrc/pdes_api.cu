@@ -98,6 +98,8 @@ struct Ops {
   virtual int resident_face_ctas() = 0;
   virtual int tile_elems() const = 0;
   virtual int record_doubles() const { return 0; }   // doubles per (element, local face) record; 0: nd * nfn
+  virtual int pipe_face_tile() const { return 0; }   // faces per CTA of the chunk-pipeline face kernel; 0: no pipeline
+  virtual bool staged_epilogue() const { return false; }   // element kernel stages its epilogue streams (rk4 scheme 2)
   virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
   // fused face + element kernel (k_fused); families without one return 0 faces per group
   virtual int fused_group_faces() const { return 0; }
@@ -122,6 +124,20 @@ struct OpsImpl : Ops {
   using UCfg = FusedCfg<DIM, NN, NFN, E, FFT, NSUB>;
   int fused_group_faces() const override { return FFT * NSUB; }
   int fused_tile_elems() const override { return E; }
+  int pipe_face_tile() const override { return FT; }
+  bool staged_epilogue() const override { return !use_warp_kernel; }
+  // chunk pipeline: programmatic stream serialization lets the CTAs of this launch start while the last wave of the
+  // previous launch is still running; the kernels synchronise through PipeArgs counters
+  template <typename K, typename A>
+  static cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Tab& tab, const A& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tab, a);
+  }
   int resident_fused_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RK, MINB_E>, UCfg::T,
@@ -207,6 +223,11 @@ struct OpsImpl : Ops {
   }
   int tma_grid = -1;
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+    if (a.pipe.on) {
+      // (an empty chunk still launches one CTA: it has to publish its completion)
+      const int64_t nt = std::max<int64_t>(1, (a.ng + FT - 1) / FT);
+      return launch_pdl(k_face_flux<DIM, NN, NFN, FT, MINB_F, false, true>, dim3((unsigned)nt), dim3(FCfg::T), 0, s, tab, a);
+    }
     if (a.ng <= 0) return cudaSuccess;
     const int64_t ntiles = (a.ng + FT - 1) / FT;
     if (a.ext_bc) {
@@ -265,6 +286,26 @@ struct OpsImpl : Ops {
     e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    {
+      // shared-memory carve-out of the SM: k_element_rk needs the largest one, k_face_flux by itself would get the
+      // smallest (largest L1).  An SM cannot change its carve-out while CTAs are resident, so launches that should
+      // overlap (chunk pipeline) must agree on it: PDES_CARVEOUT_F / _E = percent of the maximum, -1 = driver default
+      const int cf = env_int("PDES_CARVEOUT_F", -1), ce = env_int("PDES_CARVEOUT_E", -1);
+      if (cf >= 0) {
+        cudaFuncSetAttribute(k_face_flux<DIM, NN, NFN, FT, MINB_F>, cudaFuncAttributePreferredSharedMemoryCarveout, cf);
+        cudaFuncSetAttribute(k_face_flux<DIM, NN, NFN, FT, MINB_F, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cf);
+      }
+      if (ce >= 0) {
+        cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, cudaFuncAttributePreferredSharedMemoryCarveout, ce);
+        cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E, true>, cudaFuncAttributePreferredSharedMemoryCarveout, ce);
+      }
+    }
     e = cudaFuncSetAttribute(k_fused<DIM, NN, NFN, E, FFT, NSUB, EPI_RES, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UCfg::smem_bytes);
     if (e != cudaSuccess) return e;
@@ -276,6 +317,12 @@ struct OpsImpl : Ops {
   }
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    if (a.pipe.on) {
+      dim3 gridp((unsigned)((a.nE - a.e_begin + E - 1) / E)), blockp(Cfg::T);
+      if (mode == EPI_RES)
+        return launch_pdl(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E, true>, gridp, blockp, Cfg::smem_bytes, s, tab, a);
+      return launch_pdl(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E, true>, gridp, blockp, Cfg::smem_bytes, s, tab, a);
+    }
     if (use_warp_kernel && a.dx_node_stride == 0) return launch_elements_w(a, mode, s);
     if (a.nE <= a.e_begin) return cudaSuccess;
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
@@ -431,6 +478,13 @@ struct OpsImplE : Ops {
 };
 
 Ops* make_ops(const PdesConfig& c) {
+#ifdef PDES_LEAN
+  // development build (make EXTRA=-DPDES_LEAN): only the kernels of the headline workload, a fraction of the build time
+  if (!c.sparse_face && c.face_integral_type == 1 && c.volume_integral_type == 1 && c.flux_id == PDES_FLUX_ROE &&
+      c.dim == 3 && c.nn == 11 && c.nfn == 6)
+    return new OpsImpl<3, 11, 6, 32, 4, 16, 8>();
+  return nullptr;
+#else
   if (c.sparse_face) {
     // entropy-stable configuration: diag-E operator, split-form IR volume flux, Roe / IR / IRSLF interface flux
     if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR) return nullptr;
@@ -471,6 +525,7 @@ Ops* make_ops(const PdesConfig& c) {
     }
   }
   return nullptr;
+#endif
 }
 
 // one-time uploads: stream-ordered with the kernels of the (non-blocking) compute stream, then synchronised so
@@ -527,6 +582,13 @@ struct PdesCtx {
   } plan[2];
   bool fused = false, has_ext_bc = false;
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
+  int rk4_nosum = 0;       // rk4 stages without the running sum of the k's (epilogue_tile scheme 2)
+  int reverse_elems = 0, discard_split = 0;   // split kernels: element tiles swept last-to-first; consumed records dropped from L2
+  // chunk pipeline (PDES_PIPE = number of chunks): F0 F1 E0 F2 E1 ... with programmatic dependent launches
+  bool pipe = false;
+  int pipe_lag = 1, pipe_discard = 1, pipe_dbg = 0, chunk_dep[MAXC] = {0};
+  uint32_t pipe_epoch = 0;
+  unsigned* pipe_ctr = nullptr;     // [4][MAXC]: arriveF | doneF | arriveE | doneE
   Sched* sched = nullptr;
   unsigned* flags = nullptr;
   double* diag_buf = nullptr;
@@ -589,6 +651,17 @@ int reset_ctl(PdesCtx* ctx) {
   z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.norm_count = 0;
   *ctx->h_ctl = z;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->pipe_ctr) {
+    // an aborted evaluation leaves arrival counts and unpublished chunks behind: every chunk "complete at the current epoch"
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned h[4 * PdesCtx::MAXC];
+    for (int i = 0; i < PdesCtx::MAXC; ++i) {
+      h[i] = 0u; h[2 * PdesCtx::MAXC + i] = 0u;
+      h[PdesCtx::MAXC + i] = ctx->pipe_epoch; h[3 * PdesCtx::MAXC + i] = ctx->pipe_epoch;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pipe_ctr, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return PDES_OK;
 }
 
@@ -677,6 +750,10 @@ int finalize(PdesCtx* ctx) {
     const int tile = ctx->ops->tile_elems();
     int nc = env_int("PDES_CHUNKS", 0);
     if (nc <= 0) nc = 1;   // measured on C3: more chunks only add tail waves
+    const int want_pipe = env_int("PDES_PIPE", 0);
+    const bool can_pipe = want_pipe > 1 && ctx->ops->pipe_face_tile() > 0 && ctx->nS == 0 && !ctx->has_ext_bc &&
+                          env_int("PDES_FUSED", 0) == 0 && env_int("PDES_ELEM_W", 0) == 0 && env_int("PDES_FACE_TMA", 0) == 0;
+    if (can_pipe) nc = want_pipe;
     if (nc > PdesCtx::MAXC) nc = PdesCtx::MAXC;
     const int64_t ntiles = (c.nE + tile - 1) / tile;
     if (nc > ntiles) nc = (int)ntiles;
@@ -689,6 +766,26 @@ int finalize(PdesCtx* ctx) {
       ctx->chunk_g[k] = k == nc ? nIB : g;
     }
     ctx->chunk_g[0] = 0;
+    ctx->pipe = can_pipe && nc > 1;
+    if (ctx->pipe) {
+      // chunk_dep[k]: the highest element chunk touched by the faces of face chunk k (q they gather, records they write)
+      for (int k = 0; k < nc; ++k) {
+        int64_t emax = 0;
+        for (int64_t gg = ctx->chunk_g[k]; gg < ctx->chunk_g[k + 1]; ++gg) {
+          emax = std::max<int64_t>(emax, faces[gg].elL);
+          if (faces[gg].kind == FK_INTERIOR) emax = std::max<int64_t>(emax, faces[gg].elR);
+        }
+        int d = k;
+        while (d + 1 < nc && ctx->chunk_e[d + 1] <= emax) ++d;
+        ctx->chunk_dep[k] = d;
+      }
+      ctx->pipe_lag = std::max(0, env_int("PDES_PIPE_LAG", 1));
+      ctx->pipe_discard = env_int("PDES_PIPE_DISCARD", 1);
+      ctx->pipe_dbg = env_int("PDES_PIPE_DBG", 0) & 6;      // measurement only: 2 = no acquire fence, 4 = no release fence
+      if (!ctx->pipe_ctr) CUDA_TRY(ctx, cudaMalloc((void**)&ctx->pipe_ctr, sizeof(unsigned) * 4 * PdesCtx::MAXC));
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->pipe_ctr, 0, sizeof(unsigned) * 4 * PdesCtx::MAXC, ctx->stream));
+      ctx->pipe_epoch = 0;
+    }
 
     // k_fused schedule (see residual_kernels.cuh): the faces an element tile integrates are a prefix of the sorted list
     const int FPG = ctx->ops->fused_group_faces();
@@ -767,6 +864,12 @@ int finalize(PdesCtx* ctx) {
   CUDA_TRY(ctx, ctx->ops->prepare());
   ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas() / 8);   // measured optimum: ~half a wave
   ctx->prefetch_ahead_faces = env_int("PDES_PREFETCH_AHEAD_F", ctx->ops->resident_face_ctas());
+  // k_face_flux sweeps the (element-sorted) face list upwards, so when it ends the L2 holds the records and the gathered
+  // q of the HIGHEST elements; k_element_rk sweeping downwards starts on those lines and ends on the lowest elements,
+  // whose q_next the next stage's k_face_flux asks for first
+  ctx->rk4_nosum = env_int("PDES_RK4_NOSUM", 1) != 0 && ctx->ops->staged_epilogue();
+  ctx->reverse_elems = env_int("PDES_REV", 1);
+  ctx->discard_split = env_int("PDES_DISCARD_SPLIT", 1);
   if (ctx->fused) {
     const int res = ctx->ops->resident_fused_ctas();
     ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", res / 8);
@@ -790,6 +893,8 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->dx_el_stride = ctx->dx_compact ? dd : ctx->cfg.nn * dd;
   a->dx_node_stride = ctx->dx_compact ? 0 : dd;
   a->prefetch_ahead = ctx->prefetch_ahead;
+  a->reverse = ctx->reverse_elems;
+  a->discard_records = ctx->pipe ? ctx->pipe_discard : ctx->discard_split;
 }
 
 // startSolutionExchange (Utils/parallel.jl:29-49): pack on the compute stream, send/recv on the comm stream
@@ -858,6 +963,50 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
     return PDES_OK;
   }
   const int nc = ctx->nchunks;
+  if (ctx->pipe) {
+    // chunk pipeline on ONE stream: F0 .. F_lag E0 F_lag+1 E1 ...  Every launch may start while its predecessor drains
+    // (programmatic stream serialization); F_k waits for the element chunks <= chunk_dep[k] of the PREVIOUS evaluation
+    // (its q, and the record slots it overwrites), E_k for the face chunks <= k of this one.  The records of a chunk
+    // are consumed a launch or two after they were written: they stay in L2 and are discarded there (no write-back).
+    const uint32_t ep = ++ctx->pipe_epoch;
+    unsigned* ctr = ctx->pipe_ctr;
+    const int M = PdesCtx::MAXC, FT = ctx->ops->pipe_face_tile(), ET = ctx->ops->tile_elems();
+    for (int i = 0; i < nc + ctx->pipe_lag; ++i) {
+      if (i < nc) {
+        fa.g0 = ctx->chunk_g[i]; fa.ng = ctx->chunk_g[i + 1] - ctx->chunk_g[i];
+        PipeArgs& pp = fa.pipe;
+        pp.arrive = ctr; pp.done_self = ctr + M; pp.done_dep = ctr + 3 * M;
+        pp.on = 1 | ctx->pipe_dbg; pp.chunk = i; pp.ncta = (int32_t)std::max<int64_t>(1, (fa.ng + FT - 1) / FT);
+        pp.dep_chunk = ctx->chunk_dep[i]; pp.epoch = ep; pp.dep_epoch = ep - 1;
+        CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
+        ctx->launches++;
+      }
+      const int k = i - ctx->pipe_lag;
+      if (k >= 0 && k < nc) {
+        a.e_begin = ctx->chunk_e[k]; a.nE = ctx->chunk_e[k + 1];
+        PipeArgs& pp = a.pipe;
+        pp.arrive = ctr + 2 * M; pp.done_self = ctr + 3 * M; pp.done_dep = ctr + M;
+        pp.on = 1 | ctx->pipe_dbg; pp.chunk = k; pp.ncta = (int32_t)((a.nE - a.e_begin + ET - 1) / ET);
+        pp.dep_chunk = k; pp.epoch = ep; pp.dep_epoch = ep;
+        CUDA_TRY(ctx, ctx->ops->launch_elements(a, mode, ctx->stream));
+        ctx->launches++;
+      }
+    }
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1); cfg.blockDim = dim3(1); cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, k_pipe_join, (const unsigned*)(ctr + 3 * M + nc - 1), (unsigned)ep, ctx->ctl));
+      ctx->launches++;
+    }
+    a.e_begin = 0; a.nE = c.nE;
+    memset(&a.pipe, 0, sizeof(a.pipe));
+    ctx->n_evals++;
+    return PDES_OK;
+  }
   cudaStream_t fs = nc > 1 ? ctx->face_stream : ctx->stream;
   if (nc > 1) {
     // q of this evaluation is complete once everything enqueued so far on the compute stream has run
@@ -929,6 +1078,7 @@ int enqueue_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int
   for (int s = 0; s < 4; ++s) {
     fill_args(ctx, &a, in[s]);
     a.x_old = A; a.ksum = ctx->ksum; a.q_next = out[s]; a.ah = ah[s]; a.h6 = h / 6; a.stage = s + 1;
+    a.scheme = ctx->rk4_nosum ? 2 : 0;
     int rc = enqueue_residual(ctx, a, EPI_RK);
     if (rc) return rc;
     if (s == 0) {

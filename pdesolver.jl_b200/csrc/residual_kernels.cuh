@@ -79,6 +79,19 @@ struct PhysPar {
 
 enum EpiMode { EPI_RES = 0, EPI_RK = 1 };
 
+// Chunk pipeline (PDES_PIPE, pdes_api.cu: enqueue_residual_pipe): the face list and the element range are cut into
+// chunks and launched alternately, F0 F1 E0 F2 E1 ..., every launch with programmatic stream serialization, so that
+// the CTAs of a launch start as soon as the LAST WAVE of the previous launch is resident (no drain between launches).
+// Data dependencies are then carried by counters instead of kernel boundaries: the last CTA of chunk c of a family
+// publishes done[c] = epoch, in chunk order.
+struct PipeArgs {
+  unsigned* arrive;          // [chunk] CTAs of this launch that have finished (re-armed by the last one)
+  unsigned* done_self;       // [chunk] epoch of the last complete launch of this family on chunk c
+  const unsigned* done_dep;  // the other family's done[]: what this launch consumes
+  int32_t on, chunk, ncta, dep_chunk;   // wait for done_dep[dep_chunk] >= dep_epoch (publication is in chunk order)
+  uint32_t epoch, dep_epoch;
+};
+
 struct FaceArgs {
   const double* q;             // [ND,NN,nE]
   const FaceRec* faces;        // [nF + nB + nS]
@@ -94,6 +107,7 @@ struct FaceArgs {
   int32_t ext_bc;              // some boundary face uses a functor of bc_flux_ext (bc >= 5)
   const Ctl* ctl;
   PhysPar ph;
+  PipeArgs pipe;
 };
 
 struct ElemArgs {
@@ -114,14 +128,72 @@ struct ElemArgs {
   double ah;                   // a_s * h
   double h6;                   // h/6 (last stage)
   double hh;                   // LSERK54: delta_t  (then ah = a_s, h6 = b_s, ksum = dq_vec, x_old = q)
-  int32_t scheme;              // 0: rk4 (rk4.jl:244-319), 1: lserk54 (lserk.jl:183-205)
+  int32_t scheme;              // 0: rk4 (rk4.jl:244-319), 1: lserk54 (lserk.jl:183-205), 2: rk4 without the running sum
   int32_t stage;               // 1..4 (rk4) | 1..5 (lserk54)
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
-  int32_t discard_records;     // k_fused: drop the consumed face records from L2 (discard.global.L2)
+  int32_t discard_records;     // drop the consumed face records from L2 (discard.global.L2): no write-back
+  int32_t reverse;             // k_element_rk sweeps its tiles from the last to the first (see pdes_api.cu: L2 reuse)
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
+  PipeArgs pipe;
 };
+
+// ---- chunk pipeline primitives -------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_relaxed_u32(const void* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// the launch that follows this one in the stream may start (its CTAs fill the slots our last wave leaves free)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// returns when the launch that precedes this one in the stream has completed and flushed
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// one thread: wait until *p >= target (epochs wrap: signed difference).  Deadlock-free: the launch that publishes *p is
+// earlier in the stream and every one of its CTAs is resident or done before ours may start (launch_dependents is
+// the first thing a CTA does).  The wait gives up when another CTA raised `stop` and after ~1 s (err_code 3) instead
+// of hanging the device.
+__device__ __forceinline__ bool pipe_spin(const unsigned* p, unsigned target, Ctl* ctl) {
+  for (unsigned it = 0;; ++it) {
+    if ((int)(ld_relaxed_u32(p) - target) >= 0) return true;
+    if ((it & 31u) == 31u && ld_relaxed_u32(&ctl->stop)) return false;
+    if (it > (1u << 22)) {
+      atomicExch(&ctl->err_code, 3);
+      atomicExch(&ctl->stop, 1);
+      return false;
+    }
+    __nanosleep(100);
+  }
+}
+// consumer side, called by ONE thread before the block barrier that precedes the first dependent access
+__device__ __forceinline__ void pipe_acquire(const PipeArgs& pp, Ctl* ctl) {
+  if (pp.dep_chunk >= 0) pipe_spin(pp.done_dep + pp.dep_chunk, pp.dep_epoch, ctl);
+  if (!(pp.on & 2)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// producer side, called by ONE thread after a block barrier that follows the CTA's last store
+__device__ __forceinline__ void pipe_release(const PipeArgs& pp, Ctl* ctl) {
+  if (!(pp.on & 4)) __threadfence();
+  const unsigned old = atomicAdd(pp.arrive + pp.chunk, 1u);
+  if (old + 1u == (unsigned)pp.ncta) {
+    pp.arrive[pp.chunk] = 0u;                                  // re-armed for the next evaluation
+    // publication in chunk order: done[c] >= e then implies done[c'] >= e for every c' < c
+    if (pp.chunk > 0) pipe_spin(pp.done_self + pp.chunk - 1, pp.epoch, ctl);
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pp.done_self + pp.chunk), "r"(pp.epoch) : "memory");
+  }
+}
+
+// Last launch of a pipelined evaluation (one thread).  A launch that does not wait for its predecessor may COMPLETE
+// before it, so an ordinary stream operation that follows the evaluation (norm reduction, copy, event) must not rely
+// on the completion of the last chunk alone: this kernel completes only when every element chunk -- and with them every
+// face chunk -- of the evaluation has published its results.
+__global__ void k_pipe_join(const unsigned* done_elem_last, unsigned epoch, Ctl* ctl) {
+  pdl_launch_dependents();
+  if (ld_relaxed_u32(&ctl->stop)) return;
+  pipe_spin(done_elem_last, epoch, ctl);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   if (!(PDES_SKEL & 8)) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -478,15 +550,19 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
 
 // EXTBC: boundary faces may carry one of the functors of bc_flux_ext (a separate instantiation, launched only when the
 // mesh uses one, so that the kernel of the named configurations is unchanged by them)
-template <int DIM, int NN, int NFN, int FT, int MINB, bool EXTBC = false>
+template <int DIM, int NN, int NFN, int FT, int MINB, bool EXTBC = false, bool PIPE = false>
 __global__ void __launch_bounds__((FaceCfg<DIM, NN, NFN, FT>::T), MINB)
 k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
   // one CTA per tile: a persistent loop over tiles was measured (no gain, and under the 80-register cap the loop
   // state spills: 1.134 vs 1.093 ms per RK4 step on C3)
   constexpr int T = FaceCfg<DIM, NN, NFN, FT>::T;
   __shared__ FaceTileSmem<DIM, NN, NFN, FT> sm;
-  if (a.ctl->stop) return;
   const int tid = threadIdx.x;
+  if (PIPE) pdl_launch_dependents();
+  if (a.ctl->stop) return;
+  // PIPE: q (and the record slots this tile overwrites) belong to the element chunks of the previous evaluation; one
+  // thread waits for them while the others fetch the tile's (static) face records -- face_tile's first barrier joins
+  if (PIPE && tid == T - 1) pipe_acquire(a.pipe, const_cast<Ctl*>(a.ctl));
   const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FT;
   const int64_t rem = a.g0 + a.ng - g0;
   const int nf = (int)(rem < FT ? rem : FT);
@@ -498,6 +574,10 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
   }
   face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
   face_tile<DIM, NN, NFN, FT, T, false, false, EXTBC>(op, a, sm, g0, nf, ga, tid);
+  if (PIPE) {
+    __syncthreads();
+    if (tid == 0) pipe_release(a.pipe, const_cast<Ctl*>(a.ctl));
+  }
 }
 
 // k_face_flux_p (PDES_FACE_P=1): persistent form of k_face_flux.  One wave of CTAs strides over the tiles; the
@@ -775,7 +855,7 @@ k_face_flux_tma(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_con
 // (rk4.jl:244-319); two dofs per access, CH accesses in flight per thread.
 // STAGED: the source / x_old / ksum tiles were copied to shared memory (sStr = [srcm | x_old | ksum], E*EL each).
 // WARP: the tile belongs to one warp (T = 32, tid = lane): no block barrier, the warp writes its own norm partial.
-template <int NN, int ND, int E, int T, int MODE, bool STAGED = false, bool WARP = false>
+template <int NN, int ND, int E, int T, int MODE, bool STAGED = false, bool WARP = false, bool MINV = false>
 __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* sq, int ne, int64_t e0, int tid,
                                               double* s_red, const double* sStr = nullptr) {
   constexpr int EL = NN * ND;
@@ -788,7 +868,7 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
     const double2* sq2 = reinterpret_cast<const double2*>(sq);
     const double* psrc = MODE == EPI_RES ? a.srcw : a.srcm;
     for (int i0 = 0; i0 < npair; i0 += CH * T) {
-      double2 v[CH], sv[CH], xo[CH], ks[CH];
+      double2 v[CH], sv[CH], xo[CH], ks[CH], mw[CH];
       bool ok[CH], two[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
@@ -796,19 +876,37 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         ok[u] = i2 < npair;
         two[u] = ok[u] && (2 * i2 + 1 < ntile);
         const int64_t dof = base + 2 * i2;
-        sv[u] = xo[u] = ks[u] = make_double2(0.0, 0.0);
+        sv[u] = xo[u] = ks[u] = mw[u] = make_double2(0.0, 0.0);
+        double2 mi = make_double2(1.0, 1.0);
+        if (MINV && ok[u]) {
+          // pde_post_func (res_vec *= Minv) applied here, to the staged raw rows: the loads join the batch instead of
+          // standing between the face products and the staging stores (4.7 % of the kernel's stall samples)
+          const double* it = a.minv + e0 * NN;
+          mi.x = __ldg(it + (2 * i2) / ND);
+          if (two[u]) mi.y = __ldg(it + (2 * i2 + 1) / ND);
+        }
+        if (!(PDES_OPT & 16) && MODE == EPI_RK && a.stage == 1 && ok[u]) {
+          // calcNorm weights M = w_j/jac_j of the two dofs (the tile's nodes are contiguous in M: node = dof / ND);
+          // requested with the other loads of the batch: a load next to its use cost 25 us per step (stall profile)
+          const double* mt = a.mass + e0 * NN;
+          mw[u].x = __ldg(mt + (2 * i2) / ND);
+          if (two[u]) mw[u].y = __ldg(mt + (2 * i2 + 1) / ND);
+        }
         if (STAGED && ok[u]) {
           const double2* s2 = reinterpret_cast<const double2*>(sStr);
+          // scheme 2 (rk4 without the running sum): slot 1 = x_old (stage 4: q4), slot 2 = q2 (stage 2) | w' (stage 4)
+          const bool has_src = psrc && !(a.scheme == 2 && a.stage == 4);
+          const bool has_ks = a.scheme == 2 ? (a.stage == 2 || a.stage == 4) : a.stage > 1;
           if (two[u]) {
             v[u] = sq2[i2];
-            if (psrc) sv[u] = s2[i2];
+            if (has_src) sv[u] = s2[i2];
             xo[u] = s2[(E * EL) / 2 + i2];
-            if (a.stage > 1) ks[u] = s2[E * EL + i2];
+            if (has_ks) ks[u] = s2[E * EL + i2];
           } else {
             v[u] = make_double2(sq[2 * i2], 0.0);
-            if (psrc) sv[u].x = sStr[2 * i2];
+            if (has_src) sv[u].x = sStr[2 * i2];
             xo[u].x = sStr[E * EL + 2 * i2];
-            if (a.stage > 1) ks[u].x = sStr[2 * E * EL + 2 * i2];
+            if (has_ks) ks[u].x = sStr[2 * E * EL + 2 * i2];
           }
         } else if (two[u]) {
           v[u] = sq2[i2];
@@ -825,6 +923,7 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
             if (a.stage > 1) ks[u].x = a.ksum[dof];
           }
         }
+        if (MINV && ok[u]) { v[u].x *= mi.x; v[u].y *= mi.y; }
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
@@ -836,15 +935,33 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         if (MODE == EPI_RK && a.stage == 1) {
           // calcNorm: sum res*M*res (Utils.jl:427-449); the tile's nodes are contiguous in M: node = dof / ND
           // (a multiplication by the stored M as in the reference: an FP64 division per dof cost 25 us per step)
-          const double* mt = a.mass + e0 * NN;
-          nrm2 = fma(k.x * __ldg(mt + (2 * i2) / ND), k.x, nrm2);
-          if (two[u]) nrm2 = fma(k.y * __ldg(mt + (2 * i2 + 1) / ND), k.y, nrm2);
+          if (PDES_OPT & 16) {
+            const double* mt = a.mass + e0 * NN;
+            mw[u].x = __ldg(mt + (2 * i2) / ND);
+            if (two[u]) mw[u].y = __ldg(mt + (2 * i2 + 1) / ND);
+          }
+          nrm2 = fma(k.x * mw[u].x, k.x, nrm2);
+          if (two[u]) nrm2 = fma(k.y * mw[u].y, k.y, nrm2);
         }
         if (MODE == EPI_RK && a.scheme == 1) {
           // lserk54: dq = a_s*dq + delta_t*res ; q += b_s*dq
           if (a.stage == 1) o1 = make_double2(a.hh * k.x, a.hh * k.y);
           else o1 = make_double2(a.ah * ks[u].x + a.hh * k.x, a.ah * ks[u].y + a.hh * k.y);
           o2 = make_double2(xo[u].x + a.h6 * o1.x, xo[u].y + a.h6 * o1.y);
+        } else if (MODE == EPI_RK && a.scheme == 2) {
+          // classical RK4 without the running sum k1 + 2 k2 + 2 k3 (4 of the 17 state-vector passes of a step):
+          //   q2 = x + h/2 k1, q3 = x + h/2 k2, q4 = x + h k3  =>  h/6 (k1 + 2 k2 + 2 k3) = (q2 + 2 q3 + q4)/3 - 4x/3
+          //   stage 2 stores  w' = q2 + 2 q3 - x + (h/2) srcm        (the only extra vector)
+          //   stage 4         x_new = (w' + q4)/3 + (h/6) Minv R(q4)  [(h/6) srcm of k4 is the srcm term of w']
+          // identical in exact arithmetic to rk4.jl:244-319; the rounding differs by a few ulp of |q| per step
+          if (a.stage == 4) {
+            const double third = 1.0 / 3.0;
+            o2 = make_double2(fma(a.h6, v[u].x, (ks[u].x + xo[u].x) * third), fma(a.h6, v[u].y, (ks[u].y + xo[u].y) * third));
+          } else {
+            o2 = make_double2(xo[u].x + a.ah * k.x, xo[u].y + a.ah * k.y);
+            if (a.stage == 2)
+              o1 = make_double2(ks[u].x + 2.0 * o2.x - xo[u].x + a.ah * sv[u].x, ks[u].y + 2.0 * o2.y - xo[u].y + a.ah * sv[u].y);
+          }
         } else if (MODE == EPI_RK) {
           if (a.stage == 1) {
             o1 = k;                                                                   // ksum
@@ -859,7 +976,7 @@ __device__ __forceinline__ void epilogue_tile(const ElemArgs& a, const double* s
         if (MODE == EPI_RES) {
           if (two[u]) *reinterpret_cast<double2*>(a.res + dof) = k; else a.res[dof] = k.x;
         } else {
-          if (a.scheme == 1 || a.stage < 4) {
+          if (a.scheme == 1 || (a.scheme == 0 && a.stage < 4) || (a.scheme == 2 && a.stage == 2)) {
             if (two[u]) __stcs(reinterpret_cast<double2*>(a.ksum + dof), o1); else __stcs(a.ksum + dof, o1.x);
           }
           if (two[u]) *reinterpret_cast<double2*>(a.q_next + dof) = o2; else a.q_next[dof] = o2.x;
@@ -929,9 +1046,10 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
         prefetch_l2(reinterpret_cast<const char*>(a.q) + b0 + o);
         if (MODE == EPI_RES && a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
         if (MODE == EPI_RK) {
-          if (a.srcm) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
-          prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
-          if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+          const bool s2 = a.scheme == 2;
+          if (a.srcm && !(s2 && a.stage == 4)) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
+          if (!(s2 && a.stage == 4)) prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+          if (s2 ? a.stage == 4 : a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
         }
       }
       if (!COHERENT)     // (fused kernel: the records are written into L2 shortly before they are consumed)
@@ -947,14 +1065,21 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
     for (int64_t o = (int64_t)tid * 128; o < nb; o += (int64_t)T * 128) {
       if (MODE == EPI_RES && a.srcw) prefetch_l2(reinterpret_cast<const char*>(a.srcw) + b0 + o);
       if (MODE == EPI_RK) {
-        if (a.srcm) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
-        prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
-        if (a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
+        const bool s2 = a.scheme == 2;
+        if (a.srcm && !(s2 && a.stage == 4)) prefetch_l2(reinterpret_cast<const char*>(a.srcm) + b0 + o);
+        if (!(s2 && a.stage == 4)) prefetch_l2(reinterpret_cast<const char*>(a.x_old) + b0 + o);
+        if (s2 ? a.stage == 4 : a.stage > 1) prefetch_l2(reinterpret_cast<const char*>(a.ksum) + b0 + o);
       }
     }
     if (!COHERENT)
       for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NF * FL * 8; o += (int64_t)T * 128)
         prefetch_l2(reinterpret_cast<const char*>(a.fluxe) + e0 * NF * FL * 8 + o);
+    if ((PDES_OPT & 64) && MODE == EPI_RK)
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.minv + e0 * NN) + o);
+    if (!(PDES_OPT & 32) && MODE == EPI_RK && a.stage == 1)
+      for (int64_t o = (int64_t)tid * 128; o < (int64_t)ne * NN * 8; o += (int64_t)T * 128)
+        prefetch_l2(reinterpret_cast<const char*>(a.mass + e0 * NN) + o);
   }
   // the metrics of this thread's first node are requested before the wait for the q tile, those of the next node
   // before the current one is processed (they are L2 hits after the prefetch, but still ~1000 cycles away)
@@ -1072,10 +1197,24 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
     __syncthreads();
     const unsigned long long pol = policy_evict_first();
     if (!(PDES_SKEL & 64)) {
+    if (a.scheme == 2) {
+      // rk4 without the running sum (see epilogue_tile): stage 2 re-reads its own input rows (q2: L2 hits, the tile was
+      // loaded by this CTA microseconds ago), stage 4 reads w' and its own input rows (q4) and neither x_old nor srcm
+      if (a.stage < 4) {
+        if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
+        if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);
+        else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
+        if (a.stage == 2) async_tile(sF + 2 * E * EL, a.q + e0 * EL, ne * EL, tid, T);
+      } else {
+        async_tile(sF + E * EL, a.q + e0 * EL, ne * EL, tid, T);
+        async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
+      }
+    } else {
     if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
     if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);   // x_old == q of this stage
     else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
     if (a.stage > 1) async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
+    }
     }
     cp_async_commit();
   }
@@ -1113,7 +1252,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
       }
     }
     // pde_post_func: res_vec *= Minv (EPI_RK); staged for the coalesced epilogue
-    if (MODE == EPI_RK) {
+    if (MODE == EPI_RK && !(PDES_OPT & 64)) {
 #pragma unroll
       for (int u = 0; u < NN; ++u) {
         if (PDES_OPT & 4) {
@@ -1134,7 +1273,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
   }
   if (STAGED) cp_async_wait<0>();
   __syncthreads();
-  if (COHERENT && a.discard_records) {
+  if (a.discard_records) {
     // every thread has consumed its records: drop the tile's full 128-byte lines (tiles are line-aligned whenever
     // E*NF*FL*8 is a multiple of 128; partial lines at the ends are left alone)
     const uintptr_t b = reinterpret_cast<uintptr_t>(a.fluxe + e0 * (NF * FL));
@@ -1144,24 +1283,37 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
   }
 
   // ---- S4: coalesced epilogue (source, res | fused RK4 stage, stage-1 norm partial) ----------------------------
-  epilogue_tile<NN, ND, E, T, MODE, STAGED>(a, sq, ne, e0, tid, s_red, sF);
+  epilogue_tile<NN, ND, E, T, MODE, STAGED, false, (MODE == EPI_RK) && (PDES_OPT & 64) != 0>(a, sq, ne, e0, tid, s_red, sF);
 }
 
-template <int DIM, int NN, int NFN, int E, int MODE, int MINB>
+template <int DIM, int NN, int NFN, int E, int MODE, int MINB, bool PIPE = false>
 __global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
 k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[Cfg::T / 32];
-  if (a.ctl->stop) return;
   const int tid = threadIdx.x;
-  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
+  if (PIPE) pdl_launch_dependents();
+  if (a.ctl->stop) return;
+  if (PIPE) {
+    // the face chunks 0..chunk of THIS evaluation (which in turn waited for the previous evaluation's element chunks)
+    if (tid == 0) pipe_acquire(a.pipe, a.ctl);
+    __syncthreads();
+  }
+  // reverse: CTAs are dispatched in blockIdx order, so the sweep starts with the elements whose face records (and q
+  // gathers) k_face_flux touched LAST and which are therefore still in L2; "ahead" then means lower tiles
+  const int64_t bid = a.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+  const int64_t e0 = a.e_begin + bid * E;
   const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
-  int64_t ea = e0 + (int64_t)a.prefetch_ahead * E;
+  int64_t ea = a.reverse ? e0 - (int64_t)a.prefetch_ahead * E : e0 + (int64_t)a.prefetch_ahead * E;
   int na = 0;
-  if (a.prefetch_ahead > 0 && ea < a.nE) na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
+  if (a.prefetch_ahead > 0 && ea < a.nE && ea >= a.e_begin) na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
   else ea = -1;
   element_tile<DIM, NN, NFN, E, MODE, Cfg::T, false>(op, a, smem_raw, s_red, e0, ne, ea, na, tid);
+  if (PIPE) {
+    __syncthreads();
+    if (tid == 0) pipe_release(a.pipe, a.ctl);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -496,6 +496,76 @@ def test_fused_kernel_bitwise_equals_split(case, n, monkeypatch):
     assert out["0"][3] == out["1"][3]
 
 
+@pytest.mark.parametrize("case,n,chunks,lag", [("c1_2d_p1_roe", 20, 4, 1), ("2d_p2_roe", 9, 3, 0), ("3d_p1_roe_src", 6, 5, 2),
+                                               ("c3_3d_p2_roe_src", 9, 8, 1), ("c3_3d_p2_roe_src", 7, 16, 1)])
+def test_chunk_pipeline_bitwise_equals_split(case, n, chunks, lag, monkeypatch):
+    """PDES_PIPE (face / element chunks launched alternately with programmatic dependent launches, dependencies carried
+    by device counters, consumed records discarded in L2) runs the same tile bodies as the two-launch schedule:
+    residual, RK4 trajectory and norms must be bit-identical; one evaluation is 2 * chunks launches."""
+    out = {}
+    for pipe in ("0", str(chunks)):
+        monkeypatch.setenv("PDES_PIPE", pipe)
+        monkeypatch.setenv("PDES_PIPE_LAG", str(lag))
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=11)
+        eqn.q[...] = q0
+        n0 = eqn.kernel_launch_count()
+        pd.evalResidual(mesh, op, eqn, opts)
+        launches = eqn.kernel_launch_count() - n0
+        res = eqn.res.copy(order="F")
+        pd.rk4(pd.evalResidual, 1e-4, 12e-4, mesh, op, eqn, opts)
+        out[pipe] = (launches, res, eqn.q.copy(order="F"), list(eqn.convergence))
+    a, b = out["0"], out[str(chunks)]
+    assert a[0] == 2 and b[0] == 2 * chunks + 1
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3]
+
+
+def test_chunk_pipeline_survives_physics_error(monkeypatch):
+    """A negative density raised in the middle of the pipeline stops it (no hang), the error carries the reference's
+    message, and the context is usable afterwards (counters re-armed)."""
+    monkeypatch.setenv("PDES_PIPE", "6")
+    op, mesh, opts, orc, q0, eqn = setup("c3_3d_p2_roe_src", 6, shuffle_seed=3)
+    bad = q0.copy(order="F")
+    bad[0, 2, q0.shape[2] // 2] = -1.0
+    eqn.q[...] = bad
+    with pytest.raises(pd.PhysicsError, match="Negative density"):
+        pd.evalResidual(mesh, op, eqn, opts)
+    eqn.q[...] = q0
+    with pytest.raises(pd.PhysicsError):
+        eqn.q[...] = bad
+        pd.rk4(pd.evalResidual, 1e-4, 3e-4, mesh, op, eqn, opts)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < 1e-12
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 12), ("c3_3d_p2_roe_src", 6)])
+def test_rk4_schedules_agree(case, n, monkeypatch):
+    """The stage kernels have three independent scheduling switches, all on by default: element tiles swept last to first
+    (PDES_REV), consumed face records discarded in L2 (PDES_DISCARD_SPLIT) -- both bit-neutral -- and the RK4 update
+    without the running sum of the k's (PDES_RK4_NOSUM; rk4.jl:244-319 regrouped, a few ulp of |q| per step)."""
+    h, nsteps = 1e-4, 12
+    out = {}
+    for key, env in {"default": {}, "ref": {"PDES_REV": "0", "PDES_DISCARD_SPLIT": "0", "PDES_RK4_NOSUM": "0"},
+                     "sum": {"PDES_RK4_NOSUM": "0"}}.items():
+        for k in ("PDES_REV", "PDES_DISCARD_SPLIT", "PDES_RK4_NOSUM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=5)
+        opts["use_itermax"] = False
+        eqn.q[...] = q0
+        t = pd.rk4(pd.evalResidual, h, nsteps * h, mesh, op, eqn, opts)
+        out[key] = (t, eqn.q.copy(order="F"), list(eqn.convergence))
+    assert np.array_equal(out["ref"][1], out["sum"][1]) and out["ref"][2] == out["sum"][2]
+    assert out["default"][0] == out["ref"][0]
+    assert rel_l2(out["default"][1], out["ref"][1]) < 1e-14
+    assert np.allclose(out["default"][2], out["ref"][2], rtol=1e-12, atol=0)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, nsteps * h)
+    assert rel_l2(out["default"][1], q_ref) < RK_TOL and rel_l2(out["ref"][1], q_ref) < RK_TOL
+
+
 def test_gmres_solves_jacobian_system():
     """pdes_gmres (the linear solve of the matrix-free Newton path, newton_setup.jl:632-662 +
     PETSc GMRES defaults read_input.jl:493-496, 560-570): x must satisfy dR/dq x = b, checked against a dense
