@@ -13,6 +13,10 @@
 #pragma once
 #include "residual_kernels.cuh"
 
+#ifndef PDES_SPLITN_UNROLL
+#define PDES_SPLITN_UNROLL 2      // C2: 17.88 ms per RK4 step; 1: 18.16, 4: 19.3, 11: 22.8 (instruction cache)
+#endif
+
 namespace pdes {
 
 template <int DIM, int NN, int NFN>
@@ -401,6 +405,154 @@ k_element_split(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_co
     for (int u = 0; u < (DENSEREC ? NF : DIM); ++u) acc += grec[u];
     if (MODE == EPI_RK) acc *= mv;
     sq[it] = acc;
+  }
+  __syncthreads();
+  epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_element_split_n: node-centric form of k_element_split.  One thread per (element, node i) evaluates the nn-1
+// two-point fluxes F(q_i, q_m) of ITS node and accumulates -2 S[i,m,d] F_d in registers.  Every flux is evaluated
+// twice (once per end point), but nothing is exchanged between threads: no pair-flux tile (68 of the 85 KB of
+// k_element_split), no gather stage (60 shared-memory loads per residual entry), one block barrier less; the kernel's
+// instructions become mostly the FP64 work itself (k_element_split: 21 % FP64-pipe utilisation, barrier and
+// shared-memory stalls on top, profiles/r1_es_element_split.txt).  The Ismail-Roe flux is bitwise symmetric in its two
+// states and the sum over m runs in the same order, so the result equals k_element_split's bit for bit.
+// ------------------------------------------------------------------------------------------------------
+template <int DIM, int NN, int NFN, int E>
+struct SplitNCfg {
+  static constexpr int ND = DIM + 2, NF = DIM + 1;
+  static constexpr int NZ = DIM + 4;                             // z1, zv[DIM], z5, log z1, log z5
+  static constexpr int T = ((E * NN + 31) / 32) * 32;
+  static constexpr int ZS = E * NN + 1;                          // component stride of the node tile (odd)
+  static constexpr size_t smem_bytes = sizeof(double) * ((size_t)E * NN * ND + (size_t)NZ * ZS + DIM * NN * NN);
+  static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
+};
+
+template <int DIM, int NN, int NFN, int E, int MODE, bool DENSEREC, int MINB>
+__global__ void __launch_bounds__((SplitNCfg<DIM, NN, NFN, E>::T), MINB)
+k_element_split_n(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
+  using Cfg = SplitNCfg<DIM, NN, NFN, E>;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, NZ = Cfg::NZ, T = Cfg::T, ZS = Cfg::ZS;
+  constexpr int EL = NN * ND, FL = NFN * ND;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sq = reinterpret_cast<double*>(smem_raw);     // [E][EL]       q tile, later the staged output
+  double* sZ = sq + E * EL;                             // [NZ][E*NN]    component-major (conflict-free)
+  double* sS2 = sZ + NZ * ZS;                           // [DIM][NN][NN]
+  __shared__ double s_red[T / 32];
+
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
+  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
+  const double gami = a.ph.gamma - 1.0;
+
+  async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
+  cp_async_commit();
+  for (int idx = tid; idx < DIM * NN * NN; idx += T) sS2[idx] = (&op.S2[0][0][0])[idx];
+  const bool act = tid < ne * NN;
+  const int s = tid / NN, i = tid - s * NN;
+  // face records, Minv and (node-independent) metrics of this thread's node: in flight during the node stage
+  double grec[(DENSEREC ? NF : DIM) * ND], mv = 1.0, dx0[DIM][DIM];
+  if (act) {
+    if (DENSEREC) {
+      const double* G = a.fluxe + (e0 + s) * (NF * EL) + i * ND;
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int c = 0; c < ND; ++c) grec[f * ND + c] = __ldg(G + f * EL + c);
+    } else {
+      const double* G = a.fluxe + (e0 + s) * (NF * FL);
+#pragma unroll
+      for (int u = 0; u < DIM; ++u) {
+        const int slot = op.inv[i][u];
+#pragma unroll
+        for (int c = 0; c < ND; ++c) grec[u * ND + c] = slot >= 0 ? __ldg(G + slot * ND + c) : 0.0;
+      }
+    }
+    if (MODE == EPI_RK) mv = __ldg(a.minv + (e0 + s) * NN + i);
+    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + i * a.dx_node_stride;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int p = 0; p < DIM; ++p) dx0[d][p] = __ldg(dx + d + DIM * p);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- node stage: checks + Ismail-Roe parameter vector and its logarithms (kept in registers and published) ----
+  IRNode<DIM> zi;
+  if (act) {
+    double qn[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qn[k] = sq[tid * ND + k];
+    const double press = calc_pressure<DIM>(qn, gami);
+    if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
+      const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
+      const unsigned long long loc = ((unsigned long long)(e0 + s) << 8) | (unsigned)i;
+      atomicMin(&a.ctl->err_loc, ((unsigned long long)(code - 1) << 62) | loc);
+      atomicExch(&a.ctl->err_code, 1);
+      atomicExch(&a.ctl->stop, 1);
+      qn[0] = 1.0; qn[DIM + 1] = 1.0;       // keep the arithmetic finite; the result is discarded
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) qn[1 + d] = 0.0;
+    }
+    zi = ir_node<DIM>(qn, gami);
+    sZ[0 * ZS + tid] = zi.z1;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) sZ[(1 + d) * ZS + tid] = zi.zv[d];
+    sZ[(DIM + 1) * ZS + tid] = zi.z5; sZ[(DIM + 2) * ZS + tid] = zi.l1; sZ[(DIM + 3) * ZS + tid] = zi.l5;
+  }
+  __syncthreads();       // node tile complete; nobody reads the q tile any more (it becomes the output staging tile)
+
+  // ---- res[:, i] = -sum_m 2 S[i,m,d] F_d(q_max(i,m), q_min(i,m)) with the directions of node max(i,m) -----------
+  if (act) {
+    double acc[ND];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) acc[c] = 0.0;
+    const double* Sc = sS2 + i * NN;
+    const int n0 = s * NN;
+    // (partners enumerated without the node itself -- S[i][i] = 0 -- so that the loop is branch-free and can be
+    // unrolled: independent two-point fluxes interleave, the flux itself being one long dependent chain)
+    constexpr int UNR = PDES_SPLITN_UNROLL;
+#pragma unroll UNR
+    for (int mm = 0; mm < NN - 1; ++mm) {
+      const int m = mm + (mm >= i ? 1 : 0);
+      IRNode<DIM> zm;
+      zm.z1 = sZ[n0 + m];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) zm.zv[d] = sZ[(1 + d) * ZS + n0 + m];
+      zm.z5 = sZ[(DIM + 1) * ZS + n0 + m]; zm.l1 = sZ[(DIM + 2) * ZS + n0 + m]; zm.l5 = sZ[(DIM + 3) * ZS + n0 + m];
+      double dirs[DIM][DIM], F[DIM][ND];
+      if (a.dx_node_stride != 0 && m > i) {
+        // curved elements: the two-point flux of the pair uses the metrics of its higher-numbered node
+        const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + m * a.dx_node_stride;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+          for (int p = 0; p < DIM; ++p) dirs[d][p] = __ldg(dx + d + DIM * p);
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+          for (int p = 0; p < DIM; ++p) dirs[d][p] = dx0[d][p];
+      }
+      if (m > i) ir_flux<DIM, DIM>(zm, zi, dirs, a.ph.gamma, F);
+      else ir_flux<DIM, DIM>(zi, zm, dirs, a.ph.gamma, F);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const double sc = -Sc[d * NN * NN + m];
+#pragma unroll
+        for (int c = 0; c < ND; ++c) acc[c] = fma(sc, F[d][c], acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+#pragma unroll
+      for (int u = 0; u < (DENSEREC ? NF : DIM); ++u) acc[c] += grec[u * ND + c];
+      if (MODE == EPI_RK) acc[c] *= mv;
+      sq[tid * ND + c] = acc[c];
+    }
   }
   __syncthreads();
   epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);

@@ -174,17 +174,16 @@ __device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* 
 // entropy-stable two-point fluxes (config 2)
 // ---------------------------------------------------------------------------------------------------------
 
-// bc_solvers.jl:942-956 logavg(aL, aR) with log(aL/aR) supplied as lL - lR (logs tabulated per node: two per
-// node instead of two per node pair); f = (xi-1)/(xi+1) is evaluated as (aL-aR)/(aL+aR)
-__device__ __forceinline__ double logavg_pre(double aL, double aR, double lL, double lR, double inv_sum) {
+// bc_solvers.jl:942-956 logavg(aL, aR) = (aL + aR) / (2 F) with log(aL/aR) supplied as lL - lR (logs tabulated per node:
+// two per node instead of two per node pair); f = (xi-1)/(xi+1) is evaluated as (aL-aR)/(aL+aR).  Returns 2 F.
+__device__ __forceinline__ double logavg_2F(double aL, double aR, double lL, double lR, double inv_sum) {
   const double f = (aL - aR) * inv_sum;
   const double u = f * f;
   double F;
   if (u < 1e-3) F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0 + u * (1.0 / 9.0))));
   else F = 0.5 * (lL - lR) * fast_rcp(f);
-  return (aL + aR) * fast_rcp(2.0 * F);
+  return 2.0 * F;
 }
-
 // per-node quantities of the Ismail-Roe flux: z1 = sqrt(rho/p), z_{1+d} = z1*u_d, z5 = sqrt(rho*p), log z1, log z5
 template <int DIM>
 struct IRNode {
@@ -212,15 +211,20 @@ __device__ __forceinline__ void ir_flux(const IRNode<DIM>& L, const IRNode<DIM>&
   const double gamma_1 = gamma - 1.0;
   const double s1 = L.z1 + R.z1, s5 = L.z5 + R.z5;
   const double is1 = fast_rcp(s1), is5 = fast_rcp(s5);
-  const double la5 = logavg_pre(L.z5, R.z5, L.l5, R.l5, is5);
-  const double la1 = logavg_pre(L.z1, R.z1, L.l1, R.l1, is1);
+  // with logavg(a) = s_a / (2 F_a) the quotients of the reference formulas need three reciprocals instead of six
+  // (the two-point flux is FP64-pipe bound: the reciprocals were 21 % of k_element_split_n's samples):
+  //   z5_ln / z1_ln = p1_hat * (2 F_1) / (2 F_5),   1 / rho_hat = 2 (2 F_5) / (s1 s5)
+  const double tF5 = logavg_2F(L.z5, R.z5, L.l5, R.l5, is5);
+  const double tF1 = logavg_2F(L.z1, R.z1, L.l1, R.l1, is1);
+  const double itF5 = fast_rcp(tF5);
+  const double la5 = s5 * itF5;                       // z5_ln
   const double rho_hat = 0.5 * s1 * la5;
   double vh[DIM], vv = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { vh[d] = (L.zv[d] + R.zv[d]) * is1; vv += vh[d] * vh[d]; }
   const double p1_hat = s5 * is1;
-  const double p2_hat = ((gamma + 1) / (2 * gamma)) * la5 * fast_rcp(la1) + (gamma_1 / (2 * gamma)) * p1_hat;
-  const double h_hat = gamma * p2_hat * fast_rcp(rho_hat * gamma_1) + 0.5 * vv;
+  const double p2_hat = ((gamma + 1) / (2 * gamma)) * (p1_hat * tF1 * itF5) + (gamma_1 / (2 * gamma)) * p1_hat;
+  const double h_hat = (gamma / gamma_1) * p2_hat * (2.0 * tF5 * is1 * is5) + 0.5 * vv;
 #pragma unroll
   for (int i = 0; i < NDIR; ++i) {
     double un = 0.0;

@@ -394,12 +394,32 @@ struct OpsImplS : Ops {
     e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RES, false, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RK, false, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    node_centric = env_int("PDES_SPLIT_N", 1) != 0;
     attr_set = true;
     return cudaSuccess;
   }
+  // node-centric split-form kernel (k_element_split_n): every two-point flux evaluated at both of its end points
+  using NCfg = SplitNCfg<DIM, NN, NFN, E>;
+#ifndef PDES_SPLITN_MINB
+#define PDES_SPLITN_MINB 4
+#endif
+  static constexpr int NMINB = PDES_SPLITN_MINB;
+  bool node_centric = true;
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if (node_centric) {
+      dim3 gridn((unsigned)grid_for(a.nE - a.e_begin)), blockn(NCfg::T);
+      if (mode == EPI_RES) k_element_split_n<DIM, NN, NFN, E, EPI_RES, false, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tab, a);
+      else k_element_split_n<DIM, NN, NFN, E, EPI_RK, false, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tab, a);
+      return cudaGetLastError();
+    }
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES) k_element_split<DIM, NN, NFN, E, EPI_RES><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
     else k_element_split<DIM, NN, NFN, E, EPI_RK><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);
@@ -461,12 +481,28 @@ struct OpsImplE : Ops {
     e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RES, true, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RK, true, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    node_centric = env_int("PDES_SPLIT_N", 1) != 0;
     attr_set = true;
     return cudaSuccess;
   }
+  using NCfg = SplitNCfg<DIM, NN, NFN, E>;
+  static constexpr int NMINB = 3;
+  bool node_centric = true;
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if (node_centric) {
+      dim3 gridn((unsigned)grid_for(a.nE - a.e_begin)), blockn(NCfg::T);
+      if (mode == EPI_RES) k_element_split_n<DIM, NN, NFN, E, EPI_RES, true, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tabs, a);
+      else k_element_split_n<DIM, NN, NFN, E, EPI_RK, true, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tabs, a);
+      return cudaGetLastError();
+    }
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES) k_element_split<DIM, NN, NFN, E, EPI_RES, true><<<grid, block, Cfg::smem_bytes, s>>>(tabs, a);
     else k_element_split<DIM, NN, NFN, E, EPI_RK, true><<<grid, block, Cfg::smem_bytes, s>>>(tabs, a);
@@ -482,7 +518,14 @@ Ops* make_ops(const PdesConfig& c) {
   // development build (make EXTRA=-DPDES_LEAN): only the kernels of the headline workload, a fraction of the build time
   if (!c.sparse_face && c.face_integral_type == 1 && c.volume_integral_type == 1 && c.flux_id == PDES_FLUX_ROE &&
       c.dim == 3 && c.nn == 11 && c.nfn == 6)
-    return new OpsImpl<3, 11, 6, 32, 4, 16, 8>();
+#ifndef PDES_DEV_E
+#define PDES_DEV_E 32
+#define PDES_DEV_MINB_E 4
+#define PDES_DEV_FT 16
+#define PDES_DEV_MINB_F 8
+#endif
+    return new OpsImpl<3, 11, 6, PDES_DEV_E, PDES_DEV_MINB_E, PDES_DEV_FT, PDES_DEV_MINB_F>();
+  if (c.sparse_face && c.dim == 2 && c.nn == 12 && c.nfn == 4 && c.volume_integral_type == 2) return new OpsImplS<2, 12, 4, 16>();
   return nullptr;
 #else
   if (c.sparse_face) {

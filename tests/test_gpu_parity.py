@@ -566,6 +566,27 @@ def test_rk4_schedules_agree(case, n, monkeypatch):
     assert rel_l2(out["default"][1], q_ref) < RK_TOL and rel_l2(out["ref"][1], q_ref) < RK_TOL
 
 
+@pytest.mark.parametrize("case,n", [("c2_2d_p2_es", 9), ("2d_p2_es_ir", 7), ("2d_p2_es_roe", 6)])
+def test_node_centric_split_kernel(case, n, monkeypatch):
+    """k_element_split_n (default; every two-point flux evaluated at both end points, nothing exchanged between threads)
+    against k_element_split (PDES_SPLIT_N=0; each flux once, pair tile + gather): same fluxes summed in the same
+    order, so residual and RK4 trajectory agree to the last bits."""
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PDES_SPLIT_N", flag)
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=7)
+        eqn.q[...] = q0
+        pd.evalResidual(mesh, op, eqn, opts)
+        res = eqn.res.copy(order="F")
+        pd.rk4(pd.evalResidual, 1e-4, 6e-4, mesh, op, eqn, opts)
+        out[flag] = (res, eqn.q.copy(order="F"), list(eqn.convergence))
+    # same fluxes, same summation order; the two kernels inline the flux into different code, so the compiler's
+    # multiply-add contraction may differ in the last bit
+    assert rel_l2(out["0"][0], out["1"][0]) < 1e-14
+    assert rel_l2(out["0"][1], out["1"][1]) < 1e-15
+    assert np.allclose(out["0"][2], out["1"][2], rtol=1e-13, atol=0)
+
+
 def test_gmres_solves_jacobian_system():
     """pdes_gmres (the linear solve of the matrix-free Newton path, newton_setup.jl:632-662 +
     PETSc GMRES defaults read_input.jl:493-496, 560-570): x must satisfy dR/dq x = b, checked against a dense
