@@ -558,4 +558,177 @@ k_element_split_n(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_
   epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// k_element_split_r: k_element_split_n with every two-point flux evaluated ONCE.  The node-centric kernel is FP64-pipe
+// bound (68 % busy) and evaluates each flux at both of its end points; here the nn(nn-1)/2 pairs of an element are
+// scheduled in nn/2 rounds of disjoint pairs (round k: {i, i+k mod nn}, a round-robin tournament): the thread of node i
+// evaluates the flux, keeps its share and passes the flux to node i+k through a double-buffered shared-memory tile
+// (one barrier per round, a regular access pattern: no index tables, no separate gather stage).  The sum over the partner
+// nodes runs in round order instead of node order: results differ from k_element_split(_n) by rounding only.
+// ------------------------------------------------------------------------------------------------------
+template <int DIM, int NN, int NFN, int E>
+struct SplitRCfg {
+  static constexpr int ND = DIM + 2, NF = DIM + 1;
+  static constexpr int NZ = DIM + 4;                             // z1, zv[DIM], z5, log z1, log z5
+  static constexpr int T = ((E * NN + 31) / 32) * 32;
+  static constexpr int ZS = E * NN + 1;                          // component stride of the node tile (odd)
+  static constexpr int NC = DIM * ND;                            // flux components per pair
+  static constexpr int XS = E * NN + 1;                          // component stride of the exchange tile (odd)
+  static constexpr size_t smem_bytes =
+      sizeof(double) * ((size_t)E * NN * ND + (size_t)NZ * ZS + DIM * NN * NN + 2 * (size_t)NC * XS);
+  static_assert(E % 2 == 0, "tile bases must stay 16-byte aligned");
+};
+
+template <int DIM, int NN, int NFN, int E, int MODE, bool DENSEREC, int MINB>
+__global__ void __launch_bounds__((SplitRCfg<DIM, NN, NFN, E>::T), MINB)
+k_element_split_r(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
+  using Cfg = SplitRCfg<DIM, NN, NFN, E>;
+  constexpr int ND = Cfg::ND, NF = Cfg::NF, NZ = Cfg::NZ, T = Cfg::T, ZS = Cfg::ZS, NC = Cfg::NC, XS = Cfg::XS;
+  constexpr int EL = NN * ND, FL = NFN * ND;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sq = reinterpret_cast<double*>(smem_raw);     // [E][EL]       q tile, later the staged output
+  double* sZ = sq + E * EL;                             // [NZ][E*NN]    component-major (conflict-free)
+  double* sS2 = sZ + NZ * ZS;                           // [DIM][NN][NN]
+  double* sX = sS2 + DIM * NN * NN;                     // [2][NC][E*NN]  pair fluxes on their way to the other end point
+  __shared__ double s_red[T / 32];
+
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t e0 = a.e_begin + (int64_t)blockIdx.x * E;
+  const int ne = (int)((a.nE - e0) < E ? (a.nE - e0) : E);
+  const double gami = a.ph.gamma - 1.0;
+
+  async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
+  cp_async_commit();
+  for (int idx = tid; idx < DIM * NN * NN; idx += T) sS2[idx] = (&op.S2[0][0][0])[idx];
+  const bool act = tid < ne * NN;
+  const int s = tid / NN, i = tid - s * NN;
+  // face records, Minv and (node-independent) metrics of this thread's node: in flight during the node stage
+  double grec[(DENSEREC ? NF : DIM) * ND], mv = 1.0, dx0[DIM][DIM];
+  if (act) {
+    if (DENSEREC) {
+      const double* G = a.fluxe + (e0 + s) * (NF * EL) + i * ND;
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int c = 0; c < ND; ++c) grec[f * ND + c] = __ldg(G + f * EL + c);
+    } else {
+      const double* G = a.fluxe + (e0 + s) * (NF * FL);
+#pragma unroll
+      for (int u = 0; u < DIM; ++u) {
+        const int slot = op.inv[i][u];
+#pragma unroll
+        for (int c = 0; c < ND; ++c) grec[u * ND + c] = slot >= 0 ? __ldg(G + slot * ND + c) : 0.0;
+      }
+    }
+    if (MODE == EPI_RK) mv = __ldg(a.minv + (e0 + s) * NN + i);
+    const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + i * a.dx_node_stride;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int p = 0; p < DIM; ++p) dx0[d][p] = __ldg(dx + d + DIM * p);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- node stage: checks + Ismail-Roe parameter vector and its logarithms (kept in registers and published) ----
+  IRNode<DIM> zi;
+  if (act) {
+    double qn[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) qn[k] = sq[tid * ND + k];
+    const double press = calc_pressure<DIM>(qn, gami);
+    if ((a.ph.check_density && !(qn[0] > 0.0)) || (a.ph.check_pressure && !(press > 0.0))) {
+      const int code = (a.ph.check_density && !(qn[0] > 0.0)) ? 1 : 2;
+      const unsigned long long loc = ((unsigned long long)(e0 + s) << 8) | (unsigned)i;
+      atomicMin(&a.ctl->err_loc, ((unsigned long long)(code - 1) << 62) | loc);
+      atomicExch(&a.ctl->err_code, 1);
+      atomicExch(&a.ctl->stop, 1);
+      qn[0] = 1.0; qn[DIM + 1] = 1.0;       // keep the arithmetic finite; the result is discarded
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) qn[1 + d] = 0.0;
+    }
+    zi = ir_node<DIM>(qn, gami);
+    sZ[0 * ZS + tid] = zi.z1;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) sZ[(1 + d) * ZS + tid] = zi.zv[d];
+    sZ[(DIM + 1) * ZS + tid] = zi.z5; sZ[(DIM + 2) * ZS + tid] = zi.l1; sZ[(DIM + 3) * ZS + tid] = zi.l5;
+  }
+  __syncthreads();       // node tile complete; nobody reads the q tile any more (it becomes the output staging tile)
+
+  // ---- rounds k = 1 .. nn/2: thread (s, i) evaluates the pair {i, i+k mod nn} ONCE, adds its own share and hands the flux
+  // to the other end point through shared memory (double-buffered: one barrier per round).  For even nn the last round
+  // holds each pair twice (i+k+k = i): only the threads i < nn/2 evaluate it.
+  double acc[ND];
+#pragma unroll
+  for (int c = 0; c < ND; ++c) acc[c] = 0.0;
+  {
+    constexpr int NR = NN / 2;
+    const double* Sc = sS2 + i * NN;
+    const int n0 = s * NN;
+#pragma unroll 1
+    for (int k = 1; k <= NR; ++k) {
+      double* xb = sX + (k & 1) * (NC * XS);
+      const bool half = (NN % 2 == 0) && (k == NR);
+      int m = i + k;
+      if (m >= NN) m -= NN;
+      if (act && (!half || i < NR)) {
+        IRNode<DIM> zm;
+        zm.z1 = sZ[n0 + m];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) zm.zv[d] = sZ[(1 + d) * ZS + n0 + m];
+        zm.z5 = sZ[(DIM + 1) * ZS + n0 + m]; zm.l1 = sZ[(DIM + 2) * ZS + n0 + m]; zm.l5 = sZ[(DIM + 3) * ZS + n0 + m];
+        double dirs[DIM][DIM], F[DIM][ND];
+        if (a.dx_node_stride != 0 && m > i) {
+          // curved elements: the two-point flux of the pair uses the metrics of its higher-numbered node
+          const double* dx = a.dxidx + (e0 + s) * a.dx_el_stride + m * a.dx_node_stride;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int p = 0; p < DIM; ++p) dirs[d][p] = __ldg(dx + d + DIM * p);
+        } else {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int p = 0; p < DIM; ++p) dirs[d][p] = dx0[d][p];
+        }
+        if (m > i) ir_flux<DIM, DIM>(zm, zi, dirs, a.ph.gamma, F);
+        else ir_flux<DIM, DIM>(zi, zm, dirs, a.ph.gamma, F);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          const double sc = -Sc[d * NN * NN + m];
+#pragma unroll
+          for (int c = 0; c < ND; ++c) {
+            acc[c] = fma(sc, F[d][c], acc[c]);
+            xb[(d * ND + c) * XS + tid] = F[d][c];
+          }
+        }
+      }
+      __syncthreads();
+      int ip = i - k;
+      if (ip < 0) ip += NN;
+      if (act && (!half || ip < NR)) {
+        const double* xr = xb + n0 + ip;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          const double sc = -Sc[d * NN * NN + ip];
+#pragma unroll
+          for (int c = 0; c < ND; ++c) acc[c] = fma(sc, xr[(d * ND + c) * XS], acc[c]);
+        }
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+#pragma unroll
+      for (int u = 0; u < (DENSEREC ? NF : DIM); ++u) acc[c] += grec[u * ND + c];
+      if (MODE == EPI_RK) acc[c] *= mv;
+      sq[tid * ND + c] = acc[c];
+    }
+  }
+  __syncthreads();
+  epilogue_tile<NN, ND, E, T, MODE>(a, sq, ne, e0, tid, s_red);
+}
+
 }  // namespace pdes

@@ -258,6 +258,25 @@ __device__ __forceinline__ void convert_to_ir(const double* qc, double gamma, do
   qe[DIM + 1] = -qc[0] * fac * gamma_1i;
 }
 
+// convertToIR_ with the logarithms of the Ismail-Roe parameter vector: z1 = sqrt(rho/p), z5 = sqrt(rho p) give
+// log rho = l1 + l5, log p = l5 - l1, and gamma_1 rho_int = p, so the physical entropy s = log(p / rho^gamma) needs neither
+// the pow nor the log of conversion.jl:170-175 (they were ~40 % of k_face_flux_sparse's instructions)
+template <int DIM>
+__device__ __forceinline__ void convert_to_ir_z(const double* qc, const IRNode<DIM>& z, double gamma, double* qe) {
+  const double gamma_1 = gamma - 1.0, gamma_1i = 1.0 / gamma_1;
+  double k1 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) k1 += qc[1 + d] * qc[1 + d];
+  k1 = 0.5 * k1 * fast_rcp(qc[0]);
+  const double rho_int = qc[DIM + 1] - k1;
+  const double s = (z.l5 - z.l1) - gamma * (z.l1 + z.l5);
+  const double fac = fast_rcp(rho_int);
+  qe[0] = ((rho_int * (gamma + 1 - s) - qc[DIM + 1]) * fac) * gamma_1i;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) qe[1 + d] = qc[1 + d] * fac * gamma_1i;
+  qe[DIM + 1] = -qc[0] * fac * gamma_1i;
+}
+
 template <int DIM>
 __device__ __forceinline__ void irslf_flux(const double* qL, const double* qR, const double* n, double gamma, double* F) {
   constexpr int ND = DIM + 2;
@@ -270,13 +289,18 @@ __device__ __forceinline__ void irslf_flux(const double* qL, const double* qR, c
   double qa[ND], vL[ND], vR[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) qa[i] = 0.5 * (qL[i] + qR[i]);
+#ifdef PDES_IRSLF_POW
   convert_to_ir<DIM>(qL, gamma, vL);
   convert_to_ir<DIM>(qR, gamma, vR);
+#else
+  convert_to_ir_z<DIM>(qL, zL, gamma, vL);
+  convert_to_ir_z<DIM>(qR, zR, gamma, vR);
+#endif
 #pragma unroll
   for (int i = 0; i < ND; ++i) vL[i] -= vR[i];
   // A0 = dq/dw at q_avg (symmetric), applied to delta w
   const double p = calc_pressure<DIM>(qa, gami);
-  const double rho = qa[0], rhoe = qa[DIM + 1], rhoinv = 1.0 / rho;
+  const double rho = qa[0], rhoe = qa[DIM + 1], rhoinv = fast_rcp(rho);
   const double h = (rhoe + p) * rhoinv, a2 = gamma * p * rhoinv;
   double out[ND];
   out[0] = rho * vL[0] + rhoe * vL[DIM + 1];

@@ -84,6 +84,10 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+#ifndef PDES_SPLIT_DEFAULT
+#define PDES_SPLIT_DEFAULT 2     // split-form volume kernel: 0 k_element_split, 1 k_element_split_n, 2 k_element_split_r
+#endif
+
 // type-erased launcher for one (DIM, NN, NFN) operator family
 struct Ops {
   virtual ~Ops() {}
@@ -400,20 +404,35 @@ struct OpsImplS : Ops {
     e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RK, false, NMINB>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
     if (e != cudaSuccess) return e;
-    node_centric = env_int("PDES_SPLIT_N", 1) != 0;
+    e = cudaFuncSetAttribute(k_element_split_r<DIM, NN, NFN, E, EPI_RES, false, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_r<DIM, NN, NFN, E, EPI_RK, false, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    node_centric = env_int("PDES_SPLIT_N", PDES_SPLIT_DEFAULT);
     attr_set = true;
     return cudaSuccess;
   }
-  // node-centric split-form kernel (k_element_split_n): every two-point flux evaluated at both of its end points
+  // node-centric split-form kernels: k_element_split_n (1: every two-point flux evaluated at both of its end points) and
+  // k_element_split_r (2: every flux once, round-robin pair schedule, exchange through shared memory)
+  using RCfg = SplitRCfg<DIM, NN, NFN, E>;
   using NCfg = SplitNCfg<DIM, NN, NFN, E>;
-#ifndef PDES_SPLITN_MINB
-#define PDES_SPLITN_MINB 4
-#endif
+#ifdef PDES_SPLITN_MINB
   static constexpr int NMINB = PDES_SPLITN_MINB;
-  bool node_centric = true;
+#else
+  static constexpr int NMINB = NCfg::T <= 96 ? 8 : 4;      // 80 registers per thread either way
+#endif
+  int node_centric = 1;
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if (node_centric == 2) {
+      dim3 gridr((unsigned)grid_for(a.nE - a.e_begin)), blockr(RCfg::T);
+      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, a);
+      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, a);
+      return cudaGetLastError();
+    }
     if (node_centric) {
       dim3 gridn((unsigned)grid_for(a.nE - a.e_begin)), blockn(NCfg::T);
       if (mode == EPI_RES) k_element_split_n<DIM, NN, NFN, E, EPI_RES, false, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tab, a);
@@ -487,16 +506,29 @@ struct OpsImplE : Ops {
     e = cudaFuncSetAttribute(k_element_split_n<DIM, NN, NFN, E, EPI_RK, true, NMINB>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NCfg::smem_bytes);
     if (e != cudaSuccess) return e;
-    node_centric = env_int("PDES_SPLIT_N", 1) != 0;
+    e = cudaFuncSetAttribute(k_element_split_r<DIM, NN, NFN, E, EPI_RES, true, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_element_split_r<DIM, NN, NFN, E, EPI_RK, true, NMINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    node_centric = env_int("PDES_SPLIT_N", PDES_SPLIT_DEFAULT);
     attr_set = true;
     return cudaSuccess;
   }
   using NCfg = SplitNCfg<DIM, NN, NFN, E>;
+  using RCfg = SplitRCfg<DIM, NN, NFN, E>;
   static constexpr int NMINB = 3;
-  bool node_centric = true;
+  int node_centric = 1;
   cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if (node_centric == 2) {
+      dim3 gridr((unsigned)grid_for(a.nE - a.e_begin)), blockr(RCfg::T);
+      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, a);
+      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, a);
+      return cudaGetLastError();
+    }
     if (node_centric) {
       dim3 gridn((unsigned)grid_for(a.nE - a.e_begin)), blockn(NCfg::T);
       if (mode == EPI_RES) k_element_split_n<DIM, NN, NFN, E, EPI_RES, true, NMINB><<<gridn, blockn, NCfg::smem_bytes, s>>>(tabs, a);
@@ -525,7 +557,10 @@ Ops* make_ops(const PdesConfig& c) {
 #define PDES_DEV_MINB_F 8
 #endif
     return new OpsImpl<3, 11, 6, PDES_DEV_E, PDES_DEV_MINB_E, PDES_DEV_FT, PDES_DEV_MINB_F>();
-  if (c.sparse_face && c.dim == 2 && c.nn == 12 && c.nfn == 4 && c.volume_integral_type == 2) return new OpsImplS<2, 12, 4, 16>();
+#ifndef PDES_DEV_ES_E
+#define PDES_DEV_ES_E 8
+#endif
+  if (c.sparse_face && c.dim == 2 && c.nn == 12 && c.nfn == 4 && c.volume_integral_type == 2) return new OpsImplS<2, 12, 4, PDES_DEV_ES_E>();
   return nullptr;
 #else
   if (c.sparse_face) {
@@ -533,7 +568,8 @@ Ops* make_ops(const PdesConfig& c) {
     if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR) return nullptr;
     if (c.face_integral_type != 1) return nullptr;      // diagonal-E operators keep face_integral_type 1 (read_input.jl:742-755)
     if (c.flux_id != PDES_FLUX_ROE && c.flux_id != PDES_FLUX_IR && c.flux_id != PDES_FLUX_IRSLF) return nullptr;
-    if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 16>();
+    // 8 elements = 96 threads per CTA (C2, k_element_split_r: 13.9 ms per RK4 step; 16: 14.3, 24: 15.2, 32: 15.3)
+    if (c.dim == 2 && c.nn == 12 && c.nfn == 4) return new OpsImplS<2, 12, 4, 8>();
     return nullptr;
   }
   if (c.face_integral_type == 2) {

@@ -587,6 +587,26 @@ def test_node_centric_split_kernel(case, n, monkeypatch):
     assert np.allclose(out["0"][2], out["1"][2], rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("case,n", [("c2_2d_p2_es", 9), ("2d_p2_es_ir", 7), ("2d_p2_es_roe", 6)])
+def test_round_robin_split_kernel(case, n, monkeypatch):
+    """k_element_split_r (PDES_SPLIT_N=2): every two-point flux once, pairs scheduled in nn/2 rounds, shares exchanged through
+    shared memory.  The partner sum runs in round order: parity with the oracle at the residual tolerance, agreement with
+    the node-centric kernel at rounding level."""
+    out = {}
+    for flag in ("1", "2"):
+        monkeypatch.setenv("PDES_SPLIT_N", flag)
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=7)
+        eqn.q[...] = q0
+        pd.evalResidual(mesh, op, eqn, opts)
+        res = eqn.res.copy(order="F")
+        assert rel_l2(res, orc.eval_residual(q0)) < RES_TOL
+        pd.rk4(pd.evalResidual, 1e-4, 6e-4, mesh, op, eqn, opts)
+        out[flag] = (res, eqn.q.copy(order="F"), list(eqn.convergence))
+    assert rel_l2(out["1"][0], out["2"][0]) < RES_TOL
+    assert rel_l2(out["1"][1], out["2"][1]) < 1e-14
+    assert np.allclose(out["1"][2], out["2"][2], rtol=1e-11, atol=0)
+
+
 def test_gmres_solves_jacobian_system():
     """pdes_gmres (the linear solve of the matrix-free Newton path, newton_setup.jl:632-662 +
     PETSc GMRES defaults read_input.jl:493-496, 560-570): x must satisfy dR/dq x = b, checked against a dense
