@@ -638,7 +638,8 @@ struct PdesCtx {
   int nchunks = 1;
   int64_t chunk_e[MAXC + 1] = {0}, chunk_g[MAXC + 1] = {0};
   cudaEvent_t ev_face[MAXC] = {nullptr}, ev_elem = nullptr;
-  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_norm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_norm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q = nullptr;
+  bool comm_overlap = true;     // shared-face branch (pack, exchange, flux) on the communication stream
   // state
   double* qbuf[3] = {nullptr, nullptr, nullptr};
   int cur = 0;
@@ -947,6 +948,7 @@ int finalize(PdesCtx* ctx) {
   // q of the HIGHEST elements; k_element_rk sweeping downwards starts on those lines and ends on the lowest elements,
   // whose q_next the next stage's k_face_flux asks for first
   ctx->rk4_nosum = env_int("PDES_RK4_NOSUM", 1) != 0 && ctx->ops->staged_epilogue();
+  ctx->comm_overlap = env_int("PDES_COMM_INLINE", 0) == 0 && !ctx->fused;
   ctx->reverse_elems = env_int("PDES_REV", 1);
   ctx->discard_split = env_int("PDES_DISCARD_SPLIT", 1);
   if (ctx->fused) {
@@ -976,14 +978,26 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->discard_records = ctx->pipe ? ctx->pipe_discard : ctx->discard_split;
 }
 
-// startSolutionExchange (Utils/parallel.jl:29-49): pack on the compute stream, send/recv on the comm stream
+// startSolutionExchange (Utils/parallel.jl:29-49).  With a communicator the whole shared-face branch runs on the
+// communication stream, concurrently with the interior faces on the compute stream:
+//     comm stream : [q ready] -> k_pack_send -> ncclSend/Recv -> k_face_flux over the shared faces -> [ev_recv]
+// (PDES_COMM_INLINE=1: pack and shared-face flux on the compute stream, as before: 4 small kernels serialised per evaluation)
 int start_exchange(PdesCtx* ctx, const double* q) {
   if (ctx->nS == 0) return PDES_OK;
-  CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl, ctx->stream));
+  const bool overlap = ctx->comm && ctx->comm_overlap;
+  cudaStream_t ps = overlap ? ctx->comm_stream : ctx->stream;
+  if (overlap) {
+    // q of this evaluation is complete once everything enqueued so far on the compute stream has run
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_q, 0));
+  }
+  CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl, ps));
   ctx->launches++;
   if (!ctx->comm) return PDES_OK;   // test mode: receive buffer injected by hand
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+  if (!overlap) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+  }
   const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
   ncclResult_t r = g_nccl.GroupStart();
   for (auto& p : ctx->peers) {
@@ -997,7 +1011,7 @@ int start_exchange(PdesCtx* ctx, const double* q) {
     set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
     return PDES_ERR_COMM;
   }
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
+  if (!overlap) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
   return PDES_OK;
 }
 
@@ -1099,10 +1113,17 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
     if (nc > 1) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_face[k], fs));
   }
   if (ctx->nS > 0) {
-    if (ctx->comm) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
+    const bool overlap = ctx->comm && ctx->comm_overlap;
+    if (ctx->comm && !overlap) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
     fa.g0 = c.nF + c.nB; fa.ng = ctx->nS;
-    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
+    // overlap: stream order on the communication stream puts the kernel behind the receive; it writes the record slots
+    // of the shared faces only, while the interior-face kernel is still running on the compute stream
+    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, overlap ? ctx->comm_stream : ctx->stream));
     ctx->launches++;
+    if (overlap) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
+    }
   }
   for (int k = 0; k < nc; ++k) {
     if (nc > 1) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_face[k], 0));
@@ -1315,11 +1336,17 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
     CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CUDA_TRY(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
   }
-  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the shared-face branch must not queue behind the thousands of interior-face CTAs it overlaps with
+    int lo = 0, hi = 0;
+    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(c, cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  }
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->face_stream, cudaStreamNonBlocking));
   for (int i = 0; i < PdesCtx::MAXC; ++i) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_face[i], cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_elem, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_q, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_norm, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreate(&c->ev_t0));
@@ -1354,6 +1381,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+  if (ctx->ev_q) cudaEventDestroy(ctx->ev_q);
   if (ctx->ev_recv) cudaEventDestroy(ctx->ev_recv);
   if (ctx->ev_norm) cudaEventDestroy(ctx->ev_norm);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
