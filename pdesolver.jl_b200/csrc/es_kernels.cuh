@@ -600,7 +600,10 @@ k_element_split_r(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_
 
   async_tile(sq, a.q + e0 * EL, ne * EL, tid, T);
   cp_async_commit();
-  for (int idx = tid; idx < DIM * NN * NN; idx += T) sS2[idx] = (&op.S2[0][0][0])[idx];
+  // (the operator table comes from its device copy: an indexed read of the kernel-parameter bank per entry held 8 % of
+  // the kernel's stall samples once a CTA had only 8 elements to amortise it over)
+  for (int idx = tid; idx < DIM * NN * NN; idx += T) cp_async8(sS2 + idx, a.s2_dev + idx);
+  cp_async_commit();
   const bool act = tid < ne * NN;
   const int s = tid / NN, i = tid - s * NN;
   // face records, Minv and (node-independent) metrics of this thread's node: in flight during the node stage
@@ -616,7 +619,7 @@ k_element_split_r(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_
       const double* G = a.fluxe + (e0 + s) * (NF * FL);
 #pragma unroll
       for (int u = 0; u < DIM; ++u) {
-        const int slot = op.inv[i][u];
+        const int slot = __ldg(a.inv_dev + i * DIM + u);
 #pragma unroll
         for (int c = 0; c < ND; ++c) grec[u * ND + c] = slot >= 0 ? __ldg(G + slot * ND + c) : 0.0;
       }

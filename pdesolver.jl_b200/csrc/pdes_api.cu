@@ -411,9 +411,26 @@ struct OpsImplS : Ops {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
     if (e != cudaSuccess) return e;
     node_centric = env_int("PDES_SPLIT_N", PDES_SPLIT_DEFAULT);
+    e = upload_tab();
+    if (e != cudaSuccess) return e;
     attr_set = true;
     return cudaSuccess;
   }
+  // device copy of S2 | inv for k_element_split_r
+  double* d_s2 = nullptr;
+  int32_t* d_inv = nullptr;
+  cudaError_t upload_tab() {
+    if (!d_s2) {
+      cudaError_t e = cudaMalloc((void**)&d_s2, sizeof(tab.S2));
+      if (e != cudaSuccess) return e;
+      e = cudaMalloc((void**)&d_inv, sizeof(tab.inv));
+      if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaMemcpy(d_s2, &tab.S2[0][0][0], sizeof(tab.S2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(d_inv, &tab.inv[0][0], sizeof(tab.inv), cudaMemcpyHostToDevice);
+  }
+  ~OpsImplS() override { cudaFree(d_s2); cudaFree(d_inv); }
   // node-centric split-form kernels: k_element_split_n (1: every two-point flux evaluated at both of its end points) and
   // k_element_split_r (2: every flux once, round-robin pair schedule, exchange through shared memory)
   using RCfg = SplitRCfg<DIM, NN, NFN, E>;
@@ -429,8 +446,10 @@ struct OpsImplS : Ops {
     if (a.nE <= a.e_begin) return cudaSuccess;
     if (node_centric == 2) {
       dim3 gridr((unsigned)grid_for(a.nE - a.e_begin)), blockr(RCfg::T);
-      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, a);
-      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, a);
+      ElemArgs b = a;
+      b.s2_dev = d_s2; b.inv_dev = d_inv;
+      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, b);
+      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, false, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tab, b);
       return cudaGetLastError();
     }
     if (node_centric) {
@@ -513,9 +532,22 @@ struct OpsImplE : Ops {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCfg::smem_bytes);
     if (e != cudaSuccess) return e;
     node_centric = env_int("PDES_SPLIT_N", PDES_SPLIT_DEFAULT);
+    if (!d_s2) {
+      e = cudaMalloc((void**)&d_s2, sizeof(tabs.S2));
+      if (e != cudaSuccess) return e;
+      e = cudaMalloc((void**)&d_inv, sizeof(tabs.inv));
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaMemcpy(d_s2, &tabs.S2[0][0][0], sizeof(tabs.S2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(d_inv, &tabs.inv[0][0], sizeof(tabs.inv), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
     attr_set = true;
     return cudaSuccess;
   }
+  double* d_s2 = nullptr;
+  int32_t* d_inv = nullptr;
+  ~OpsImplE() override { cudaFree(d_s2); cudaFree(d_inv); }
   using NCfg = SplitNCfg<DIM, NN, NFN, E>;
   using RCfg = SplitRCfg<DIM, NN, NFN, E>;
   static constexpr int NMINB = 3;
@@ -525,8 +557,10 @@ struct OpsImplE : Ops {
     if (a.nE <= a.e_begin) return cudaSuccess;
     if (node_centric == 2) {
       dim3 gridr((unsigned)grid_for(a.nE - a.e_begin)), blockr(RCfg::T);
-      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, a);
-      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, a);
+      ElemArgs b = a;
+      b.s2_dev = d_s2; b.inv_dev = d_inv;
+      if (mode == EPI_RES) k_element_split_r<DIM, NN, NFN, E, EPI_RES, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, b);
+      else k_element_split_r<DIM, NN, NFN, E, EPI_RK, true, NMINB><<<gridr, blockr, RCfg::smem_bytes, s>>>(tabs, b);
       return cudaGetLastError();
     }
     if (node_centric) {

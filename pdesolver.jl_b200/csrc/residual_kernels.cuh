@@ -137,6 +137,8 @@ struct ElemArgs {
   Ctl* ctl;
   PhysPar ph;
   PipeArgs pipe;
+  const double* s2_dev;        // split-form kernels: device copy of OpTabS::S2 (staged by cp.async) ...
+  const int32_t* inv_dev;      // ... and of OpTabS::inv
 };
 
 // ---- chunk pipeline primitives -------------------------------------------------------------------------------------
