@@ -167,6 +167,8 @@ struct OpsImpl : Ops {
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
+    attr_set = false;                       // device copies of the tables are refreshed by the next prepare()
+    if (d_ftab) { cudaFree(d_ftab); d_ftab = nullptr; }
     use_tma = env_int("PDES_FACE_TMA", 0) != 0;
     use_warp_kernel = env_int("PDES_ELEM_W", 0) != 0;
     const int ss = c.ss;
@@ -226,7 +228,11 @@ struct OpsImpl : Ops {
     return cudaGetLastError();
   }
   int tma_grid = -1;
-  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+  int32_t* d_ftab = nullptr;       // perm | nbrperm
+  ~OpsImpl() override { cudaFree(d_ftab); }
+  cudaError_t launch_faces(const FaceArgs& a_in, cudaStream_t s) override {
+    FaceArgs a = a_in;
+    a.tab_dev = d_ftab;
     if (a.pipe.on) {
       // (an empty chunk still launches one CTA: it has to publish its completion)
       const int64_t nt = std::max<int64_t>(1, (a.ng + FT - 1) / FT);
@@ -284,8 +290,18 @@ struct OpsImpl : Ops {
   }
   cudaError_t prepare() override {
     if (attr_set) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    cudaError_t e;
+    if (!d_ftab && env_int("PDES_FACE_TAB_DEV", 1)) {
+      std::vector<int32_t> h((DIM + 1) * NN + Tab::NOR * NFN);
+      memcpy(h.data(), &tab.perm[0][0], sizeof(int32_t) * (DIM + 1) * NN);
+      memcpy(h.data() + (DIM + 1) * NN, &tab.nbrperm[0][0], sizeof(int32_t) * Tab::NOR * NFN);
+      e = cudaMalloc((void**)&d_ftab, sizeof(int32_t) * h.size());
+      if (e != cudaSuccess) return e;
+      e = cudaMemcpy(d_ftab, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
@@ -362,6 +378,7 @@ struct OpsImplS : Ops {
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
+    attr_set = false;
     flux_id = c.flux_id;
     for (int d = 0; d < DIM; ++d)
       for (int i = 0; i < NN; ++i)
@@ -487,6 +504,7 @@ struct OpsImplE : Ops {
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
     memset(&tabs, 0, sizeof(tabs));
+    attr_set = false;
     fei = c.face_element_id;
     const int ss = c.ss;
     for (int d = 0; d < DIM; ++d)

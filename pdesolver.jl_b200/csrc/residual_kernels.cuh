@@ -108,6 +108,7 @@ struct FaceArgs {
   const Ctl* ctl;
   PhysPar ph;
   PipeArgs pipe;
+  const int32_t* tab_dev;      // device copy of OpTab::perm | OpTab::nbrperm (or nullptr)
 };
 
 struct ElemArgs {
@@ -368,10 +369,18 @@ struct FaceTileSmem {
 };
 
 template <int DIM, int NN, int NFN, int FT, int TB>
-__device__ __forceinline__ void face_tables(const OpTab<DIM, NN, NFN>& op, FaceTileSmem<DIM, NN, NFN, FT>& sm, int tid) {
-  constexpr int NF = DIM + 1;
+__device__ __forceinline__ void face_tables(const OpTab<DIM, NN, NFN>& op, FaceTileSmem<DIM, NN, NFN, FT>& sm, int tid,
+                                            const int32_t* dev = nullptr) {
+  constexpr int NF = DIM + 1, NOR = OpTab<DIM, NN, NFN>::NOR;
+  if (dev) {
+    // device copy (perm | nbrperm): one coalesced load per warp; the parameter bank is read with a per-thread index
+    // otherwise, which the hardware serialises address by address (4 % of k_face_flux's stall samples)
+    for (int idx = tid; idx < NF * NN; idx += TB) (&sm.s_perm[0][0])[idx] = __ldg(dev + idx);
+    for (int idx = tid; idx < NOR * NFN; idx += TB) (&sm.s_nbrperm[0][0])[idx] = __ldg(dev + NF * NN + idx);
+    return;
+  }
   for (int idx = tid; idx < NF * NN; idx += TB) sm.s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
-  for (int idx = tid; idx < OpTab<DIM, NN, NFN>::NOR * NFN; idx += TB)
+  for (int idx = tid; idx < NOR * NFN; idx += TB)
     sm.s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
 }
 
@@ -574,7 +583,7 @@ k_face_flux(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
 #pragma unroll
     for (int o = 0; o < FT * 16; o += 128) prefetch_l2(pr + o);
   }
-  face_tables<DIM, NN, NFN, FT, T>(op, sm, tid);
+  face_tables<DIM, NN, NFN, FT, T>(op, sm, tid, a.tab_dev);
   face_tile<DIM, NN, NFN, FT, T, false, false, EXTBC>(op, a, sm, g0, nf, ga, tid);
   if (PIPE) {
     __syncthreads();
