@@ -364,7 +364,7 @@ struct FaceTileSmem {
   double sR[FT * FS];
   FaceRec sRec[FT];
   int s_dst[2 * FT];            // (element*NF + face) of the record each side of a face writes, or -1
-  int s_perm[DIM + 1][NN];
+  int s_perm[DIM + 1][NN];      // BYTE offset of volume node perm[j,f] inside an element block (8 * ND * perm)
   int s_nbrperm[OpTab<DIM, NN, NFN>::NOR][NFN];
 };
 
@@ -375,11 +375,11 @@ __device__ __forceinline__ void face_tables(const OpTab<DIM, NN, NFN>& op, FaceT
   if (dev) {
     // device copy (perm | nbrperm): one coalesced load per warp; the parameter bank is read with a per-thread index
     // otherwise, which the hardware serialises address by address (4 % of k_face_flux's stall samples)
-    for (int idx = tid; idx < NF * NN; idx += TB) (&sm.s_perm[0][0])[idx] = __ldg(dev + idx);
+    for (int idx = tid; idx < NF * NN; idx += TB) (&sm.s_perm[0][0])[idx] = __ldg(dev + idx) * ((DIM + 2) * 8);
     for (int idx = tid; idx < NOR * NFN; idx += TB) (&sm.s_nbrperm[0][0])[idx] = __ldg(dev + NF * NN + idx);
     return;
   }
-  for (int idx = tid; idx < NF * NN; idx += TB) sm.s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN];
+  for (int idx = tid; idx < NF * NN; idx += TB) sm.s_perm[idx / NN][idx % NN] = op.perm[idx / NN][idx % NN] * ((DIM + 2) * 8);
   for (int idx = tid; idx < NOR * NFN; idx += TB)
     sm.s_nbrperm[idx / NFN][idx % NFN] = op.nbrperm[idx / NFN][idx % NFN];
 }
@@ -435,12 +435,16 @@ __device__ __forceinline__ void face_tile(const OpTab<DIM, NN, NFN>& op, const F
     {
       const double* b = a.q + (int64_t)r.elL * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) ql[j] = (PDES_SKEL & 16) ? 1.0 + j : __ldg(b + sm.s_perm[r.fL][j] * ND);
+      for (int j = 0; j < NN; ++j)      // (one 64-bit add per address: the index arithmetic was 6 of 7 instructions per load)
+        ql[j] = (PDES_SKEL & 16) ? 1.0 + j
+                                 : __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(b) + (unsigned)sm.s_perm[r.fL][j]));
     }
     if (r.kind == FK_INTERIOR) {
       const double* b = a.q + (int64_t)r.elR * EL + k;
 #pragma unroll
-      for (int j = 0; j < NN; ++j) qr[j] = (PDES_SKEL & 16) ? 2.0 + j : __ldg(b + sm.s_perm[r.fR][j] * ND);
+      for (int j = 0; j < NN; ++j)
+        qr[j] = (PDES_SKEL & 16) ? 2.0 + j
+                                 : __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(b) + (unsigned)sm.s_perm[r.fR][j]));
     } else {
 #pragma unroll
       for (int j = 0; j < NN; ++j) qr[j] = 0.0;
