@@ -42,7 +42,10 @@ __device__ __forceinline__ void numerical_flux(int flux_id, const double* qL, co
 
 // one thread per (face, face node): no interpolation, states are read at the coinciding volume nodes
 template <int DIM, int NN, int NFN>
-__global__ void __launch_bounds__(128)
+#ifndef PDES_SPARSE_MINB
+#define PDES_SPARSE_MINB 8      // 64 registers, 8 CTAs per SM: C2 12.27 ms per RK4 step (1: 12.57, 6: 12.42, 10: 12.56)
+#endif
+__global__ void __launch_bounds__(128, PDES_SPARSE_MINB)
 k_face_flux_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a, int flux_id) {
   constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, FL = NFN * ND;
   if (a.ctl->stop) return;
