@@ -342,7 +342,9 @@ def main():
                 "evalResidual_dof_per_s": ndof_total / dt_res},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_face_flux + k_element_rk<EPI_RK> (one residual evaluation + RK4 stage)",
+                     "traffic": traffic,
+                     "kernel": ("k_face_flux_sparse + k_element_split_r<EPI_RK>" if wl.get("kind") == "diage"
+                                else "k_face_flux + k_element_rk<EPI_RK>") + " (one residual evaluation + RK4 stage)",
                      "algorithmic_bytes_per_dof": b_stage,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
     }
