@@ -138,29 +138,44 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   // index is replayed once per distinct address)
   __shared__ double sA[NN][NFN];            // interp[i][k]
   __shared__ double sB[NN][DIM][NFN];       // interp[j][nbrperm[k]] * wface[k] * nrm[d,k]
+  __shared__ double swf[NFN];               // wface
+  __shared__ int spL[NN], spR[NN], snbr[NFN];   // perm[:, fL], perm[:, fR], nbrperm[:, orient]
+  __shared__ double sWf[2][NFN][ND], sQf[2][NFN][ND];   // face-interpolated entropy variables / their conservative states
   if (a.ctl->stop) return;
   const int tid = threadIdx.x;
   const int64_t g = a.g0 + blockIdx.x;
   const FaceRec r = a.faces[g];
   const bool interior = r.kind == FK_INTERIOR;
+  // operator tables from their device copies (tab_dev: perm | nbrperm, optab_dev: interp | wface): a read of the
+  // kernel-parameter bank with a per-thread index is replayed once per distinct address
+  if (tid < NN) {
+    spL[tid] = __ldg(a.tab_dev + r.fL * NN + tid);
+    spR[tid] = interior ? __ldg(a.tab_dev + r.fR * NN + tid) : 0;
+  }
+  if (tid >= 32 && tid < 32 + NFN) {
+    const int k = tid - 32;
+    snbr[k] = __ldg(a.tab_dev + NF * NN + (interior ? r.orient : 0) * NFN + k);
+    swf[k] = __ldg(a.optab_dev + NN * NFN + k);
+  }
+  for (int idx = tid; idx < NN * NFN; idx += T) sA[idx / NFN][idx % NFN] = __ldg(a.optab_dev + idx);
+  __syncthreads();
   for (int idx = tid; idx < NN * ND; idx += T) {
     const int j = idx / ND, k = idx - j * ND;
-    sq[0][j][k] = __ldg(a.q + (int64_t)r.elL * EL + op.perm[r.fL][j] * ND + k);
-    sq[1][j][k] = interior ? __ldg(a.q + (int64_t)r.elR * EL + op.perm[r.fR][j] * ND + k) : 0.0;
+    sq[0][j][k] = __ldg(a.q + (int64_t)r.elL * EL + spL[j] * ND + k);
+    sq[1][j][k] = interior ? __ldg(a.q + (int64_t)r.elR * EL + spR[j] * ND + k) : 0.0;
     srec[0][j][k] = 0.0;
     srec[1][j][k] = 0.0;
   }
   for (int idx = tid; idx < DIM * NFN; idx += T) {
     const int d = idx / NFN, k = idx - d * NFN;
-    sc[d][k] = op.wface[k] * __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
+    sc[d][k] = swf[k] * __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
   }
   __syncthreads();
-  const int* nbr = op.nbrperm[interior ? r.orient : 0];
+  const int* nbr = snbr;
   if (interior) {
-    for (int idx = tid; idx < NN * NFN; idx += T) sA[idx / NFN][idx % NFN] = op.interp[idx / NFN][idx % NFN];
     for (int idx = tid; idx < NN * DIM * NFN; idx += T) {
       const int j = idx / (DIM * NFN), d = (idx / NFN) % DIM, k = idx % NFN;
-      sB[j][d][k] = op.interp[j][nbr[k]] * sc[d][k];
+      sB[j][d][k] = sA[j][nbr[k]] * sc[d][k];
     }
   }
 
@@ -172,7 +187,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
       for (int p = 0; p < ND; ++p) qb[p] = 0.0;
       for (int j = 0; j < NN; ++j) {
-        const double c = op.interp[j][k];
+        const double c = sA[j][k];
 #pragma unroll
         for (int p = 0; p < ND; ++p) qb[p] = fma(c, sq[0][j][p], qb[p]);
       }
@@ -181,13 +196,13 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
       for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d); }
       bc_flux_any<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
 #pragma unroll
-      for (int p = 0; p < ND; ++p) spen[k][p] = op.wface[k] * fb[p];
+      for (int p = 0; p < ND; ++p) spen[k][p] = swf[k] * fb[p];
     }
     __syncthreads();
     for (int idx = tid; idx < NN * ND; idx += T) {
       const int j = idx / ND, p = idx - j * ND;
       double s = 0.0;
-      for (int k = 0; k < NFN; ++k) s = fma(op.interp[j][k], spen[k][p], s);
+      for (int k = 0; k < NFN; ++k) s = fma(sA[j][k], spen[k][p], s);
       srec[0][j][p] = -s;
     }
     __syncthreads();
@@ -230,25 +245,37 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
     if (fei == FEI_ELF_PENALTY || fei == FEI_ESLF) {
       for (int idx = tid; idx < 2 * NN; idx += T) convert_to_ir<DIM>(sq[idx / NN][idx % NN], a.ph.gamma, sw[idx / NN][idx % NN]);
       __syncthreads();
+      // entropy variables interpolated to the face nodes: one thread per (side, face node, variable) ...
+      for (int idx = tid; idx < 2 * NFN * ND; idx += T) {
+        const int sd = idx / (NFN * ND), k = (idx / ND) % NFN, p = idx % ND;
+        const int kk = sd == 0 ? k : nbr[k];
+        double w = 0.0;
+        for (int j = 0; j < NN; ++j) w += sA[j][kk] * sw[sd][j][p];
+        sWf[sd][k][p] = w;
+      }
+      __syncthreads();
+      // ... their conservative states: one thread per (side, face node) ...
+      if (tid < 2 * NFN) {
+        const int sd = tid / NFN, k = tid - sd * NFN;
+        double wv[ND], qv[ND];
+#pragma unroll
+        for (int p = 0; p < ND; ++p) wv[p] = sWf[sd][k][p];
+        convert_from_ir<DIM>(wv, a.ph.gamma, qv);
+#pragma unroll
+        for (int p = 0; p < ND; ++p) sQf[sd][k][p] = qv[p];
+      }
+      __syncthreads();
+      // ... and the Lax-Friedrichs entropy kernel: one thread per face node
       if (tid < NFN) {
-        const int k = tid, nk = nbr[k];
-        double wL[ND], wR[ND], qL[ND], qR[ND], qa[ND], dw[ND], fl[ND], nrm[DIM];
+        const int k = tid;
+        double qa[ND], dw[ND], fl[ND], nrm[DIM];
 #pragma unroll
-        for (int p = 0; p < ND; ++p) { wL[p] = 0.0; wR[p] = 0.0; }
-        for (int j = 0; j < NN; ++j) {
-          const double cL = sA[j][k], cR = sA[j][nk];
-#pragma unroll
-          for (int p = 0; p < ND; ++p) { wL[p] += cL * sw[0][j][p]; wR[p] += cR * sw[1][j][p]; }
-        }
-        convert_from_ir<DIM>(wL, a.ph.gamma, qL);
-        convert_from_ir<DIM>(wR, a.ph.gamma, qR);
-#pragma unroll
-        for (int p = 0; p < ND; ++p) { qa[p] = 0.5 * (qL[p] + qR[p]); dw[p] = wL[p] - wR[p]; }
+        for (int p = 0; p < ND; ++p) { qa[p] = 0.5 * (sQf[0][k][p] + sQf[1][k][p]); dw[p] = sWf[0][k][p] - sWf[1][k][p]; }
 #pragma unroll
         for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
         lf_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
 #pragma unroll
-        for (int p = 0; p < ND; ++p) spen[k][p] = fl[p] * op.wface[k];
+        for (int p = 0; p < ND; ++p) spen[k][p] = fl[p] * swf[k];
       }
       __syncthreads();
       for (int idx = tid; idx < NN * ND; idx += T) {
@@ -267,8 +294,8 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   // records in element node order: stencil node j of face f is volume node perm[f][j]
   for (int idx = tid; idx < NN * ND; idx += T) {
     const int j = idx / ND, p = idx - j * ND;
-    a.fluxe[((int64_t)r.elL * NF + r.fL) * EL + op.perm[r.fL][j] * ND + p] = srec[0][j][p];
-    if (interior) a.fluxe[((int64_t)r.elR * NF + r.fR) * EL + op.perm[r.fR][j] * ND + p] = srec[1][j][p];
+    a.fluxe[((int64_t)r.elL * NF + r.fL) * EL + spL[j] * ND + p] = srec[0][j][p];
+    if (interior) a.fluxe[((int64_t)r.elR * NF + r.fR) * EL + spR[j] * ND + p] = srec[1][j][p];
   }
 }
 

@@ -524,8 +524,13 @@ struct OpsImplE : Ops {
   int resident_element_ctas() override { return 0; }
   int resident_face_ctas() override { return 0; }
   int record_doubles() const override { return NN * (DIM + 2); }
-  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
-    if (a.ng <= 0) return cudaSuccess;
+  int32_t* d_ftab = nullptr;       // perm | nbrperm
+  double* d_otab = nullptr;        // interp | wface
+  cudaError_t launch_faces(const FaceArgs& a_in, cudaStream_t s) override {
+    if (a_in.ng <= 0) return cudaSuccess;
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    FaceArgs a = a_in;
+    a.tab_dev = d_ftab; a.optab_dev = d_otab;
     k_face_element<DIM, NN, NFN><<<(unsigned)a.ng, 128, 0, s>>>(tab, a, fei);
     return cudaGetLastError();
   }
@@ -560,12 +565,30 @@ struct OpsImplE : Ops {
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(d_inv, &tabs.inv[0][0], sizeof(tabs.inv), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
+    {
+      std::vector<int32_t> hi((DIM + 1) * NN + Tab::NOR * NFN);
+      memcpy(hi.data(), &tab.perm[0][0], sizeof(int32_t) * (DIM + 1) * NN);
+      memcpy(hi.data() + (DIM + 1) * NN, &tab.nbrperm[0][0], sizeof(int32_t) * Tab::NOR * NFN);
+      std::vector<double> hd(NN * NFN + NFN);
+      memcpy(hd.data(), &tab.interp[0][0], sizeof(double) * NN * NFN);
+      memcpy(hd.data() + NN * NFN, &tab.wface[0], sizeof(double) * NFN);
+      if (!d_ftab) {
+        e = cudaMalloc((void**)&d_ftab, sizeof(int32_t) * hi.size());
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc((void**)&d_otab, sizeof(double) * hd.size());
+        if (e != cudaSuccess) return e;
+      }
+      e = cudaMemcpy(d_ftab, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return e;
+      e = cudaMemcpy(d_otab, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
     return cudaSuccess;
   }
   double* d_s2 = nullptr;
   int32_t* d_inv = nullptr;
-  ~OpsImplE() override { cudaFree(d_s2); cudaFree(d_inv); }
+  ~OpsImplE() override { cudaFree(d_s2); cudaFree(d_inv); cudaFree(d_ftab); cudaFree(d_otab); }
   using NCfg = SplitNCfg<DIM, NN, NFN, E>;
   using RCfg = SplitRCfg<DIM, NN, NFN, E>;
   static constexpr int NMINB = 3;

@@ -109,6 +109,7 @@ struct FaceArgs {
   PhysPar ph;
   PipeArgs pipe;
   const int32_t* tab_dev;      // device copy of OpTab::perm | OpTab::nbrperm (or nullptr)
+  const double* optab_dev;     // device copy of OpTab::interp | OpTab::wface (k_face_element)
 };
 
 struct ElemArgs {
