@@ -341,8 +341,9 @@ __device__ __forceinline__ void convert_from_ir(const double* qe, double gamma, 
   for (int d = 0; d < DIM; ++d) k1 += qe[1 + d] * qe[1 + d];
   k1 = 0.5 * gamma_1 * k1 / qe[DIM + 1];
   const double s = gamma - gamma_1 * qe[0] + k1;
-  double rho_int = exp(-s / gamma_1) * pow(gamma_1 / pow(-gamma_1 * qe[DIM + 1], gamma), 1.0 / gamma_1);
-  rho_int *= gamma_1;
+  // conversion.jl:240-243: rho_int = gamma_1 exp(-s/gamma_1) (gamma_1 / (-gamma_1 w_last)^gamma)^(1/gamma_1), evaluated
+  // as ONE exponential of the collected exponent (one log + one exp instead of two pow + one exp)
+  const double rho_int = gamma_1 * exp((log(gamma_1) - s - gamma * log(-gamma_1 * qe[DIM + 1])) / gamma_1);
   qc[0] = -qe[DIM + 1] * rho_int;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) qc[1 + d] = qe[1 + d] * rho_int;
