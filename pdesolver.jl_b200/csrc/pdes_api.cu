@@ -51,6 +51,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -64,7 +65,7 @@ struct NcclApi {
     if (!h) { *why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
 #define SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) { *why = std::string("missing symbol ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return true;
@@ -715,6 +716,17 @@ struct PdesCtx {
   cudaEvent_t ev_face[MAXC] = {nullptr}, ev_elem = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_recv = nullptr, ev_norm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q = nullptr;
   bool comm_overlap = true;     // shared-face branch (pack, exchange, flux) on the communication stream
+  // peer-to-peer halo (default with a communicator): the packed face states go straight into the neighbour's receive buffer
+  // (CUDA IPC mapping, copy engine over NVLink) and a flag; no NCCL kernel competes with the interior faces for SMs
+  int p2p = -1;                 // -1: not set up yet, 0: NCCL send/recv, 1: peer-to-peer
+  double* halo_buf = nullptr;   // [2][nsend] receive buffers (ping-pong by evaluation parity) | flags[npeers]
+  unsigned* halo_flags = nullptr;
+  size_t halo_nsend = 0;
+  uint32_t halo_epoch = 0;
+  double* q_recv_eval = nullptr;
+  struct PeerMap { double* base = nullptr; int64_t remote_nsend = 0, remote_off = 0; unsigned* flag = nullptr; void* mapped = nullptr; };
+  std::vector<PeerMap> pmap;
+  unsigned** d_flag_ptrs = nullptr;   // device array of the neighbours' flag slots
   // state
   double* qbuf[3] = {nullptr, nullptr, nullptr};
   int cur = 0;
@@ -826,6 +838,10 @@ int fetch_ctl(PdesCtx* ctx) {
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->comm_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->h_ctl->err_code == 4) {
+    set_err(ctx, "halo exchange: a neighbour's face states did not arrive within 120 s");
+    return PDES_ERR_COMM;
+  }
   if (ctx->h_ctl->err_code == 3) {
     set_err(ctx, "k_fused: an element tile waited for face groups that never completed (scheduler time-out)");
     return PDES_ERR_CUDA;
@@ -1053,11 +1069,94 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->discard_records = ctx->pipe ? ctx->pipe_discard : ctx->discard_split;
 }
 
+// One-time set-up of the peer-to-peer halo: every rank exports its receive buffer (CUDA IPC), the handles and the layout of
+// every rank's shared-face list travel by ncclAllGather, each neighbour's buffer is mapped.  All ranks take the same
+// decision (ncclAllReduce of the local outcome): 1 = peer-to-peer, 0 = ncclSend/ncclRecv.
+struct HaloRec {
+  cudaIpcMemHandle_t handle;
+  int64_t nsend;                 // doubles per receive buffer
+  int32_t npeers, ok;
+  int32_t peer_rank[32];
+  int64_t peer_off[32], peer_n[32];   // in faces
+};
+
+int setup_p2p(PdesCtx* ctx) {
+  ctx->p2p = 0;
+  if (!ctx->comm) return PDES_OK;
+  const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
+  const size_t nsend = (size_t)ctx->nS * per_face;
+  const int np = (int)ctx->peers.size();
+  HaloRec mine;
+  memset(&mine, 0, sizeof(mine));
+  bool ok = env_int("PDES_HALO_NCCL", 0) == 0 && np <= 32 && g_nccl.AllGather != nullptr;
+  if (ok) {
+    const size_t bytes = 2 * nsend * sizeof(double) + 256 + 32 * sizeof(unsigned);
+    ok = cudaMalloc((void**)&ctx->halo_buf, bytes) == cudaSuccess && cudaMemset(ctx->halo_buf, 0, bytes) == cudaSuccess;
+    if (ok) {
+      ctx->halo_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->halo_buf) + 2 * nsend * sizeof(double) + 256);
+      ok = cudaIpcGetMemHandle(&mine.handle, ctx->halo_buf) == cudaSuccess;
+    }
+  }
+  cudaGetLastError();
+  mine.nsend = (int64_t)nsend; mine.npeers = np; mine.ok = ok ? 1 : 0;
+  for (int i = 0; i < np && i < 32; ++i) {
+    mine.peer_rank[i] = ctx->peers[i].rank; mine.peer_off[i] = ctx->peers[i].offset; mine.peer_n[i] = ctx->peers[i].nfaces;
+  }
+  // gather every rank's record
+  HaloRec* d_all = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_all, sizeof(HaloRec) * ctx->nranks));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_all + ctx->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->comm_stream));
+  ncclResult_t r = g_nccl.AllGather ? g_nccl.AllGather(d_all + ctx->rank, d_all, sizeof(HaloRec), ncclChar, ctx->comm, ctx->comm_stream)
+                                    : ncclSuccess;
+  if (r != ncclSuccess) { set_err(ctx, "ncclAllGather failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  std::vector<HaloRec> all(ctx->nranks);
+  CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(HaloRec) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  cudaFree(d_all);
+  if (!g_nccl.AllGather) ok = false;
+  ctx->pmap.assign(np, PdesCtx::PeerMap());
+  std::vector<unsigned*> flag_ptrs(np > 0 ? np : 1, nullptr);
+  for (int i = 0; i < np && ok; ++i) {
+    const int rr = ctx->peers[i].rank;
+    if (rr < 0 || rr >= ctx->nranks || !all[rr].ok) { ok = false; break; }
+    const HaloRec& o = all[rr];
+    int slot = -1;
+    for (int k = 0; k < o.npeers; ++k) if (o.peer_rank[k] == ctx->rank) slot = k;
+    if (slot < 0 || o.peer_n[slot] != ctx->peers[i].nfaces) { ok = false; break; }
+    void* mapped = nullptr;
+    if (cudaIpcOpenMemHandle(&mapped, o.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    PdesCtx::PeerMap& m = ctx->pmap[i];
+    m.mapped = mapped; m.base = static_cast<double*>(mapped); m.remote_nsend = o.nsend; m.remote_off = o.peer_off[slot];
+    m.flag = reinterpret_cast<unsigned*>(static_cast<char*>(mapped) + 2 * (size_t)o.nsend * sizeof(double) + 256) + slot;
+    flag_ptrs[i] = m.flag;
+  }
+  // the same decision everywhere
+  int* d_ok = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_ok, sizeof(int)));
+  const int h_ok = ok ? 1 : 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, ctx->comm_stream));
+  r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, ctx->comm, ctx->comm_stream);
+  if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  int all_ok = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->comm_stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  cudaFree(d_ok);
+  if (all_ok) {
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_flag_ptrs, sizeof(unsigned*) * flag_ptrs.size()));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_flag_ptrs, flag_ptrs.data(), sizeof(unsigned*) * flag_ptrs.size(), cudaMemcpyHostToDevice));
+    ctx->halo_nsend = nsend;
+    ctx->p2p = 1;
+  }
+  return PDES_OK;
+}
+
 // startSolutionExchange (Utils/parallel.jl:29-49).  With a communicator the whole shared-face branch runs on the
 // communication stream, concurrently with the interior faces on the compute stream:
 //     comm stream : [q ready] -> k_pack_send -> ncclSend/Recv -> k_face_flux over the shared faces -> [ev_recv]
 // (PDES_COMM_INLINE=1: pack and shared-face flux on the compute stream, as before: 4 small kernels serialised per evaluation)
 int start_exchange(PdesCtx* ctx, const double* q) {
+  // (collective: every rank of the communicator passes here at its first evaluation, shared faces or not)
+  if (ctx->comm && ctx->p2p < 0) { int rc = setup_p2p(ctx); if (rc) return rc; }
   if (ctx->nS == 0) return PDES_OK;
   const bool overlap = ctx->comm && ctx->comm_overlap;
   cudaStream_t ps = overlap ? ctx->comm_stream : ctx->stream;
@@ -1074,6 +1173,29 @@ int start_exchange(PdesCtx* ctx, const double* q) {
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
   }
   const size_t per_face = (size_t)ctx->cfg.nfn * ctx->nd;
+  if (ctx->p2p == 1) {
+    // copy engine -> the neighbour's receive buffer of this evaluation's parity (it consumed that buffer two evaluations
+    // ago: it cannot be more than one evaluation behind, since this rank needed ITS data to finish the previous one),
+    // then the flag; the wait for the neighbours' flags sits right in front of the shared-face kernel
+    const uint32_t ep = ++ctx->halo_epoch;
+    const size_t par = ep & 1u;
+    for (size_t i = 0; i < ctx->peers.size(); ++i) {
+      const Peer& p = ctx->peers[i];
+      const PdesCtx::PeerMap& m = ctx->pmap[i];
+      double* dst = m.base + par * (size_t)m.remote_nsend + (size_t)m.remote_off * per_face;
+      CUDA_TRY(ctx, cudaMemcpyAsync(dst, ctx->q_send + p.offset * per_face, sizeof(double) * p.nfaces * per_face,
+                                    cudaMemcpyDeviceToDevice, ctx->comm_stream));
+    }
+    const int np = (int)ctx->peers.size();
+    k_halo_signal<<<1, 32, 0, ctx->comm_stream>>>(ctx->d_flag_ptrs, np, ep, ctx->ctl);
+    CUDA_TRY(ctx, cudaGetLastError());
+    k_halo_wait<<<1, 32, 0, ctx->comm_stream>>>(ctx->halo_flags, np, ep, ctx->ctl);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    ctx->q_recv_eval = ctx->halo_buf + par * ctx->halo_nsend;
+    if (!overlap) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
+    return PDES_OK;
+  }
   ncclResult_t r = g_nccl.GroupStart();
   for (auto& p : ctx->peers) {
     if (r != ncclSuccess) break;
@@ -1102,7 +1224,8 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   FaceArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
-  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.q_recv = (ctx->comm && ctx->p2p == 1) ? ctx->q_recv_eval : ctx->q_recv;
+  fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.prefetch_ahead = ctx->prefetch_ahead_faces;
@@ -1445,6 +1568,9 @@ void pdes_destroy(PdesCtx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
   for (int i = 0; i < 3; ++i) if (ctx->step_graph[i]) cudaGraphExecDestroy(ctx->step_graph[i]);
+  for (auto& m : ctx->pmap) if (m.mapped) cudaIpcCloseMemHandle(m.mapped);
+  if (ctx->halo_buf) cudaFree(ctx->halo_buf);
+  if (ctx->d_flag_ptrs) cudaFree(ctx->d_flag_ptrs);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,

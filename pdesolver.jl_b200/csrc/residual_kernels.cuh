@@ -1713,6 +1713,39 @@ __global__ void k_pack_send(const __grid_constant__ OpTab<DIM, NN, NFN> op, cons
 }
 
 // second pass of the stage-1 norm: deterministic sum of the per-CTA partials of this rank
+// ---- peer-to-peer halo exchange (pdes_api.cu: start_exchange) -------------------------------------------------------
+// after the copies into the neighbours' receive buffers (same stream): publish "my data of evaluation `epoch` has landed"
+__global__ void k_halo_signal(unsigned* const* peer_flags, int npeers, unsigned epoch, const Ctl* ctl) {
+  if (ctl->stop) return;
+  const int p = threadIdx.x;
+  if (p >= npeers) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p]), "r"(epoch) : "memory");
+}
+// before the shared-face fluxes: every neighbour's data of evaluation `epoch` is in the local receive buffer.  The wait
+// ends when this rank has raised `stop`, and after two minutes (err_code 4) instead of hanging the device for ever.
+__global__ void k_halo_wait(const unsigned* flags, int npeers, unsigned epoch, Ctl* ctl) {
+  const int p = threadIdx.x;
+  if (p >= npeers) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (unsigned it = 0;; ++it) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if ((it & 63u) == 63u) {
+      if (ld_relaxed_u32(&ctl->stop)) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 120000000000ull) {
+        atomicExch(&ctl->err_code, 4);
+        atomicExch(&ctl->stop, 1);
+        break;
+      }
+    }
+    __nanosleep(200);
+  }
+}
+
 __global__ void k_norm_reduce(const double* __restrict__ partials, int n1, double* norm_sq_out, const Ctl* ctl) {
   __shared__ double sh[256];
   if (ctl->stop) return;

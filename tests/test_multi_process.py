@@ -18,11 +18,12 @@ def _free_port():
     return p
 
 
-def _torchrun(mode, nproc, timeout):
+def _torchrun(mode, nproc, timeout, extra_env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "mp_worker.py"), mode]
     env = dict(os.environ, OMP_NUM_THREADS="2")
+    env.update(extra_env or {})
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
@@ -33,10 +34,15 @@ def test_partitioned_oracle_gloo_world2():
 
 
 @pytest.mark.gpu
-def test_nccl_halo_exchange_matches_serial():
+@pytest.mark.parametrize("transport", ["p2p", "nccl", "nccl-inline"])
+def test_nccl_halo_exchange_matches_serial(transport):
+    """P-way result == serial result through the library's own halo exchange: peer-to-peer copies into the neighbour's
+    IPC-mapped receive buffer + flags (default), ncclSend/ncclRecv (PDES_HALO_NCCL=1), and the latter with pack and
+    shared-face flux on the compute stream (PDES_COMM_INLINE=1)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    out = _torchrun("nccl-b200", 2 if n < 4 else 4, 600)
+    env = {"p2p": {}, "nccl": {"PDES_HALO_NCCL": "1"}, "nccl-inline": {"PDES_HALO_NCCL": "1", "PDES_COMM_INLINE": "1"}}[transport]
+    out = _torchrun("nccl-b200", 2 if n < 4 else 4, 600, env)
     assert "nccl-b200 ok" in out
