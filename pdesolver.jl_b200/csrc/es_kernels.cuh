@@ -97,7 +97,7 @@ k_face_flux_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const __grid
 template <int DIM, int NN, int NFN>
 __global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> op, const double* __restrict__ q,
                                    const int32_t* __restrict__ sh_el, const uint8_t* __restrict__ sh_face, int64_t nS,
-                                   double* __restrict__ q_send, const Ctl* ctl) {
+                                   double* __restrict__ q_send, double* const* __restrict__ face_dst, const Ctl* ctl) {
   constexpr int ND = DIM + 2;
   if (ctl->stop) return;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,9 @@ __global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> 
   int k = (int)(t % ND);
   int i = (int)((t / ND) % NFN);
   int64_t j = t / (ND * NFN);
-  q_send[t] = q[((int64_t)sh_el[j] * NN + op.perm[sh_face[j]][i]) * ND + k];
+  const double v = q[((int64_t)sh_el[j] * NN + op.perm[sh_face[j]][i]) * ND + k];
+  if (face_dst) face_dst[j][i * ND + k] = v;      // peer-to-peer halo: straight into the neighbour's receive buffer
+  else q_send[t] = v;
 }
 
 

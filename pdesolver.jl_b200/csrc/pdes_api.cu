@@ -97,7 +97,7 @@ struct Ops {
   virtual cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) = 0;
   virtual cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) = 0;
   virtual cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS,
-                                  double* q_send, const Ctl* ctl, cudaStream_t s) = 0;
+                                  double* q_send, double* const* face_dst, const Ctl* ctl, cudaStream_t s) = 0;
   virtual int64_t grid_for(int64_t nelems) const = 0;
   virtual int resident_element_ctas() = 0;   // CTAs of k_element_rk the device holds at once
   virtual int resident_face_ctas() = 0;
@@ -354,10 +354,10 @@ struct OpsImpl : Ops {
     return cudaGetLastError();
   }
   cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
-                          const Ctl* ctl, cudaStream_t s) override {
+                          double* const* face_dst, const Ctl* ctl, cudaStream_t s) override {
     if (nS <= 0) return cudaSuccess;
     int64_t n = nS * NFN * (DIM + 2);
-    k_pack_send<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, ctl);
+    k_pack_send<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, face_dst, ctl);
     return cudaGetLastError();
   }
   cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) override {
@@ -482,10 +482,10 @@ struct OpsImplS : Ops {
     return cudaGetLastError();
   }
   cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
-                          const Ctl* ctl, cudaStream_t s) override {
+                          double* const* face_dst, const Ctl* ctl, cudaStream_t s) override {
     if (nS <= 0) return cudaSuccess;
     int64_t n = nS * NFN * (DIM + 2);
-    k_pack_send_sparse<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, ctl);
+    k_pack_send_sparse<DIM, NN, NFN><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, face_dst, ctl);
     return cudaGetLastError();
   }
 };
@@ -616,7 +616,8 @@ struct OpsImplE : Ops {
     else k_element_split<DIM, NN, NFN, E, EPI_RK, true><<<grid, block, Cfg::smem_bytes, s>>>(tabs, a);
     return cudaGetLastError();
   }
-  cudaError_t launch_pack(const double*, const int32_t*, const uint8_t*, int64_t nS, double*, const Ctl*, cudaStream_t) override {
+  cudaError_t launch_pack(const double*, const int32_t*, const uint8_t*, int64_t nS, double*, double* const*, const Ctl*,
+                          cudaStream_t) override {
     return nS <= 0 ? cudaSuccess : cudaErrorNotSupported;
   }
 };
@@ -727,6 +728,7 @@ struct PdesCtx {
   struct PeerMap { double* base = nullptr; int64_t remote_nsend = 0, remote_off = 0; unsigned* flag = nullptr; void* mapped = nullptr; };
   std::vector<PeerMap> pmap;
   unsigned** d_flag_ptrs = nullptr;   // device array of the neighbours' flag slots
+  double** d_face_dst = nullptr;      // [2][nS] per shared face: its slot in the neighbour's receive buffer
   // state
   double* qbuf[3] = {nullptr, nullptr, nullptr};
   int cur = 0;
@@ -1146,6 +1148,19 @@ int setup_p2p(PdesCtx* ctx) {
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_flag_ptrs, flag_ptrs.data(), sizeof(unsigned*) * flag_ptrs.size(), cudaMemcpyHostToDevice));
     ctx->halo_nsend = nsend;
     ctx->p2p = 1;
+    if (env_int("PDES_HALO_COPY", 0) == 0 && ctx->nS > 0) {
+      // per shared face and evaluation parity: its slot in the neighbour's receive buffer (k_pack_send stores there)
+      std::vector<double*> dst(2 * (size_t)ctx->nS, nullptr);
+      for (int par = 0; par < 2; ++par)
+        for (int i = 0; i < np; ++i) {
+          const Peer& p = ctx->peers[i];
+          const PdesCtx::PeerMap& m = ctx->pmap[i];
+          for (int64_t j = 0; j < p.nfaces; ++j)
+            dst[(size_t)par * ctx->nS + p.offset + j] = m.base + (size_t)par * m.remote_nsend + (size_t)(m.remote_off + j) * per_face;
+        }
+      CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_face_dst, sizeof(double*) * dst.size()));
+      CUDA_TRY(ctx, cudaMemcpy(ctx->d_face_dst, dst.data(), sizeof(double*) * dst.size(), cudaMemcpyHostToDevice));
+    }
   }
   return PDES_OK;
 }
@@ -1165,7 +1180,10 @@ int start_exchange(PdesCtx* ctx, const double* q) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_q, 0));
   }
-  CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl, ps));
+  const bool put = ctx->comm && ctx->p2p == 1 && ctx->d_face_dst != nullptr;
+  const uint32_t ep_next = ctx->halo_epoch + 1;
+  CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send,
+                                      put ? ctx->d_face_dst + (size_t)(ep_next & 1u) * ctx->nS : nullptr, ctx->ctl, ps));
   ctx->launches++;
   if (!ctx->comm) return PDES_OK;   // test mode: receive buffer injected by hand
   if (!overlap) {
@@ -1179,7 +1197,7 @@ int start_exchange(PdesCtx* ctx, const double* q) {
     // then the flag; the wait for the neighbours' flags sits right in front of the shared-face kernel
     const uint32_t ep = ++ctx->halo_epoch;
     const size_t par = ep & 1u;
-    for (size_t i = 0; i < ctx->peers.size(); ++i) {
+    for (size_t i = 0; i < ctx->peers.size() && !put; ++i) {      // (PDES_HALO_COPY=1: copy engine instead of remote stores)
       const Peer& p = ctx->peers[i];
       const PdesCtx::PeerMap& m = ctx->pmap[i];
       double* dst = m.base + par * (size_t)m.remote_nsend + (size_t)m.remote_off * per_face;
@@ -1571,6 +1589,7 @@ void pdes_destroy(PdesCtx* ctx) {
   for (auto& m : ctx->pmap) if (m.mapped) cudaIpcCloseMemHandle(m.mapped);
   if (ctx->halo_buf) cudaFree(ctx->halo_buf);
   if (ctx->d_flag_ptrs) cudaFree(ctx->d_flag_ptrs);
+  if (ctx->d_face_dst) cudaFree(ctx->d_face_dst);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
@@ -1788,7 +1807,7 @@ int pdes_pack_send(PdesCtx* ctx, int32_t peer_idx, double* q_send_out) {
   if (rc) return rc;
   if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size()) return usage(ctx, "peer index out of range");
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
-  CUDA_TRY(ctx, ctx->ops->launch_pack(ctx->qbuf[ctx->cur], ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, ctx->ctl,
+  CUDA_TRY(ctx, ctx->ops->launch_pack(ctx->qbuf[ctx->cur], ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, nullptr, ctx->ctl,
                                       ctx->stream));
   ctx->launches++;
   const Peer& p = ctx->peers[peer_idx];

@@ -1697,7 +1697,7 @@ k_element_w(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constan
 template <int DIM, int NN, int NFN>
 __global__ void k_pack_send(const __grid_constant__ OpTab<DIM, NN, NFN> op, const double* __restrict__ q,
                             const int32_t* __restrict__ sh_el, const uint8_t* __restrict__ sh_face, int64_t nS,
-                            double* __restrict__ q_send, const Ctl* ctl) {
+                            double* __restrict__ q_send, double* const* __restrict__ face_dst, const Ctl* ctl) {
   constexpr int ND = DIM + 2;
   if (ctl->stop) return;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1709,7 +1709,10 @@ __global__ void k_pack_send(const __grid_constant__ OpTab<DIM, NN, NFN> op, cons
   int f = sh_face[j];
   double s = 0.0;
   for (int n = 0; n < NN; ++n) s = fma(op.interp[n][i], b[op.perm[f][n] * ND], s);
-  q_send[t] = s;
+  // face_dst (peer-to-peer halo): the face's slot in the NEIGHBOUR's receive buffer -- the interpolated states are
+  // stored straight into peer memory over NVLink, no send buffer and no copy in between
+  if (face_dst) face_dst[j][i * ND + k] = s;
+  else q_send[t] = s;
 }
 
 // second pass of the stage-1 norm: deterministic sum of the per-CTA partials of this rank
