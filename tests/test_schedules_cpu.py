@@ -1,0 +1,54 @@
+"""Host-side checks of two schedules the CUDA kernels rely on (no GPU needed):
+
+* the round-robin pair schedule of k_element_split_r (es_kernels.cuh): nn/2 rounds of disjoint node pairs must cover every
+  pair {i, m} of an element exactly once, for odd and even nn;
+* the RK4 stage update without the running sum of the k's (residual_kernels.cuh, epilogue_tile scheme 2): the regrouped
+  update must equal the reference's x + h/6 (k1 + 2 k2 + 2 k3 + k4) (NonlinearSolvers/rk4.jl:244-319) to rounding."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("nn", [3, 4, 6, 11, 12])
+def test_round_robin_rounds_cover_every_pair_once(nn):
+    seen = {}
+    for k in range(1, nn // 2 + 1):
+        half = nn % 2 == 0 and k == nn // 2
+        senders = set()
+        for i in range(nn):
+            if half and i >= nn // 2:
+                continue
+            m = (i + k) % nn
+            pair = (min(i, m), max(i, m))
+            seen[pair] = seen.get(pair, 0) + 1
+            senders.add(i)
+        # the receiver of round k is node i + k: it reads the slot of node (i' - k) mod nn, which must have evaluated
+        for ip in range(nn):
+            src = (ip - k) % nn
+            assert (src in senders) == (not half or src < nn // 2)
+    assert len(seen) == nn * (nn - 1) // 2 and set(seen.values()) == {1}
+
+
+def test_rk4_without_running_sum_equals_reference_form():
+    rng = np.random.RandomState(3)
+    n = 400
+    A = rng.standard_normal((n, n)) / np.sqrt(n)
+    src = rng.standard_normal(n)            # the tabulated, time-independent source Minv * srcw
+
+    def minv_R(q):                          # Minv * R(q) without the source, as the kernel's accumulator holds it
+        return A @ q + 0.1 * np.sin(q)
+
+    x = rng.standard_normal(n)
+    h = 1e-2
+    # reference form
+    k1 = minv_R(x) + src
+    k2 = minv_R(x + 0.5 * h * k1) + src
+    k3 = minv_R(x + 0.5 * h * k2) + src
+    k4 = minv_R(x + h * k3) + src
+    ref = x + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+    # scheme 2: q2, q3, the one extra vector w', q4, and the final combination (stage 4 reads neither x nor src)
+    q2 = x + 0.5 * h * (minv_R(x) + src)
+    q3 = x + 0.5 * h * (minv_R(q2) + src)
+    w = q2 + 2.0 * q3 - x + 0.5 * h * src
+    q4 = x + h * (minv_R(q3) + src)
+    new = (w + q4) * (1.0 / 3.0) + (h / 6.0) * minv_R(q4)
+    assert np.linalg.norm(new - ref) / np.linalg.norm(ref) < 5e-16 * 10
