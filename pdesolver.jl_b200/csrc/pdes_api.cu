@@ -170,6 +170,7 @@ struct OpsImpl : Ops {
     memset(&tab, 0, sizeof(tab));
     attr_set = false;                       // device copies of the tables are refreshed by the next prepare()
     if (d_ftab) { cudaFree(d_ftab); d_ftab = nullptr; }
+    if (d_qr) { cudaFree(d_qr); d_qr = nullptr; }
     use_tma = env_int("PDES_FACE_TMA", 0) != 0;
     use_warp_kernel = env_int("PDES_ELEM_W", 0) != 0;
     const int ss = c.ss;
@@ -230,7 +231,11 @@ struct OpsImpl : Ops {
   }
   int tma_grid = -1;
   int32_t* d_ftab = nullptr;       // perm | nbrperm
-  ~OpsImpl() override { cudaFree(d_ftab); }
+  // FP64 tensor-core operator products (PDES_MMA=1): the p=2 tet operator with the default tile only
+  static constexpr bool HAS_MMA = DIM == 3 && NN == 11 && E == 32 && MINB_E == 4 && FT == 16 && MINB_F == 8 && WMINB == 4;
+  bool use_mma = false;
+  double* d_qr = nullptr;          // Qt | RfN
+  ~OpsImpl() override { cudaFree(d_ftab); cudaFree(d_qr); }
   cudaError_t launch_faces(const FaceArgs& a_in, cudaStream_t s) override {
     FaceArgs a = a_in;
     a.tab_dev = d_ftab;
@@ -301,6 +306,24 @@ struct OpsImpl : Ops {
       e = cudaMemcpy(d_ftab, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) return e;
     }
+    if constexpr (HAS_MMA) {
+      use_mma = env_int("PDES_MMA", 0) != 0;
+      if (use_mma && !d_qr) {
+        std::vector<double> h((size_t)(DIM * NN + (DIM + 1) * NFN) * NN);
+        memcpy(h.data(), &tab.Qt[0][0], sizeof(double) * DIM * NN * NN);
+        memcpy(h.data() + DIM * NN * NN, &tab.RfN[0][0], sizeof(double) * (DIM + 1) * NFN * NN);
+        e = cudaMalloc((void**)&d_qr, sizeof(double) * h.size());
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(d_qr, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E, false, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E, false, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+        if (e != cudaSuccess) return e;
+      }
+    }
     e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
@@ -346,6 +369,17 @@ struct OpsImpl : Ops {
     }
     if (use_warp_kernel && a.dx_node_stride == 0) return launch_elements_w(a, mode, s);
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if constexpr (HAS_MMA) if (use_mma && d_qr) {
+      // operator products on the FP64 tensor-core path (element_tile<..., MMA>)
+      ElemArgs b = a;
+      b.s2_dev = d_qr;
+      dim3 gridm((unsigned)grid_for(a.nE - a.e_begin)), blockm(Cfg::T);
+      if (mode == EPI_RES)
+        k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E, false, true><<<gridm, blockm, Cfg::smem_bytes, s>>>(tab, b);
+      else
+        k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E, false, true><<<gridm, blockm, Cfg::smem_bytes, s>>>(tab, b);
+      return cudaGetLastError();
+    }
     dim3 grid((unsigned)grid_for(a.nE - a.e_begin)), block(Cfg::T);
     if (mode == EPI_RES)
       k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E><<<grid, block, Cfg::smem_bytes, s>>>(tab, a);

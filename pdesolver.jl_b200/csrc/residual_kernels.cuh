@@ -1038,7 +1038,7 @@ struct TileCfg {
 // tile whose inputs are prefetched into L2 (or < 0); na its size.  COHERENT: the face records were written by other
 // CTAs of the SAME launch (fused kernel): plain loads instead of the read-only path, and the consumed records are
 // dropped from L2 without a write-back (discard.global.L2), since nothing reads them again.
-template <int DIM, int NN, int NFN, int E, int MODE, int TB, bool COHERENT>
+template <int DIM, int NN, int NFN, int E, int MODE, int TB, bool COHERENT, bool MMA = false>
 __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, const ElemArgs& a, unsigned char* smem_raw,
                                              double* s_red, int64_t e0, int ne, int64_t ea, int na, int tid) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
@@ -1161,6 +1161,126 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
     cp_async_commit();
   }
 
+  constexpr bool STAGED = (MODE == EPI_RK);
+  if constexpr (MMA) {
+    // ---- S2 + S3 on the FP64 tensor-core path (mma.sync.m8n8k4.f64): both operator products are small dense GEMMs
+    //   out[(s,k), i] = sum_(d,j) F[(s,k), (d,j)] Qt[(d,j), i]  +  sum_(f,n) rec[(s,k), (f,n)] RfN[(f,n), i]
+    // with M = E*ND rows (8 per tile), N = NN (two 8-column tiles), K = DIM*NN (+ padding) and NF*NFN.  As DFMA they are
+    // 39 % of this kernel's warp instructions (one LDCU per two DFMA); one DMMA does the work of eight DFMA issues.
+    // A fragments come straight from the volume-flux tile / the face records, B fragments (the operator) are held in
+    // registers, the accumulators go to the staging tile in fragment layout.
+    constexpr int K2 = DIM * NN, KS2 = (K2 + 3) / 4, K3 = NF * NFN, KS3 = (K3 + 3) / 4, NT = (NN + 7) / 8;
+    constexpr int MT = (E * ND + 7) / 8, WARPS = T / 32, MPW = (MT + WARPS - 1) / WARPS;
+    const int warp = tid >> 5, lane = tid & 31, gr = lane >> 2, gc = lane & 3;
+    const double* tabQ = a.s2_dev;                 // device copy of Qt [K2][NN] | RfN [K3][NN]
+    const double* tabR = a.s2_dev + K2 * NN;
+    double cfr[MPW][NT][2];
+#pragma unroll
+    for (int m = 0; m < MPW; ++m)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { cfr[m][n][0] = 0.0; cfr[m][n][1] = 0.0; }
+    {
+      double bq[KS2][NT];
+#pragma unroll
+      for (int t = 0; t < KS2; ++t)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const int kr = 4 * t + gc, col = 8 * n + gr;
+          bq[t][n] = (kr < K2 && col < NN) ? __ldg(tabQ + kr * NN + col) : 0.0;
+        }
+#pragma unroll
+      for (int m = 0; m < MPW; ++m) {
+        const int mt = warp + m * WARPS;
+        if (mt < MT) {
+          const int r = mt * 8 + gr;
+          const double* Arow = sF + (r < E * ND ? r : 0) * K2;
+#pragma unroll
+          for (int t = 0; t < KS2; ++t) {
+            const int kc = 4 * t + gc;
+            const double av = kc < K2 ? Arow[kc] : 0.0;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cfr[m][n][0]), "+d"(cfr[m][n][1]) : "d"(av), "d"(bq[t][n]));
+          }
+        }
+      }
+    }
+    if (STAGED) {
+      // the volume-flux tile is dead: its storage receives the epilogue's streams (srcm | x_old | ksum), which are
+      // in flight while the face products run.  The Minv tile (requested before S2) has landed.
+      cp_async_wait<0>();
+      __syncthreads();
+      const unsigned long long pol = policy_evict_first();
+      if (!(PDES_SKEL & 64)) {
+      if (a.scheme == 2) {
+        // rk4 without the running sum (see epilogue_tile): stage 2 re-reads its own input rows (q2: L2 hits, the tile was
+        // loaded by this CTA microseconds ago), stage 4 reads w' and its own input rows (q4) and neither x_old nor srcm
+        if (a.stage < 4) {
+          if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
+          if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);
+          else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
+          if (a.stage == 2) async_tile(sF + 2 * E * EL, a.q + e0 * EL, ne * EL, tid, T);
+        } else {
+          async_tile(sF + E * EL, a.q + e0 * EL, ne * EL, tid, T);
+          async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
+        }
+      } else {
+      if (a.srcm) async_tile_stream(sF, a.srcm + e0 * EL, ne * EL, tid, T, pol);
+      if (a.stage == 1) async_tile(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T);   // x_old == q of this stage
+      else async_tile_stream(sF + E * EL, a.x_old + e0 * EL, ne * EL, tid, T, pol);
+      if (a.stage > 1) async_tile_stream(sF + 2 * E * EL, a.ksum + e0 * EL, ne * EL, tid, T, pol);
+      }
+      }
+      cp_async_commit();
+    }
+    {
+      double br[KS3][NT];
+#pragma unroll
+      for (int t = 0; t < KS3; ++t)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const int kr = 4 * t + gc, col = 8 * n + gr;
+          br[t][n] = (kr < K3 && col < NN) ? __ldg(tabR + kr * NN + col) : 0.0;
+        }
+#pragma unroll
+      for (int m = 0; m < MPW; ++m) {
+        const int mt = warp + m * WARPS;
+        if (mt < MT) {
+          const int r = mt * 8 + gr;
+          const int sr = r / ND, kr_ = r - sr * ND;
+          const bool rok = sr < ne;
+          const double* G = a.fluxe + (e0 + (rok ? sr : 0)) * (NF * FL) + kr_;
+          double av[KS3];
+#pragma unroll
+          for (int t = 0; t < KS3; ++t) {
+            const int kc = 4 * t + gc;
+            av[t] = (rok && kc < K3) ? ldrec(G + kc * ND) : 0.0;
+          }
+#pragma unroll
+          for (int t = 0; t < KS3; ++t)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cfr[m][n][0]), "+d"(cfr[m][n][1]) : "d"(av[t]), "d"(br[t][n]));
+          // accumulator fragment: row gr of the tile, columns 2 gc, 2 gc + 1 of each 8-column tile -> staging tile
+          if (rok) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 8 * n + 2 * gc + h;
+                if (i < NN) {
+                  double v = cfr[m][n][h];
+                  if (MODE == EPI_RK) v *= __ldg(a.minv + (e0 + sr) * NN + i);      // pde_post_func: res_vec *= Minv
+                  sq[sr * SQ + i * ND + kr_] = v;
+                }
+              }
+          }
+        }
+      }
+    }
+  } else {
   // ---- S2 + S3: variable threads -------------------------------------------------------------------
   const int vp = tid / ND, vk = tid - vp * ND;
   const int s0 = vp, s1 = vp + HP;
@@ -1205,7 +1325,6 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
       }
     }
   }
-  constexpr bool STAGED = (MODE == EPI_RK);
   if (STAGED) {
     // the volume-flux tile is dead: its storage receives the epilogue's streams (srcm | x_old | ksum), which are
     // in flight while the face products run.  The Minv tile (requested before S2) has landed.
@@ -1287,6 +1406,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
       for (int u = 0; u < NN; ++u) sq[s1 * SQ + u * ND + vk] = acc1[u];
     }
   }
+  }
   if (STAGED) cp_async_wait<0>();
   __syncthreads();
   if (a.discard_records) {
@@ -1302,7 +1422,7 @@ __device__ __forceinline__ void element_tile(const OpTab<DIM, NN, NFN>& op, cons
   epilogue_tile<NN, ND, E, T, MODE, STAGED, false, (MODE == EPI_RK) && (PDES_OPT & 64) != 0>(a, sq, ne, e0, tid, s_red, sF);
 }
 
-template <int DIM, int NN, int NFN, int E, int MODE, int MINB, bool PIPE = false>
+template <int DIM, int NN, int NFN, int E, int MODE, int MINB, bool PIPE = false, bool MMA = false>
 __global__ void __launch_bounds__((TileCfg<DIM, NN, NFN, E>::T), MINB)
 k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = TileCfg<DIM, NN, NFN, E>;
@@ -1325,7 +1445,7 @@ k_element_rk(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_consta
   int na = 0;
   if (a.prefetch_ahead > 0 && ea < a.nE && ea >= a.e_begin) na = (int)((a.nE - ea) < E ? (a.nE - ea) : E);
   else ea = -1;
-  element_tile<DIM, NN, NFN, E, MODE, Cfg::T, false>(op, a, smem_raw, s_red, e0, ne, ea, na, tid);
+  element_tile<DIM, NN, NFN, E, MODE, Cfg::T, false, MMA>(op, a, smem_raw, s_red, e0, ne, ea, na, tid);
   if (PIPE) {
     __syncthreads();
     if (tid == 0) pipe_release(a.pipe, a.ctl);

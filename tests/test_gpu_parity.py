@@ -607,6 +607,25 @@ def test_round_robin_split_kernel(case, n, monkeypatch):
     assert np.allclose(out["1"][2], out["2"][2], rtol=1e-11, atol=0)
 
 
+def test_dmma_operator_products(monkeypatch):
+    """PDES_MMA=1: the volume and face operator products of k_element_rk as mma.sync.m8n8k4.f64 GEMMs (opt-in, measured
+    slower).  Same parity bar as the DFMA path; the two differ by the summation order inside the tensor-core instruction."""
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PDES_MMA", flag)
+        for n in (5, 3):          # 750 and 162 elements: full tiles and a ragged last tile
+            op, mesh, opts, orc, q0, eqn = setup("c3_3d_p2_roe_src", n, shuffle_seed=9)
+            eqn.q[...] = q0
+            pd.evalResidual(mesh, op, eqn, opts)
+            assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+            res = eqn.res.copy(order="F")
+            pd.rk4(pd.evalResidual, 5e-5, 3e-4, mesh, op, eqn, opts)
+            out[(flag, n)] = (res, eqn.q.copy(order="F"))
+    for n in (5, 3):
+        assert rel_l2(out[("0", n)][0], out[("1", n)][0]) < RES_TOL
+        assert rel_l2(out[("0", n)][1], out[("1", n)][1]) < 1e-13
+
+
 def test_gmres_solves_jacobian_system():
     """pdes_gmres (the linear solve of the matrix-free Newton path, newton_setup.jl:632-662 +
     PETSc GMRES defaults read_input.jl:493-496, 560-570): x must satisfy dR/dq x = b, checked against a dense
