@@ -44,7 +44,7 @@ enum {
   PDES_ERR_COMM = -4
 };
 /* faceElementIntegrals.jl:735-741 FaceElementDict (face_integral_type 2; the Lax-Wendroff kernels are unsupported) */
-enum { PDES_FEI_EC = 1, PDES_FEI_ELF_PENALTY = 2, PDES_FEI_ESLF = 3 };
+enum { PDES_FEI_EC = 1, PDES_FEI_ELF_PENALTY = 2, PDES_FEI_ESLF = 3, PDES_FEI_ELW2_PENALTY = 4, PDES_FEI_ESLW2 = 5 };
 
 
 /* FluxDict names (src/solver/euler/flux.jl) -> ids */

@@ -18,7 +18,8 @@ FLUX_IDS = {"RoeFlux": 1, "IRFlux": 2, "IRSLFFlux": 3, "StandardFlux": 4}
 BC_IDS = {"isentropicVortexBC": 1, "ExpBC": 2, "FreeStreamBC": 3, "noPenetrationBC": 4, "Rho1E2U3BC": 5,
           "allOnesBC": 6, "ZeroFluxBC": 7, "noPenetrationESBC": 8}
 SRC_IDS = {"SRC0": 0, "SRCExp": 1}
-FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3}
+FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3, "ELW2PenaltyFaceIntegral": 4,
+           "ESLW2FaceIntegral": 5}
 
 
 def build(force=False):
@@ -64,6 +65,10 @@ def lib(omp=False):
         L.orc_ir_flux.argtypes = [i, d, p, p, p, i, p]
         L.orc_convert_to_ir.argtypes = [i, d, p, p]
         L.orc_ira0.argtypes = [i, d, p, p]
+        L.orc_evals_x.argtypes = [i, d, p, p]
+        L.orc_evecs_x.argtypes = [i, d, p, p]
+        L.orc_escaling_x.argtypes = [i, d, p, p]
+        L.orc_lw2_entropy_kernel.argtypes = [i, d, p, p, p, p]
         L.orc_lambda_max.restype = d
         L.orc_lambda_max.argtypes = [i, d, p, p]
         L.orc_irslf_flux.argtypes = [i, d, p, p, p, p]

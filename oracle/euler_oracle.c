@@ -38,7 +38,7 @@ enum { ORC_BC_ISENTROPIC_VORTEX = 1, ORC_BC_EXP = 2, ORC_BC_FREESTREAM = 3,
        ORC_BC_NOPENETRATION_ES = 8 };
 enum { ORC_SRC_NONE = 0, ORC_SRC_EXP = 1 };
 /* faceElementIntegrals.jl:735-741 FaceElementDict (the Lax-Wendroff kernels are not restated) */
-enum { ORC_FEI_EC = 1, ORC_FEI_ELF_PENALTY = 2, ORC_FEI_ESLF = 3 };
+enum { ORC_FEI_EC = 1, ORC_FEI_ELF_PENALTY = 2, ORC_FEI_ESLF = 3, ORC_FEI_ELW2_PENALTY = 4, ORC_FEI_ESLW2 = 5 };
 
 typedef struct {
   int32_t dim, nd, nn, nfn, ss, nfaces, norient, sparse_face;
@@ -827,6 +827,131 @@ static void calc_ec_face_integral(const OrcProblem *P, const OrcInterface *f, co
 /* faceElementIntegrals.jl:209-290 calcEntropyPenaltyIntegral (DenseFace) with the LFKernel (:455-468):
  * the entropy variables are interpolated to the face, the penalty lambda_max A0(q_avg) (wL - wR) wface is
  * interpolated back */
+/* ---- eigensystem of the x-direction flux Jacobian and the Lax-Wendroff entropy kernel ---------------------------------
+ * calcEvalsx (eigensystem.jl:301-364), calcEvecsx (:479-615, columns of Y, column-major Y[r + nd*c]), calcEScalingx
+ * (:853-909: A0 = Y diag(S2) Y^T, Merriam's scaling); pinned by test_3d.jl:107-148 / test_lowlevel.jl:440-470
+ * (Y Lambda Y^-1 = dF/dq, Y S2 Y^T = A0, 1e-12). */
+void orc_evals_x(int dim, double gamma, const double *q, double *Lambda) {
+  double gami = gamma - 1.0, t2 = 1.0 / q[0], u = q[1] * t2, ke = 0.0;
+  for (int d = 0; d < dim; ++d) ke += q[1 + d] * q[1 + d] * 0.5;
+  double a = sqrt(gami * t2 * gamma * (q[dim + 1] - t2 * ke));
+  for (int i = 0; i < dim; ++i) Lambda[i] = u;
+  Lambda[dim] = u + a;
+  Lambda[dim + 1] = u - a;
+}
+
+void orc_evecs_x(int dim, double gamma, const double *q, double *Y) {
+  int nd = dim + 2;
+  double gami = gamma - 1.0, q1 = q[0], t2 = 1.0 / q1, ke = 0.0, vsq = 0.0;
+  for (int d = 0; d < dim; ++d) { ke += q[1 + d] * q[1 + d] * 0.5; vsq += q[1 + d] * q[1 + d] * t2 * t2; }
+  double a2 = gami * t2 * gamma * (q[dim + 1] - t2 * ke), a = sqrt(a2), ia = 1.0 / a;
+  double r2 = sqrt(2.0) * 0.5;
+  double c1 = q1 * r2 * ia;                       /* t13 / t15: rho / (sqrt(2) a) */
+  double u = q[1] * t2;
+  double H = (1.0 / gami) * (a2 + gami * vsq * 0.5);   /* t25 / t29 */
+  double ua = q[1] * t2 * a;                      /* t26 / t30 */
+  for (int i = 0; i < nd * nd; ++i) Y[i] = 0.0;
+  /* column 1: entropy wave */
+  Y[0] = 1.0;
+  for (int d = 0; d < dim; ++d) Y[1 + d] = q[1 + d] * t2;
+  Y[dim + 1] = 0.5 * vsq;
+  if (dim == 2) {
+    /* column 2: shear wave */
+    Y[2 + nd * 1] = -q1;
+    Y[3 + nd * 1] = -q[2];
+  } else {
+    Y[3 + nd * 1] = q1;                           /* R[4,2] = q1, R[5,2] = q4 */
+    Y[4 + nd * 1] = q[3];
+    Y[2 + nd * 2] = -q1;                          /* R[3,3] = -q1, R[5,3] = -q3 */
+    Y[4 + nd * 2] = -q[2];
+  }
+  /* acoustic waves */
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    int c = dim + sgn;
+    double s = sgn == 0 ? 1.0 : -1.0;
+    Y[0 + nd * c] = c1;
+    Y[1 + nd * c] = c1 * (u + s * a);
+    for (int d = 1; d < dim; ++d) Y[1 + d + nd * c] = q[1 + d] * r2 * ia;
+    Y[dim + 1 + nd * c] = c1 * (H + s * ua);
+  }
+}
+
+void orc_escaling_x(int dim, double gamma, const double *q, double *S) {
+  double gami = gamma - 1.0, q1 = q[0], t2 = 1.0 / (q1 * q1 * q1), m2 = 0.0;
+  for (int d = 0; d < dim; ++d) m2 += q[1 + d] * q[1 + d];
+  double t = -gami * t2 * (m2 - q1 * q[dim + 1] * 2.0) * 0.5;
+  S[0] = (gami * q1) / gamma;
+  for (int i = 1; i < dim + 2; ++i) S[i] = t;
+}
+
+/* getOrthogonalVector / getBinormalVector / getProjectionMatrix (Utils/projections.jl:25-206): rows 2..dim+1 of P */
+static void projection_rows(int dim, const double *n, double (*Pm)[3]) {
+  const double add_fac = 1e-50;
+  if (dim == 2) {
+    double v1 = 1.0, v2 = -n[0] / (n[1] + add_fac), w1 = -n[1] / (n[0] + add_fac), w2 = 1.0;
+    double fac = rint(fabs(n[1]));   /* Julia round(): ties to even */
+    double t1 = fac * v1 + (1 - fac) * w1, t2 = fac * v2 + (1 - fac) * w2;
+    double len = sqrt(t1 * t1 + t2 * t2);
+    Pm[0][0] = n[0]; Pm[0][1] = n[1]; Pm[0][2] = 0.0;
+    Pm[1][0] = t1 / len; Pm[1][1] = t2 / len; Pm[1][2] = 0.0;
+    return;
+  }
+  double n1 = n[0], n2 = n[1], n3 = n[2];
+  double v1 = 1.0, v2 = 1.0, v3 = -(n1 + n2) / (n3 + add_fac);
+  double w1 = 1.0, w2 = -(n1 + n3) / (n2 + add_fac), w3 = 1.0;
+  double x1 = -(n2 + n3) / (n1 + add_fac), x2 = 1.0, x3 = 1.0;
+  double fac = rint(fabs(n3));
+  double z1 = fac * x1 + (1 - fac) * w1, z2 = fac * x2 + (1 - fac) * w2, z3 = fac * x3 + (1 - fac) * w3;
+  fac = rint(fabs(n1));
+  double t1 = fac * v1 + (1 - fac) * z1, t2 = fac * v2 + (1 - fac) * z2, t3 = fac * v3 + (1 - fac) * z3;
+  double len = sqrt(t1 * t1 + t2 * t2 + t3 * t3);
+  t1 /= len; t2 /= len; t3 /= len;
+  Pm[0][0] = n1; Pm[0][1] = n2; Pm[0][2] = n3;
+  Pm[1][0] = t1; Pm[1][1] = t2; Pm[1][2] = t3;
+  Pm[2][0] = n2 * t3 - n3 * t2; Pm[2][1] = -(n1 * t3 - n3 * t1); Pm[2][2] = n1 * t2 - n2 * t1;
+}
+
+/* applyEntropyKernel(LW2Kernel) (faceElementIntegrals.jl:393-440): P^T Y |Lambda| S2 Y^T P delta_w * |nrm|, the eigensystem
+ * taken in the face-normal direction by rotating q_avg into normal-tangential coordinates */
+void orc_lw2_entropy_kernel(int dim, double gamma, const double *q_avg, const double *delta_w, const double *nrm_in,
+                            double *flux) {
+  int nd = dim + 2;
+  double len_fac = 0.0, n[3] = {0, 0, 0}, Pm[3][3], qp[ORC_MAXD], t1[ORC_MAXD], t2v[ORC_MAXD];
+  double Y[ORC_MAXD * ORC_MAXD], Lambda[ORC_MAXD], S2[ORC_MAXD];
+  for (int d = 0; d < dim; ++d) len_fac += nrm_in[d] * nrm_in[d];
+  len_fac = sqrt(len_fac);
+  for (int d = 0; d < dim; ++d) n[d] = nrm_in[d] / len_fac;
+  projection_rows(dim, n, Pm);
+  /* projectToNT */
+  qp[0] = q_avg[0]; qp[dim + 1] = q_avg[dim + 1];
+  t1[0] = delta_w[0]; t1[dim + 1] = delta_w[dim + 1];
+  for (int r = 0; r < dim; ++r) {
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < dim; ++c) { a += Pm[r][c] * q_avg[1 + c]; b += Pm[r][c] * delta_w[1 + c]; }
+    qp[1 + r] = a; t1[1 + r] = b;
+  }
+  orc_evecs_x(dim, gamma, qp, Y);
+  orc_evals_x(dim, gamma, qp, Lambda);
+  orc_escaling_x(dim, gamma, qp, S2);
+  for (int j = 0; j < nd; ++j) {                    /* smallmatTvec!: Y^T t1 */
+    double s = 0.0;
+    for (int r = 0; r < nd; ++r) s += Y[r + nd * j] * t1[r];
+    t2v[j] = s * (len_fac * fabs(Lambda[j]) * S2[j]);
+  }
+  for (int r = 0; r < nd; ++r) {                    /* smallmatvec!: Y t2 */
+    double s = 0.0;
+    for (int j = 0; j < nd; ++j) s += Y[r + nd * j] * t2v[j];
+    t1[r] = s;
+  }
+  /* projectToXY */
+  flux[0] = t1[0]; flux[dim + 1] = t1[dim + 1];
+  for (int c = 0; c < dim; ++c) {
+    double a = 0.0;
+    for (int r = 0; r < dim; ++r) a += Pm[r][c] * t1[1 + r];
+    flux[1 + c] = a;
+  }
+}
+
 static void calc_entropy_penalty_integral(const OrcProblem *P, const OrcInterface *f, const double *qL,
                                           const double *qR, const double *nrm_face, double *resL, double *resR) {
   int nd = P->nd, dim = P->dim, ss = P->ss, nfn = P->nfn;
@@ -847,13 +972,17 @@ static void calc_entropy_penalty_integral(const OrcProblem *P, const OrcInterfac
     orc_convert_from_ir(dim, P->gamma, wL_i, qL_i);
     orc_convert_from_ir(dim, P->gamma, wR_i, qR_i);
     for (int j = 0; j < nd; ++j) { q_avg[j] = 0.5 * (qL_i[j] + qR_i[j]); delta_w[j] = wL_i[j] - wR_i[j]; }
-    /* applyEntropyKernel(LFKernel): lambda_max * A0 * delta_w */
-    orc_ira0(dim, P->gamma, q_avg, A0);
-    double lambda_max = orc_lambda_max(dim, P->gamma, q_avg, dir);
-    for (int r = 0; r < nd; ++r) {
-      double s = 0.0;
-      for (int c = 0; c < nd; ++c) s += A0[r + nd * c] * delta_w[c];
-      flux[r] = s * lambda_max;
+    if (P->face_element_id == ORC_FEI_ELW2_PENALTY || P->face_element_id == ORC_FEI_ESLW2) {
+      orc_lw2_entropy_kernel(dim, P->gamma, q_avg, delta_w, dir, flux);
+    } else {
+      /* applyEntropyKernel(LFKernel): lambda_max * A0 * delta_w */
+      orc_ira0(dim, P->gamma, q_avg, A0);
+      double lambda_max = orc_lambda_max(dim, P->gamma, q_avg, dir);
+      for (int r = 0; r < nd; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < nd; ++c) s += A0[r + nd * c] * delta_w[c];
+        flux[r] = s * lambda_max;
+      }
     }
     for (int j = 0; j < nd; ++j) flux[j] *= P->wface[i];
     for (int j = 0; j < ss; ++j) {
@@ -875,9 +1004,10 @@ static void face_element_integrals(const OrcProblem *P, const double *q, double 
     const double *qL = q + (int64_t)nd * nn * f->elementL, *qR = q + (int64_t)nd * nn * f->elementR;
     double *resL = res + (int64_t)nd * nn * f->elementL, *resR = res + (int64_t)nd * nn * f->elementR;
     const double *nrm = P->nrm_face + (int64_t)dim * nfn * i;
-    if (P->face_element_id == ORC_FEI_EC || P->face_element_id == ORC_FEI_ESLF)
+    if (P->face_element_id == ORC_FEI_EC || P->face_element_id == ORC_FEI_ESLF || P->face_element_id == ORC_FEI_ESLW2)
       calc_ec_face_integral(P, f, qL, qR, nrm, resL, resR);
-    if (P->face_element_id == ORC_FEI_ELF_PENALTY || P->face_element_id == ORC_FEI_ESLF)
+    if (P->face_element_id == ORC_FEI_ELF_PENALTY || P->face_element_id == ORC_FEI_ESLF ||
+        P->face_element_id == ORC_FEI_ELW2_PENALTY || P->face_element_id == ORC_FEI_ESLW2)
       calc_entropy_penalty_integral(P, f, qL, qR, nrm, resL, resR);
   }
 }

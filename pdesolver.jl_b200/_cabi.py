@@ -25,7 +25,8 @@ FLUX_IDS = {"RoeFlux": 1, "IRFlux": 2, "IRSLFFlux": 3, "StandardFlux": 4}
 BC_IDS = {"isentropicVortexBC": 1, "ExpBC": 2, "FreeStreamBC": 3, "noPenetrationBC": 4, "Rho1E2U3BC": 5,
           "allOnesBC": 6, "ZeroFluxBC": 7, "noPenetrationESBC": 8}
 SRC_IDS = {"SRC0": 0, "SRCExp": 1}
-FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3}
+FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral": 3, "ELW2PenaltyFaceIntegral": 4,
+           "ESLW2FaceIntegral": 5}
 
 EXPORTS = [
     "pdes_create", "pdes_destroy", "pdes_last_error", "pdes_last_error_location",

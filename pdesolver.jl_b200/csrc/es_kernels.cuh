@@ -123,7 +123,7 @@ __global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> 
 // One CTA per face.  The result is one record per (element, local face) holding the contribution to EVERY volume node
 // of the element ([nd, nn], element node order), which k_element_split<..., DENSEREC> adds: atomic-free, deterministic.
 // ------------------------------------------------------------------------------------------------------
-enum FaceElementId { FEI_EC = 1, FEI_ELF_PENALTY = 2, FEI_ESLF = 3 };
+enum FaceElementId { FEI_EC = 1, FEI_ELF_PENALTY = 2, FEI_ESLF = 3, FEI_ELW2_PENALTY = 4, FEI_ESLW2 = 5 };
 
 template <int DIM, int NN, int NFN>
 __global__ void __launch_bounds__(128)
@@ -209,7 +209,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
     }
     __syncthreads();
   } else {
-    if (fei == FEI_EC || fei == FEI_ESLF) {
+    if (fei == FEI_EC || fei == FEI_ESLF || fei == FEI_ESLW2) {
       for (int idx = tid; idx < 2 * NN; idx += T) sZ[idx / NN][idx % NN] = ir_node<DIM>(sq[idx / NN][idx % NN], a.ph.gamma - 1.0);
       __syncthreads();
       for (int pr = tid; pr < NN * NN; pr += T) {
@@ -244,7 +244,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
       }
       __syncthreads();
     }
-    if (fei == FEI_ELF_PENALTY || fei == FEI_ESLF) {
+    if (fei != FEI_EC) {      // ELF / ELW2 penalty, alone or on top of the entropy-conservative integral
       for (int idx = tid; idx < 2 * NN; idx += T) convert_to_ir<DIM>(sq[idx / NN][idx % NN], a.ph.gamma, sw[idx / NN][idx % NN]);
       __syncthreads();
       // entropy variables interpolated to the face nodes: one thread per (side, face node, variable) ...
@@ -275,7 +275,8 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
         for (int p = 0; p < ND; ++p) { qa[p] = 0.5 * (sQf[0][k][p] + sQf[1][k][p]); dw[p] = sWf[0][k][p] - sWf[1][k][p]; }
 #pragma unroll
         for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(a.nrm + g * a.nrm_face_stride + k * a.nrm_node_stride + d);
-        lf_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
+        if (fei == FEI_ELW2_PENALTY || fei == FEI_ESLW2) lw2_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
+        else lf_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
 #pragma unroll
         for (int p = 0; p < ND; ++p) spen[k][p] = fl[p] * swf[k];
       }

@@ -386,6 +386,121 @@ __device__ __forceinline__ void lf_entropy_kernel(const double* qa, const double
   for (int i = 0; i < DIM + 2; ++i) out[i] *= lambda_max;
 }
 
+// applyEntropyKernel(LW2Kernel) (faceElementIntegrals.jl:393-440): |n| P^T Y |Lambda| S2 Y^T P delta_w with the
+// eigensystem of the x-direction flux Jacobian at q_avg rotated into normal-tangential coordinates: getProjectionMatrix /
+// getOrthogonalVector / getBinormalVector / projectToNT / projectToXY (Utils/projections.jl:25-375), calcEvecsx / calcEvalsx
+// / calcEScalingx (eigensystem.jl:301-364, 479-615, 853-909).  Column c of Y is applied on the fly (no matrix stored).
+template <int DIM>
+__device__ __forceinline__ void lw2_entropy_kernel(const double* qa, const double* dw, const double* nrm_in, double gamma,
+                                                   double* out) {
+  constexpr int ND = DIM + 2;
+  const double gami = gamma - 1.0;
+  double len_fac = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) len_fac += nrm_in[d] * nrm_in[d];
+  len_fac = sqrt(len_fac);
+  double n[3] = {0.0, 0.0, 0.0}, Pm[DIM][DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) n[d] = nrm_in[d] / len_fac;
+  const double add_fac = 1e-50;
+  if (DIM == 2) {
+    const double v1 = 1.0, v2 = -n[0] / (n[1] + add_fac), w1 = -n[1] / (n[0] + add_fac), w2 = 1.0;
+    const double fac = rint(fabs(n[1]));
+    double t1 = fac * v1 + (1 - fac) * w1, t2 = fac * v2 + (1 - fac) * w2;
+    const double len = sqrt(t1 * t1 + t2 * t2);
+    Pm[0][0] = n[0]; Pm[0][1] = n[1];
+    Pm[1][0] = t1 / len; Pm[1][1] = t2 / len;
+  } else {
+    const double n1 = n[0], n2 = n[1], n3 = n[2];
+    const double v3 = -(n1 + n2) / (n3 + add_fac), w2 = -(n1 + n3) / (n2 + add_fac), x1 = -(n2 + n3) / (n1 + add_fac);
+    double fac = rint(fabs(n3));
+    const double z1 = fac * x1 + (1 - fac) * 1.0, z2 = fac * 1.0 + (1 - fac) * w2, z3 = fac * 1.0 + (1 - fac) * 1.0;
+    fac = rint(fabs(n1));
+    double t1 = fac * 1.0 + (1 - fac) * z1, t2 = fac * 1.0 + (1 - fac) * z2, t3 = fac * v3 + (1 - fac) * z3;
+    const double len = sqrt(t1 * t1 + t2 * t2 + t3 * t3);
+    t1 /= len; t2 /= len; t3 /= len;
+    Pm[0][0] = n1; Pm[0][1] = n2; Pm[0][DIM - 1] = n3;
+    Pm[1][0] = t1; Pm[1][1] = t2; Pm[1][DIM - 1] = t3;
+    Pm[DIM - 1][0] = n2 * t3 - n3 * t2; Pm[DIM - 1][1] = -(n1 * t3 - n3 * t1); Pm[DIM - 1][DIM - 1] = n1 * t2 - n2 * t1;
+  }
+  // projectToNT
+  double q[ND], t1v[ND];
+  q[0] = qa[0]; q[DIM + 1] = qa[DIM + 1];
+  t1v[0] = dw[0]; t1v[DIM + 1] = dw[DIM + 1];
+#pragma unroll
+  for (int r = 0; r < DIM; ++r) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) { a += Pm[r][c] * qa[1 + c]; b += Pm[r][c] * dw[1 + c]; }
+    q[1 + r] = a; t1v[1 + r] = b;
+  }
+  // eigensystem in the (rotated) x direction
+  const double q1 = q[0], t2 = 1.0 / q1;
+  double ke = 0.0, vsq = 0.0, m2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { ke += q[1 + d] * q[1 + d] * 0.5; vsq += q[1 + d] * q[1 + d] * t2 * t2; m2 += q[1 + d] * q[1 + d]; }
+  const double a2 = gami * t2 * gamma * (q[DIM + 1] - t2 * ke), a = sqrt(a2), ia = 1.0 / a;
+  const double r2 = sqrt(2.0) * 0.5, c1 = q1 * r2 * ia, u = q[1] * t2;
+  const double H = (1.0 / gami) * (a2 + gami * vsq * 0.5), ua = q[1] * t2 * a;
+  double Y[ND][ND];      // Y[r][c]
+#pragma unroll
+  for (int r = 0; r < ND; ++r)
+#pragma unroll
+    for (int c = 0; c < ND; ++c) Y[r][c] = 0.0;
+  Y[0][0] = 1.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) Y[1 + d][0] = q[1 + d] * t2;
+  Y[DIM + 1][0] = 0.5 * vsq;
+  if (DIM == 2) {
+    Y[2][1] = -q1; Y[3][1] = -q[2];
+  } else {
+    Y[3][1] = q1; Y[DIM + 1][1] = q[DIM];
+    Y[2][DIM - 1] = -q1; Y[DIM + 1][DIM - 1] = -q[2];
+  }
+#pragma unroll
+  for (int sg = 0; sg < 2; ++sg) {
+    const int c = DIM + sg;
+    const double s = sg == 0 ? 1.0 : -1.0;
+    Y[0][c] = c1;
+    Y[1][c] = c1 * (u + s * a);
+#pragma unroll
+    for (int d = 1; d < DIM; ++d) Y[1 + d][c] = q[1 + d] * r2 * ia;
+    Y[DIM + 1][c] = c1 * (H + s * ua);
+  }
+  double lam[ND], S2[ND];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) lam[i] = u;
+  lam[DIM] = u + a; lam[DIM + 1] = u - a;
+  S2[0] = (gami * q1) / gamma;
+  const double sc = -gami * (1.0 / (q1 * q1 * q1)) * (m2 - q1 * q[DIM + 1] * 2.0) * 0.5;
+#pragma unroll
+  for (int i = 1; i < ND; ++i) S2[i] = sc;
+  double t2v[ND];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < ND; ++r) s += Y[r][j] * t1v[r];
+    t2v[j] = s * (len_fac * fabs(lam[j]) * S2[j]);
+  }
+#pragma unroll
+  for (int r = 0; r < ND; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) s += Y[r][j] * t2v[j];
+    t1v[r] = s;
+  }
+  // projectToXY
+  out[0] = t1v[0]; out[DIM + 1] = t1v[DIM + 1];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) s += Pm[r][c] * t1v[1 + r];
+    out[1 + c] = s;
+  }
+}
+
 template <int DIM>
 __device__ __forceinline__ void ir_flux_single(const double* qL, const double* qR, const double* n, double gamma, double* F) {
   constexpr int ND = DIM + 2;

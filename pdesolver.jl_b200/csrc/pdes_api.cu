@@ -686,7 +686,7 @@ Ops* make_ops(const PdesConfig& c) {
   if (c.face_integral_type == 2) {
     // entropy-stable scheme on SBP-Omega operators: split-form IR volume flux + face-element integrals with the IR flux
     if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR || c.flux_id != PDES_FLUX_IR) return nullptr;
-    if (c.face_element_id < PDES_FEI_EC || c.face_element_id > PDES_FEI_ESLF) return nullptr;
+    if (c.face_element_id < PDES_FEI_EC || c.face_element_id > PDES_FEI_ESLW2) return nullptr;
     if (c.dim == 2 && c.nn == 3 && c.nfn == 2) return new OpsImplE<2, 3, 2, 32>();
     if (c.dim == 2 && c.nn == 6 && c.nfn == 3) return new OpsImplE<2, 6, 3, 32>();
     if (c.dim == 3 && c.nn == 4 && c.nfn == 3) return new OpsImplE<3, 4, 3, 32>();

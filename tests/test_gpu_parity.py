@@ -759,7 +759,8 @@ ES2 = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_typ
 
 
 @pytest.mark.parametrize("dim,p,n", [(2, 1, 7), (2, 2, 5), (3, 1, 3), (3, 2, 2)])
-@pytest.mark.parametrize("name", ["ECFaceIntegral", "ELFPenaltyFaceIntegral", "ESLFFaceIntegral"])
+@pytest.mark.parametrize("name", ["ECFaceIntegral", "ELFPenaltyFaceIntegral", "ESLFFaceIntegral", "ELW2PenaltyFaceIntegral",
+                                  "ESLW2FaceIntegral"])
 def test_face_element_integrals(dim, p, n, name):
     """face_integral_type = 2 on SBP-Omega operators (getFaceElementIntegral flux.jl:132-160,
     calcECFaceIntegral / calcEntropyPenaltyIntegral faceElementIntegrals.jl:58-117, 209-290) + split-form volume
@@ -774,7 +775,7 @@ def test_face_element_integrals(dim, p, n, name):
     eqn.q[...] = q0
     pd.evalResidual(mesh, op, eqn, opts)
     assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
-    if name == "ESLFFaceIntegral":
+    if name in ("ESLFFaceIntegral", "ESLW2FaceIntegral"):
         h = 1e-3 if dim == 2 else 1e-4
         t = pd.rk4(pd.evalResidual, h, 6 * h, mesh, op, eqn, opts)
         t_ref, q_ref, norms_ref = orc.rk4(q0, h, 6 * h)
@@ -787,8 +788,8 @@ def test_face_element_option_errors():
     mesh = pd.structured_mesh(op, 2)
     with pytest.raises(pd.PDESolverError):          # euler.jl:796 "Unsupported face integral type"
         pd.EulerData(mesh, op, dict(ES2, face_integral_type=3, BC1_name="isentropicVortexBC"))
-    with pytest.raises(pd.PDESolverError):          # the Lax-Wendroff kernels are not implemented
-        pd.EulerData(mesh, op, dict(ES2, FaceElementIntegral_name="ESLW2FaceIntegral", BC1_name="isentropicVortexBC"))
+    with pytest.raises(pd.PDESolverError):          # a functor outside FaceElementDict (faceElementIntegrals.jl:733-741)
+        pd.EulerData(mesh, op, dict(ES2, FaceElementIntegral_name="ELW3PenaltyFaceIntegral", BC1_name="isentropicVortexBC"))
     with pytest.raises(pd.PDESolverError):          # face-element integrals need the two-point IR flux
         pd.EulerData(mesh, op, dict(ES2, Flux_name="RoeFlux", BC1_name="isentropicVortexBC"))
     ope = pd.build_operator(2, 2, "diage")          # diagonal-E keeps face_integral_type 1 (read_input.jl:742-755)

@@ -160,3 +160,108 @@ def test_entropy_conservation_of_the_ec_scheme():
     assert abs(total - bpsi) < 1e-11
     pen = oracle.Problem(mesh, op, es_opts("ELFPenaltyFaceIntegral")).face_integrals(q0)
     assert (w * pen).sum() < -1e-10
+
+
+# --- Lax-Wendroff entropy kernel (ELW2PenaltyFaceIntegral / ESLW2FaceIntegral) ------------------------------------------
+def _jac_x(q, gamma=1.4, h=1e-7):
+    """dF_x/dq by central differences of the oracle's Euler flux (the reference uses the complex step, test_3d.jl:78-104)."""
+    import ctypes as C
+    L = oracle.lib()
+    nd = len(q)
+    dim = nd - 2
+    dirx = np.zeros(dim)
+    dirx[0] = 1.0
+    A = np.zeros((nd, nd))
+    for j in range(nd):
+        fp, fm = np.zeros(nd), np.zeros(nd)
+        dq = np.zeros(nd)
+        dq[j] = h
+        qp, qm = q + dq, q - dq
+        L.orc_euler_flux(dim, gamma, qp.ctypes.data_as(C.c_void_p), dirx.ctypes.data_as(C.c_void_p), fp.ctypes.data_as(C.c_void_p))
+        L.orc_euler_flux(dim, gamma, qm.ctypes.data_as(C.c_void_p), dirx.ctypes.data_as(C.c_void_p), fm.ctypes.data_as(C.c_void_p))
+        A[:, j] = (fp - fm) / (2 * h)
+    return A
+
+
+@pytest.mark.parametrize("q", [[1.0, 0.3, -0.2, 2.0], [1.2, -0.5, 0.1, 3.0], [1.1, 0.3, -0.2, 0.4, 2.5], [0.9, -0.1, 0.6, -0.3, 2.2]])
+def test_eigensystem_identities(q):
+    """test_3d.jl:107-148 / test_lowlevel.jl:440-470: Y Lambda Y^-1 is the flux Jacobian and Y S2 Y^T = A0 = dq/dw."""
+    import ctypes as C
+    L = oracle.lib()
+    q = np.array(q)
+    nd = len(q)
+    dim = nd - 2
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    Y = np.zeros((nd, nd), order="F")
+    lam, S2 = np.zeros(nd), np.zeros(nd)
+    A0 = np.zeros((nd, nd), order="F")
+    L.orc_evecs_x(dim, 1.4, ptr(q), ptr(Y))
+    L.orc_evals_x(dim, 1.4, ptr(q), ptr(lam))
+    L.orc_escaling_x(dim, 1.4, ptr(q), ptr(S2))
+    L.orc_ira0(dim, 1.4, ptr(q), ptr(A0))
+    assert np.allclose(Y @ np.diag(lam) @ np.linalg.inv(Y), _jac_x(q), atol=2e-7)
+    assert np.allclose(Y @ np.diag(S2) @ Y.T, A0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_lw2_kernel_is_rotated_eigen_dissipation(dim):
+    """applyEntropyKernel(LW2Kernel) (faceElementIntegrals.jl:393-440) = |n| Y_n |Lambda_n| S2 Y_n^T dw with the eigensystem
+    of the flux Jacobian in direction n: symmetric positive semi-definite (dw^T flux >= 0), homogeneous of degree 1 in n,
+    bounded by the Lax-Friedrichs kernel (|lambda| <= lambda_max) and equal to the x-direction formula for n = e_x."""
+    import ctypes as C
+    L = oracle.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.RandomState(5)
+    nd = dim + 2
+    q = np.array([1.0, 0.3, -0.2, 2.0] if dim == 2 else [1.1, 0.3, -0.2, 0.4, 2.5])
+    for trial in range(6):
+        n = rng.standard_normal(dim) * 0.7
+        if trial == 0:
+            n = np.eye(dim)[0] * 0.5
+        M = np.zeros((nd, nd))
+        for j in range(nd):
+            e = np.zeros(nd)
+            e[j] = 1.0
+            f = np.zeros(nd)
+            L.orc_lw2_entropy_kernel(dim, 1.4, ptr(q), ptr(e), ptr(n), ptr(f))
+            M[:, j] = f
+        assert np.allclose(M, M.T, atol=1e-12)
+        ev = np.linalg.eigvalsh(0.5 * (M + M.T))
+        assert ev.min() > -1e-12
+        f2 = np.zeros(nd)
+        dw = rng.standard_normal(nd)
+        n2 = 3.0 * n
+        L.orc_lw2_entropy_kernel(dim, 1.4, ptr(q), ptr(dw), ptr(n2), ptr(f2))
+        assert np.allclose(f2, 3.0 * (M @ dw), rtol=1e-12, atol=1e-13)
+        # Lax-Friedrichs bound: lambda_max A0 - M is positive semi-definite
+        A0 = np.zeros((nd, nd), order="F")
+        L.orc_ira0(dim, 1.4, ptr(q), ptr(A0))
+        L.orc_lambda_max.restype = C.c_double
+        lmax = L.orc_lambda_max(dim, 1.4, ptr(q), ptr(n))
+        assert np.linalg.eigvalsh(lmax * A0 - M).min() > -1e-10
+        if trial == 0:
+            Y = np.zeros((nd, nd), order="F")
+            lam, S2 = np.zeros(nd), np.zeros(nd)
+            L.orc_evecs_x(dim, 1.4, ptr(q), ptr(Y))
+            L.orc_evals_x(dim, 1.4, ptr(q), ptr(lam))
+            L.orc_escaling_x(dim, 1.4, ptr(q), ptr(S2))
+            assert np.allclose(M, 0.5 * Y @ np.diag(np.abs(lam) * S2) @ Y.T, atol=1e-12)
+
+
+@pytest.mark.parametrize("dim,p,n", [(2, 1, 3), (2, 2, 2), (3, 1, 2), (3, 2, 1)])
+def test_lw2_penalty_is_conservative_and_dissipative(dim, p, n):
+    """runESTest(..., penalty_lw2) (test_ESS.jl:583-705, 993): the Lax-Wendroff penalty conserves, dissipates entropy and
+    vanishes for a continuous state; ESLW2 = EC + penalty."""
+    op, mesh, q0 = setup(dim, p, n, "ELW2PenaltyFaceIntegral")
+    for i in range(0, mesh.numInterfaces, max(1, mesh.numInterfaces // 9)):
+        res = oracle.Problem(one_interface(mesh, i), op, es_opts("ELW2PenaltyFaceIntegral")).face_integrals(q0)
+        it = mesh.interfaces[i]
+        eL, eR = int(it["elementL"]), int(it["elementR"])
+        assert np.allclose(res[:, :, eL].sum(axis=1), -res[:, :, eR].sum(axis=1), rtol=0, atol=1e-13)
+        ds = (entropy_vars(q0[:, :, eL]) * res[:, :, eL]).sum() + (entropy_vars(q0[:, :, eR]) * res[:, :, eR]).sum()
+        assert ds < -1e-12
+    P = {k: oracle.Problem(mesh, op, es_opts(k)) for k in ("ECFaceIntegral", "ELW2PenaltyFaceIntegral", "ESLW2FaceIntegral")}
+    tot = P["ECFaceIntegral"].face_integrals(q0) + P["ELW2PenaltyFaceIntegral"].face_integrals(q0)
+    assert np.allclose(P["ESLW2FaceIntegral"].face_integrals(q0), tot, rtol=1e-13, atol=1e-14)
+    qc = np.asfortranarray(np.broadcast_to(q0[:, :1, :1], q0.shape))
+    assert np.abs(P["ELW2PenaltyFaceIntegral"].face_integrals(qc)).max() < 1e-13
