@@ -44,7 +44,8 @@ class OrcProblem(C.Structure):
 
 class OrcPeer(C.Structure):
     _fields_ = [("nfaces", C.c_int64), ("bndries_local", C.c_void_p), ("interfaces", C.c_void_p),
-                ("nrm_sharedface", C.c_void_p), ("q_send", C.c_void_p), ("q_recv", C.c_void_p)]
+                ("nrm_sharedface", C.c_void_p), ("q_send", C.c_void_p), ("q_recv", C.c_void_p),
+                ("q_recv_el", C.c_void_p), ("el_offset", C.c_int64)]
 
 
 _libs = {}
@@ -167,6 +168,20 @@ class Problem:
             pr.bndries_local, pr.interfaces = _ptr(keep[f"bl{p}"]), _ptr(keep[f"si{p}"])
             pr.nrm_sharedface = _ptr(keep[f"ns{p}"])
             pr.q_send, pr.q_recv = _ptr(self.q_send[p]), _ptr(self.q_recv[p])
+            pr.q_recv_el, pr.el_offset = None, 0
+        self.q_recv_el = [None] * mesh.npeers
+
+    def set_recv_elements(self, p, q_el):
+        """parallel_data = element: whole remote elements [nd, nn, n_remote] of peer index p, in the order of the remote
+        element numbers (first one = mesh.shared_element_offsets[p]); the receive side of getSendDataElement."""
+        self.q_recv_el[p] = np.asfortranarray(q_el, dtype=np.float64)
+        self.peers[p].q_recv_el = _ptr(self.q_recv_el[p])
+        self.peers[p].el_offset = int(self.mesh.shared_element_offsets[p])
+
+    @staticmethod
+    def get_send_data_element(q, local_elements):
+        """getSendDataElement (Utils/parallel.jl:276-293): send_buff[:, :, j] = q[:, :, local_element_lists[idx][j]]"""
+        return np.asfortranarray(q[:, :, np.asarray(local_elements, dtype=np.int64)])
 
     @property
     def shape(self):

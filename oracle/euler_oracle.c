@@ -62,6 +62,10 @@ typedef struct {               /* one SharedFaceData (Utils/parallel_types.jl:70
   const OrcInterface *interfaces;
   const double *nrm_sharedface; /* [dim,nfn,nfaces] */
   double *q_send, *q_recv;      /* [nd,nfn,nfaces] */
+  /* parallel_data = element (face_integral_type 2): the peer's elements adjacent to this part, whole elements
+   * [nd,nn,n_remote] in the order of the remote element numbers, and the number of the first one (shared_element_offsets) */
+  const double *q_recv_el;
+  int64_t el_offset;
 } OrcPeer;
 
 /* ------------------------------------------------------------------------ */
@@ -996,6 +1000,27 @@ static void calc_entropy_penalty_integral(const OrcProblem *P, const OrcInterfac
 }
 
 /* flux.jl:132-160 getFaceElementIntegral + the functors of faceElementIntegrals.jl:586-655 */
+/* calcSharedFaceElementIntegrals_element_inner (flux.jl:442-496): the face-element integral of a shared face needs every
+ * volume node of the remote element, received whole (getSendDataElement, Utils/parallel.jl:276-293); only elementL is
+ * updated, the remote contribution goes to a throw-away array */
+static void shared_face_element_integrals(const OrcProblem *P, const OrcPeer *peer, const double *q, double *res) {
+  int nd = P->nd, nn = P->nn, dim = P->dim, nfn = P->nfn;
+  double resR[ORC_MAXD * 32];
+  for (int64_t j = 0; j < peer->nfaces; ++j) {
+    const OrcInterface *f = &peer->interfaces[j];
+    const double *qL = q + (int64_t)nd * nn * f->elementL;
+    const double *qR = peer->q_recv_el + (int64_t)nd * nn * (f->elementR - peer->el_offset);
+    double *resL = res + (int64_t)nd * nn * f->elementL;
+    const double *nrm = peer->nrm_sharedface + (int64_t)dim * nfn * j;
+    for (int k = 0; k < nd * nn; ++k) resR[k] = 0.0;
+    if (P->face_element_id == ORC_FEI_EC || P->face_element_id == ORC_FEI_ESLF || P->face_element_id == ORC_FEI_ESLW2)
+      calc_ec_face_integral(P, f, qL, qR, nrm, resL, resR);
+    if (P->face_element_id == ORC_FEI_ELF_PENALTY || P->face_element_id == ORC_FEI_ESLF ||
+        P->face_element_id == ORC_FEI_ELW2_PENALTY || P->face_element_id == ORC_FEI_ESLW2)
+      calc_entropy_penalty_integral(P, f, qL, qR, nrm, resL, resR);
+  }
+}
+
 static void face_element_integrals(const OrcProblem *P, const double *q, double *res) {
   int nd = P->nd, nn = P->nn, dim = P->dim, nfn = P->nfn;
   if (P->ss > 32) { fprintf(stderr, "oracle: stencil too large\n"); abort(); }
@@ -1090,12 +1115,18 @@ int orc_eval_residual(const OrcProblem *P, const double *q, double *res, double 
   boundary_integrate(P, W.bndryflux, res);
   /* evalFaceIntegrals euler.jl:770-802 */
   if (P->face_element_id) {                              /* face_integral_type == 2 (euler.jl:783-793) */
-    if (npeers) { fprintf(stderr, "oracle: face-element integrals on partitioned meshes are not restated\n"); abort(); }
     face_element_integrals(P, q, res);
   } else if (precompute) interior_face_integrate(P, W.flux_face, res);
   else calc_face_integral_nopre(P, q, res);
   /* evalSharedFaceIntegrals euler.jl:843-867 */
-  for (int p = 0; p < npeers; ++p) shared_face_integrals(P, &peers[p], res);
+  for (int p = 0; p < npeers; ++p) {
+    if (P->face_element_id) {
+      if (!peers[p].q_recv_el) { fprintf(stderr, "oracle: face_integral_type 2 needs parallel_data = element\n"); abort(); }
+      shared_face_element_integrals(P, &peers[p], q, res);
+    } else {
+      shared_face_integrals(P, &peers[p], res);
+    }
+  }
   /* evalSourceTerm euler.jl:889-901 */
   if (P->src_id == ORC_SRC_EXP) apply_source_term(P, res);
   (void)nfn;

@@ -64,6 +64,7 @@ class Mesh:
     shared_interfaces: list = field(default_factory=list)   # per peer INTERFACE_DTYPE
     nrm_sharedface: list = field(default_factory=list)      # per peer [dim,nfn,nfaces]
     shared_element_offsets: list = field(default_factory=list)
+    remote_global_elnum: list = field(default_factory=list)  # per peer: global numbers of its elements in this part's halo
     global_elnum: np.ndarray = None                         # local -> global element id
     elem_vtx_coords: np.ndarray = None                      # [nE, dim+1, dim]
 
@@ -252,6 +253,9 @@ def _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of):
             mesh.shared_interfaces.append(si)
             mesh.nrm_sharedface.append(face_normals(sl[m][o2], sfl[m][o2], dxidx_e))
             mesh.shared_element_offsets.append(int(np.nonzero(el_owner == p)[0].min()))
+            # global numbers of the peer's elements in this part's halo, in remote-element order: what the peer's
+            # local_element_lists entry for this part must contain (negotiated once at mesh load, as PUMI does)
+            mesh.remote_global_elnum.append(gel[el_owner == p].copy())
     return mesh
 
 

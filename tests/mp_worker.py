@@ -66,6 +66,60 @@ def run_gloo_oracle(rank, world, case="c3_3d_p2_roe_src", n=4):
     assert abs(loc.item() - float(np.sum(rs * Ms * rs))) < 1e-12 * loc.item()
 
 
+def run_gloo_oracle_es2(rank, world, dim=3, p=1, n=3):
+    """face_integral_type = 2 on a partitioned mesh (element-data halo): each rank tells its peers which
+    of their elements it needs (the negotiation PUMI does at mesh load), every rank sends those elements whole
+    (getSendDataElement, Utils/parallel.jl:276-293) and evaluates calcSharedFaceElementIntegrals_element_inner
+    (flux.jl:442-496); the result must equal the serial one."""
+    import torch
+    import torch.distributed as dist
+    import oracle
+    import pdesolver_jl_b200 as pd
+    from common import perturbed, rel_l2
+    op = pd.build_operator(dim, p)
+    parts = PARTS[world][dim]
+    serial = pd.structured_mesh(op, n, shuffle_seed=4)
+    local = pd.structured_mesh(op, n, parts=parts, rank=rank, shuffle_seed=4)
+    ic, bc = ("ICIsentropicVortex", "isentropicVortexBC") if dim == 2 else ("ICExp", "ExpBC")
+    opts = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2, "face_integral_type": 2,
+            "FaceElementIntegral_name": "ESLFFaceIntegral", "BC1_name": bc}
+    orc_s = oracle.Problem(serial, op, opts)
+    q_s = perturbed(orc_s.exact_state(ic), amp=1e-2)
+    pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
+    idx = np.array([pos[int(g)] for g in local.global_elnum])
+    q = np.asfortranarray(q_s[:, :, idx])
+    orc = oracle.Problem(local, op, opts)
+    mine = {int(g): i for i, g in enumerate(local.global_elnum)}
+    # 1. negotiation: the global numbers of the peer's elements in my halo, in my remote-element order
+    want, reqs = {}, []
+    for pi, pr in enumerate(local.peer_parts):
+        ask = torch.from_numpy(np.ascontiguousarray(local.remote_global_elnum[pi], dtype=np.int64))
+        cnt = torch.tensor([len(ask)], dtype=torch.int64)
+        other = torch.zeros(1, dtype=torch.int64)
+        r1, r2 = dist.isend(cnt, dst=pr), dist.irecv(other, src=pr)
+        r1.wait(); r2.wait()
+        want[pi] = torch.zeros(int(other.item()), dtype=torch.int64)
+        reqs += [dist.isend(ask, dst=pr), dist.irecv(want[pi], src=pr)]
+    for r in reqs:
+        r.wait()
+    local_element_lists = {pi: [mine[int(g)] for g in w.numpy()] for pi, w in want.items()}
+    # 2. exchange of whole elements
+    reqs, bufs = [], []
+    for pi, pr in enumerate(local.peer_parts):
+        send = torch.from_numpy(np.ascontiguousarray(orc.get_send_data_element(q, local_element_lists[pi]).ravel(order="F")))
+        nrem = len(local.remote_global_elnum[pi])
+        recv = torch.empty(q.shape[0] * q.shape[1] * nrem, dtype=torch.float64)
+        bufs.append((pi, recv, nrem))
+        reqs += [dist.isend(send, dst=pr), dist.irecv(recv, src=pr)]
+    for r in reqs:
+        r.wait()
+    for pi, recv, nrem in bufs:
+        orc.set_recv_elements(pi, recv.numpy().reshape((q.shape[0], q.shape[1], nrem), order="F"))
+    res = orc.eval_residual(q)
+    err = rel_l2(res, orc_s.eval_residual(q_s)[:, :, idx])
+    assert err < 1e-13, f"rank {rank}: partitioned type-2 oracle != serial oracle ({err:.2e})"
+
+
 def run_nccl_b200(rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -105,6 +159,10 @@ def main():
     if mode == "gloo-oracle":
         dist.init_process_group("gloo")
         run_gloo_oracle(rank, world)
+    elif mode == "gloo-oracle-es2":
+        dist.init_process_group("gloo")
+        run_gloo_oracle_es2(rank, world, dim=3, p=1, n=3)
+        run_gloo_oracle_es2(rank, world, dim=2, p=2, n=4)
     else:
         import torch
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

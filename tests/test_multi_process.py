@@ -33,6 +33,11 @@ def test_partitioned_oracle_gloo_world2():
     _torchrun("gloo-oracle", 2, 300)
 
 
+def test_partitioned_type2_element_halo_gloo_world2():
+    """face_integral_type 2 on a 2-way partition: element-data halo (parallel_data = element) through gloo, oracle only"""
+    _torchrun("gloo-oracle-es2", 2, 300)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["p2p", "nccl", "nccl-inline"])
 def test_nccl_halo_exchange_matches_serial(transport):
