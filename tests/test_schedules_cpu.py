@@ -52,3 +52,37 @@ def test_rk4_without_running_sum_equals_reference_form():
     q4 = x + h * (minv_R(q3) + src)
     new = (w + q4) * (1.0 / 3.0) + (h / 6.0) * minv_R(q4)
     assert np.linalg.norm(new - ref) / np.linalg.norm(ref) < 5e-16 * 10
+
+
+@pytest.mark.parametrize("dim,parts", [(2, (2, 1)), (2, (2, 2)), (2, (4, 2)), (3, (2, 1, 1)), (3, (2, 2, 1)), (3, (2, 2, 2))])
+def test_partition_bookkeeping_is_symmetric(dim, parts):
+    """What the halo transports rely on (pdes_api.cu setup_p2p, ncclSend/ncclRecv pairs, the element-data halo): if rank r
+    lists peer p then p lists r with the same number of shared faces, in the same (global) face order, and the halo element
+    lists a rank asks for are elements its peer owns.  Checked for every partition bench.py uses (2 / 4 / 8 ranks)."""
+    import pdesolver_jl_b200 as pd
+    op = pd.build_operator(dim, 1)
+    nranks = int(np.prod(parts))
+    n = tuple(3 * p for p in parts)
+    meshes = [pd.structured_mesh(op, n, parts=parts, rank=r, shuffle_seed=2) for r in range(nranks)]
+    total = 0
+    for r, m in enumerate(meshes):
+        assert len(set(m.peer_parts)) == len(m.peer_parts) and r not in m.peer_parts
+        for pi, p in enumerate(m.peer_parts):
+            o = meshes[p]
+            assert r in o.peer_parts, f"rank {p} does not list rank {r}"
+            po = o.peer_parts.index(r)
+            assert len(m.bndries_local[pi]) == len(o.bndries_local[po]) > 0
+            # same faces in the same order: the global numbers of (local element, remote element) mirror each other
+            mine_l = m.global_elnum[m.shared_interfaces[pi]["elementL"]]
+            mine_r = m.remote_global_elnum[pi][m.shared_interfaces[pi]["elementR"] - m.shared_element_offsets[pi]]
+            theirs_l = o.global_elnum[o.shared_interfaces[po]["elementL"]]
+            theirs_r = o.remote_global_elnum[po][o.shared_interfaces[po]["elementR"] - o.shared_element_offsets[po]]
+            assert np.array_equal(mine_l, theirs_r) and np.array_equal(mine_r, theirs_l)
+            assert np.array_equal(m.shared_interfaces[pi]["faceL"], o.shared_interfaces[po]["faceR"])
+            assert np.array_equal(m.shared_interfaces[pi]["orient"], o.shared_interfaces[po]["orient"])
+            # shared normals are equal and opposite
+            assert np.allclose(m.nrm_sharedface[pi][:, 0, :], -o.nrm_sharedface[po][:, 0, :], atol=1e-14)
+            assert set(m.remote_global_elnum[pi].tolist()) <= set(o.global_elnum.tolist())
+            total += len(m.bndries_local[pi])
+        assert len(m.peer_parts) <= 32          # HaloRec capacity of the peer-to-peer set-up
+    assert total > 0 and total % 2 == 0
