@@ -122,7 +122,14 @@ int pdes_set_peer(PdesCtx *ctx, int32_t peer_idx, int32_t peer_rank, int64_t nfa
                   const double *nrm_sharedface);
 
 /* Multi-GPU: NCCL communicator from a 128-byte ncclUniqueId the host broadcast
- * (replaces mesh.comm / MPI.Isend/Irecv!, parallel_types.jl:620-684). */
+ * (replaces mesh.comm / MPI.Isend/Irecv!, parallel_types.jl:620-684).
+ * The communicator carries the set-up and the 8-byte norm all-reduce.  The per-
+ * evaluation halo (startSolutionExchange / finishExchangeData, Utils/parallel.jl:
+ * 29-208) goes peer to peer: at the FIRST evaluation after this call -- which is
+ * therefore collective over all ranks -- every rank exports its receive buffer
+ * through CUDA IPC (one process per GPU, same node) and maps its neighbours';
+ * if any mapping fails all ranks fall back to ncclSend/ncclRecv together.  Every
+ * rank must then issue the same sequence of evaluations, as with MPI. */
 int pdes_get_unique_id(uint8_t id_out[128]);
 int pdes_set_comm(PdesCtx *ctx, const uint8_t id[128], int32_t rank, int32_t nranks);
 /* Test hook when no second GPU exists: expose the packed send buffer and
