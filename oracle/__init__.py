@@ -70,6 +70,7 @@ def lib(omp=False):
         L.orc_evecs_x.argtypes = [i, d, p, p]
         L.orc_escaling_x.argtypes = [i, d, p, p]
         L.orc_lw2_entropy_kernel.argtypes = [i, d, p, p, p, p]
+        L.orc_projection_matrix.argtypes = [i, p, p]
         L.orc_lambda_max.restype = d
         L.orc_lambda_max.argtypes = [i, d, p, p]
         L.orc_irslf_flux.argtypes = [i, d, p, p, p, p]

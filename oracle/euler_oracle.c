@@ -915,6 +915,19 @@ static void projection_rows(int dim, const double *n, double (*Pm)[3]) {
   Pm[2][0] = n2 * t3 - n3 * t2; Pm[2][1] = -(n1 * t3 - n3 * t1); Pm[2][2] = n1 * t2 - n2 * t1;
 }
 
+/* getProjectionMatrix (Utils/projections.jl:25-69) as the full [nd x nd] matrix, column-major; pinned by
+ * test/euler/Utils.jl:236-325 (P^T = P^-1, unit tangent orthogonal to the normal, round trip) */
+void orc_projection_matrix(int dim, const double *nrm, double *Pout) {
+  int nd = dim + 2;
+  double Pm[3][3];
+  projection_rows(dim, nrm, Pm);
+  for (int i = 0; i < nd * nd; ++i) Pout[i] = 0.0;
+  Pout[0] = 1.0;
+  Pout[(nd - 1) + nd * (nd - 1)] = 1.0;
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) Pout[(1 + r) + nd * (1 + c)] = Pm[r][c];
+}
+
 /* applyEntropyKernel(LW2Kernel) (faceElementIntegrals.jl:393-440): P^T Y |Lambda| S2 Y^T P delta_w * |nrm|, the eigensystem
  * taken in the face-normal direction by rotating q_avg into normal-tangential coordinates */
 void orc_lw2_entropy_kernel(int dim, double gamma, const double *q_avg, const double *delta_w, const double *nrm_in,

@@ -265,3 +265,29 @@ def test_lw2_penalty_is_conservative_and_dissipative(dim, p, n):
     assert np.allclose(P["ESLW2FaceIntegral"].face_integrals(q0), tot, rtol=1e-13, atol=1e-14)
     qc = np.asfortranarray(np.broadcast_to(q0[:, :1, :1], q0.shape))
     assert np.abs(P["ELW2PenaltyFaceIntegral"].face_integrals(qc)).max() < 1e-13
+
+
+def test_projection_matrix_properties():
+    """test/euler/Utils.jl:236-325 (test_utils_projection): for normals swept over the circle / sphere the projection to
+    normal-tangential coordinates is orthogonal, keeps density and energy, keeps the momentum magnitude, its second row is
+    the normal and the tangent is a unit vector orthogonal to it; projectToXY inverts projectToNT."""
+    import ctypes as C
+    L = oracle.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    q2, q3 = np.array([1.0, 2.0, 3.0, 7.0]), np.array([1.0, 2.0, 3.0, 4.0, 15.0])
+    normals = [(2, np.array([np.cos(t), np.sin(t)])) for t in np.arange(0.0, 2 * np.pi, 0.1)]
+    normals += [(3, np.array([np.sin(t) * np.cos(f), np.sin(t) * np.sin(f), np.cos(t)]))
+                for t in np.arange(0.0, np.pi, 0.1) for f in np.arange(0.0, 2 * np.pi, 0.1)]
+    for dim, n in normals:
+        nd = dim + 2
+        P = np.zeros((nd, nd), order="F")
+        L.orc_projection_matrix(dim, ptr(n), ptr(P))
+        assert np.allclose(P @ P.T, np.eye(nd), atol=1e-12)
+        assert np.allclose(P[1, 1:1 + dim], n, atol=1e-15)
+        t = P[2, 1:1 + dim]
+        assert abs(np.linalg.norm(t) - 1.0) < 1e-12 and abs(t @ n) < 1e-13
+        q = q2 if dim == 2 else q3
+        qp = P @ q
+        assert qp[0] == q[0] and qp[-1] == q[-1]
+        assert abs(np.sum(qp[1:-1] ** 2) - np.sum(q[1:-1] ** 2)) < 1e-12
+        assert np.allclose(P.T @ qp, q, atol=1e-12)
