@@ -566,3 +566,17 @@ def test_rho1e2u3_uniform_state_zero_residual(dim, p):
     q[0], q[dim + 1] = 1.0, 2.0
     q[1:1 + dim] = 0.35355
     assert np.abs(P.eval_residual(q)).max() < 1e-13
+
+
+def test_calc_norm_matches_reference_definition():
+    """test/euler/Utils.jl:111-135 (test_utils_misc): calcNorm(eqn, v) = sqrt(sum v M v) (Utils.jl:427-449), the strong
+    form with Minv in place of M."""
+    import ctypes as C
+    rng = np.random.RandomState(11)
+    M = rng.rand(10) + 0.1
+    data = rng.rand(10)
+    L.orc_calc_norm.restype = C.c_double
+    L.orc_calc_norm.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
+    assert np.isclose(L.orc_calc_norm(10, _ptr(M), _ptr(data)), np.sqrt(np.sum(data * M * data)), rtol=1e-15)
+    Minv = 1.0 / M
+    assert np.isclose(L.orc_calc_norm(10, _ptr(Minv), _ptr(data)), np.sqrt(np.sum(data * Minv * data)), rtol=1e-15)
