@@ -86,3 +86,22 @@ def test_partition_bookkeeping_is_symmetric(dim, parts):
             total += len(m.bndries_local[pi])
         assert len(m.peer_parts) <= 32          # HaloRec capacity of the peer-to-peer set-up
     assert total > 0 and total % 2 == 0
+
+
+def test_documented_switches_exist_in_the_sources():
+    """README.md lists the run-time switches: every PDES_* name it documents must be read somewhere in the library or the
+    Python host, so that the table cannot drift from the code."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    readme = open(os.path.join(root, "README.md")).read()
+    table = readme[readme.index("## Run-time switches"):]
+    names = set(re.findall(r"`(PDES_[A-Z0-9_]+)", table))
+    assert len(names) >= 15
+    src = ""
+    for d in ("pdesolver.jl_b200/csrc", "pdesolver.jl_b200"):
+        for f in os.listdir(os.path.join(root, d)):
+            if f.endswith((".cu", ".cuh", ".py")) or f == "Makefile":
+                src += open(os.path.join(root, d, f)).read()
+    missing = sorted(n for n in names if n not in src)
+    assert not missing, f"documented but not read anywhere: {missing}"
