@@ -112,14 +112,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(wl, rank, nranks):
+def build_problem(wl, rank, nranks, scaling="weak"):
     import pdesolver_jl_b200 as pd
     from pdesolver_jl_b200 import ic
     op = pd.build_operator(wl["dim"], wl["p"], wl.get("kind", "omega"))
     parts = PARTS[nranks][:wl["dim"]]
     if nranks > 1 and wl["dim"] == 2:
         parts = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
-    n = tuple(wl["n"] * p for p in parts)
+    # weak: every rank owns an n^dim block (the box grows); strong: ONE n^dim mesh cut into the blocks (BASELINE.json
+    # configs[3]: the 54^3 x 6-tet, 51.96 M-DOF mesh partitioned 2 / 4 / 8 ways)
+    n = tuple(wl["n"] * p for p in parts) if scaling == "weak" else tuple(wl["n"] for _ in parts)
     # 2D: the reference's benchmark meshes cut every square along the "\\" diagonal (tests/test_smb.py)
     mesh = pd.structured_mesh(op, n, parts=parts, rank=rank, diagonal="\\")
     opts = dict(wl["opts"])
@@ -127,6 +129,31 @@ def build_problem(wl, rank, nranks):
     params = pd.ParamType(opts)
     q0 = perturbed(ic.ICDict[wl["ic"]](mesh.coords, params))
     return pd, op, mesh, opts, q0, parts, n
+
+
+def make_config(args, wl, nranks):
+    """The `config` object of the JSON line: identical in the B200 arm and in the reference arm (no GPU needed)."""
+    import pdesolver_jl_b200 as pd
+    dim = wl["dim"]
+    parts = PARTS[nranks][:dim]
+    if nranks > 1 and dim == 2:
+        parts = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
+    if args.scaling == "strong":
+        cells = [int(wl["n"] // p) for p in parts]
+    else:
+        cells = [int(wl["n"])] * dim
+    op = pd.build_operator(dim, wl["p"], wl.get("kind", "omega"))
+    nel_rank = int(np.prod(cells)) * (2 if dim == 2 else 6)
+    ndof_rank = nel_rank * op.numnodes * (dim + 2)
+    nd, nn = dim + 2, op.numnodes
+    dx_bytes = nel_rank * nn * dim * dim * 8
+    return {"workload": args.workload, "dim": dim, "degree": wl["p"],
+            "operator": "SBPDiagonalE" if wl.get("kind") == "diage" else "SBPOmega",
+            "flux": wl["opts"]["Flux_name"], "cells_per_rank": cells, "partition": list(parts),
+            "elements_per_rank": nel_rank, "dof_total": ndof_rank * nranks,
+            "step": "1 RK4 step = 4 fused residual+stage launches + the stage-1 residual norm", "delta_t": wl["h"],
+            "l2": "working set (4 state vectors + metrics, %.0f MB) exceeds the 126 MB L2; no flush"
+                  % ((4 * ndof_rank * 8 + dx_bytes) / 1e6)}
 
 
 def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
@@ -158,23 +185,121 @@ def cpu_reference_rate(wl, steps, warmup, sample_cells=None):
 
 
 def run_reference(args, wl, rank, nranks):
+    """CPU arm: the reference's algorithm (oracle port: reference-faithful pass structure, OpenMP over elements / faces, all
+    host threads) on this arm's config.  Every one of the K steps is one RK4 step of a bounded sample of the workload: the
+    per-rank mesh when K + W steps of it fit in ~3 minutes, else a smaller mesh of the same kind (said in `sample`)."""
     if rank != 0:
         return
-    # bounded sample: the per-rank mesh of the B200 arm, a few RK4 steps (~7 s each on 8 cores)
-    steps = min(args.steps, 2)
-    rate, spstep, cores, ndof, n = cpu_reference_rate(wl, steps, min(args.warmup, 1))
-    sample = f"{steps} RK4 steps ({4 * steps} evalResidual) of the {n}^{wl['dim']}-cell mesh ({ndof} DOF), OpenMP"
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    wl_s = dict(wl)
+    if args.scaling == "strong":
+        wl_s["n"] = max(4, int(round(wl["n"] / nranks ** (1.0 / wl["dim"]))))
+    # calibrate: one residual evaluation of a small mesh of the same kind -> seconds per DOF-eval
+    rate0, _, _, _, _ = cpu_reference_rate(dict(wl_s, n=min(wl_s.get("cpu_cells", wl_s["n"]), 12 if wl["dim"] == 3 else 120)), 1, 1)
+    nel = (wl_s.get("cpu_cells", wl_s["n"]) ** wl["dim"]) * (2 if wl["dim"] == 2 else 6)
+    import pdesolver_jl_b200 as pd
+    op = pd.build_operator(wl["dim"], wl["p"], wl.get("kind", "omega"))
+    dof = nel * op.numnodes * (wl["dim"] + 2)
+    est = dof * 4 * (steps + warmup) / rate0
+    cells = wl_s.get("cpu_cells", wl_s["n"])
+    if est > 180.0:
+        cells = max(4, int(cells * (180.0 / est) ** (1.0 / wl["dim"])))
+    rate, spstep, cores, ndof, n = cpu_reference_rate(wl_s, steps, warmup, sample_cells=cells)
+    sample = (f"{steps} RK4 steps ({4 * steps} evalResidual) + {warmup} warm-up evaluations of the {n}^{wl['dim']}-cell mesh "
+              f"({ndof} DOF" + ("" if n == wl_s["n"] else f", reduced from {wl_s['n']}^{wl['dim']} to bound the run") + "), OpenMP")
     line = {
         "impl": "reference", "metric": "DOF-residual-evals/sec", "value": rate, "unit": "DOF-evals/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": spstep * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "cells_per_side": n, "dof": ndof,
-                   "note": "CPU port of the reference algorithm (oracle/, Julia reference cannot run here)"},
-        "cpu_baseline": {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spstep * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(args, wl, nranks),
+        "cpu_baseline": {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU port of the reference algorithm (oracle/); the Julia reference cannot run here"},
         "e2e": {"value": rate, "unit": "DOF-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _omp_threads(n):
+    # libgomp reads OMP_NUM_THREADS when liborc_omp.so is first loaded (torchrun exports 1 to its children)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, int(n)))
+
+
+def run_parity(pd, wl, args, eqn, mesh, op, opts, q0, rank, nranks, local_rank):
+    """Untimed value checks against the CPU oracle, on the hardware and through the transport that are benchmarked
+    (tests/test_multi_process.py holds the same checks, but a 1-GPU test box skips them):
+      full_size_rel_l2  one evalResidual of the benchmarked (per-rank) mesh vs the OpenMP oracle; at N > 1 the oracle's
+                        shared-face states travel through a gloo group (the MPI Isend/Irecv of Utils/parallel.jl:82-141)
+      rk4_rel_l2        N = 1: two RK4 steps of the benchmarked mesh; N > 1: ten steps of the small partitioned case
+      halo_rel_l2       N > 1: small partitioned mesh (c3, 4 cells per side) through the library's default halo
+                        transport vs the SERIAL oracle (runtests_parallel2.jl:43-52: serial == parallel)
+    Tolerances: 1e-12 (residual), 1e-10 (trajectory) -- BASELINE.json north_star."""
+    import torch.distributed as dist
+    import oracle
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    cores = os.cpu_count() or 1
+    _omp_threads(cores // max(nranks, 1))
+    out = {}
+    P = oracle.Problem(mesh, op, opts)
+    if nranks > 1:
+        gl = dist.new_group(backend="gloo")
+        import torch
+        P.start_exchange(q0, omp=True)
+        reqs, bufs = [], []
+        for pi, pr in enumerate(mesh.peer_parts):
+            send = torch.from_numpy(np.ascontiguousarray(P.q_send[pi].ravel(order="F")))
+            recv = torch.empty_like(send)
+            bufs.append((pi, recv))
+            reqs.append(dist.isend(send, dst=int(pr), group=gl))
+            reqs.append(dist.irecv(recv, src=int(pr), group=gl))
+        for r in reqs:
+            r.wait()
+        for pi, recv in bufs:
+            P.q_recv[pi][...] = recv.numpy().reshape(P.q_recv[pi].shape, order="F")
+    ref = P.eval_residual(q0, omp=True)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    out["full_size_rel_l2"] = rel(eqn.res, ref)
+    h = wl["h"]
+    if nranks == 1:
+        eqn.q[...] = q0
+        pd.rk4(pd.evalResidual, h, 2 * h, mesh, op, eqn, opts)
+        _, q_ref, norms_ref = P.rk4(q0, h, 2 * h, omp=True)
+        out["rk4_rel_l2"] = rel(eqn.q, q_ref)
+        out["rk4_norm_rel"] = float(np.max(np.abs(eqn.convergence - norms_ref) / norms_ref))
+        out["rk4_steps"] = 2
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mp_worker import serial_and_local
+        case, n = ("c3_3d_p2_roe_src", 4) if wl["dim"] == 3 else ("c1_2d_p1_roe", 8)
+        pd2, op2, opts2, serial, local, orc_s, q_s, idx = serial_and_local(case, n, rank, nranks)
+        ids = [pd.EulerData.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        e2 = pd.EulerData(local, op2, opts2, device=local_rank, comm=(ids[0], rank, nranks))
+        e2.q[...] = q_s[:, :, idx]
+        pd.evalResidual(local, op2, e2, opts2)
+        out["halo_rel_l2"] = rel(e2.res, orc_s.eval_residual(q_s)[:, :, idx])
+        hs = 5e-5 if wl["dim"] == 3 else 1e-3
+        opts2["use_itermax"] = False
+        e2.q[...] = q_s[:, :, idx]
+        pd.rk4(pd.evalResidual, hs, 10 * hs, local, op2, e2, opts2)
+        _, q_ref, norms_ref = orc_s.rk4(q_s, hs, 10 * hs)
+        out["rk4_rel_l2"] = rel(e2.q, q_ref[:, :, idx])
+        # SURVEY Appendix E.2: the parallel norm is reduced twice -> sqrt(P) x the serial norm
+        out["rk4_norm_rel"] = float(np.max(np.abs(e2.convergence / np.sqrt(nranks) - norms_ref) / norms_ref))
+        out["rk4_steps"] = 10
+        out["halo_case"] = f"{case} n={n}, {nranks} parts, default transport"
+        e2.close()
+        dist.barrier()
+        import torch
+        t = torch.tensor([out["full_size_rel_l2"], out["halo_rel_l2"], out["rk4_rel_l2"], out["rk4_norm_rel"]],
+                         device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["full_size_rel_l2"], out["halo_rel_l2"], out["rk4_rel_l2"], out["rk4_norm_rel"] = [float(x) for x in t.tolist()]
+    out["tolerance"] = {"residual": 1e-12, "trajectory": 1e-10}
+    out["ok"] = bool(out["full_size_rel_l2"] < 1e-12 and out.get("halo_rel_l2", 0.0) < 1e-12 and out["rk4_rel_l2"] < 1e-10
+                     and out["rk4_norm_rel"] < 1e-10)
+    return out
 
 
 def main():
@@ -184,11 +309,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_3d_p2_roe", choices=sorted(WORKLOADS))
-    ap.add_argument("--cells", type=int, default=None, help="override per-rank cells per side")
+    ap.add_argument("--cells", type=int, default=None, help="override cells per side (per rank: weak; whole mesh: strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns an n^dim block; strong: one n^dim mesh (default 54^3: configs[3]) cut N ways")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle checks (kernel A/B runs)")
     ap.add_argument("--e2e-rk-steps", type=int, default=10, help="RK4 steps per public rk4() call in the e2e leg")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.scaling == "strong" and args.workload == "c3_3d_p2_roe":
+        wl["n"] = 54
     if args.cells:
         wl["n"] = args.cells
     rank = int(os.environ.get("RANK", "0"))
@@ -209,7 +339,7 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     nranks = world
 
-    pd, op, mesh, opts, q0, parts, ncells = build_problem(wl, rank, nranks)
+    pd, op, mesh, opts, q0, parts, ncells = build_problem(wl, rank, nranks, args.scaling)
     eqn = pd.EulerData(mesh, op, opts, device=local_rank)
     L, ctx = eqn._L, eqn._ctx
     if nranks > 1:
@@ -218,15 +348,26 @@ def main():
         eqn.set_comm(ids[0], rank, nranks)
     h = wl["h"]
     ndof = mesh.numDof
-    eqn.q[...] = q0
-    eqn._check(L.pdes_set_q(ctx, eqn.q.ctypes.data_as(ctypes.c_void_p)))
-    stream = torch.cuda.ExternalStream(L.pdes_stream(ctx), device=torch.device("cuda", local_rank))
 
     def barrier():
         torch.cuda.synchronize()
         if nranks > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity (untimed, before the timed region) -------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = run_parity(pd, wl, args, eqn, mesh, op, opts, q0, rank, nranks, local_rank)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"parity": parity, "error": "GPU result differs from the oracle"}), flush=True)
+            raise SystemExit(3)
+        barrier()
+
+    eqn.q[...] = q0
+    eqn._check(L.pdes_set_q(ctx, eqn.q.ctypes.data_as(ctypes.c_void_p)))
+    stream = torch.cuda.ExternalStream(L.pdes_stream(ctx), device=torch.device("cuda", local_rank))
 
     # ---- device-resident leg: `value` --------------------------------------------------------------
     # the clock sampler (nvidia-smi -lms 50) needs up to a second to emit its first row on a fresh box: start it before the
@@ -264,12 +405,23 @@ def main():
         ndof_total = ndof
     # the timed region may be shorter than the 50 ms sampling period: keep the SAME load running (identical untimed steps,
     # the same count on every rank: `ms` is the all-reduced time) until the sampler has seen it for ~0.4 s, and report the
-    # clocks over [start of the timed region, end of that tail]
+    # clocks over [start of the timed region, end of that tail].  The tail is also timed in blocks of K steps: the median
+    # block is reported next to the contract's single K-step bracket ("median of 5").
     tail_steps = min(max(0, int(np.ceil(400.0 / max(ms / args.steps, 1e-3))) - args.steps), 5000)
-    for _ in range(tail_steps):
+    nblocks = min(5, tail_steps // max(args.steps, 1))
+    block_ms = []
+    for b in range(nblocks):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            eqn._check(L.pdes_rk4_steps_async(ctx, h, 1))
+        e1.record(stream)
+        block_ms.append((e0, e1))
+    for _ in range(tail_steps - nblocks * args.steps):
         eqn._check(L.pdes_rk4_steps_async(ctx, h, 1))
     eqn._check(L.pdes_sync(ctx))
     barrier()
+    block_ms = [a.elapsed_time(b) / args.steps for a, b in block_ms]
     clocks = sampler.stop(t_wall0, max(t_wall1, time.time())) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "timed region + %d identical untimed steps (same kernels, same data)" % tail_steps
@@ -313,8 +465,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # one residual evaluation = k_face_flux + k_element_rk<EPI_RK>: 4 such pairs per step; the two norm kernels (one CTA each)
-    # are inside the bracket, so the per-launch duration is slightly over-estimated
+    # one residual evaluation + RK4 stage = one launch group (face kernel + element kernel): 4 per step.  The stage-1 norm
+    # kernels (k_norm_reduce / k_norm_commit, one CTA each) are inside the bracket: the per-group time is slightly over-estimated
     launch_s = (ms * 1e-3) / (4 * args.steps)
     achieved = b_stage * ndof * 1e-9 / launch_s
     traffic = None
@@ -323,24 +475,25 @@ def main():
         traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
+    cfg = make_config(args, wl, nranks)
+    assert cfg["elements_per_rank"] == mesh.numEl or args.scaling == "strong", (cfg["elements_per_rank"], mesh.numEl)
     line = {
         "metric": "DOF-residual-evals/sec", "value": value, "unit": "DOF-evals/s", "n_gpus": nranks,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "dim": dim, "degree": wl["p"],
-                   "operator": "SBPDiagonalE" if wl.get("kind") == "diage" else "SBPOmega",
-                   "flux": opts["Flux_name"], "cells_per_rank": [int(c // p) for c, p in zip(ncells, parts)],
-                   "partition": list(parts), "elements_per_rank": mesh.numEl, "dof_total": ndof_total,
-                   "step": "1 RK4 step = 4 fused residual+stage launches", "delta_t": h,
-                   "l2": "working set (4 state vectors + metrics, %.0f MB) exceeds the 126 MB L2; no flush"
-                         % ((4 * ndof * 8 + mesh.dxidx.nbytes) / 1e6)},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "DOF-evals/s", "h2d_bytes_per_step": int(ndof * 8),
-                "d2h_bytes_per_step": int(ndof * 8 + S * 8), "rk4_steps_per_call": S, "calls": e2e_calls,
-                "api": "rk4(evalResidual, h, t_max, mesh, sbp, eqn, opts)",
+        "ms_per_step_blocks": {"median": float(np.median(block_ms)) if block_ms else None, "blocks": block_ms,
+                               "note": "blocks of K steps timed after the contract's bracket (same kernels, same data)"},
+        "e2e": {"value": e2e_value, "unit": "DOF-evals/s",
+                "h2d_bytes_per_step": int(ndof * 8 // S), "d2h_bytes_per_step": int((ndof * 8 + S * 8) // S),
+                "h2d_bytes_per_call": int(ndof * 8), "d2h_bytes_per_call": int(ndof * 8 + S * 8),
+                "rk4_steps_per_call": S, "calls": e2e_calls,
+                "api": "rk4(evalResidual, h, t_max, mesh, sbp, eqn, opts): eqn.q up and down once per call of S steps",
                 "evalResidual_call_ms": dt_res * 1e3,
                 "evalResidual_dof_per_s": ndof_total / dt_res},
         "gpu_launches": int(launches),
+        "parity": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "kernel": ("k_face_flux_sparse + k_element_split_r<EPI_RK>" if wl.get("kind") == "diage"
@@ -349,6 +502,7 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
     }
     if nranks == 1 and not args.no_cpu_baseline:
+        _omp_threads(os.cpu_count() or 1)
         rate, spstep, cores, nd_s, n_s = cpu_reference_rate(wl, 1, 0)
         line["cpu_baseline"] = {"value": rate, "unit": "DOF-evals/s", "cores": cores, "kind": "port",
                                 "sample": f"1 RK4 step (4 evalResidual) of the {n_s}^{dim}-cell mesh ({nd_s} DOF), "

@@ -63,7 +63,7 @@ struct NcclApi {
       if (h) break;
     }
     if (!h) { *why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
-#define SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) { *why = std::string("missing symbol ") + name; return false; }
+#define SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) { *why = std::string("missing symbol ") + name; dlclose(h); h = nullptr; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
@@ -1621,6 +1621,19 @@ void pdes_destroy(PdesCtx* ctx) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 3; ++i) if (ctx->step_graph[i]) cudaGraphExecDestroy(ctx->step_graph[i]);
   for (auto& m : ctx->pmap) if (m.mapped) cudaIpcCloseMemHandle(m.mapped);
+  if (ctx->halo_buf && ctx->comm && ctx->p2p == 1 && g_nccl.AllReduce) {
+    // the receive buffer is mapped by the neighbours (CUDA IPC): freeing it while a peer still holds the mapping is
+    // undefined, so every rank closes its imported handles first (above) and the ranks meet here before the export
+    // goes away -- pdes_destroy is collective over the communicator, like the ncclCommDestroy that follows
+    int* d_tok = nullptr;
+    if (cudaMalloc((void**)&d_tok, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(d_tok, 0, sizeof(int), ctx->comm_stream);
+      if (g_nccl.AllReduce(d_tok, d_tok, 1, ncclInt32, ncclSum, ctx->comm, ctx->comm_stream) == ncclSuccess)
+        cudaStreamSynchronize(ctx->comm_stream);
+      cudaFree(d_tok);
+    }
+    cudaGetLastError();
+  }
   if (ctx->halo_buf) cudaFree(ctx->halo_buf);
   if (ctx->d_flag_ptrs) cudaFree(ctx->d_flag_ptrs);
   if (ctx->d_face_dst) cudaFree(ctx->d_face_dst);
@@ -1967,13 +1980,16 @@ int pdes_eval_jvp(PdesCtx* ctx, const double* v, double* out) {
   return PDES_OK;
 }
 
+// every step carries what the reference's rk4 does per step (rk4.jl:244-319, 446-457): four stages AND the stage-1
+// residual norm (k_norm_reduce / k_norm_commit, at N > 1 the 8-byte all-reduce); the norms are not kept (no buffer)
 int pdes_rk4_steps_async(PdesCtx* ctx, double h, int64_t nsteps) {
   if (!ctx) return usage(ctx, "null ctx");
   int rc = finalize(ctx);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  static const bool with_norm = env_int("PDES_STEPS_NO_NORM", 0) == 0;
   for (int64_t i = 0; i < nsteps; ++i) {
-    rc = launch_rk4_step(ctx, h, false, -1.0, 0);
+    rc = launch_rk4_step(ctx, h, with_norm, -1.0, 0);
     if (rc) return rc;
   }
   return PDES_OK;
@@ -2005,7 +2021,7 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
   int64_t full = 0;        // completed full steps
   double t = 0.0;
   int status = PDES_OK;
-  bool stopped_head = false;
+
   const int64_t poll = 32;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
   for (int64_t i = 2; i <= t_steps + 1; ++i) {
@@ -2014,7 +2030,7 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
     rc = head_only ? enqueue_rk4_step(ctx, h, true, res_tol, pseudo, true) : launch_rk4_step(ctx, h, true, res_tol, pseudo);
     if (rc) return rc;
     ++heads;
-    if (head_only) { stopped_head = true; break; }
+    if (head_only) break;
     ++full;
     if ((full % poll) == 0 || i == t_steps + 1) {
       status = fetch_ctl(ctx);
@@ -2026,9 +2042,12 @@ int pdes_rk4(PdesCtx* ctx, double h, double t_max, int64_t itermax, double res_t
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
   ctx->tm.t_timemarch += ms * 1e-3;
-  if (status == PDES_OK && ctx->h_ctl->stop && ctx->h_ctl->converged_step >= 0 && !stopped_head) {
+
+  if (status == PDES_OK && ctx->h_ctl->stop && ctx->h_ctl->converged_step >= 0) {
     // norm < res_tol at step head c: the reference breaks right after stage 1 (rk4.jl:258-267); every later
-    // kernel was a no-op, so the state is x_old + (h/2) k1 in buffer B of that step
+    // kernel was a no-op, so the state is x_old + (h/2) k1 in buffer B of that step.  This also holds when the
+    // itermax head-only exit was enqueued after c (solver/common.jl:543 passes res_tol together with use_itermax):
+    // for c == heads-1 the correction reproduces the head-only bookkeeping.
     const int64_t c = ctx->h_ctl->converged_step;
     heads = c + 1;
     ctx->cur = (int)((cur0 + 2 * c + 1) % 3);

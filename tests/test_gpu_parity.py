@@ -133,6 +133,25 @@ def test_rk4_res_tol_stop():
     assert len(eqn.convergence) == 40
 
 
+def test_rk4_res_tol_with_itermax():
+    # solver/common.jl:543 passes res_tol = opts["res_abstol"] together with use_itermax: the convergence exit at step head c
+    # must win over an itermax head-only exit that the host had already enqueued (c < itermax, no poll in between)
+    op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 8)
+    h = 1e-3
+    _, _, norms = orc.rk4(q0, h, 40 * h)
+    assert norms[5] < norms[4], "the case must have a decreasing norm history"
+    tol = 0.5 * (norms[4] + norms[5])
+    for itermax in (20, 6, 5):           # the convergence at c = 5 precedes / coincides with / follows the itermax exit
+        opts.update({"use_itermax": True, "itermax": itermax})
+        t_ref, q_ref, norms_ref = orc.rk4(q0, h, 1.0, itermax=itermax, res_tol=tol)
+        eqn.q[...] = q0
+        t = pd.rk4(pd.evalResidual, h, 1.0, mesh, op, eqn, opts, res_tol=tol)
+        assert len(eqn.convergence) == len(norms_ref), (itermax, len(eqn.convergence), len(norms_ref))
+        assert abs(t - t_ref) < 1e-15, (itermax, t, t_ref)
+        assert rel_l2(eqn.q, q_ref) < RK_TOL, itermax
+        assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+
+
 def test_negative_density_and_pressure_raise():
     op, mesh, opts, orc, q0, eqn = setup("c1_2d_p1_roe", 6)
     q = q0.copy(order="F")
@@ -404,7 +423,8 @@ def test_against_committed_fixtures(case):
 
 @pytest.mark.parametrize("workload", ["c3", "c1", "c2"])
 def test_full_size_properties(workload):
-    """BASELINE.json's full sizes, where the oracle is too slow to be the checker: size-independent properties.
+    """BASELINE.json's full sizes: size-independent properties (the value check against the OpenMP oracle at these sizes is
+    test_full_size_matches_oracle).
     (1) free-stream preservation: a uniform state gives a zero residual (test_dg.jl:115-128);
     (2) conservation checksum: the sum of the residual over all nodes equals the boundary-flux sum plus the source sum
         (interior face terms cancel pairwise, Q^T 1 = 0), both evaluated independently on the CPU in O(boundary);
@@ -455,6 +475,39 @@ def test_full_size_properties(workload):
         w = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
         Jv, Jw = pd.evaldRdqProduct(mesh, op, eqn, opts, v), pd.evaldRdqProduct(mesh, op, eqn, opts, w)
         assert rel_l2(pd.evaldRdqProduct(mesh, op, eqn, opts, v - 2.0 * w), Jv - 2.0 * Jw) < 1e-12
+
+
+@pytest.mark.parametrize("workload", ["c3", "c2"])
+def test_full_size_matches_oracle(workload):
+    """The BASELINE-size meshes that bench.py times (22,704 / 5,586-CTA grids, the reverse sweep, the L2 discard, 64-bit
+    offsets) against the OpenMP oracle: one evalResidual and two RK4 steps.  C3 = configs[2] (31^3 x 6 tets, 9.83 M DOF);
+    C2 = configs[1] at 1000^2 x 2 triangles (96 M DOF)."""
+    import os
+    from pdesolver_jl_b200 import ic
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    if workload == "c3":
+        op = pd.build_operator(3, 2)
+        n, icn, h, opts = 31, "ICExp", 5e-5, {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}
+        amp = 1e-3
+    else:
+        op = pd.build_operator(2, 2, "diage")
+        n, icn, h, opts = 1000, "ICIsentropicVortex", 2e-5, {"Flux_name": "IRSLFFlux", "Volume_flux_name": "IRFlux",
+                                                              "volume_integral_type": 2, "BC1_name": "isentropicVortexBC"}
+        amp = 1e-2
+    mesh = pd.structured_mesh(op, n, diagonal="\\")
+    q0 = perturbed(ic.ICDict[icn](mesh.coords, pd.ParamType(opts)), amp=amp)
+    orc = oracle.Problem(mesh, op, opts)
+    eqn = pd.EulerData(mesh, op, opts)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0, omp=True)) < RES_TOL
+    opts["use_itermax"] = False
+    eqn.q[...] = q0
+    t = pd.rk4(pd.evalResidual, h, 2 * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 2 * h, omp=True)
+    assert abs(t - t_ref) < 1e-15 and rel_l2(eqn.q, q_ref) < RK_TOL
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+    eqn.close()
 
 
 def test_reference_convergence_golden_gpu():
