@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <timeout_s> <logfile> [--gpus N] -- '<command>'
+# retries while the pod answers busy (exit code 3: nothing charged)
+T=$1; LOG=$2; shift 2
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$T" "$@" > "$LOG" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
