@@ -20,6 +20,7 @@
 
 #include "../../include/pdes_euler_b200.h"
 #include "residual_kernels.cuh"
+#include "element_tma.cuh"
 #include "es_kernels.cuh"
 #include "jvp_kernels.cuh"
 #include "krylov_kernels.cuh"
@@ -85,6 +86,9 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+#ifndef PDES_TMA_NS
+#define PDES_TMA_NS 1       // warps per tile group of k_element_tma (2: measured slower, profiles/r2_d_element_tma_v2.txt)
+#endif
 #ifndef PDES_SPLIT_DEFAULT
 #define PDES_SPLIT_DEFAULT 2     // split-form volume kernel: 0 k_element_split, 1 k_element_split_n, 2 k_element_split_r
 #endif
@@ -130,7 +134,7 @@ struct OpsImpl : Ops {
   int fused_group_faces() const override { return FFT * NSUB; }
   int fused_tile_elems() const override { return E; }
   int pipe_face_tile() const override { return FT; }
-  bool staged_epilogue() const override { return !use_warp_kernel; }
+  bool staged_epilogue() const override { return use_tma_elem || !use_warp_kernel; }
   // chunk pipeline: programmatic stream serialization lets the CTAs of this launch start while the last wave of the
   // previous launch is still running; the kernels synchronise through PipeArgs counters
   template <typename K, typename A>
@@ -165,9 +169,22 @@ struct OpsImpl : Ops {
   Tab tab;
   bool attr_set = false;
   bool use_tma = false;
+  // k_element_tma (default): persistent warp-autonomous bulk-copy pipeline, G elements per warp tile
+  using TabP = OpTabP<DIM, NN, NFN>;
+  using PCfg0 = ElemTmaCfg<DIM, NN, NFN, false>;
+  using PCfg1 = ElemTmaCfg<DIM, NN, NFN, true>;
+  static constexpr int SMEM_MAX = 232448;      // 227 KB: the opt-in dynamic shared memory of an sm_100 CTA
+  static constexpr int NSW = PDES_TMA_NS;                // warps per tile group (they split the output nodes of the operator products)
+  static constexpr int nw_cap(int m) { return m > 15 ? 15 : (m < 1 ? 1 : m); }     // groups per CTA (one named barrier each)
+  static constexpr int NW0 = nw_cap(PCfg0::max_groups(SMEM_MAX)), NW1 = nw_cap(PCfg1::max_groups(SMEM_MAX));
+  TabP tabp;
+  bool use_tma_elem = true;
+  int sm_count = 0;
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
                     const int64_t* nbrperm, const double* wface, int base) override {
     memset(&tab, 0, sizeof(tab));
+    use_tma_elem = env_int("PDES_ELEM_TMA", 1) != 0 && env_int("PDES_FUSED", 0) == 0 && env_int("PDES_PIPE", 0) <= 1 &&
+                   env_int("PDES_ELEM_W", 0) == 0 && env_int("PDES_MMA", 0) == 0;
     attr_set = false;                       // device copies of the tables are refreshed by the next prepare()
     if (d_ftab) { cudaFree(d_ftab); d_ftab = nullptr; }
     if (d_qr) { cudaFree(d_qr); d_qr = nullptr; }
@@ -187,12 +204,33 @@ struct OpsImpl : Ops {
     for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
     for (int o = 0; o < Tab::NOR; ++o)
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
+    memset(&tabp, 0, sizeof(tabp));
+    for (int r = 0; r < DIM * NN; ++r)
+      for (int i = 0; i < NN; ++i) tabp.Qt[r][i] = tab.Qt[r][i];
+    for (int r = 0; r < (DIM + 1) * NFN; ++r)
+      for (int i = 0; i < NN; ++i) tabp.RfN[r][i] = tab.RfN[r][i];
     (void)w;
   }
   int64_t grid_for(int64_t nelems) const override {
+    if (use_tma_elem) return NSW * ((nelems + PCfg0::G - 1) / PCfg0::G);        // one norm partial per warp of a tile group
     return use_warp_kernel ? (nelems + GW - 1) / GW : (nelems + E - 1) / E;     // norm partials per tile / per warp
   }
-  int tile_elems() const override { return use_warp_kernel ? GW * WPC : E; }
+  int tile_elems() const override { return use_tma_elem ? PCfg0::G : (use_warp_kernel ? GW * WPC : E); }
+  template <int MODE, bool DXN, int NW>
+  cudaError_t launch_elements_tma(const ElemArgs& a, cudaStream_t s) {
+    using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
+    const int64_t ntiles = (a.nE - a.e_begin + C::G - 1) / C::G;
+    const int64_t nblk = std::min<int64_t>((ntiles + NW - 1) / NW, (int64_t)sm_count);
+    const size_t smem = 256 + (size_t)NW * C::WS * sizeof(double);
+    k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW><<<dim3((unsigned)nblk), dim3(32 * NW * NSW), smem, s>>>(tabp, a);
+    return cudaGetLastError();
+  }
+  template <int MODE, bool DXN, int NW>
+  cudaError_t prepare_tma() {
+    using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
+    return cudaFuncSetAttribute(k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(256 + (size_t)NW * C::WS * sizeof(double)));
+  }
   int resident_element_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
     cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RK, MINB_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -324,6 +362,16 @@ struct OpsImpl : Ops {
         if (e != cudaSuccess) return e;
       }
     }
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count <= 0) sm_count = 148;
+      if ((e = prepare_tma<EPI_RES, false, NW0>()) != cudaSuccess) return e;
+      if ((e = prepare_tma<EPI_RK, false, NW0>()) != cudaSuccess) return e;
+      if ((e = prepare_tma<EPI_RES, true, NW1>()) != cudaSuccess) return e;
+      if ((e = prepare_tma<EPI_RK, true, NW1>()) != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(k_element_rk<DIM, NN, NFN, E, EPI_RES, MINB_E>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
@@ -369,6 +417,11 @@ struct OpsImpl : Ops {
     }
     if (use_warp_kernel && a.dx_node_stride == 0) return launch_elements_w(a, mode, s);
     if (a.nE <= a.e_begin) return cudaSuccess;
+    if (use_tma_elem) {
+      if (a.dx_node_stride == 0)
+        return mode == EPI_RES ? launch_elements_tma<EPI_RES, false, NW0>(a, s) : launch_elements_tma<EPI_RK, false, NW0>(a, s);
+      return mode == EPI_RES ? launch_elements_tma<EPI_RES, true, NW1>(a, s) : launch_elements_tma<EPI_RK, true, NW1>(a, s);
+    }
     if constexpr (HAS_MMA) if (use_mma && d_qr) {
       // operator products on the FP64 tensor-core path (element_tile<..., MMA>)
       ElemArgs b = a;

@@ -533,6 +533,7 @@ def test_fused_kernel_bitwise_equals_split(case, n, monkeypatch):
     runs the same tile bodies as k_face_flux + k_element_rk: residual and RK4 trajectory must be bit-identical,
     and one evaluation is one launch."""
     out = {}
+    monkeypatch.setenv("PDES_ELEM_TMA", "0")      # the two-launch schedule built from the same tile bodies (k_element_rk)
     for fused in ("0", "1"):
         monkeypatch.setenv("PDES_FUSED", fused)
         op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=11)
@@ -556,6 +557,7 @@ def test_chunk_pipeline_bitwise_equals_split(case, n, chunks, lag, monkeypatch):
     by device counters, consumed records discarded in L2) runs the same tile bodies as the two-launch schedule:
     residual, RK4 trajectory and norms must be bit-identical; one evaluation is 2 * chunks launches."""
     out = {}
+    monkeypatch.setenv("PDES_ELEM_TMA", "0")      # the two-launch schedule built from the same tile bodies (k_element_rk)
     for pipe in ("0", str(chunks)):
         monkeypatch.setenv("PDES_PIPE", pipe)
         monkeypatch.setenv("PDES_PIPE_LAG", str(lag))
@@ -617,6 +619,35 @@ def test_rk4_schedules_agree(case, n, monkeypatch):
     assert np.allclose(out["default"][2], out["ref"][2], rtol=1e-12, atol=0)
     t_ref, q_ref, norms_ref = orc.rk4(q0, h, nsteps * h)
     assert rel_l2(out["default"][1], q_ref) < RK_TOL and rel_l2(out["ref"][1], q_ref) < RK_TOL
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 13), ("2d_p2_roe", 9), ("3d_p1_roe_src", 5), ("c3_3d_p2_roe_src", 7)])
+@pytest.mark.parametrize("nosum", ["1", "0"])
+def test_tma_element_kernel_equals_tile_kernel(case, n, nosum, monkeypatch):
+    """k_element_tma (default: persistent warp-autonomous bulk-copy pipeline, one row per lane, volume flux rebuilt from
+    (q, U_d, p)) against k_element_rk (PDES_ELEM_TMA=0: block-synchronous tiles): the operator products are summed in a
+    different order, so the two agree at rounding level -- residual, both RK4 schemes, lserk54 and the per-step norms.
+    n is chosen so that the last warp tile is ragged (plain loads instead of bulk copies)."""
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("PDES_ELEM_TMA", tma)
+        monkeypatch.setenv("PDES_RK4_NOSUM", nosum)
+        op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=9)
+        opts["use_itermax"] = False
+        eqn.q[...] = q0
+        pd.evalResidual(mesh, op, eqn, opts)
+        res = eqn.res.copy(order="F")
+        pd.rk4(pd.evalResidual, 1e-4, 8e-4, mesh, op, eqn, opts)
+        q_rk, norms = eqn.q.copy(order="F"), np.array(eqn.convergence)
+        eqn.q[...] = q0
+        pd.lserk54(pd.evalResidual, 1e-4, 5e-4, mesh, op, eqn, opts)
+        out[tma] = (res, q_rk, norms, eqn.q.copy(order="F"))
+        if tma == "1":
+            assert rel_l2(res, orc.eval_residual(q0)) < RES_TOL
+    assert rel_l2(out["1"][0], out["0"][0]) < 1e-12
+    assert rel_l2(out["1"][1], out["0"][1]) < 1e-14
+    assert np.allclose(out["1"][2], out["0"][2], rtol=1e-12, atol=0)
+    assert rel_l2(out["1"][3], out["0"][3]) < 1e-14
 
 
 @pytest.mark.parametrize("case,n", [("c2_2d_p2_es", 9), ("2d_p2_es_ir", 7), ("2d_p2_es_roe", 6)])
