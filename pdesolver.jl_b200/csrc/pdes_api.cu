@@ -21,6 +21,7 @@
 #include "../../include/pdes_euler_b200.h"
 #include "residual_kernels.cuh"
 #include "element_tma.cuh"
+#include "face_tma.cuh"
 #include "es_kernels.cuh"
 #include "jvp_kernels.cuh"
 #include "krylov_kernels.cuh"
@@ -178,6 +179,20 @@ struct OpsImpl : Ops {
   static constexpr int nw_cap(int m) { return m > 15 ? 15 : (m < 1 ? 1 : m); }     // groups per CTA (one named barrier each)
   static constexpr int NW0 = nw_cap(PCfg0::max_groups(SMEM_MAX)), NW1 = nw_cap(PCfg1::max_groups(SMEM_MAX));
   TabP tabp;
+  // k_face_tma (default): warp-autonomous face tiles, element blocks staged by bulk copies
+  using TabF = FaceTabP<DIM, NN, NFN>;
+  using FWCfg = FaceTmaWCfg<DIM, NN, NFN>;
+  static constexpr int NWF = FWCfg::max_warps(SMEM_MAX) > 16 ? 16 : FWCfg::max_warps(SMEM_MAX);
+  TabF tabf;
+  bool use_tma_face = true;
+  template <bool EXTBC>
+  cudaError_t launch_faces_tma(const FaceArgs& a, cudaStream_t s) {
+    const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW;
+    const int64_t nblk = std::min<int64_t>((ntiles + NWF - 1) / NWF, (int64_t)sm_count);
+    const size_t smem = 512 + (size_t)NWF * FWCfg::WS * sizeof(double);
+    k_face_tma<DIM, NN, NFN, NWF, EXTBC><<<dim3((unsigned)nblk), dim3(32 * NWF), smem, s>>>(tabf, a);
+    return cudaGetLastError();
+  }
   bool use_tma_elem = true;
   int sm_count = 0;
   void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
@@ -204,6 +219,16 @@ struct OpsImpl : Ops {
     for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
     for (int o = 0; o < Tab::NOR; ++o)
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
+    use_tma_face = env_int("PDES_FACE_WTMA", 1) != 0 && env_int("PDES_FUSED", 0) == 0 && env_int("PDES_PIPE", 0) <= 1 &&
+                   env_int("PDES_FACE_TMA", 0) == 0 && env_int("PDES_FACE_W", 0) == 0 && env_int("PDES_FACE_P", 0) == 0;
+    memset(&tabf, 0, sizeof(tabf));
+    for (int j = 0; j < NN; ++j)
+      for (int i = 0; i < NFN; ++i) tabf.interp[j][i] = tab.interp[j][i];
+    for (int i = 0; i < NFN; ++i) tabf.wface[i] = tab.wface[i];
+    for (int f = 0; f < DIM + 1; ++f)
+      for (int j = 0; j < NN; ++j) tabf.perm_pk[f] |= (unsigned long long)(tab.perm[f][j] & 15) << (4 * j);
+    for (int o = 0; o < Tab::NOR; ++o)
+      for (int i = 0; i < NFN; ++i) tabf.nbr_pk[o] |= (unsigned long long)(tab.nbrperm[o][i] & 15) << (4 * i);
     memset(&tabp, 0, sizeof(tabp));
     for (int r = 0; r < DIM * NN; ++r)
       for (int i = 0; i < NN; ++i) tabp.Qt[r][i] = tab.Qt[r][i];
@@ -283,6 +308,10 @@ struct OpsImpl : Ops {
       return launch_pdl(k_face_flux<DIM, NN, NFN, FT, MINB_F, false, true>, dim3((unsigned)nt), dim3(FCfg::T), 0, s, tab, a);
     }
     if (a.ng <= 0) return cudaSuccess;
+    if (use_tma_face) {
+      { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+      return a.ext_bc ? launch_faces_tma<true>(a, s) : launch_faces_tma<false>(a, s);
+    }
     const int64_t ntiles = (a.ng + FT - 1) / FT;
     if (a.ext_bc) {
       // a boundary functor outside the four scoped ones is in use: the instantiation with the extended dispatch
@@ -367,6 +396,11 @@ struct OpsImpl : Ops {
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       if (sm_count <= 0) sm_count = 148;
+      {
+        const int fsm = (int)(512 + (size_t)NWF * FWCfg::WS * sizeof(double));
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+      }
       if ((e = prepare_tma<EPI_RES, false, NW0>()) != cudaSuccess) return e;
       if ((e = prepare_tma<EPI_RK, false, NW0>()) != cudaSuccess) return e;
       if ((e = prepare_tma<EPI_RES, true, NW1>()) != cudaSuccess) return e;

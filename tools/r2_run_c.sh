@@ -12,4 +12,4 @@ try:
 except Exception as e: print("failed", e)
 PY
 tail -3 gpurun_out/r2_${T}_bench.err
-ncu --set full --clock-control none --import-source on -k regex:k_element_tma -s 9 -c 1 -o gpurun_out/r2_${T}_elem python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:${2:-k_element_tma} -s 9 -c 1 -o gpurun_out/r2_${T}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > /dev/null 2>&1
