@@ -43,8 +43,15 @@ struct ElemTmaCfg {
   static constexpr int QW = G * EL, RW = G * NF * FL, MW = G * NN, XW = G * DXE;
   static constexpr int UPN = 4;                              // (U_1..U_dim, p) per node, 32-byte slots
   static constexpr int UW = G * NN * UPN;
-  static constexpr int STAGE = QW + RW + MW + XW;            // doubles per ring stage
-  static constexpr int WS = 2 * STAGE + UW;                  // doubles per warp
+  static constexpr int STAGE = QW + RW + MW + XW;            // doubles per ring stage (records double-buffered with q)
+  static constexpr int WS = 2 * STAGE + UW;                  // doubles per group
+  // RSB layout (records single-buffered): [q | Minv | dxidx] x 2, one record tile, one (U_d, p) / staging tile
+  static constexpr int QSTAGE = QW + MW + XW;
+  static constexpr int UOW = UW > QW ? UW : QW;
+  static constexpr int WS_RSB = 2 * QSTAGE + RW + UOW;
+  static constexpr int HDR = 512;                            // mbarriers: 4 per group
+  static constexpr int ws(bool rsb) { return rsb ? WS_RSB : WS; }
+  static constexpr int max_groups_l(int smem_budget, bool rsb) { return (smem_budget - HDR) / (ws(rsb) * 8); }
   static_assert(G >= 2 && QW % 2 == 0 && RW % 2 == 0 && MW % 2 == 0 && XW % 2 == 0, "bulk copies need 16-byte multiples");
   static_assert(RW >= QW, "the result rows are staged in the record tile");
   static constexpr int max_groups(int smem_budget) { return (smem_budget - 256) / (WS * 8); }
@@ -75,8 +82,8 @@ struct NodeSlice {
   // operator products of one warp: rows (element, variable) x output nodes [U0, U0 + NC)
   static constexpr int ND = DIM + 2, NF = DIM + 1, FL = NFN * ND;
   template <bool DXN>
-  static __device__ __forceinline__ void run(const OpTabP<DIM, NN, NFN>& op, const double* sQ, const double* sR,
-                                             const double* sX, const double* sU, int sc, int k, double* acc) {
+  static __device__ __forceinline__ void run_s2(const OpTabP<DIM, NN, NFN>& op, const double* sQ, const double* sX,
+                                                const double* sU, int sc, int k, double* acc) {
     constexpr int EL = NN * ND, DD = DIM * DIM, UPN = 4;
     static_assert(U0 % 2 == 0 && NC % 2 == 0, "coefficient pairs are 16-byte aligned");
     // S2: res[k,i] = sum_d sum_j Q[j,i,d] F_d[k,j] (weakdifferentiate!, trans=true) with F rebuilt from (q, U_d, p):
@@ -116,6 +123,8 @@ struct NodeSlice {
         }
       }
     }
+  }
+  static __device__ __forceinline__ void run_s3(const OpTabP<DIM, NN, NFN>& op, const double* sR, int sc, int k, double* acc) {
     // S3: res[k,node] += sum_f sum_i RfN[f,i][node] * (-+ w_i f*[k,i])  (interiorfaceintegrate!, boundaryintegrate!)
     const double* grow = sR + sc * (NF * FL) + k;
 #pragma unroll
@@ -139,7 +148,7 @@ struct NodeSlice {
 };
 
 // NP groups of NS warps per CTA; one CTA per SM (persistent), tiles strided over the groups of the grid
-template <int DIM, int NN, int NFN, int MODE, bool DXN, int NP, int NS>
+template <int DIM, int NN, int NFN, int MODE, bool DXN, int NP, int NS, bool RSB = false, bool HOIST = true>
 __global__ void __launch_bounds__(32 * NP * NS, 1)
 k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = ElemTmaCfg<DIM, NN, NFN, DXN>;
@@ -154,9 +163,12 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   // (the shuffle tells the compiler that the warp index is warp-uniform)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int grp = warp / NS, half = warp - grp * NS;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_tma) + 2 * grp;        // [2] per group
-  double* wbase = reinterpret_cast<double*>(smem_tma + 256) + (size_t)grp * Cfg::WS;
-  double* sU = wbase + 2 * Cfg::STAGE;
+  // mbarriers per group: [0,1] the two q stages, [2,3] the record tile(s)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_tma) + 4 * grp;
+  double* wbase = reinterpret_cast<double*>(smem_tma + Cfg::HDR) + (size_t)grp * (RSB ? Cfg::WS_RSB : Cfg::WS);
+  constexpr int QST = RSB ? Cfg::QSTAGE : Cfg::STAGE;        // stride of a q stage
+  double* sRbase = RSB ? wbase + 2 * Cfg::QSTAGE : wbase + Cfg::QW + Cfg::MW + Cfg::XW;   // record tile (of stage 0)
+  double* sU = RSB ? sRbase + Cfg::RW : wbase + 2 * Cfg::STAGE;
   const int64_t ntiles = (a.nE - a.e_begin + G - 1) / G;
   const int64_t W = (int64_t)gridDim.x * NP;
   const int64_t gw = (int64_t)blockIdx.x * NP + grp;
@@ -168,6 +180,8 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   if (half == 0 && lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   group_sync();
@@ -179,16 +193,17 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   auto tile_e0 = [&](int64_t t) { return a.e_begin + (a.reverse ? (ntiles - 1 - t) : t) * G; };
   auto tile_ne = [&](int64_t e0) { return (int)((a.nE - e0) < G ? (a.nE - e0) : G); };
 
-  // fills ring stage st with tile t: bulk copies for a full tile, plain loads for the (single) ragged one
-  auto issue = [&](int64_t t, int st) {
+  // stage layout: q stage st = [q | Minv | dxidx]; record tile rst (RSB: the only one; else the one of stage st)
+  auto q_stage = [&](int st) { return wbase + st * QST; };
+  auto r_tile = [&](int st) { return RSB ? sRbase : sRbase + st * QST; };
+  // fills q stage st with tile t: bulk copies for a full tile, plain loads for the (single) ragged one
+  auto issue_q = [&](int64_t t, int st) {
     const int64_t e0 = tile_e0(t);
     const int ne = tile_ne(e0);
-    double* sQ = wbase + st * Cfg::STAGE;
-    double* sR = sQ + Cfg::QW;
-    double* sM = sR + Cfg::RW;
+    double* sQ = q_stage(st);
+    double* sM = sQ + Cfg::QW;
     double* sX = sM + Cfg::MW;
     const double* gq = a.q + e0 * EL;
-    const double* gr = a.fluxe + e0 * (NF * FL);
     const double* gm = a.minv + e0 * NN;
     const double* gx = a.dxidx + e0 * a.dx_el_stride;
     if (half == 0) {
@@ -196,16 +211,14 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
         if (lane == 0) {
           // the stage was read / written through the generic proxy by this group (ordered by the barrier that ends a tile)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          constexpr unsigned bytes = (unsigned)(Cfg::QW + Cfg::RW + (MODE == EPI_RK ? Cfg::MW : 0) + Cfg::XW) * 8u;
+          constexpr unsigned bytes = (unsigned)(Cfg::QW + (MODE == EPI_RK ? Cfg::MW : 0) + Cfg::XW) * 8u;
           mbar_expect_tx(&bars[st], bytes);
           bulk_g2s(sQ, gq, Cfg::QW * 8, &bars[st]);
-          bulk_g2s_hint(sR, gr, Cfg::RW * 8, &bars[st], pol_first);          // records: read once, then discarded
           if (MODE == EPI_RK) bulk_g2s(sM, gm, Cfg::MW * 8, &bars[st]);
           bulk_g2s(sX, gx, Cfg::XW * 8, &bars[st]);
         }
       } else {
         for (int i = lane; i < ne * EL; i += 32) sQ[i] = __ldg(gq + i);
-        for (int i = lane; i < ne * NF * FL; i += 32) sR[i] = __ldg(gr + i);
         if (MODE == EPI_RK) for (int i = lane; i < ne * NN; i += 32) sM[i] = __ldg(gm + i);
         for (int i = lane; i < ne * DXE; i += 32) sX[i] = __ldg(gx + i);
         __syncwarp();
@@ -230,20 +243,48 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
       }
     }
   };
+  // the face records of tile t into record tile rst
+  auto issue_r = [&](int64_t t, int rst) {
+    const int64_t e0 = tile_e0(t);
+    const int ne = tile_ne(e0);
+    double* sR = r_tile(rst);
+    const double* gr = a.fluxe + e0 * (NF * FL);
+    if (half == 0) {
+      if (ne == G) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&bars[2 + rst], (unsigned)Cfg::RW * 8u);
+          bulk_g2s_hint(sR, gr, Cfg::RW * 8, &bars[2 + rst], pol_first);       // records: read once, then discarded
+        }
+      } else {
+        for (int i = lane; i < ne * NF * FL; i += 32) sR[i] = __ldg(gr + i);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + rst]);
+      }
+    }
+  };
 
-  issue(gw, 0);
+  issue_q(gw, 0);
+  issue_r(gw, 0);
+  // identical tiles keep the warps of an SM in lockstep (all in the FP64-bound products, then all in the latency-bound
+  // epilogue); a staggered start spreads the phases over the tile period
+  if (a.stagger_ns > 0) __nanosleep((unsigned)(a.stagger_ns * (grp & 3)));
   int it = 0;
 #pragma unroll 1
   for (int64_t t = gw; t < ntiles; t += W, ++it) {
     int st = it & 1;
     asm volatile("" : "+r"(st));          // opaque: keeps ONE copy of the (fully unrolled) tile body in the instruction cache
-    if (t + W < ntiles) issue(t + W, st ^ 1);
+    const bool more = t + W < ntiles;
+    if (more) {
+      issue_q(t + W, st ^ 1);
+      if (!RSB) issue_r(t + W, st ^ 1);
+    }
     const int64_t e0 = tile_e0(t);
     const int ne = tile_ne(e0);
-    double* sQ = wbase + st * Cfg::STAGE;
-    double* sR = sQ + Cfg::QW;
-    double* sM = sR + Cfg::RW;
+    double* sQ = q_stage(st);
+    double* sM = sQ + Cfg::QW;
     double* sX = sM + Cfg::MW;
+    double* sR = r_tile(st);
     mbar_wait_sleep(&bars[st], (unsigned)((it >> 1) & 1));
 
     // ---- S1 (node items, split over the group): density / pressure checks, pressure, U_d = dxidx[d,:].u ---------------
@@ -316,29 +357,30 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     const bool ks_smem = MODE == EPI_RK && sch2 && a.stage == 2;          // q2: the stage's own input rows
     const bool need_ks = MODE == EPI_RK && (a.scheme == 1 ? a.stage > 1 : (sch2 ? a.stage == 4 : a.stage > 1));
     const bool need_mw = MODE == EPI_RK && a.stage == 1;
-    double2 sv[CH], xo[CH], ks[CH];
-    double2 (&mw)[CH] = xo;          // stage 1 takes x_old from the q tile: the slot carries the norm weights instead
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i2 = c * TG + gl;
-      sv[c] = xo[c] = ks[c] = make_double2(0.0, 0.0);
-      if (i2 < npair) {
-        const int64_t dof = base + 2 * i2;
-        if (need_src) sv[c] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
-        if (MODE == EPI_RK) {
-          if (need_ks) ks[c] = *reinterpret_cast<const double2*>(a.ksum + dof);
-          if (need_mw) {
-            // calcNorm weights M = w_j/jac_j (Utils.jl:427-449): node = dof / ND.  (Exclusive with the x_old load below:
-            // two loads into the same registers would serialise on the write-after-write hazard.)
-            const double* mt = a.mass + e0 * NN;
-            mw[c] = make_double2(__ldg(mt + (2 * i2) / ND), __ldg(mt + (2 * i2 + 1) / ND));
-          } else if (!xo_smem) {
-            xo[c] = __ldg(reinterpret_cast<const double2*>(a.x_old + dof));
+    double2 sv[CH], xo[CH], ks[CH], mw[CH];      // (separate registers: two predicated loads into one register serialise)
+    auto load_streams = [&]() {
+  #pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int i2 = c * TG + gl;
+        sv[c] = xo[c] = ks[c] = mw[c] = make_double2(0.0, 0.0);
+        if (i2 < npair) {
+          const int64_t dof = base + 2 * i2;
+          if (need_src) sv[c] = __ldg(reinterpret_cast<const double2*>(psrc + dof));
+          if (MODE == EPI_RK) {
+            if (need_ks) ks[c] = *reinterpret_cast<const double2*>(a.ksum + dof);
+            if (need_mw) {
+              // calcNorm weights M = w_j/jac_j (Utils.jl:427-449): node = dof / ND.  (Exclusive with the x_old load below:
+              // two loads into the same registers would serialise on the write-after-write hazard.)
+              const double* mt = a.mass + e0 * NN;
+              mw[c] = make_double2(__ldg(mt + (2 * i2) / ND), __ldg(mt + (2 * i2 + 1) / ND));
+            } else if (!xo_smem) {
+              xo[c] = __ldg(reinterpret_cast<const double2*>(a.x_old + dof));
+            }
           }
         }
       }
-    }
-
+    };
+    if (HOIST) load_streams();
 
     // ---- S2 + S3 (row lanes): lane = (element s, variable k); this warp's slice of the output nodes ---------------------
     const int s = lane / ND, k = lane - s * ND;
@@ -348,15 +390,23 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
 #pragma unroll
     for (int u = 0; u < NC; ++u) acc[u] = 0.0;
     const int u0 = half * NC;
-    if (NS == 1 || half == 0) NodeSlice<DIM, NN, NFN, 0, NC>::template run<DXN>(op, sQ, sR, sX, sU, sc, k, acc);
-    else NodeSlice<DIM, NN, NFN, (NS == 1 ? 0 : NC), NC>::template run<DXN>(op, sQ, sR, sX, sU, sc, k, acc);
+    using Slice0 = NodeSlice<DIM, NN, NFN, 0, NC>;
+    using Slice1 = NodeSlice<DIM, NN, NFN, (NS == 1 ? 0 : NC), NC>;
+    if (NS == 1 || half == 0) Slice0::template run_s2<DXN>(op, sQ, sX, sU, sc, k, acc);
+    else Slice1::template run_s2<DXN>(op, sQ, sX, sU, sc, k, acc);
+    mbar_wait_sleep(&bars[2 + (RSB ? 0 : st)], (unsigned)(RSB ? (it & 1) : ((it >> 1) & 1)));
+    if (NS == 1 || half == 0) Slice0::run_s3(op, sR, sc, k, acc);
+    else Slice1::run_s3(op, sR, sc, k, acc);
     if (MODE == EPI_RK) {      // pde_post_func: res_vec *= Minv
 #pragma unroll
       for (int u = 0; u < NC; ++u)
         if (u0 + u < NN) acc[u] *= sM[sc * NN + u0 + u];
     }
-    group_sync();              // every lane of the group has consumed its records: the record tile becomes the staging tile
-    double* sOut = sR;
+    group_sync();              // every lane of the group has consumed its records and (U_d, p)
+    // RSB: the record tile is free -- the next tile's records start to arrive while this tile is staged and written out;
+    // the results are staged in the (dead) (U_d, p) tile.  Otherwise the (dead) record tile is the staging tile.
+    if (RSB && more) issue_r(t + W, 0);
+    double* sOut = RSB ? sU : sR;
     if (act) {
 #pragma unroll
       for (int u = 0; u < NC; ++u)
@@ -374,6 +424,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     // ---- S4: coalesced epilogue, two dofs per access, items split over the group -----------------------------------------
     {
       const double2* out2 = reinterpret_cast<const double2*>(sOut);
+      if (!HOIST) load_streams();
       double nrm2 = 0.0;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -381,7 +432,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
         if (i2 >= npair) continue;
         const int64_t dof = base + 2 * i2;
         const double2 v = out2[i2];
-        const double2 mwc = xo[c];                       // (stage 1: the norm weights)
+        const double2 mwc = mw[c];
         const double2 xoc = xo_smem ? q2[i2] : xo[c];
         const double2 ksc = ks_smem ? q2[i2] : ks[c];
         const double2 kk = make_double2(v.x + sv[c].x, v.y + sv[c].y);

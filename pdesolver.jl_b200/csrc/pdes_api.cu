@@ -87,6 +87,12 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+#ifndef PDES_TMA_RSB
+#define PDES_TMA_RSB 1      // k_element_tma: face records single-buffered (more resident warp groups)
+#endif
+#ifndef PDES_TMA_HOIST
+#define PDES_TMA_HOIST 0    // k_element_tma: epilogue streams requested before the operator products (held in registers)
+#endif
 #ifndef PDES_TMA_NS
 #define PDES_TMA_NS 1       // warps per tile group of k_element_tma (2: measured slower, profiles/r2_d_element_tma_v2.txt)
 #endif
@@ -177,7 +183,9 @@ struct OpsImpl : Ops {
   static constexpr int SMEM_MAX = 232448;      // 227 KB: the opt-in dynamic shared memory of an sm_100 CTA
   static constexpr int NSW = PDES_TMA_NS;                // warps per tile group (they split the output nodes of the operator products)
   static constexpr int nw_cap(int m) { return m > 15 ? 15 : (m < 1 ? 1 : m); }     // groups per CTA (one named barrier each)
-  static constexpr int NW0 = nw_cap(PCfg0::max_groups(SMEM_MAX)), NW1 = nw_cap(PCfg1::max_groups(SMEM_MAX));
+  static constexpr bool RSB = PDES_TMA_RSB != 0, HOIST = PDES_TMA_HOIST != 0;
+  static constexpr int nw_thr(int m) { return m * NSW > 32 ? 32 / NSW : m; }        // <= 1024 threads per CTA
+  static constexpr int NW0 = nw_thr(nw_cap(PCfg0::max_groups_l(SMEM_MAX, RSB))), NW1 = nw_thr(nw_cap(PCfg1::max_groups_l(SMEM_MAX, RSB)));
   TabP tabp;
   // k_face_tma (default): warp-autonomous face tiles, element blocks staged by bulk copies
   using TabF = FaceTabP<DIM, NN, NFN>;
@@ -246,15 +254,15 @@ struct OpsImpl : Ops {
     using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
     const int64_t ntiles = (a.nE - a.e_begin + C::G - 1) / C::G;
     const int64_t nblk = std::min<int64_t>((ntiles + NW - 1) / NW, (int64_t)sm_count);
-    const size_t smem = 256 + (size_t)NW * C::WS * sizeof(double);
-    k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW><<<dim3((unsigned)nblk), dim3(32 * NW * NSW), smem, s>>>(tabp, a);
+    const size_t smem = C::HDR + (size_t)NW * C::ws(RSB) * sizeof(double);
+    k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST><<<dim3((unsigned)nblk), dim3(32 * NW * NSW), smem, s>>>(tabp, a);
     return cudaGetLastError();
   }
   template <int MODE, bool DXN, int NW>
   cudaError_t prepare_tma() {
     using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
-    return cudaFuncSetAttribute(k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(256 + (size_t)NW * C::WS * sizeof(double)));
+    return cudaFuncSetAttribute(k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C::HDR + (size_t)NW * C::ws(RSB) * sizeof(double)));
   }
   int resident_element_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
@@ -873,6 +881,7 @@ struct PdesCtx {
   bool fused = false, has_ext_bc = false;
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
   int rk4_nosum = 0;       // rk4 stages without the running sum of the k's (epilogue_tile scheme 2)
+  int stagger_ns = 0;
   int reverse_elems = 0, discard_split = 0;   // split kernels: element tiles swept last-to-first; consumed records dropped from L2
   // chunk pipeline (PDES_PIPE = number of chunks): F0 F1 E0 F2 E1 ... with programmatic dependent launches
   bool pipe = false;
@@ -1164,6 +1173,7 @@ int finalize(PdesCtx* ctx) {
   ctx->rk4_nosum = env_int("PDES_RK4_NOSUM", 1) != 0 && ctx->ops->staged_epilogue();
   ctx->comm_overlap = env_int("PDES_COMM_INLINE", 0) == 0 && !ctx->fused;
   ctx->reverse_elems = env_int("PDES_REV", 1);
+  ctx->stagger_ns = env_int("PDES_STAGGER_NS", 0);
   ctx->discard_split = env_int("PDES_DISCARD_SPLIT", 1);
   if (ctx->fused) {
     const int res = ctx->ops->resident_fused_ctas();
@@ -1189,6 +1199,7 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->dx_node_stride = ctx->dx_compact ? 0 : dd;
   a->prefetch_ahead = ctx->prefetch_ahead;
   a->reverse = ctx->reverse_elems;
+  a->stagger_ns = ctx->stagger_ns;
   a->discard_records = ctx->pipe ? ctx->pipe_discard : ctx->discard_split;
 }
 

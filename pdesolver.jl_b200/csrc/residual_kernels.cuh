@@ -135,6 +135,7 @@ struct ElemArgs {
   int32_t prefetch_ahead;      // tiles between this CTA and the one whose inputs it prefetches into L2
   int32_t discard_records;     // drop the consumed face records from L2 (discard.global.L2): no write-back
   int32_t reverse;             // k_element_rk sweeps its tiles from the last to the first (see pdes_api.cu: L2 reuse)
+  int32_t stagger_ns;          // k_element_tma: warp w starts (w mod 4) * stagger_ns later (de-synchronises the tile phases)
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
