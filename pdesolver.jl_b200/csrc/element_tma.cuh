@@ -159,6 +159,8 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   static_assert(NP <= 15, "one named barrier per group");
   extern __shared__ __align__(128) unsigned char smem_tma[];
   if (a.ctl->stop) return;
+  // fused halo: the face launch of this evaluation is complete (stream order) -- close the evaluation
+  if (a.halo_epoch && blockIdx.x == 0 && threadIdx.x == 0) *a.halo_epoch += 1u;
   const int lane = threadIdx.x & 31;
   // (the shuffle tells the compiler that the warp index is warp-uniform)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);

@@ -56,14 +56,29 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
   constexpr int ND = Cfg::ND, NF = Cfg::NF, EL = Cfg::EL, FL = Cfg::FL, FW = Cfg::FW, SLOTD = Cfg::SLOTD, FS = Cfg::FS;
   constexpr int NFNP = FaceTabP<DIM, NN, NFN>::NFNP;
   extern __shared__ __align__(128) unsigned char smem_ftma[];
-  if (a.ctl->stop) return;
+  const HaloArgs& hx = a.halo;
+  if (a.ctl->stop) {
+    // a rank stopped by an error never sends: tell the neighbours (abort slots) instead of letting them wait for the
+    // time-out (a res_tol stop is taken by every rank at the same step head: nobody waits)
+    if (hx.on && a.ctl->err_code != 0 && blockIdx.x == 0 && (int)threadIdx.x < hx.npeers) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hx.peer_flags[threadIdx.x] + 32), "r"(1u) : "memory");
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_ftma) + 2 * warp;
   double* wbase = reinterpret_cast<double*>(smem_ftma + 512) + (size_t)warp * Cfg::WS;
   double* sL = wbase + 2 * Cfg::STAGE;
   double* sR = sL + FW * FS;
-  const int64_t ntiles = (a.ng + FW - 1) / FW;
+  // fused halo: the first npk tiles are the SEND pass over this rank's shared faces; the shared faces come again, as the
+  // last tiles of the face list, for their fluxes
+  const int64_t npk = hx.on ? (hx.nS + FW - 1) / FW : 0;
+  const int64_t ntiles = npk + (a.ng + FW - 1) / FW;
+  const unsigned hE = hx.on ? ld_relaxed_u32(hx.ctr) + 1u : 0u;          // number of this evaluation
+  const double* q_recv = hx.on ? hx.recv_base + (size_t)(hE & 1u) * hx.nsend : a.q_recv;
+  bool h_waited = false;
   const int64_t W = (int64_t)gridDim.x * NW;
   const int64_t gw = (int64_t)blockIdx.x * NW + warp;
   if (gw >= ntiles) return;
@@ -80,7 +95,15 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
   // exposed its full latency: 9 % of the samples of the first version)
   auto load_rec = [&](int64_t t) {
     int4 v = make_int4(0, 0, (int)(255u << 24), 0);
-    const int64_t g = a.g0 + t * FW + lane;
+    if (t < npk) {
+      const int64_t u = t * FW + lane;
+      if (lane < FW && u < hx.nS) {
+        v = __ldg(reinterpret_cast<const int4*>(a.faces + hx.s0 + u));
+        v.z = (int)(((unsigned)v.z & 0x00ffffffu) | ((unsigned)FK_PACK << 24));
+      }
+      return v;
+    }
+    const int64_t g = a.g0 + (t - npk) * FW + lane;
     if (t < ntiles && lane < FW && g < gend) v = __ldg(reinterpret_cast<const int4*>(a.faces + g));
     return v;
   };
@@ -129,13 +152,38 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
     const bool more = t + W < ntiles;
     if (more) issue(rn, st ^ 1);
     const int4 rn2 = load_rec(t + 2 * W);         // records of the tile after next (consumed two iterations later)
-    const int64_t g0 = a.g0 + t * FW;
-    const int nf = (int)((gend - g0) < FW ? (gend - g0) : FW);
+    const bool is_pack = t < npk;
+    const int64_t g0 = is_pack ? hx.s0 + t * FW : a.g0 + (t - npk) * FW;
+    const int64_t gstop = is_pack ? hx.s0 + hx.nS : gend;
+    const int nf = (int)((gstop - g0) < FW ? (gstop - g0) : FW);
     const double* sQ = wbase + st * Cfg::STAGE;
+    if (hx.on && !is_pack && !h_waited && __any_sync(0xffffffffu, lane < FW && ((unsigned)rc.z >> 24) == FK_SHARED)) {
+      // finishExchangeData: every neighbour's states of evaluation hE are in the local receive buffer
+      if (lane < hx.npeers) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (unsigned spin = 0;; ++spin) {
+          unsigned v, ab;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(hx.flags + lane) : "memory");
+          if ((int)(v - hE) >= 0) break;
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(ab) : "l"(hx.flags + 32 + lane) : "memory");
+          Ctl* ctl = const_cast<Ctl*>(a.ctl);
+          if (ab) { atomicCAS(&ctl->err_code, 0, 5); atomicExch(&ctl->stop, 1); break; }
+          if ((spin & 63u) == 63u) {
+            if (ld_relaxed_u32(&ctl->stop)) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 120000000000ull) { atomicCAS(&ctl->err_code, 0, 4); atomicExch(&ctl->stop, 1); break; }
+          }
+          __nanosleep(100);
+        }
+      }
+      __syncwarp();
+      h_waited = true;
+    }
 
     // ---- node lanes: the normal of this lane's face node (depends on the face number only), requested before the wait
     const int nfi = lane / NFN, ni = lane - nfi * NFN;
-    const bool nact = lane < nf * NFN;
+    const bool nact = !is_pack && lane < nf * NFN;
     double nrm[DIM];
     if (nact) {
       const double* np_ = a.nrm + (g0 + nfi) * a.nrm_face_stride + ni * a.nrm_node_stride;
@@ -188,7 +236,12 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
           }
         }
       }
-      if (vact) {
+      if (vact && kind == FK_PACK) {
+        // getSendDataFace (Utils/parallel.jl:249-258): own face-node order, straight into the neighbour's receive buffer
+        double* dst = hx.face_dst[(size_t)(hE & 1u) * hx.nS + (g0 - hx.s0) + fi];
+#pragma unroll
+        for (int i = 0; i < NFN; ++i) dst[i * ND + k] = sLv[i];
+      } else if (vact) {
 #pragma unroll
         for (int i = 0; i < NFN; ++i) {
           sL[fi * FS + i * ND + k] = sLv[i];
@@ -198,13 +251,31 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
         }
         if (kind == FK_SHARED) {
           // permuteinterface! (Utils/parallel.jl:198-201): received node i of the peer is own node nbrperm[i,orient]
-          const double* b = a.q_recv + (int64_t)aux * (NFN * ND) + k;
+          const double* b = q_recv + (int64_t)aux * (NFN * ND) + k;
 #pragma unroll
           for (int i = 0; i < NFN; ++i) sR[fi * FS + (int)((pkN >> (4 * i)) & 15ull) * ND + k] = b[i * ND];
         }
       }
     }
     __syncwarp();
+    if (is_pack) {
+      // this tile's states are on their way: the warp that completes the send pass publishes the evaluation number in
+      // every neighbour's flag slot (fence.sys by the storing warp, cumulative through the counter, fence.sys + release)
+      if (lane == 0) {
+        __threadfence_system();
+        const unsigned old = atomicAdd(hx.ctr + 1, 1u);
+        if (old + 1u == (unsigned)npk) {
+          hx.ctr[1] = 0u;
+          __threadfence_system();
+          for (int p = 0; p < hx.npeers; ++p)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hx.peer_flags[p]), "r"(hE) : "memory");
+        }
+      }
+      __syncwarp();
+      rc = rn;
+      rn = rn2;
+      continue;
+    }
 
     // ---- B: numerical flux at every face node (node lanes) ----------------------------------------------------------
     // results overwrite the face-state tiles: sL <- -w f* in elementL's node order, sR <- +w f* in elementR's node order

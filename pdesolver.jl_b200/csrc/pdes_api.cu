@@ -116,6 +116,7 @@ struct Ops {
   virtual int record_doubles() const { return 0; }   // doubles per (element, local face) record; 0: nd * nfn
   virtual int pipe_face_tile() const { return 0; }   // faces per CTA of the chunk-pipeline face kernel; 0: no pipeline
   virtual bool staged_epilogue() const { return false; }   // element kernel stages its epilogue streams (rk4 scheme 2)
+  virtual bool fused_halo() const { return false; }        // the face kernel sends / receives the shared-face states itself (HaloArgs)
   virtual cudaError_t prepare() = 0;         // one-time function attributes (must not happen inside a graph capture)
   // fused face + element kernel (k_fused); families without one return 0 faces per group
   virtual int fused_group_faces() const { return 0; }
@@ -142,6 +143,7 @@ struct OpsImpl : Ops {
   int fused_tile_elems() const override { return E; }
   int pipe_face_tile() const override { return FT; }
   bool staged_epilogue() const override { return use_tma_elem || !use_warp_kernel; }
+  bool fused_halo() const override { return use_tma_elem && use_tma_face; }
   // chunk pipeline: programmatic stream serialization lets the CTAs of this launch start while the last wave of the
   // previous launch is still running; the kernels synchronise through PipeArgs counters
   template <typename K, typename A>
@@ -195,7 +197,7 @@ struct OpsImpl : Ops {
   bool use_tma_face = true;
   template <bool EXTBC>
   cudaError_t launch_faces_tma(const FaceArgs& a, cudaStream_t s) {
-    const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW;
+    const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW + (a.halo.on ? (a.halo.nS + FWCfg::FW - 1) / FWCfg::FW : 0);
     const int64_t nblk = std::min<int64_t>((ntiles + NWF - 1) / NWF, (int64_t)sm_count);
     const size_t smem = 512 + (size_t)NWF * FWCfg::WS * sizeof(double);
     k_face_tma<DIM, NN, NFN, NWF, EXTBC><<<dim3((unsigned)nblk), dim3(32 * NWF), smem, s>>>(tabf, a);
@@ -853,8 +855,16 @@ struct PdesCtx {
   unsigned* halo_flags = nullptr;
   size_t halo_nsend = 0;
   uint32_t halo_epoch = 0;
+  bool halo_fused = false;      // send pass, flags and receive wait inside the one face launch (HaloArgs); epoch on the device
+  unsigned* halo_ctr = nullptr; // device: {evaluations completed, pack tiles done, norms committed}
+  // calcNorm's all-reduce through peer memory (NormX): every rank's buffer mapped, slot rings behind the flags
+  std::vector<void*> rank_mapped;     // [nranks] imported mappings (nullptr for this rank)
+  double** d_norm_slots = nullptr;    // device: [nranks] slot ring of every rank
+  bool norm_p2p = false;
+  bool norm_pending = false;          // a k_norm_reduce whose k_norm_commit has been deferred to the end of the step
+  double pend_tol = -1.0; int pend_pseudo = 0;
   double* q_recv_eval = nullptr;
-  struct PeerMap { double* base = nullptr; int64_t remote_nsend = 0, remote_off = 0; unsigned* flag = nullptr; void* mapped = nullptr; };
+  struct PeerMap { double* base = nullptr; int64_t remote_nsend = 0, remote_off = 0; unsigned* flag = nullptr; };
   std::vector<PeerMap> pmap;
   unsigned** d_flag_ptrs = nullptr;   // device array of the neighbours' flag slots
   double** d_face_dst = nullptr;      // [2][nS] per shared face: its slot in the neighbour's receive buffer
@@ -902,6 +912,7 @@ struct PdesCtx {
   cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr};
   double g_h = -1.0, g_tol = 0.0;
   bool g_norm = false, no_graph = false;
+  bool capturing = false, norm_branch_open = false;   // graph capture of a multi-GPU step: the all-reduce branch joins at the end
   int g_pseudo = 0, g_launches = 0;
   std::vector<double> h_w;
   // partition
@@ -972,6 +983,11 @@ int fetch_ctl(PdesCtx* ctx) {
   if (ctx->comm_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
   if (ctx->h_ctl->err_code == 4) {
     set_err(ctx, "halo exchange: a neighbour's face states did not arrive within 120 s");
+    return PDES_ERR_COMM;
+  }
+  if (ctx->h_ctl->err_code == 5) {
+    set_err(ctx, "halo exchange: a neighbouring rank stopped (physics error there); re-establish the communicator "
+                 "(pdes_set_comm) on every rank before the next evaluation");
     return PDES_ERR_COMM;
   }
   if (ctx->h_ctl->err_code == 3) {
@@ -1224,7 +1240,8 @@ int setup_p2p(PdesCtx* ctx) {
   memset(&mine, 0, sizeof(mine));
   bool ok = env_int("PDES_HALO_NCCL", 0) == 0 && np <= 32 && g_nccl.AllGather != nullptr;
   if (ok) {
-    const size_t bytes = 2 * nsend * sizeof(double) + 256 + 32 * sizeof(unsigned);
+    // + flags | abort | ctr | norm slot ring
+    const size_t bytes = 2 * nsend * sizeof(double) + 256 + (32 + 32 + 4) * sizeof(unsigned) + NORM_RING * 32 * 2 * sizeof(double);
     ok = cudaMalloc((void**)&ctx->halo_buf, bytes) == cudaSuccess && cudaMemset(ctx->halo_buf, 0, bytes) == cudaSuccess;
     if (ok) {
       ctx->halo_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->halo_buf) + 2 * nsend * sizeof(double) + 256);
@@ -1250,24 +1267,39 @@ int setup_p2p(PdesCtx* ctx) {
   if (!g_nccl.AllGather) ok = false;
   ctx->pmap.assign(np, PdesCtx::PeerMap());
   std::vector<unsigned*> flag_ptrs(np > 0 ? np : 1, nullptr);
+  // every rank's buffer is mapped once (the norm slots of all ranks, the receive buffers of the neighbours)
+  ctx->rank_mapped.assign(ctx->nranks, nullptr);
+  std::vector<double*> slot_ptrs(ctx->nranks, nullptr);
+  auto tail_of = [](void* base, int64_t ns) { return static_cast<char*>(base) + 2 * (size_t)ns * sizeof(double) + 256; };
+  bool all_mapped = ok && ctx->nranks <= 32;
+  for (int rr = 0; rr < ctx->nranks && ok; ++rr) {
+    void* mapped = ctx->halo_buf;
+    if (rr != ctx->rank) {
+      mapped = nullptr;
+      if (!all[rr].ok || cudaIpcOpenMemHandle(&mapped, all[rr].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError(); mapped = nullptr; all_mapped = false;
+      }
+      ctx->rank_mapped[rr] = mapped;
+    }
+    if (mapped) slot_ptrs[rr] = reinterpret_cast<double*>(tail_of(mapped, all[rr].nsend) + (32 + 32 + 4) * sizeof(unsigned));
+  }
   for (int i = 0; i < np && ok; ++i) {
     const int rr = ctx->peers[i].rank;
-    if (rr < 0 || rr >= ctx->nranks || !all[rr].ok) { ok = false; break; }
+    if (rr < 0 || rr >= ctx->nranks || rr == ctx->rank || !ctx->rank_mapped[rr]) { ok = false; break; }
     const HaloRec& o = all[rr];
     int slot = -1;
     for (int k = 0; k < o.npeers; ++k) if (o.peer_rank[k] == ctx->rank) slot = k;
     if (slot < 0 || o.peer_n[slot] != ctx->peers[i].nfaces) { ok = false; break; }
-    void* mapped = nullptr;
-    if (cudaIpcOpenMemHandle(&mapped, o.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    void* mapped = ctx->rank_mapped[rr];
     PdesCtx::PeerMap& m = ctx->pmap[i];
-    m.mapped = mapped; m.base = static_cast<double*>(mapped); m.remote_nsend = o.nsend; m.remote_off = o.peer_off[slot];
-    m.flag = reinterpret_cast<unsigned*>(static_cast<char*>(mapped) + 2 * (size_t)o.nsend * sizeof(double) + 256) + slot;
+    m.base = static_cast<double*>(mapped); m.remote_nsend = o.nsend; m.remote_off = o.peer_off[slot];
+    m.flag = reinterpret_cast<unsigned*>(tail_of(mapped, o.nsend)) + slot;
     flag_ptrs[i] = m.flag;
   }
   // the same decision everywhere
   int* d_ok = nullptr;
   CUDA_TRY(ctx, cudaMalloc((void**)&d_ok, sizeof(int)));
-  const int h_ok = ok ? 1 : 0;
+  const int h_ok = ok ? (all_mapped ? 2 : 1) : 0;           // 2: every rank mapped every buffer (norm through peer memory)
   CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, ctx->comm_stream));
   r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, ctx->comm, ctx->comm_stream);
   if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
@@ -1279,7 +1311,13 @@ int setup_p2p(PdesCtx* ctx) {
     CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_flag_ptrs, sizeof(unsigned*) * flag_ptrs.size()));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_flag_ptrs, flag_ptrs.data(), sizeof(unsigned*) * flag_ptrs.size(), cudaMemcpyHostToDevice));
     ctx->halo_nsend = nsend;
+    ctx->halo_ctr = ctx->halo_flags + 64;
     ctx->p2p = 1;
+    if (all_ok == 2 && env_int("PDES_NORM_NCCL", 0) == 0) {
+      CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_norm_slots, sizeof(double*) * ctx->nranks));
+      CUDA_TRY(ctx, cudaMemcpy(ctx->d_norm_slots, slot_ptrs.data(), sizeof(double*) * ctx->nranks, cudaMemcpyHostToDevice));
+      ctx->norm_p2p = true;
+    }
     if (env_int("PDES_HALO_COPY", 0) == 0 && ctx->nS > 0) {
       // per shared face and evaluation parity: its slot in the neighbour's receive buffer (k_pack_send stores there)
       std::vector<double*> dst(2 * (size_t)ctx->nS, nullptr);
@@ -1292,6 +1330,8 @@ int setup_p2p(PdesCtx* ctx) {
         }
       CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_face_dst, sizeof(double*) * dst.size()));
       CUDA_TRY(ctx, cudaMemcpy(ctx->d_face_dst, dst.data(), sizeof(double*) * dst.size(), cudaMemcpyHostToDevice));
+      ctx->halo_fused = env_int("PDES_HALO_FUSED", 1) != 0 && ctx->ops->fused_halo() && ctx->nchunks == 1 && !ctx->fused &&
+                        !ctx->pipe;
     }
   }
   return PDES_OK;
@@ -1304,7 +1344,7 @@ int setup_p2p(PdesCtx* ctx) {
 int start_exchange(PdesCtx* ctx, const double* q) {
   // (collective: every rank of the communicator passes here at its first evaluation, shared faces or not)
   if (ctx->comm && ctx->p2p < 0) { int rc = setup_p2p(ctx); if (rc) return rc; }
-  if (ctx->nS == 0) return PDES_OK;
+  if (ctx->nS == 0 || ctx->halo_fused) return PDES_OK;      // (fused halo: the face kernel is the exchange)
   const bool overlap = ctx->comm && ctx->comm_overlap;
   cudaStream_t ps = overlap ? ctx->comm_stream : ctx->stream;
   if (overlap) {
@@ -1448,6 +1488,23 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
     ctx->n_evals++;
     return PDES_OK;
   }
+  if (ctx->halo_fused) {
+    // ONE face launch: send pass over the shared faces, interior + boundary faces, then the shared faces once the
+    // neighbours' states have arrived; the element kernel closes the evaluation (++epoch)
+    HaloArgs& hx = fa.halo;
+    hx.on = 1; hx.npeers = (int32_t)ctx->peers.size(); hx.nS = ctx->nS; hx.s0 = c.nF + c.nB;
+    hx.face_dst = ctx->d_face_dst; hx.peer_flags = ctx->d_flag_ptrs; hx.flags = ctx->halo_flags; hx.ctr = ctx->halo_ctr;
+    hx.recv_base = ctx->halo_buf; hx.nsend = (int64_t)ctx->halo_nsend;
+    fa.g0 = 0; fa.ng = c.nF + c.nB + ctx->nS;
+    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
+    a.halo_epoch = ctx->halo_ctr;
+    a.e_begin = 0; a.nE = c.nE;
+    CUDA_TRY(ctx, ctx->ops->launch_elements(a, mode, ctx->stream));
+    a.halo_epoch = nullptr;
+    ctx->launches += 2;
+    ctx->n_evals++;
+    return PDES_OK;
+  }
   cudaStream_t fs = nc > 1 ? ctx->face_stream : ctx->stream;
   if (nc > 1) {
     // q of this evaluation is complete once everything enqueued so far on the compute stream has run
@@ -1484,33 +1541,73 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   return PDES_OK;
 }
 
-int enqueue_norm(PdesCtx* ctx, double res_tol, int pseudo_time) {
+NormX norm_x(PdesCtx* ctx) {
+  NormX nx;
+  memset(&nx, 0, sizeof(nx));
+  if (ctx->comm && ctx->nranks > 1 && ctx->norm_p2p) {
+    nx.on = 1; nx.rank = ctx->rank; nx.nranks = ctx->nranks; nx.slots = ctx->d_norm_slots; nx.nctr = ctx->halo_ctr + 2;
+  }
+  return nx;
+}
+
+NormOut norm_out(PdesCtx* ctx, double res_tol, int pseudo_time, bool fuse) {
+  NormOut o;
+  // rk4.jl:451-453 reduces the already-reduced norm again: sqrt(P) too large in parallel runs
+  o.quirk_scale = (ctx->comm && ctx->nranks > 1) ? (double)ctx->nranks : 1.0;
+  o.norms = ctx->norms_dev; o.norms_cap = ctx->norms_cap; o.res_tol = res_tol; o.pseudo_time = pseudo_time; o.fuse = fuse ? 1 : 0;
+  return o;
+}
+
+// second half of the stage-1 norm: with the peer-memory all-reduce it may be enqueued anywhere later in the stream
+int enqueue_norm_commit(PdesCtx* ctx, double res_tol, int pseudo_time) {
+  k_norm_commit<<<1, 1, 0, ctx->stream>>>(ctx->norm_sq, norm_out(ctx, res_tol, pseudo_time, false), ctx->ctl, norm_x(ctx));
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  ctx->norm_pending = false;
+  return PDES_OK;
+}
+
+// defer: the caller enqueues the commit itself (end of the step: by then every rank's partial sum has arrived, the
+// commit never waits).  Ignored when the res_tol test needs the norm before stage 2, and on the NCCL path.
+int enqueue_norm(PdesCtx* ctx, double res_tol, int pseudo_time, bool defer = false) {
   int n1 = (int)ctx->ops->grid_for(ctx->cfg.nE);
   const bool parallel = ctx->comm && ctx->nranks > 1;
+  if (!parallel || ctx->norm_p2p) {
+    // one GPU: the reduction kernel commits the norm itself
+    k_norm_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_sq, ctx->ctl, norm_x(ctx),
+                                               norm_out(ctx, res_tol, pseudo_time, !parallel));
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (!parallel) return PDES_OK;
+    if (defer && !(pseudo_time && res_tol >= 0.0)) {
+      ctx->norm_pending = true; ctx->pend_tol = res_tol; ctx->pend_pseudo = pseudo_time;
+      return PDES_OK;
+    }
+    return enqueue_norm_commit(ctx, res_tol, pseudo_time);
+  }
   // the norm only feeds back into the time loop through the res_tol test; when that test is off the
   // Allreduce + commit run on the communication stream and never stall the stage kernels
-  const bool async = parallel && !(pseudo_time && res_tol >= 0.0);
-  if (parallel) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_norm, 0));   // norm_sq of the previous step consumed
-  k_norm_reduce<<<1, 256, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_sq, ctx->ctl);
+  const bool async = !(pseudo_time && res_tol >= 0.0);
+  // norm_sq of the previous step consumed (inside a graph capture the step itself joins the branch before it ends)
+  if (!ctx->capturing) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_norm, 0));
+  k_norm_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->norm_partials, n1, ctx->norm_sq, ctx->ctl, NormX{},
+                                             norm_out(ctx, res_tol, pseudo_time, false));
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
-  double quirk = 1.0;
   cudaStream_t st = ctx->stream;
-  if (parallel) {
-    if (async) {
-      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-      st = ctx->comm_stream;
-    }
-    // calcNorm's Allreduce (Utils.jl:443-448): 8 bytes, once per step
-    ncclResult_t r = g_nccl.AllReduce(ctx->norm_sq, ctx->norm_sq, 1, ncclFloat64, ncclSum, ctx->comm, st);
-    if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
-    quirk = (double)ctx->nranks;   // rk4.jl:451-453 reduces the already-reduced norm again
+  if (async) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+    st = ctx->comm_stream;
   }
-  k_norm_commit<<<1, 1, 0, st>>>(ctx->norm_sq, quirk, ctx->norms_dev, ctx->norms_cap, res_tol, pseudo_time, ctx->ctl);
+  // calcNorm's Allreduce (Utils.jl:443-448): 8 bytes, once per step
+  ncclResult_t r = g_nccl.AllReduce(ctx->norm_sq, ctx->norm_sq, 1, ncclFloat64, ncclSum, ctx->comm, st);
+  if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  k_norm_commit<<<1, 1, 0, st>>>(ctx->norm_sq, norm_out(ctx, res_tol, pseudo_time, false), ctx->ctl, NormX{});
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
-  if (parallel) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_norm, st));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_norm, st));
+  ctx->norm_branch_open = async;
   return PDES_OK;
 }
 
@@ -1530,10 +1627,11 @@ int enqueue_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int
     int rc = enqueue_residual(ctx, a, EPI_RK);
     if (rc) return rc;
     if (s == 0) {
-      if (with_norm) { rc = enqueue_norm(ctx, res_tol, pseudo_time); if (rc) return rc; }
+      if (with_norm) { rc = enqueue_norm(ctx, res_tol, pseudo_time, !only_head); if (rc) return rc; }
       if (only_head) { ctx->cur = (ctx->cur + 1) % 3; return PDES_OK; }
     }
   }
+  if (ctx->norm_pending) { int rc = enqueue_norm_commit(ctx, ctx->pend_tol, ctx->pend_pseudo); if (rc) return rc; }
   ctx->cur = (ctx->cur + 2) % 3;
   return PDES_OK;
 }
@@ -1571,7 +1669,13 @@ int enqueue_lserk_step(PdesCtx* ctx, double h, double res_tol, int pseudo_time, 
 // One full RK4 step as a CUDA graph (single-GPU, single-stream schedule): the ten launches of a step are
 // captured once per buffer rotation (three graphs) and replayed; small meshes are launch-bound otherwise.
 int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int pseudo_time) {
-  const bool graphable = !ctx->comm && ctx->nS == 0 && ctx->nchunks == 1 && !ctx->no_graph;
+  // (collective one-time set-up of the peer-to-peer halo: not inside a capture)
+  if (ctx->comm && ctx->p2p < 0) { int rc = setup_p2p(ctx); if (rc) return rc; }
+  // multi-GPU: the fused halo has no host-side state (evaluation number on the device), the step is two launches per stage
+  // plus the norm branch (k_norm_reduce -> ncclAllReduce -> k_norm_commit), all capturable
+  static const bool graph_mp = env_int("PDES_GRAPH_MP", 1) != 0;
+  const bool graphable = ctx->nchunks == 1 && !ctx->no_graph &&
+                         (ctx->comm ? (graph_mp && (ctx->nS == 0 || ctx->halo_fused)) : ctx->nS == 0);
   if (!graphable) return enqueue_rk4_step(ctx, h, with_norm, res_tol, pseudo_time, false);
   if (ctx->g_h != h || ctx->g_norm != with_norm || ctx->g_tol != res_tol || ctx->g_pseudo != pseudo_time) {
     for (int i = 0; i < 3; ++i)
@@ -1583,7 +1687,10 @@ int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int 
     const int64_t l0 = ctx->launches, n0 = ctx->n_evals;
     cudaGraph_t g = nullptr;
     CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true; ctx->norm_branch_open = false;
     int rc = enqueue_rk4_step(ctx, h, with_norm, res_tol, pseudo_time, false);
+    if (ctx->norm_branch_open) cudaStreamWaitEvent(ctx->stream, ctx->ev_norm, 0);       // join the all-reduce branch
+    ctx->capturing = false; ctx->norm_branch_open = false;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
     ctx->cur = slot;                       // the capture only recorded the step; it is executed below
     ctx->g_launches = (int)(ctx->launches - l0);
@@ -1718,7 +1825,7 @@ void pdes_destroy(PdesCtx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
   for (int i = 0; i < 3; ++i) if (ctx->step_graph[i]) cudaGraphExecDestroy(ctx->step_graph[i]);
-  for (auto& m : ctx->pmap) if (m.mapped) cudaIpcCloseMemHandle(m.mapped);
+  for (void* m : ctx->rank_mapped) if (m) cudaIpcCloseMemHandle(m);
   if (ctx->halo_buf && ctx->comm && ctx->p2p == 1 && g_nccl.AllReduce) {
     // the receive buffer is mapped by the neighbours (CUDA IPC): freeing it while a peer still holds the mapping is
     // undefined, so every rank closes its imported handles first (above) and the ranks meet here before the export
@@ -1735,6 +1842,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->halo_buf) cudaFree(ctx->halo_buf);
   if (ctx->d_flag_ptrs) cudaFree(ctx->d_flag_ptrs);
   if (ctx->d_face_dst) cudaFree(ctx->d_face_dst);
+  if (ctx->d_norm_slots) cudaFree(ctx->d_norm_slots);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,

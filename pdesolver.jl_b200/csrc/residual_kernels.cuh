@@ -50,7 +50,8 @@ struct __align__(16) FaceRec {
   uint8_t fL, fR, orient, kind;
   int32_t aux;       // boundary: BC functor id; shared: index into the receive buffer
 };
-enum FaceKind : uint8_t { FK_INTERIOR = 0, FK_BOUNDARY = 2, FK_SHARED = 3 };
+enum FaceKind : uint8_t { FK_INTERIOR = 0, FK_BOUNDARY = 2, FK_SHARED = 3,
+                          FK_PACK = 4 /* k_face_tma only: a shared face in its send pass (never stored in the face list) */ };
 
 struct Ctl {               // device-resident control block
   int32_t stop;            // kernels return immediately when set (physics error or res_tol reached)
@@ -92,6 +93,22 @@ struct PipeArgs {
   uint32_t epoch, dep_epoch;
 };
 
+// Halo exchange fused into the face kernel (k_face_tma; pdes_api.cu: start_exchange).  Replaces startSolutionExchange /
+// finishExchangeData (Utils/parallel.jl:29-49, 178-208) AND the launches around them: the warps of the ONE face launch of an
+// evaluation first interpolate the shared faces of this rank and store the states straight into the neighbours' receive
+// buffers (peer memory over NVLink), the last of them publishes the evaluation number in every neighbour's flag slot; the
+// shared faces are the last tiles of the same launch and poll the local flags before they read the received states.
+struct HaloArgs {
+  int32_t on, npeers;
+  int64_t nS, s0;                  // shared faces: count, index of the first one in the face list
+  double* const* face_dst;         // [2][nS] (by evaluation parity) slot of the face in the neighbour's receive buffer
+  unsigned* const* peer_flags;     // [npeers] this rank's flag slot in the neighbour's buffer (+32: abort slot)
+  const unsigned* flags;           // [32] evaluation number per neighbour | [32] abort | [2] {epoch, pack counter}
+  unsigned* ctr;                   // -> {epoch of the last complete evaluation, pack tiles done} (local)
+  const double* recv_base;         // [2][nsend] local receive buffers
+  int64_t nsend;
+};
+
 struct FaceArgs {
   const double* q;             // [ND,NN,nE]
   const FaceRec* faces;        // [nF + nB + nS]
@@ -110,6 +127,7 @@ struct FaceArgs {
   PipeArgs pipe;
   const int32_t* tab_dev;      // device copy of OpTab::perm | OpTab::nbrperm (or nullptr)
   const double* optab_dev;     // device copy of OpTab::interp | OpTab::wface (k_face_element)
+  HaloArgs halo;
 };
 
 struct ElemArgs {
@@ -136,6 +154,7 @@ struct ElemArgs {
   int32_t discard_records;     // drop the consumed face records from L2 (discard.global.L2): no write-back
   int32_t reverse;             // k_element_rk sweeps its tiles from the last to the first (see pdes_api.cu: L2 reuse)
   int32_t stagger_ns;          // k_element_tma: warp w starts (w mod 4) * stagger_ns later (de-synchronises the tile phases)
+  unsigned* halo_epoch;        // fused halo (HaloArgs): the evaluation is complete -> ++*halo_epoch (block 0), or nullptr
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
@@ -1870,31 +1889,94 @@ __global__ void k_halo_wait(const unsigned* flags, int npeers, unsigned epoch, C
   }
 }
 
-__global__ void k_norm_reduce(const double* __restrict__ partials, int n1, double* norm_sq_out, const Ctl* ctl) {
-  __shared__ double sh[256];
+// calcNorm's MPI.Allreduce (Utils.jl:443-448) through peer memory: every rank's receive buffer carries a ring of
+// NORM_RING x 32 slots {value, tag}; k_norm_reduce stores this rank's partial sum and the step tag straight into slot
+// [step % NORM_RING][rank] of EVERY rank (remote stores over NVLink, release at system scope), k_norm_commit -- enqueued where the
+// values have long arrived -- waits for the tags and adds the slots in rank order (the same sum, bit for bit, on all ranks).
+// Ring depth: a rank is at most one evaluation ahead of a neighbour, i.e. < NORM_RING steps ahead of anybody for <= 32 ranks.
+constexpr int NORM_RING = 16;
+struct NormX {
+  int32_t on, rank, nranks;
+  double* const* slots;        // [nranks] slot ring of every rank (own one included)
+  unsigned* nctr;              // local: number of committed norms (the step tag)
+};
+
+// what k_norm_commit stores (also the tail of k_norm_reduce on one GPU: one launch less per step)
+struct NormOut {
+  double quirk_scale;          // reproduces the reference's double reduction in parallel runs (rk4.jl:451-453); 1 in serial
+  double* norms;
+  int64_t norms_cap;
+  double res_tol;
+  int32_t pseudo_time, fuse;   // fuse: k_norm_reduce commits the norm itself (no other rank contributes)
+};
+__device__ __forceinline__ void norm_commit(double sum, const NormOut& o, Ctl* ctl) {
+  const double nv = sqrt(sum * o.quirk_scale);
+  const int slot = ctl->norm_count;
+  if (slot < o.norms_cap) o.norms[slot] = nv;
+  ctl->norm_count = slot + 1;
+  if (o.pseudo_time && nv < o.res_tol) { ctl->converged_step = slot; ctl->stop = 1; }
+}
+
+// second pass of the stage-1 norm: deterministic sum of the per-tile partials of this rank (fixed assignment of the
+// partials to 1024 threads x 4 independent accumulators, fixed tree)
+__global__ void __launch_bounds__(1024, 1)
+k_norm_reduce(const double* __restrict__ partials, int n1, double* norm_sq_out, Ctl* ctl, NormX nx, NormOut no) {
+  __shared__ double sh[1024];
   if (ctl->stop) return;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n1; i += 256) s += partials[i];
-  sh[threadIdx.x] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * 1024 < n1; i += 4 * 1024) {
+    s0 += partials[i]; s1 += partials[i + 1024]; s2 += partials[i + 2048]; s3 += partials[i + 3072];
+  }
+  for (; i < n1; i += 1024) s0 += partials[i];
+  sh[threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *norm_sq_out = sh[0];
+  if (threadIdx.x == 0) {
+    *norm_sq_out = sh[0];
+    if (no.fuse) norm_commit(sh[0], no, ctl);
+  }
+  if (nx.on && (int)threadIdx.x < nx.nranks) {
+    const unsigned step = ld_relaxed_u32(nx.nctr);
+    double* slot = nx.slots[threadIdx.x] + ((size_t)(step % NORM_RING) * 32 + nx.rank) * 2;
+    slot[0] = sh[0];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"((unsigned long long)step + 1ull) : "memory");
+  }
 }
 
 // norm_sq is the (all-reduced) sum over ranks.  quirk_scale reproduces the reference's double reduction in
 // parallel runs (Utils.jl:443-448 then rk4.jl:451-453: the logged norm is sqrt(P) too large); 1 in serial.
 // The slot is a device-side counter so that a captured CUDA graph of one RK4 step can be replayed unchanged.
-__global__ void k_norm_commit(const double* norm_sq, double quirk_scale, double* norms, int64_t norms_cap,
-                              double res_tol, int pseudo_time, Ctl* ctl) {
+__global__ void k_norm_commit(const double* norm_sq, NormOut no, Ctl* ctl, NormX nx) {
   if (ctl->stop) return;
-  const double nv = sqrt(*norm_sq * quirk_scale);
-  const int slot = ctl->norm_count;
-  if (slot < norms_cap) norms[slot] = nv;
-  ctl->norm_count = slot + 1;
-  if (pseudo_time && nv < res_tol) { ctl->converged_step = slot; ctl->stop = 1; }
+  double sum = *norm_sq;
+  if (nx.on) {
+    const unsigned step = *nx.nctr;
+    const double* ring = nx.slots[nx.rank] + (size_t)(step % NORM_RING) * 32 * 2;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    sum = 0.0;
+    for (int r = 0; r < nx.nranks; ++r) {
+      for (unsigned it = 0;; ++it) {
+        unsigned long long tag;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(tag) : "l"(ring + 2 * r + 1) : "memory");
+        if (tag == (unsigned long long)step + 1ull) break;
+        if ((it & 63u) == 63u) {
+          if (ld_relaxed_u32(&ctl->stop)) return;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 120000000000ull) { atomicCAS(&ctl->err_code, 0, 4); atomicExch(&ctl->stop, 1); return; }
+        }
+        __nanosleep(100);
+      }
+      sum += *reinterpret_cast<const volatile double*>(ring + 2 * r);
+    }
+    *nx.nctr = step + 1u;
+  }
+  norm_commit(sum, no, ctl);
 }
 
 // applySourceTerm tabulation (source.jl:27-47): srcw[:,j,e] = (w_j / jac[j,e]) * SRCExp(coords[:,j,e])

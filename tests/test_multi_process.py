@@ -39,15 +39,17 @@ def test_partitioned_type2_element_halo_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["p2p", "nccl", "nccl-inline"])
+@pytest.mark.parametrize("transport", ["p2p", "p2p-nograph", "p2p-unfused", "nccl", "nccl-inline"])
 def test_nccl_halo_exchange_matches_serial(transport):
-    """P-way result == serial result through the library's own halo exchange: peer-to-peer copies into the neighbour's
-    IPC-mapped receive buffer + flags (default), ncclSend/ncclRecv (PDES_HALO_NCCL=1), and the latter with pack and
-    shared-face flux on the compute stream (PDES_COMM_INLINE=1)."""
+    """P-way result == serial result through the library's own halo exchange: remote stores into the neighbour's IPC-mapped
+    receive buffer + flags from inside the one face launch of an evaluation, RK4 steps replayed as CUDA graphs (default);
+    the same without graphs (PDES_GRAPH_MP=0); separate pack / signal / wait kernels on the communication stream
+    (PDES_HALO_FUSED=0); ncclSend/ncclRecv (PDES_HALO_NCCL=1), and the latter with pack and shared-face flux on the
+    compute stream (PDES_COMM_INLINE=1)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    env = {"p2p": {}, "nccl": {"PDES_HALO_NCCL": "1"}, "nccl-inline": {"PDES_HALO_NCCL": "1", "PDES_COMM_INLINE": "1"}}[transport]
+    env = {"p2p": {}, "p2p-nograph": {"PDES_GRAPH_MP": "0"}, "p2p-unfused": {"PDES_HALO_FUSED": "0"}, "nccl": {"PDES_HALO_NCCL": "1"}, "nccl-inline": {"PDES_HALO_NCCL": "1", "PDES_COMM_INLINE": "1"}}[transport]
     out = _torchrun("nccl-b200", 2 if n < 4 else 4, 600, env)
     assert "nccl-b200 ok" in out
