@@ -89,12 +89,19 @@ k_jvp_face(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant
     bc_flux_dual<DIM>(r.aux, qL, xb, nrm, a.ph, flux);
   } else {
     iR = op.nbrperm[r.orient][i];
-    const int64_t b = (int64_t)r.elR * EL;
-    for (int j = 0; j < NN; ++j) {
-      const double c = op.interp[j][iR];
-      const int64_t o = b + op.perm[r.fR][j] * ND;
+    if (r.kind == FK_SHARED) {
+      // the neighbour's interpolated state and direction, in ITS face-node order (permuteinterface!, Utils/parallel.jl:198-201)
+      const int64_t o = ((int64_t)r.aux * NFN + iR) * ND;
 #pragma unroll
-      for (int k = 0; k < ND; ++k) { qR[k].v = fma(c, a.q[o + k], qR[k].v); qR[k].d = fma(c, v[o + k], qR[k].d); }
+      for (int k = 0; k < ND; ++k) qR[k] = Dual(a.q_recv[o + k], a.v_recv[o + k]);
+    } else {
+      const int64_t b = (int64_t)r.elR * EL;
+      for (int j = 0; j < NN; ++j) {
+        const double c = op.interp[j][iR];
+        const int64_t o = b + op.perm[r.fR][j] * ND;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { qR[k].v = fma(c, a.q[o + k], qR[k].v); qR[k].d = fma(c, v[o + k], qR[k].d); }
+      }
     }
     roe_flux<DIM, Dual>(qL, qR, nrm, a.ph.gamma, flux);
   }

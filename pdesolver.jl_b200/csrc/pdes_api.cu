@@ -24,6 +24,7 @@
 #include "face_tma.cuh"
 #include "es_kernels.cuh"
 #include "jvp_kernels.cuh"
+#include "generic_kernels.cuh"
 #include "krylov_kernels.cuh"
 #include "diag_kernels.cuh"
 
@@ -753,7 +754,137 @@ struct OpsImplE : Ops {
   }
 };
 
+// Any other operator createSBPOperator can build (solver/common.jl:276-390): run-time sizes, tables in global memory
+// (generic_kernels.cuh).  dense faces + Roe flux (also J*v), or sparse faces + split form with the IR volume flux.
+template <int DIM>
+struct OpsGeneric : Ops {
+  GenTab tab{};
+  bool split = false, uploaded = false;
+  int flux_id = FLUX_ROE;
+  std::vector<double> hd;      // Qt | RfN | interp | wface | S2
+  std::vector<int32_t> hi;     // perm | nbrperm | inv
+  size_t o_Qt = 0, o_RfN = 0, o_interp = 0, o_wface = 0, o_S2 = 0, o_perm = 0, o_nbr = 0, o_inv = 0;
+  double* d_d = nullptr;
+  int32_t* d_i = nullptr;
+  ~OpsGeneric() override { cudaFree(d_d); cudaFree(d_i); }
+  void build_tables(const PdesConfig& c, const double* Q, const double* w, const double* interp, const int64_t* perm,
+                    const int64_t* nbrperm, const double* wface, int base) override {
+    const int nn = c.nn, nfn = c.nfn, ss = c.sparse_face ? 1 : c.ss, NF = DIM + 1, nor = c.norient;
+    split = c.volume_integral_type == 2;
+    flux_id = c.flux_id;
+    tab.nn = nn; tab.nfn = nfn; tab.ss = ss; tab.nor = nor; tab.sparse = c.sparse_face ? 1 : 0;
+    const int nperm = c.sparse_face ? nfn : ss;
+    o_Qt = 0; o_RfN = o_Qt + (size_t)DIM * nn * nn; o_interp = o_RfN + (size_t)NF * nfn * nn;
+    o_wface = o_interp + (size_t)ss * nfn; o_S2 = o_wface + nfn;
+    hd.assign(o_S2 + (size_t)DIM * nn * nn, 0.0);
+    o_perm = 0; o_nbr = o_perm + (size_t)NF * nperm; o_inv = o_nbr + (size_t)nor * nfn;
+    hi.assign(o_inv + (size_t)nn * NF, -1);
+    for (int d = 0; d < DIM; ++d)
+      for (int j = 0; j < nn; ++j)
+        for (int i = 0; i < nn; ++i) {
+          hd[o_Qt + ((size_t)d * nn + j) * nn + i] = Q[j + (size_t)nn * (i + (size_t)nn * d)];
+          hd[o_S2 + ((size_t)d * nn + j) * nn + i] = Q[j + (size_t)nn * (i + (size_t)nn * d)] - Q[i + (size_t)nn * (j + (size_t)nn * d)];
+        }
+    for (int f = 0; f < NF; ++f)
+      for (int j = 0; j < nperm; ++j) hi[o_perm + (size_t)f * nperm + j] = (int32_t)(perm[j + (int64_t)nperm * f] - base);
+    for (int o = 0; o < nor; ++o)
+      for (int i = 0; i < nfn; ++i) hi[o_nbr + (size_t)o * nfn + i] = (int32_t)(nbrperm[i + (int64_t)nfn * o] - base);
+    for (int i = 0; i < nfn; ++i) hd[o_wface + i] = wface[i];
+    if (c.sparse_face) {
+      for (int f = 0; f < NF; ++f)
+        for (int i = 0; i < nfn; ++i) {
+          const int n = hi[o_perm + (size_t)f * nfn + i];
+          for (int u = 0; u < NF; ++u)
+            if (hi[o_inv + (size_t)n * NF + u] < 0) { hi[o_inv + (size_t)n * NF + u] = f * nfn + i; break; }
+        }
+    } else {
+      for (int j = 0; j < ss; ++j)
+        for (int i = 0; i < nfn; ++i) hd[o_interp + (size_t)j * nfn + i] = interp[j + (size_t)ss * i];
+      for (int f = 0; f < NF; ++f)
+        for (int i = 0; i < nfn; ++i)
+          for (int j = 0; j < ss; ++j)
+            hd[o_RfN + ((size_t)f * nfn + i) * nn + hi[o_perm + (size_t)f * ss + j]] += interp[j + (size_t)ss * i];
+    }
+    uploaded = false;
+    (void)w;
+  }
+  cudaError_t prepare() override {
+    if (uploaded) return cudaSuccess;
+    cudaFree(d_d); cudaFree(d_i); d_d = nullptr; d_i = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_d, sizeof(double) * hd.size());
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&d_i, sizeof(int32_t) * hi.size())) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d_d, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d_i, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    tab.Qt = d_d + o_Qt; tab.RfN = d_d + o_RfN; tab.interp = d_d + o_interp; tab.wface = d_d + o_wface; tab.S2 = d_d + o_S2;
+    tab.perm = d_i + o_perm; tab.nbrperm = d_i + o_nbr; tab.inv = d_i + o_inv;
+    uploaded = true;
+    return cudaSuccess;
+  }
+  int64_t grid_for(int64_t nelems) const override { return (nelems * tab.nn + 127) / 128; }
+  int tile_elems() const override { return 1; }
+  int resident_element_ctas() override { return 0; }
+  int resident_face_ctas() override { return 0; }
+  cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
+    if (a.ng <= 0) return cudaSuccess;
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    const unsigned nb = (unsigned)((a.ng * tab.nfn + 127) / 128);
+    if (tab.sparse) k_gen_face_sparse<DIM><<<nb, 128, 0, s>>>(tab, a, flux_id);
+    else k_gen_face<DIM, double><<<nb, 128, 0, s>>>(tab, a, nullptr, nullptr);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_elements(const ElemArgs& a, int mode, cudaStream_t s) override {
+    if (a.nE <= a.e_begin) return cudaSuccess;
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    const unsigned nb = (unsigned)grid_for(a.nE - a.e_begin);
+    if (split) {
+      if (mode == EPI_RES) k_gen_element_split<DIM, EPI_RES><<<nb, 128, 0, s>>>(tab, a);
+      else k_gen_element_split<DIM, EPI_RK><<<nb, 128, 0, s>>>(tab, a);
+    } else {
+      if (mode == EPI_RES) k_gen_element<DIM, EPI_RES><<<nb, 128, 0, s>>>(tab, a);
+      else k_gen_element<DIM, EPI_RK><<<nb, 128, 0, s>>>(tab, a);
+    }
+    return cudaGetLastError();
+  }
+  cudaError_t launch_pack(const double* q, const int32_t* sh_el, const uint8_t* sh_face, int64_t nS, double* q_send,
+                          double* const* face_dst, const Ctl* ctl, cudaStream_t s) override {
+    if (nS <= 0) return cudaSuccess;
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    const int64_t n = nS * tab.nfn * (DIM + 2);
+    k_gen_pack<DIM><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, q, sh_el, sh_face, nS, q_send, face_dst, ctl);
+    return cudaGetLastError();
+  }
+  cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) override {
+    if (tab.sparse || split) return cudaErrorNotSupported;
+    { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+    const int64_t nfn = fa.ng * tab.nfn, nen = a.nE * tab.nn;
+    if (nfn > 0) k_gen_face<DIM, Dual><<<(unsigned)((nfn + 127) / 128), 128, 0, s>>>(tab, fa, v, fa.v_recv);
+    k_gen_jvp_element<DIM><<<(unsigned)((nen + 127) / 128), 128, 0, s>>>(tab, a, v, out);
+    return cudaGetLastError();
+  }
+};
+
+Ops* make_generic_ops(const PdesConfig& c) {
+  if (c.nn < 1 || c.nn > 255 || c.nfn < 1 || c.nfn > 255) return nullptr;      // (the error location keeps 8 bits for the node)
+  if (c.sparse_face) {
+    if (c.volume_integral_type != 2 || c.volume_flux_id != PDES_FLUX_IR || c.face_integral_type != 1) return nullptr;
+    if (c.flux_id != PDES_FLUX_ROE && c.flux_id != PDES_FLUX_IR && c.flux_id != PDES_FLUX_IRSLF) return nullptr;
+  } else {
+    if (c.face_integral_type != 1 || c.volume_integral_type != 1 || c.flux_id != PDES_FLUX_ROE) return nullptr;
+  }
+  if (c.dim == 2) return new OpsGeneric<2>();
+  if (c.dim == 3) return new OpsGeneric<3>();
+  return nullptr;
+}
+
+Ops* make_ops_tuned(const PdesConfig& c);
 Ops* make_ops(const PdesConfig& c) {
+  // PDES_GENERIC=1: the size-generic kernels also for the operators that have tuned instantiations (tests)
+  Ops* o = env_int("PDES_GENERIC", 0) ? nullptr : make_ops_tuned(c);
+  return o ? o : make_generic_ops(c);
+}
+
+Ops* make_ops_tuned(const PdesConfig& c) {
 #ifdef PDES_LEAN
   // development build (make EXTRA=-DPDES_LEAN): only the kernels of the headline workload, a fraction of the build time
   if (!c.sparse_face && c.face_integral_type == 1 && c.volume_integral_type == 1 && c.flux_id == PDES_FLUX_ROE &&
@@ -919,6 +1050,7 @@ struct PdesCtx {
   std::vector<Peer> peers;
   int64_t nS = 0;
   double *q_send = nullptr, *q_recv = nullptr;
+  double *v_send = nullptr, *v_recv = nullptr;     // J*v on a partitioned mesh: shared-face values of the direction
   int32_t* sh_el = nullptr;
   uint8_t* sh_face = nullptr;
   ncclComm_t comm = nullptr;
@@ -1707,7 +1839,10 @@ int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int 
   return PDES_OK;
 }
 
-// out = dR/dq(q) * v on device vectors (q = the resident state)
+// out = dR/dq(q) * v on device vectors (q = the resident state).  Partitioned mesh: the shared-face states AND the
+// shared-face values of the direction travel first (the reference's complex-step product exchanges the perturbed complex
+// state, newton_setup.jl:632-662 with parallel_data from read_input.jl:250-258): ncclSend/ncclRecv in stream order -- these
+// products serve the Krylov loop, not the RK4 hot loop.
 int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev) {
   const PdesConfig& c = ctx->cfg;
   ElemArgs a;
@@ -1719,6 +1854,36 @@ int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev) {
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
   fa.g0 = 0; fa.ng = c.nF + c.nB;
+  if (ctx->nS > 0) {
+    if (!ctx->comm) {
+      set_err(ctx, "J*v on a partitioned mesh needs a communicator (pdes_set_comm)");
+      return PDES_ERR_UNSUPPORTED;
+    }
+    const size_t per_face = (size_t)c.nfn * ctx->nd, nsend = (size_t)ctx->nS * per_face;
+    if (!ctx->v_send) {
+      CUDA_TRY(ctx, cudaMalloc((void**)&ctx->v_send, sizeof(double) * nsend));
+      CUDA_TRY(ctx, cudaMalloc((void**)&ctx->v_recv, sizeof(double) * nsend));
+    }
+    CUDA_TRY(ctx, ctx->ops->launch_pack(a.q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, nullptr, ctx->ctl, ctx->stream));
+    CUDA_TRY(ctx, ctx->ops->launch_pack(vdev, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->v_send, nullptr, ctx->ctl, ctx->stream));
+    ctx->launches += 2;
+    ncclResult_t r = g_nccl.GroupStart();
+    for (auto& p : ctx->peers) {
+      if (r != ncclSuccess) break;
+      const size_t off = (size_t)p.offset * per_face, cnt = (size_t)p.nfaces * per_face;
+      r = g_nccl.Recv(ctx->q_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+      if (r == ncclSuccess) r = g_nccl.Send(ctx->q_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+      if (r == ncclSuccess) r = g_nccl.Recv(ctx->v_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+      if (r == ncclSuccess) r = g_nccl.Send(ctx->v_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) {
+      set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+      return PDES_ERR_COMM;
+    }
+    fa.v_recv = ctx->v_recv;
+    fa.ng = c.nF + c.nB + ctx->nS;
+  }
   cudaError_t e = ctx->ops->launch_jvp(fa, a, vdev, odev, ctx->stream);
   if (e == cudaErrorNotSupported) {
     set_err(ctx, "pdes_eval_jvp is implemented for dense-face operators with the Roe flux only");
@@ -1846,7 +2011,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
-                  ctx->q_send, ctx->q_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
+                  ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
                   ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
                   ctx->kry.partials, ctx->kry.hdev};
@@ -1871,7 +2036,7 @@ int pdes_set_operator(PdesCtx* ctx, const double* Q, const double* w, const doub
                       const int64_t* nbrperm, const double* wface) {
   if (!ctx || !Q || !w || !interp || !perm || !nbrperm || !wface) return usage(ctx, "pdes_set_operator: null argument");
   const PdesConfig& c = ctx->cfg;
-  if (!c.sparse_face && c.ss != c.nn) return usage(ctx, "dense face operators need stencilsize == numnodes");
+  if (!c.sparse_face && (c.ss < 1 || c.ss > c.nn)) return usage(ctx, "dense face operators need 1 <= stencilsize <= numnodes");
   const int nor = c.dim == 2 ? 1 : 3;
   if (c.norient != nor) return usage(ctx, "norient must be 1 (2D) or 3 (3D)");
   const int nperm = c.sparse_face ? c.nfn : c.ss;     // sbpface.perm is [nfn, numfaces] for a SparseFace
@@ -2171,10 +2336,6 @@ int pdes_eval_jvp(PdesCtx* ctx, const double* v, double* out) {
   if (!ctx || !v || !out) return usage(ctx, "pdes_eval_jvp: null argument");
   int rc = finalize(ctx);
   if (rc) return rc;
-  if (ctx->nS > 0) {
-    set_err(ctx, "pdes_eval_jvp is not implemented for partitioned meshes");
-    return PDES_ERR_UNSUPPORTED;
-  }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   double* vdev = ctx->qbuf[(ctx->cur + 1) % 3];     // RK4 scratch buffers double as (v, out) storage
   double* odev = ctx->qbuf[(ctx->cur + 2) % 3];
@@ -2357,6 +2518,15 @@ int kry_alloc(PdesCtx* ctx, int restart) {
   return PDES_OK;
 }
 
+// inner products of distributed vectors: the rank-local sums are added over the communicator (the MPI.Allreduce of the
+// reference's PETSc / calcNorm reductions); every rank then holds the same coefficients
+int kry_allreduce(PdesCtx* ctx, double* dev, int count) {
+  if (!ctx->comm || ctx->nranks <= 1) return PDES_OK;
+  ncclResult_t r = g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+  if (r != ncclSuccess) { set_err(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return PDES_ERR_COMM; }
+  return PDES_OK;
+}
+
 // out[0..nv) = V[0..nv)^T w  (device results)
 int kry_dots(PdesCtx* ctx, const double* V, int nv, const double* w, double* out) {
   PdesCtx::Krylov& k = ctx->kry;
@@ -2365,7 +2535,7 @@ int kry_dots(PdesCtx* ctx, const double* V, int nv, const double* w, double* out
   k_reduce_rows<<<nv, KRY_T, 0, ctx->stream>>>(k.partials, k.nblk, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches += 2;
-  return PDES_OK;
+  return kry_allreduce(ctx, out, nv);
 }
 
 int kry_fetch(PdesCtx* ctx, int count) {
@@ -2494,6 +2664,8 @@ int newton_rhs(PdesCtx* ctx, double* norm_out) {
   k_reduce_rows<<<1, KRY_T, 0, ctx->stream>>>(k.partials, k.nblk, k.hdev);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches += 2;
+  rc = kry_allreduce(ctx, k.hdev, 1);
+  if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(k.hhost, k.hdev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   rc = pdes_sync(ctx);                     // also turns a negative density / pressure into the reference's exception
   if (rc) return rc;
@@ -2511,7 +2683,7 @@ int pdes_gmres(PdesCtx* ctx, const double* b, double* x, double reltol, double a
   if (restart < 1 || itermax < 1) return usage(ctx, "pdes_gmres: restart and itermax must be positive");
   int rc = finalize(ctx);
   if (rc) return rc;
-  if (ctx->nS > 0) { set_err(ctx, "pdes_gmres is not implemented for partitioned meshes"); return PDES_ERR_UNSUPPORTED; }
+  if (ctx->nS > 0 && !ctx->comm) { set_err(ctx, "pdes_gmres on a partitioned mesh needs a communicator (pdes_set_comm)"); return PDES_ERR_UNSUPPORTED; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   rc = kry_alloc(ctx, restart);
   if (rc) return rc;
@@ -2531,7 +2703,7 @@ int pdes_newton_krylov(PdesCtx* ctx, const PdesNewtonOpts* o, double* res_norms_
   if (o->krylov_restart < 1 || o->krylov_itermax < 1 || o->itermax < 0) return usage(ctx, "pdes_newton_krylov: bad options");
   int rc = finalize(ctx);
   if (rc) return rc;
-  if (ctx->nS > 0) { set_err(ctx, "pdes_newton_krylov is not implemented for partitioned meshes"); return PDES_ERR_UNSUPPORTED; }
+  if (ctx->nS > 0 && !ctx->comm) { set_err(ctx, "pdes_newton_krylov on a partitioned mesh needs a communicator (pdes_set_comm)"); return PDES_ERR_UNSUPPORTED; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   rc = kry_alloc(ctx, o->krylov_restart);
   if (rc) return rc;

@@ -117,6 +117,7 @@ struct FaceArgs {
   int32_t nrm_face_stride, nrm_node_stride;   // in doubles: (NFN*DIM, DIM) or (DIM, 0)
   const double* coords_bndry;  // [DIM,NFN,nB]
   const double* q_recv;        // [ND,NFN,nS] (peer's own face-node order)
+  const double* v_recv;        // J*v on a partitioned mesh: the direction v at the neighbours' shared-face nodes, same layout
   double* fluxe;               // [ND,NFN,dim+1,nE]: per (element, local face) the contribution the element integrates,
                                // -wface_i f*(:,i) for elementL, +wface_i f*(:,i) in elementR's own node order
   int64_t g0, ng;              // face range of this launch

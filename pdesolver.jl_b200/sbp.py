@@ -170,6 +170,15 @@ def tri_cubature(kind, degree):
         w = _solve_weights([(ov @ TRI_VTX).T, (oe @ TRI_VTX).T, (os_ @ TRI_VTX).T], 4)
         return (np.vstack([ov, oe, os_]),
                 np.r_[np.full(3, w[0]), np.full(6, w[1]), np.full(3, w[2])])
+    if kind == "omega_alt" and degree == 2:
+        # 7 interior nodes (centroid + two S21 orbits), degree 3: a valid p=2 operator whose node count has no tuned
+        # kernel instantiation (exercises the size-generic kernels; SummationByParts' SBP-Gamma p=2 also has 7 nodes)
+        a1, a2 = 0.11, 0.46
+        oc = _orbit((1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0))
+        o1, o2 = _orbit((1 - 2 * a1, a1, a1)), _orbit((1 - 2 * a2, a2, a2))
+        w = _solve_weights([(o @ TRI_VTX).T for o in (oc, o1, o2)], 3)
+        assert w.min() > 0
+        return np.vstack([oc, o1, o2]), np.r_[np.full(1, w[0]), np.full(3, w[1]), np.full(3, w[2])]
     raise ValueError(f"no triangle cubature for {kind} p={degree}")
 
 
@@ -191,6 +200,23 @@ def tet_cubature(kind, degree):
         assert w.min() > 0
         return (np.vstack([oc, o1, o2]),
                 np.r_[np.full(1, w[0]), np.full(4, w[1]), np.full(6, w[2])])
+    if kind == "omega_alt" and degree == 2:
+        # 14 interior nodes (two S31 orbits + S22), degree 3: no tuned instantiation for this size
+        a1, a2, a3 = 0.09, 0.31, 0.42
+        o1 = _orbit((1 - 3 * a1, a1, a1, a1))
+        o2 = _orbit((1 - 3 * a2, a2, a2, a2))
+        o3 = _orbit((a3, a3, 0.5 - a3, 0.5 - a3))
+        w = _solve_weights([(o @ TET_VTX).T for o in (o1, o2, o3)], 3)
+        assert w.min() > 0
+        return np.vstack([o1, o2, o3]), np.r_[np.full(4, w[0]), np.full(4, w[1]), np.full(6, w[2])]
+    if kind == "diage" and degree == 1:
+        # SBPDiagonalE on the tet, p=1 (the reference's getTetSBPDiagE, solver/common.jl:306): the face nodes -- the 3-point
+        # degree-2 rule of every face -- ARE volume nodes (12), plus the centroid; volume rule of degree 2p-1 = 1
+        oc = _orbit((0.25, 0.25, 0.25, 0.25))
+        of = _orbit((2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 0.0))
+        w = _solve_weights([(o @ TET_VTX).T for o in (oc, of)], 1)
+        assert w.min() > 0
+        return np.vstack([oc, of]), np.r_[np.full(1, w[0]), np.full(12, w[1])]
     raise ValueError(f"no tet cubature for {kind} p={degree}")
 
 
@@ -295,6 +321,7 @@ def build_operator(dim: int, degree: int, kind: str = "omega") -> SBPOperator:
         ref_n = np.array([[0.0, -1.0], [1.0, 1.0], [-1.0, 0.0]]).T
     else:
         fb, wf = tri_cubature("omega", degree)
+        wf = wf * 1.0
         ref_n = np.array([[0.0, 0.0, -1.0], [0.0, -1.0, 0.0],
                           [1.0, 1.0, 1.0], [-1.0, 0.0, 0.0]]).T
     nfn = fb.shape[0]

@@ -18,7 +18,9 @@ def rel_l2(a, b):
 
 ES_OPTS = {"Flux_name": "IRSLFFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2,
            "BC1_name": "isentropicVortexBC"}
-KIND = {"c2_2d_p2_es": "diage", "2d_p2_es_ir": "diage", "2d_p2_es_roe": "diage"}
+KIND = {"c2_2d_p2_es": "diage", "2d_p2_es_ir": "diage", "2d_p2_es_roe": "diage",
+        # operators whose node counts have no tuned kernel instantiation (size-generic kernels)
+        "2d_p2_alt_roe": "omega_alt", "3d_p2_alt_roe_src": "omega_alt", "3d_p1_es": "diage"}
 
 CASES = {
     # name: (dim, degree, IC, opts)
@@ -33,4 +35,7 @@ CASES = {
                       {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
     "c3_3d_p2_roe_src": (3, 2, "ICExp",
                          {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
+    "2d_p2_alt_roe": (2, 2, "ICIsentropicVortex", {"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}),
+    "3d_p2_alt_roe_src": (3, 2, "ICExp", {"Flux_name": "RoeFlux", "BC1_name": "ExpBC", "SRCname": "SRCExp"}),
+    "3d_p1_es": (3, 1, "ICExp", dict(ES_OPTS, BC1_name="ExpBC")),
 }

@@ -145,6 +145,31 @@ def run_nccl_b200(rank, world, local_rank):
         # the parallel norm is reduced twice -> sqrt(P) * serial norm
         assert np.allclose(eqn.convergence, np.sqrt(world) * norms_ref, rtol=1e-11, atol=0), \
             f"rank {rank} {case}: norms"
+        if case not in ("c2_2d_p2_es",):
+            # J*v and the Newton-Krylov linear solve on the partitioned mesh (newton_setup.jl:632-662 is flux- and
+            # partition-agnostic): the shared-face states AND directions are exchanged, the Krylov inner products are
+            # all-reduced.  Reference: the same product / solve by a serial context on this rank's GPU.
+            es = pd.EulerData(serial, op, opts, device=local_rank)
+            rng = np.random.RandomState(7)
+            v_s = np.asfortranarray(rng.standard_normal(q_s.shape) * np.abs(q_s))
+            es.q[...] = q_s
+            eqn.q[...] = q_s[:, :, idx]
+            Jv_s = pd.evaldRdqProduct(serial, op, es, opts, v_s)
+            Jv_p = pd.evaldRdqProduct(local, op, eqn, opts, np.asfortranarray(v_s[:, :, idx]))
+            errj = rel_l2(Jv_p, Jv_s[:, :, idx])
+            assert errj < 1e-12, f"rank {rank} {case}: partitioned J*v {errj:.2e}"
+            kopts = dict(opts, krylov_reltol=1e-10, krylov_itermax=300, krylov_restart=100)
+            b_s = np.asfortranarray(rng.standard_normal(q_s.shape))
+            x_s = pd.linearSolve(serial, op, es, kopts, b_s)
+            x_p = pd.linearSolve(local, op, eqn, kopts, np.asfortranarray(b_s[:, :, idx]))
+            ks, kp = es.krylov_info, eqn.krylov_info
+            assert kp["reason"] == ks["reason"] and abs(kp["iterations"] - ks["iterations"]) <= 2, (kp, ks)
+            if ks["reason"] > 0:
+                errx = rel_l2(x_p, x_s[:, :, idx])
+                assert errx < 1e-6, f"rank {rank} {case}: partitioned GMRES {errx:.2e}"
+            else:
+                assert abs(kp["rnorm"] - ks["rnorm"]) < 1e-6 * ks["rnorm"], (kp, ks)
+            es.close()
         eqn.close()
         dist.barrier()
     if rank == 0:

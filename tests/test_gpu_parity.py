@@ -919,3 +919,75 @@ def test_jvp_with_more_boundary_functors(bc):
     eps = 1e-6
     fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
     assert rel_l2(Jv, fd) < 1e-8
+
+
+# ---- size-generic kernels (generic_kernels.cuh): any operator createSBPOperator can build (solver/common.jl:276-390) --------
+GENERIC_CASES = [("2d_p2_alt_roe", 6, 1e-3), ("3d_p2_alt_roe_src", 3, 5e-5), ("3d_p1_es", 3, 5e-5)]
+
+
+@pytest.mark.parametrize("case,n,h", GENERIC_CASES)
+def test_generic_kernels_nontemplate_operators(case, n, h):
+    """Operators whose (numnodes, numfacenodes) have no tuned instantiation -- a 7-node p=2 triangle, a 14-node p=2 tet, the
+    13-node diagonal-E tet (the 3D entropy-stable configuration) -- run on the size-generic kernels: residual, RK4 and
+    LSERK54 trajectories, error semantics."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=3)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+    opts["use_itermax"] = False
+    eqn.q[...] = q0
+    t = pd.rk4(pd.evalResidual, h, 8 * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 8 * h)
+    assert t == t_ref and rel_l2(eqn.q, q_ref) < RK_TOL
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+    eqn.q[...] = q0
+    t = pd.lserk54(pd.evalResidual, h, 6 * h, mesh, op, eqn, opts)
+    t_ref, q_ref, norms_ref = orc.lserk54(q0, h, 6 * h)
+    assert t == t_ref and rel_l2(eqn.q, q_ref) < RK_TOL
+    assert np.allclose(eqn.convergence, norms_ref, rtol=1e-11, atol=0)
+    # negative density -> the reference's exception with the offending element and node
+    bad = q0.copy(order="F")
+    bad[0, 2, 5] = -1.0
+    eqn.q[...] = bad
+    with pytest.raises(pd.PhysicsError) as ei:
+        pd.evalResidual(mesh, op, eqn, opts)
+    assert (ei.value.element, ei.value.node) == (5, 2)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+
+
+@pytest.mark.parametrize("case,n,h", [("c1_2d_p1_roe", 8, 1e-3), ("c3_3d_p2_roe_src", 3, 5e-5), ("c2_2d_p2_es", 5, 1e-3),
+                                       ("2d_p2_es_roe", 5, 1e-3)])
+def test_generic_kernels_on_tuned_sizes(case, n, h, monkeypatch):
+    """PDES_GENERIC=1 routes the operators that DO have tuned kernels through the size-generic ones: same oracle parity,
+    and agreement with the tuned path at rounding level."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=4)
+    opts["use_itermax"] = False
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    res_t = eqn.res.copy(order="F")
+    monkeypatch.setenv("PDES_GENERIC", "1")
+    eg = pd.EulerData(mesh, op, opts)
+    eg.q[...] = q0
+    pd.evalResidual(mesh, op, eg, opts)
+    assert rel_l2(eg.res, orc.eval_residual(q0)) < RES_TOL
+    assert rel_l2(eg.res, res_t) < RES_TOL
+    eg.q[...] = q0
+    t = pd.rk4(pd.evalResidual, h, 6 * h, mesh, op, eg, opts)
+    t_ref, q_ref, norms_ref = orc.rk4(q0, h, 6 * h)
+    assert t == t_ref and rel_l2(eg.q, q_ref) < RK_TOL
+    assert np.allclose(eg.convergence, norms_ref, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("case,n", [("2d_p2_alt_roe", 5), ("3d_p2_alt_roe_src", 3)])
+def test_generic_jacobian_vector_product(case, n):
+    """J*v for an operator without tuned kernels (dual numbers through the generic kernels) vs central differences."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=6)
+    rng = np.random.RandomState(1)
+    v = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+    eqn.q[...] = q0
+    Jv = pd.evaldRdqProduct(mesh, op, eqn, opts, v)
+    eps = 1e-6
+    fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
+    assert rel_l2(Jv, fd) < 1e-8
