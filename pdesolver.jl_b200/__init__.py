@@ -6,7 +6,7 @@ top of the C ABI in ``include/pdes_euler_b200.h``; ``sbp`` and ``mesh`` are
 host-side stand-ins for the un-vendored SummationByParts.jl / PumiInterface.jl
 inputs (synthetic structured meshes, SBP operators).
 """
-from . import mesh, sbp  # noqa: F401
+from . import dump, mesh, sbp  # noqa: F401
 from .euler import (calcEntropyIntegral, calcKineticEnergy, calcKineticEnergydt, contractResEntropyVars,  # noqa: F401
                     diagnostics, integrateQ)
 from .euler import (EulerData, ParamType, PDESolverError, PhysicsError,  # noqa: F401
