@@ -121,6 +121,17 @@ int pdes_set_peer(PdesCtx *ctx, int32_t peer_idx, int32_t peer_rank, int64_t nfa
                   const PdesBoundary *bndries_local, const PdesInterface *shared_interfaces,
                   const double *nrm_sharedface);
 
+/* face_integral_type = 2 on a partitioned mesh (parallel_data = element, input/read_input.jl:250-258): the element-data
+ * halo.  local_elements[nsend] = mesh.local_element_lists[peer] (this rank's elements the peer needs, in the peer's
+ * remote-element order; getSendDataElement, Utils/parallel.jl:276-293); nrecv = number of the peer's elements in this
+ * rank's halo; shared_element_offset = mesh.shared_element_offsets[peer], the element number shared_interfaces[j].elementR
+ * starts from (calcSharedFaceElementIntegrals_element_inner, flux.jl:442-496).  index_base applies to both. */
+int pdes_set_peer_elements(PdesCtx *ctx, int32_t peer_idx, int64_t nsend, const int64_t *local_elements, int64_t nrecv,
+                           int64_t shared_element_offset);
+/* test hooks of the element-data halo when no second GPU exists ([nd,nn,nsend] / [nd,nn,nrecv], host pointers) */
+int pdes_pack_send_elements(PdesCtx *ctx, int32_t peer_idx, double *q_send_out);
+int pdes_inject_recv_elements(PdesCtx *ctx, int32_t peer_idx, const double *q_recv);
+
 /* Multi-GPU: NCCL communicator from a 128-byte ncclUniqueId the host broadcast
  * (replaces mesh.comm / MPI.Isend/Irecv!, parallel_types.jl:620-684).
  * The communicator carries the set-up and the 8-byte norm all-reduce.  The per-

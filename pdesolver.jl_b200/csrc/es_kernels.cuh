@@ -111,6 +111,17 @@ __global__ void k_pack_send_sparse(const __grid_constant__ OpTabS<DIM, NN, NFN> 
 }
 
 
+// getSendDataElement (Utils/parallel.jl:276-293): send_buff[:, :, j] = q[:, :, local_element_lists[peer][j]] (all peers'
+// lists concatenated)
+__global__ void k_pack_send_element(const double* __restrict__ q, const int32_t* __restrict__ el_list, int64_t nel, int el_len,
+                                    double* __restrict__ out, const Ctl* ctl) {
+  if (ctl->stop) return;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nel * el_len) return;
+  const int64_t j = t / el_len;
+  out[t] = q[(int64_t)el_list[j] * el_len + (t - j * el_len)];
+}
+
 // ------------------------------------------------------------------------------------------------------
 // k_face_element: face_integral_type = 2 for dense-face (SBP-Omega) operators:
 // getFaceElementIntegral (flux.jl:132-160) with the functors ECFaceIntegral / ELFPenaltyFaceIntegral /
@@ -148,15 +159,20 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   const int64_t g = a.g0 + blockIdx.x;
   const FaceRec r = a.faces[g];
   const bool interior = r.kind == FK_INTERIOR;
+  // shared face (calcSharedFaceElementIntegrals_element_inner, flux.jl:442-496): elementR is a whole element of the
+  // neighbour, received into q_recv (element-data halo, getSendDataElement Utils/parallel.jl:276-293; r.elR = its slot);
+  // only elementL's record is kept
+  const bool shared = r.kind == FK_SHARED;
+  const bool two = interior || shared;
   // operator tables from their device copies (tab_dev: perm | nbrperm, optab_dev: interp | wface): a read of the
   // kernel-parameter bank with a per-thread index is replayed once per distinct address
   if (tid < NN) {
     spL[tid] = __ldg(a.tab_dev + r.fL * NN + tid);
-    spR[tid] = interior ? __ldg(a.tab_dev + r.fR * NN + tid) : 0;
+    spR[tid] = two ? __ldg(a.tab_dev + r.fR * NN + tid) : 0;
   }
   if (tid >= 32 && tid < 32 + NFN) {
     const int k = tid - 32;
-    snbr[k] = __ldg(a.tab_dev + NF * NN + (interior ? r.orient : 0) * NFN + k);
+    snbr[k] = __ldg(a.tab_dev + NF * NN + (two ? r.orient : 0) * NFN + k);
     swf[k] = __ldg(a.optab_dev + NN * NFN + k);
   }
   for (int idx = tid; idx < NN * NFN; idx += T) sA[idx / NFN][idx % NFN] = __ldg(a.optab_dev + idx);
@@ -164,7 +180,7 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   for (int idx = tid; idx < NN * ND; idx += T) {
     const int j = idx / ND, k = idx - j * ND;
     sq[0][j][k] = __ldg(a.q + (int64_t)r.elL * EL + spL[j] * ND + k);
-    sq[1][j][k] = interior ? __ldg(a.q + (int64_t)r.elR * EL + spR[j] * ND + k) : 0.0;
+    sq[1][j][k] = two ? __ldg((shared ? a.q_recv : a.q) + (int64_t)r.elR * EL + spR[j] * ND + k) : 0.0;
     srec[0][j][k] = 0.0;
     srec[1][j][k] = 0.0;
   }
@@ -174,14 +190,14 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   }
   __syncthreads();
   const int* nbr = snbr;
-  if (interior) {
+  if (two) {
     for (int idx = tid; idx < NN * DIM * NFN; idx += T) {
       const int j = idx / (DIM * NFN), d = (idx / NFN) % DIM, k = idx % NFN;
       sB[j][d][k] = sA[j][nbr[k]] * sc[d][k];
     }
   }
 
-  if (!interior) {
+  if (!two) {
     // interpolateBoundary + BC functor + boundaryintegrate! (bc.jl:162-175, 251-284; euler.jl:669-690)
     if (tid < NFN) {
       const int k = tid;

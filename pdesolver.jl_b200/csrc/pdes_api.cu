@@ -81,6 +81,11 @@ struct Peer {
   std::vector<PdesBoundary> bndries_local;
   std::vector<PdesInterface> ifaces;
   std::vector<double> nrm;
+  // element-data halo (face_integral_type 2, parallel_data = element): my elements the peer needs, in the peer's
+  // remote-element order; the peer's elements in my halo are numbered shared_el_offset, shared_el_offset + 1, ...
+  std::vector<int64_t> send_els;
+  int64_t n_recv_el = 0, shared_el_offset = 0, el_send_off = 0, el_recv_off = 0;
+  bool have_els = false;
 };
 
 int env_int(const char* name, int dflt) {
@@ -1051,6 +1056,11 @@ struct PdesCtx {
   int64_t nS = 0;
   double *q_send = nullptr, *q_recv = nullptr;
   double *v_send = nullptr, *v_recv = nullptr;     // J*v on a partitioned mesh: shared-face values of the direction
+  // element-data halo of the type-2 face integrals
+  bool elem_halo = false;
+  int64_t n_send_el = 0, n_recv_el = 0;
+  int32_t* el_send_list = nullptr;
+  double *qel_send = nullptr, *qel_recv = nullptr;
   int32_t* sh_el = nullptr;
   uint8_t* sh_face = nullptr;
   ncclComm_t comm = nullptr;
@@ -1149,6 +1159,20 @@ int finalize(PdesCtx* ctx) {
   // shared faces are appended to the face list after the interfaces and the boundary faces
   ctx->nS = 0;
   for (auto& p : ctx->peers) { p.offset = ctx->nS; ctx->nS += p.nfaces; }
+  ctx->elem_halo = c.face_integral_type == 2 && !ctx->peers.empty();
+  ctx->n_send_el = ctx->n_recv_el = 0;
+  std::vector<int32_t> el_send;
+  if (ctx->elem_halo) {
+    for (auto& p : ctx->peers) {
+      if (!p.have_els) return usage(ctx, "face_integral_type 2 on a partitioned mesh: pdes_set_peer_elements was not called for every peer");
+      p.el_send_off = ctx->n_send_el; p.el_recv_off = ctx->n_recv_el;
+      ctx->n_send_el += (int64_t)p.send_els.size(); ctx->n_recv_el += p.n_recv_el;
+      for (int64_t e : p.send_els) {
+        if (e - base < 0 || e - base >= c.nE) return usage(ctx, "pdes_set_peer_elements: local element out of range");
+        el_send.push_back((int32_t)(e - base));
+      }
+    }
+  }
   const int64_t nG = c.nF + c.nB + ctx->nS;
   std::vector<int32_t> sh_el(ctx->nS);
   std::vector<uint8_t> sh_face(ctx->nS);
@@ -1173,7 +1197,14 @@ int finalize(PdesCtx* ctx) {
       FaceRec& fr = faces[g];
       memset(&fr, 0, sizeof(fr));
       fr.elL = (int32_t)el; fr.elR = -1; fr.fL = (uint8_t)f; fr.orient = (uint8_t)o; fr.kind = FK_SHARED;
+      fr.fR = (uint8_t)((int)p.ifaces[j].faceR - base);
       fr.aux = (int32_t)(p.offset + j);
+      if (ctx->elem_halo) {
+        // the neighbour's element behind this face: slot in the element receive buffer
+        const int64_t rel = (int64_t)p.ifaces[j].elementR - p.shared_el_offset;
+        if (rel < 0 || rel >= p.n_recv_el || fr.fR >= NF) return usage(ctx, "shared interface: remote element / face out of range");
+        fr.elR = (int32_t)(p.el_recv_off + rel);
+      }
       sh_el[p.offset + j] = (int32_t)el;
       sh_face[p.offset + j] = (uint8_t)f;
     }
@@ -1308,6 +1339,12 @@ int finalize(PdesCtx* ctx) {
   size_t nsend = (size_t)ctx->nS * c.nfn * ctx->nd;
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_send, nullptr, nsend));
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->q_recv, nullptr, nsend));
+  if (ctx->elem_halo) {
+    const size_t el_len = (size_t)c.nn * ctx->nd;
+    CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->el_send_list, el_send.data(), el_send.size()));
+    CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->qel_send, nullptr, (size_t)ctx->n_send_el * el_len));
+    CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->qel_recv, nullptr, (size_t)ctx->n_recv_el * el_len));
+  }
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
   for (int i = 0; i < 3; ++i)
     if (ctx->step_graph[i]) { cudaGraphExecDestroy(ctx->step_graph[i]); ctx->step_graph[i] = nullptr; }
@@ -1370,7 +1407,8 @@ int setup_p2p(PdesCtx* ctx) {
   const int np = (int)ctx->peers.size();
   HaloRec mine;
   memset(&mine, 0, sizeof(mine));
-  bool ok = env_int("PDES_HALO_NCCL", 0) == 0 && np <= 32 && g_nccl.AllGather != nullptr;
+  // (the element-data halo of the type-2 face integrals travels by ncclSend/ncclRecv)
+  bool ok = env_int("PDES_HALO_NCCL", 0) == 0 && np <= 32 && g_nccl.AllGather != nullptr && !ctx->elem_halo;
   if (ok) {
     // + flags | abort | ctr | norm slot ring
     const size_t bytes = 2 * nsend * sizeof(double) + 256 + (32 + 32 + 4) * sizeof(unsigned) + NORM_RING * 32 * 2 * sizeof(double);
@@ -1484,6 +1522,35 @@ int start_exchange(PdesCtx* ctx, const double* q) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_q, 0));
   }
+  if (ctx->elem_halo) {
+    // parallel_data = element (getSendDataElement, Utils/parallel.jl:276-293): whole elements of the negotiated lists
+    const int el_len = ctx->cfg.nn * ctx->nd;
+    const int64_t n = ctx->n_send_el * el_len;
+    if (n > 0) {
+      k_pack_send_element<<<(unsigned)((n + 255) / 256), 256, 0, ps>>>(q, ctx->el_send_list, ctx->n_send_el, el_len, ctx->qel_send, ctx->ctl);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches++;
+    }
+    if (!ctx->comm) return PDES_OK;   // test mode: receive buffer injected by hand
+    if (!overlap) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+    }
+    ncclResult_t r = g_nccl.GroupStart();
+    for (auto& p : ctx->peers) {
+      if (r != ncclSuccess) break;
+      r = g_nccl.Recv(ctx->qel_recv + p.el_recv_off * el_len, (size_t)p.n_recv_el * el_len, ncclFloat64, p.rank, ctx->comm, ctx->comm_stream);
+      if (r != ncclSuccess) break;
+      r = g_nccl.Send(ctx->qel_send + p.el_send_off * el_len, p.send_els.size() * (size_t)el_len, ncclFloat64, p.rank, ctx->comm, ctx->comm_stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) {
+      set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+      return PDES_ERR_COMM;
+    }
+    if (!overlap) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_recv, ctx->comm_stream));
+    return PDES_OK;
+  }
   const bool put = ctx->comm && ctx->p2p == 1 && ctx->d_face_dst != nullptr;
   const uint32_t ep_next = ctx->halo_epoch + 1;
   CUDA_TRY(ctx, ctx->ops->launch_pack(q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send,
@@ -1546,7 +1613,7 @@ int enqueue_residual(PdesCtx* ctx, ElemArgs& a, int mode) {
   FaceArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
-  fa.q_recv = (ctx->comm && ctx->p2p == 1) ? ctx->q_recv_eval : ctx->q_recv;
+  fa.q_recv = ctx->elem_halo ? ctx->qel_recv : ((ctx->comm && ctx->p2p == 1) ? ctx->q_recv_eval : ctx->q_recv);
   fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
   fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
   fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
@@ -1929,10 +1996,6 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
     set_err(nullptr, "Unsupported face integral type = %d", cfg->face_integral_type);
     return PDES_ERR_UNSUPPORTED;
   }
-  if (cfg->face_integral_type == 2 && cfg->npeers > 0) {
-    set_err(nullptr, "face_integral_type 2 needs the element-data halo (parallel_data = element), which is not implemented");
-    return PDES_ERR_UNSUPPORTED;
-  }
   if (cfg->nE <= 0 || cfg->nE * (cfg->dim + 1) > 0x7fffff00ll)
     return usage(nullptr, "pdes_create: numEl out of range (32-bit element-face indices)");
   std::unique_ptr<PdesCtx> ctx(new PdesCtx());
@@ -2011,7 +2074,7 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
-                  ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
+                  ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->el_send_list, ctx->qel_send, ctx->qel_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
                   ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
                   ctx->kry.partials, ctx->kry.hdev};
@@ -2191,6 +2254,55 @@ int pdes_set_peer(PdesCtx* ctx, int32_t peer_idx, int32_t peer_rank, int64_t nfa
   p.ifaces.assign(shared_interfaces, shared_interfaces + nfaces);
   p.nrm.assign(nrm_sharedface, nrm_sharedface + (size_t)nfaces * ctx->cfg.nfn * ctx->cfg.dim);
   ctx->finalized = false;
+  return PDES_OK;
+}
+
+int pdes_set_peer_elements(PdesCtx* ctx, int32_t peer_idx, int64_t nsend, const int64_t* local_elements, int64_t nrecv,
+                           int64_t shared_element_offset) {
+  if (!ctx) return usage(ctx, "pdes_set_peer_elements: null ctx");
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size()) return usage(ctx, "pdes_set_peer_elements: peer index out of range");
+  if (nsend < 0 || nrecv < 0 || (nsend > 0 && !local_elements)) return usage(ctx, "pdes_set_peer_elements: bad argument");
+  Peer& p = ctx->peers[peer_idx];
+  p.send_els.assign(local_elements, local_elements + nsend);
+  p.n_recv_el = nrecv;
+  p.shared_el_offset = shared_element_offset;
+  p.have_els = true;
+  ctx->finalized = false;
+  return PDES_OK;
+}
+
+int pdes_pack_send_elements(PdesCtx* ctx, int32_t peer_idx, double* q_send_out) {
+  if (!ctx || !q_send_out) return usage(ctx, "pdes_pack_send_elements: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size() || !ctx->elem_halo) return usage(ctx, "no element-data halo for this peer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const int el_len = ctx->cfg.nn * ctx->nd;
+  const int64_t n = ctx->n_send_el * el_len;
+  if (n > 0) {
+    k_pack_send_element<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->el_send_list, ctx->n_send_el,
+                                                                              el_len, ctx->qel_send, ctx->ctl);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  const Peer& p = ctx->peers[peer_idx];
+  CUDA_TRY(ctx, cudaMemcpyAsync(q_send_out, ctx->qel_send + p.el_send_off * el_len, sizeof(double) * p.send_els.size() * el_len,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PDES_OK;
+}
+
+int pdes_inject_recv_elements(PdesCtx* ctx, int32_t peer_idx, const double* q_recv) {
+  if (!ctx || !q_recv) return usage(ctx, "pdes_inject_recv_elements: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  if (peer_idx < 0 || peer_idx >= (int)ctx->peers.size() || !ctx->elem_halo) return usage(ctx, "no element-data halo for this peer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const Peer& p = ctx->peers[peer_idx];
+  const int el_len = ctx->cfg.nn * ctx->nd;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->qel_recv + p.el_recv_off * el_len, q_recv, sizeof(double) * (size_t)p.n_recv_el * el_len,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return PDES_OK;
 }
 

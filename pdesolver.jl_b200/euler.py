@@ -148,6 +148,11 @@ class EulerData:
             si = np.ascontiguousarray(mesh.shared_interfaces[pi])
             ns = _f64(mesh.nrm_sharedface[pi])
             self._check(L.pdes_set_peer(ctx, pi, int(mesh.peer_parts[pi]), len(bl), _ptr(bl), _ptr(si), _ptr(ns)))
+            if cfg.face_integral_type == 2:
+                # parallel_data = element (input/read_input.jl:250-258): the element-data halo
+                le = np.ascontiguousarray(mesh.local_element_lists[pi], dtype=np.int64)
+                self._check(L.pdes_set_peer_elements(ctx, pi, len(le), _ptr(le), len(mesh.remote_global_elnum[pi]),
+                                                     int(mesh.shared_element_offsets[pi])))
 
     def set_comm(self, unique_id: bytes, rank: int, nranks: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
@@ -182,6 +187,16 @@ class EulerData:
         self._check(self._L.pdes_set_q(self._ctx, _ptr(self.q)))
         self._check(self._L.pdes_pack_send(self._ctx, peer_idx, _ptr(out)))
         return out
+
+    def pack_send_elements(self, peer_idx):
+        n = len(self.mesh.local_element_lists[peer_idx])
+        out = np.zeros((self.mesh.numDofPerNode, self.sbp.numnodes, n), order="F")
+        self._check(self._L.pdes_set_q(self._ctx, _ptr(self.q)))
+        self._check(self._L.pdes_pack_send_elements(self._ctx, peer_idx, _ptr(out)))
+        return out
+
+    def inject_recv_elements(self, peer_idx, q_recv):
+        self._check(self._L.pdes_inject_recv_elements(self._ctx, peer_idx, _ptr(_f64(q_recv))))
 
     def inject_recv(self, peer_idx, q_recv):
         self._check(self._L.pdes_inject_recv(self._ctx, peer_idx, _ptr(_f64(q_recv))))

@@ -65,6 +65,7 @@ class Mesh:
     nrm_sharedface: list = field(default_factory=list)      # per peer [dim,nfn,nfaces]
     shared_element_offsets: list = field(default_factory=list)
     remote_global_elnum: list = field(default_factory=list)  # per peer: global numbers of its elements in this part's halo
+    local_element_lists: list = field(default_factory=list)  # per peer: my elements it needs, in ITS remote-element order
     global_elnum: np.ndarray = None                         # local -> global element id
     elem_vtx_coords: np.ndarray = None                      # [nE, dim+1, dim]
 
@@ -360,7 +361,20 @@ def structured_mesh(op: SBPOperator, n, parts=None, rank: int = 0,
         sides = [0] * (2 * dim) if bc_sides is None else bc_sides
         return np.asarray(sides)[side], int(max(sides)) + 1
 
-    return _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of)
+    mesh = _assemble(op, dim, gvid, vcoord, el_owner, gel, nE, rank, nranks, side_of)
+    # mesh.local_element_lists (PumiInterface; read by getSendDataElement, Utils/parallel.jl:276-293): the peer's ghost
+    # layer is every cell of its block extended by one, so it needs my elements in those cells, and it numbers them by
+    # global element number (the order of its remote_global_elnum entry for this part)
+    gcell_of = mesh.global_elnum // ns
+    cw = np.cumprod([1] + nv[:-1]).astype(np.int64)
+    cidx = np.stack([(gcell_of // cw[d]) % nv[d] for d in range(dim)], axis=1)
+    for pr in mesh.peer_parts:
+        plo, phi, _ = block_ranges(nv, parts, pr)
+        inside = np.ones(len(cidx), dtype=bool)
+        for d in range(dim):
+            inside &= (cidx[:, d] >= max(plo[d] - 1, 0)) & (cidx[:, d] < min(phi[d] + 1, nv[d]))
+        mesh.local_element_lists.append(np.nonzero(inside)[0].astype(np.int64))      # local elements are in global order
+    return mesh
 
 
 def two_element_mesh(op: SBPOperator) -> Mesh:

@@ -172,6 +172,37 @@ def run_nccl_b200(rank, world, local_rank):
             es.close()
         eqn.close()
         dist.barrier()
+    # type-2 entropy-stable face integrals through the element-data halo (ncclSend/ncclRecv of whole elements)
+    import oracle
+    for dim, p, n, fei in [(3, 1, 3, "ESLFFaceIntegral"), (2, 2, 4, "ESLW2FaceIntegral")]:
+        import pdesolver_jl_b200 as pd
+        from common import perturbed
+        op = pd.build_operator(dim, p)
+        parts = PARTS[world][dim]
+        serial = pd.structured_mesh(op, n, shuffle_seed=4)
+        local = pd.structured_mesh(op, n, parts=parts, rank=rank, shuffle_seed=4)
+        ic, bc = ("ICIsentropicVortex", "isentropicVortexBC") if dim == 2 else ("ICExp", "ExpBC")
+        opts = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2, "face_integral_type": 2,
+                "FaceElementIntegral_name": fei, "BC1_name": bc, "use_itermax": False}
+        orc_s = oracle.Problem(serial, op, opts)
+        q_s = perturbed(orc_s.exact_state(ic), amp=1e-2)
+        pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
+        idx = np.array([pos[int(g)] for g in local.global_elnum])
+        ids = [pd.EulerData.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eqn = pd.EulerData(local, op, opts, device=local_rank, comm=(ids[0], rank, world))
+        eqn.q[...] = q_s[:, :, idx]
+        pd.evalResidual(local, op, eqn, opts)
+        err = rel_l2(eqn.res, orc_s.eval_residual(q_s)[:, :, idx])
+        assert err < 1e-12, f"rank {rank} type-2 {dim}D p{p}: residual parity {err:.2e}"
+        h = 1e-3 if dim == 2 else 5e-5
+        eqn.q[...] = q_s[:, :, idx]
+        pd.rk4(pd.evalResidual, h, 5 * h, local, op, eqn, opts)
+        _, q_ref, _ = orc_s.rk4(q_s, h, 5 * h)
+        errq = rel_l2(eqn.q, q_ref[:, :, idx])
+        assert errq < 1e-10, f"rank {rank} type-2 {dim}D p{p}: rk4 parity {errq:.2e}"
+        eqn.close()
+        dist.barrier()
     if rank == 0:
         print(f"nccl-b200 ok on {world} ranks")
 

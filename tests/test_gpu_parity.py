@@ -991,3 +991,39 @@ def test_generic_jacobian_vector_product(case, n):
     eps = 1e-6
     fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
     assert rel_l2(Jv, fd) < 1e-8
+
+
+@pytest.mark.parametrize("dim,p,n,parts,fei", [(2, 2, 5, (2, 2), "ESLFFaceIntegral"), (3, 1, 3, (2, 2, 2), "ESLFFaceIntegral"),
+                                               (3, 2, 3, (2, 1, 1), "ESLW2FaceIntegral"), (2, 1, 6, (2, 1), "ECFaceIntegral")])
+def test_partitioned_type2_equals_serial(dim, p, n, parts, fei):
+    """SURVEY.md §8(f) N2 on a partitioned mesh: face_integral_type = 2 needs the neighbour's WHOLE element behind every shared
+    face (parallel_data = element; getSendDataElement Utils/parallel.jl:276-293, calcSharedFaceElementIntegrals_element_inner
+    flux.jl:442-496).  P-way == serial (runtests_parallel2.jl strategy), the exchange done by hand through the test hooks
+    (k_pack_send_element on the device -> host -> the peer's element receive buffer); NCCL itself: tests/test_multi_process.py."""
+    op = pd.build_operator(dim, p)
+    ic, bc = ("ICIsentropicVortex", "isentropicVortexBC") if dim == 2 else ("ICExp", "ExpBC")
+    opts = {"Flux_name": "IRFlux", "Volume_flux_name": "IRFlux", "volume_integral_type": 2, "face_integral_type": 2,
+            "FaceElementIntegral_name": fei, "BC1_name": bc}
+    nranks = int(np.prod(parts))
+    meshes = [pd.structured_mesh(op, n, parts=parts, rank=r, shuffle_seed=4) for r in range(nranks)]
+    serial = pd.structured_mesh(op, n, shuffle_seed=4)
+    orc_s = oracle.Problem(serial, op, opts)
+    q_s = perturbed(orc_s.exact_state(ic), amp=1e-2)
+    res_s = orc_s.eval_residual(q_s)
+    pos = {int(g): i for i, g in enumerate(serial.global_elnum)}
+    eqns, qs = [], []
+    for m in meshes:
+        idx = np.array([pos[int(g)] for g in m.global_elnum])
+        eq = pd.EulerData(m, op, opts)
+        eq.q[...] = q_s[:, :, idx]
+        eqns.append(eq)
+        qs.append(idx)
+    sends = [[eq.pack_send_elements(pi) for pi in range(m.npeers)] for eq, m in zip(eqns, meshes)]
+    for r, (eq, m) in enumerate(zip(eqns, meshes)):
+        for pi, pr in enumerate(m.peer_parts):
+            po = meshes[pr].peer_parts.index(r)
+            assert np.array_equal(sends[pr][po], q_s[:, :, [pos[int(g)] for g in m.remote_global_elnum[pi]]])
+            eq.inject_recv_elements(pi, sends[pr][po])
+    for eq, m, idx in zip(eqns, meshes, qs):
+        pd.evalResidual(m, op, eq, opts)
+        assert rel_l2(eq.res, res_s[:, :, idx]) < RES_TOL

@@ -105,3 +105,18 @@ def test_documented_switches_exist_in_the_sources():
                 src += open(os.path.join(root, d, f)).read()
     missing = sorted(n for n in names if n not in src)
     assert not missing, f"documented but not read anywhere: {missing}"
+
+
+def test_local_element_lists_match_the_peers_halo():
+    """mesh.local_element_lists (getSendDataElement, Utils/parallel.jl:276-293): what a part sends to a peer is exactly, and
+    in the same order, what that peer holds as its remote elements of this part."""
+    import numpy as np
+    import pdesolver_jl_b200 as pd
+    for dim, p, parts in [(2, 1, (2, 2)), (3, 1, (2, 2, 2)), (3, 2, (2, 1, 1)), (2, 2, (4, 2))]:
+        op = pd.build_operator(dim, p)
+        nr = int(np.prod(parts))
+        ms = [pd.structured_mesh(op, 5, parts=parts, rank=r, shuffle_seed=3) for r in range(nr)]
+        for r, m in enumerate(ms):
+            for pi, pr in enumerate(m.peer_parts):
+                po = ms[pr].peer_parts.index(r)
+                assert np.array_equal(m.global_elnum[m.local_element_lists[pi]], ms[pr].remote_global_elnum[po])
