@@ -180,7 +180,7 @@ int pdes_eval_jvp(PdesCtx *ctx, const double *v, double *out);
  * q += step_fac*delta_q, convergence tests of checkConvergence (newton.jl:402-445) on the strong-residual norm
  * sqrt(sum Minv res^2) (physicsRhs, jacobian/residual_evaluation.jl:64-88).  Linear-solver defaults:
  * krylov_reltol 1e-2, abstol 1e-50, dtol 1e5, itermax 1000 (read_input.jl:493-496), GMRES restart 30
- * (read_input.jl:569), no preconditioner.  The Krylov basis and all reductions stay on the device. */
+ * (read_input.jl:569), preconditioner: pdes_set_krylov_pc (default none).  The Krylov basis and all reductions stay on the device. */
 typedef struct PdesNewtonOpts {
   int64_t itermax;          /* Newton iterations (opts["itermax"]) */
   double res_abstol, res_reltol, step_tol, step_fac;
@@ -197,6 +197,12 @@ typedef struct PdesNewtonResult {
 /* res_norms_out[itermax+1]: recordResNorm history (entry 0 = initial residual); step_norms_out[itermax] */
 int pdes_newton_krylov(PdesCtx *ctx, const PdesNewtonOpts *o, double *res_norms_out, double *step_norms_out,
                        PdesNewtonResult *result);
+/* Right preconditioner of the Krylov solves (the reference: PETSc options -pc_type bjacobi -ksp_pc_side right,
+ * input/read_input.jl:560-570).  PDES_PC_ELEMENT_BLOCK_JACOBI: the element-diagonal blocks dR_e/dq_e of the DG Jacobian,
+ * built matrix-free from coloured Jacobian-vector products at every Newton iterate and inverted on the device. */
+#define PDES_PC_NONE 0
+#define PDES_PC_ELEMENT_BLOCK_JACOBI 1
+int pdes_set_krylov_pc(PdesCtx *ctx, int32_t pc_type);
 /* One linear solve dR/dq(q) x = b with the same GMRES (x0 = 0); b, x host arrays [nd,nn,nE]. */
 int pdes_gmres(PdesCtx *ctx, const double *b, double *x, double reltol, double abstol, double dtol,
                int64_t itermax, int32_t restart, int64_t *iters_out, double *rnorm_out, int32_t *reason_out);
@@ -220,7 +226,8 @@ int pdes_rk4_steps_async(PdesCtx *ctx, double h, int64_t nsteps);
 /* Functionals of majorIterationCallback (solver/euler/euler.jl:330-407) for the resident q, reduced on the device after
  * one residual evaluation: out[0] calcEntropyIntegral, out[1] contractResEntropyVars (w^T R), out[2] calcKineticEnergy,
  * out[3] calcKineticEnergydt (solver/euler/entropy_flux.jl:141-186, 414-485), out[4] mesh.volume (sum of M),
- * out[5..5+nd) integrateQ (entropy_flux.jl:231-247).  Per mesh part: the Allreduce over ranks stays with the host. */
+ * out[5..5+nd) integrateQ (entropy_flux.jl:231-247), out[5+nd] calcEnstrophy (entropy_flux.jl:322-355 with calcVorticity
+ * euler_funcs.jl:1095-1155; 3D, 0 in 2D): out holds 6+nd doubles.  Per mesh part: the Allreduce over ranks stays with the host. */
 int pdes_diagnostics(PdesCtx *ctx, double *out);
 
 /* eqn.Minv[nd,nn,nE] as the reference computes it (mass_matrix.jl:20-44) */

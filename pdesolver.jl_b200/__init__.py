@@ -7,7 +7,7 @@ host-side stand-ins for the un-vendored SummationByParts.jl / PumiInterface.jl
 inputs (synthetic structured meshes, SBP operators).
 """
 from . import dump, mesh, sbp  # noqa: F401
-from .euler import (calcEntropyIntegral, calcKineticEnergy, calcKineticEnergydt, contractResEntropyVars,  # noqa: F401
+from .euler import (calcEnstrophy, calcEntropyIntegral, calcKineticEnergy, calcKineticEnergydt, contractResEntropyVars,  # noqa: F401
                     diagnostics, integrateQ)
 from .euler import (EulerData, ParamType, PDESolverError, PhysicsError,  # noqa: F401
                     createObjects, evaldRdqProduct, evalResidual, linearSolve, lserk54, newton, rk4)
@@ -16,4 +16,4 @@ from .sbp import build_operator  # noqa: F401
 
 __all__ = ["sbp", "mesh", "EulerData", "ParamType", "PDESolverError", "PhysicsError", "createObjects",
            "evalResidual", "evaldRdqProduct", "rk4", "lserk54", "newton", "linearSolve", "diagnostics", "calcEntropyIntegral", "contractResEntropyVars", "integrateQ",
-           "calcKineticEnergy", "calcKineticEnergydt", "structured_mesh", "two_element_mesh", "build_operator"]
+           "calcKineticEnergy", "calcKineticEnergydt", "calcEnstrophy", "structured_mesh", "two_element_mesh", "build_operator"]

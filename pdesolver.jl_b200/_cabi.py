@@ -36,7 +36,7 @@ EXPORTS = [
     "pdes_rk4_steps_async", "pdes_get_minv", "pdes_get_timings", "pdes_kernel_launch_count",
     "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp", "pdes_lserk54",
     "pdes_newton_krylov", "pdes_gmres", "pdes_diagnostics",
-    "pdes_set_peer_elements", "pdes_pack_send_elements", "pdes_inject_recv_elements",
+    "pdes_set_peer_elements", "pdes_pack_send_elements", "pdes_inject_recv_elements", "pdes_set_krylov_pc",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.pdes_set_peer.argtypes = [p, i32, i32, i64, p, p, p]
         L.pdes_get_unique_id.argtypes = [p]
         L.pdes_set_comm.argtypes = [p, p, i32, i32]
+        L.pdes_set_krylov_pc.argtypes = [p, i32]
         L.pdes_set_peer_elements.argtypes = [p, i32, i64, p, i64, i64]
         L.pdes_pack_send_elements.argtypes = [p, i32, p]
         L.pdes_inject_recv_elements.argtypes = [p, i32, p]

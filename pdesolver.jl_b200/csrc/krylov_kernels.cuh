@@ -108,4 +108,90 @@ k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y
     y[idx] = b == 0.0 ? a * x[idx] : fma(a, x[idx], b * y[idx]);
 }
 
+// ---- element-block Jacobi right preconditioner --------------------------------------------------------------------
+// The reference preconditions its Krylov solves from the right with PETSc's block Jacobi (read_input.jl:560-570:
+// -pc_type bjacobi, -ksp_pc_side right).  Here the blocks are the element-diagonal blocks dR_e/dq_e of the DG Jacobian
+// ((nd*nn)^2 doubles each), obtained matrix-free: elements are coloured so that no two face neighbours share a colour, and
+// for every colour and every local dof c ONE Jacobian-vector product with the indicator of dof c on the elements of that
+// colour yields column c of all their blocks.  The blocks are inverted in place (Gauss-Jordan with partial pivoting, one
+// CTA per element) and applied as z_e = B_e^-1 r_e.
+
+// v[e*EL + x] = 1 where x == c and colour[e] == col, else 0
+__global__ void __launch_bounds__(KRY_T)
+k_probe_set(double* __restrict__ v, const int32_t* __restrict__ colour, int col, int c, int EL, int64_t nE) {
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < nE * EL; idx += (int64_t)gridDim.x * KRY_T) {
+    const int64_t e = idx / EL;
+    v[idx] = ((int)(idx - e * EL) == c && colour[e] == col) ? 1.0 : 0.0;
+  }
+}
+// column c of the blocks of colour col: blocks[e][c*EL + r] = out[e*EL + r]   (column-major blocks)
+__global__ void __launch_bounds__(KRY_T)
+k_probe_get(const double* __restrict__ out, const int32_t* __restrict__ colour, int col, int c, int EL, int64_t nE,
+            double* __restrict__ blocks) {
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < nE * EL; idx += (int64_t)gridDim.x * KRY_T) {
+    const int64_t e = idx / EL;
+    if (colour[e] == col) blocks[e * EL * EL + (int64_t)c * EL + (idx - e * EL)] = out[idx];
+  }
+}
+// in-place inverse of every block (shared memory: EL*EL doubles + EL ints)
+__global__ void __launch_bounds__(64)
+k_block_invert(double* __restrict__ blocks, int EL, int64_t nE) {
+  extern __shared__ __align__(16) unsigned char smem_blk[];
+  double* A = reinterpret_cast<double*>(smem_blk);                 // A[c*EL + r]
+  int* piv = reinterpret_cast<int*>(A + EL * EL);
+  __shared__ int s_p;
+  const int tid = threadIdx.x;
+  double* G = blocks + (int64_t)blockIdx.x * EL * EL;
+  for (int i = tid; i < EL * EL; i += 64) A[i] = G[i];
+  __syncthreads();
+  for (int k = 0; k < EL; ++k) {
+    if (tid == 0) {
+      int p = k;
+      double best = fabs(A[k * EL + k]);
+      for (int i = k + 1; i < EL; ++i) {
+        const double v = fabs(A[k * EL + i]);
+        if (v > best) { best = v; p = i; }
+      }
+      s_p = p;
+      piv[k] = p;
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != k)
+      for (int c = tid; c < EL; c += 64) { const double t = A[c * EL + k]; A[c * EL + k] = A[c * EL + p]; A[c * EL + p] = t; }
+    __syncthreads();
+    const double pinv = 1.0 / A[k * EL + k];
+    __syncthreads();
+    for (int c = tid; c < EL; c += 64) A[c * EL + k] = (c == k) ? pinv : A[c * EL + k] * pinv;      // row k
+    __syncthreads();
+    for (int i = tid; i < EL; i += 64) {
+      if (i == k) continue;
+      const double f = A[k * EL + i];
+      A[k * EL + i] = 0.0;
+      for (int c = 0; c < EL; ++c) A[c * EL + i] = fma(-f, A[c * EL + k], A[c * EL + i]);
+    }
+    __syncthreads();
+  }
+  for (int k = EL - 1; k >= 0; --k) {        // undo the row interchanges as column interchanges
+    const int p = piv[k];
+    if (p != k)
+      for (int r = tid; r < EL; r += 64) { const double t = A[k * EL + r]; A[k * EL + r] = A[p * EL + r]; A[p * EL + r] = t; }
+    __syncthreads();
+  }
+  for (int i = tid; i < EL * EL; i += 64) G[i] = A[i];
+}
+// z_e = Binv_e r_e: one thread per (element, row); consecutive rows read consecutive addresses of every column
+__global__ void __launch_bounds__(KRY_T)
+k_block_apply(const double* __restrict__ blocks, int EL, int64_t nE, const double* __restrict__ r, double* __restrict__ z) {
+  for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < nE * EL; idx += (int64_t)gridDim.x * KRY_T) {
+    const int64_t e = idx / EL;
+    const int row = (int)(idx - e * EL);
+    const double* B = blocks + e * EL * EL + row;
+    const double* re = r + e * EL;
+    double s = 0.0;
+    for (int c = 0; c < EL; ++c) s = fma(B[(int64_t)c * EL], re[c], s);
+    z[idx] = s;
+  }
+}
+
 }  // namespace pdes

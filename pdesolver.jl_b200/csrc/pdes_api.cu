@@ -1010,6 +1010,7 @@ struct PdesCtx {
   double *ksum = nullptr, *res = nullptr;
   // mesh
   double *dxidx = nullptr, *minv = nullptr, *mass = nullptr, *srcw = nullptr, *coords_bndry = nullptr, *w_dev = nullptr;
+  double* Q_dev = nullptr;          // sbp.Q [nn,nn,dim] as uploaded (calcVorticity differentiates with it)
   FaceRec* faces = nullptr;
   double *nrm_all = nullptr, *fluxe = nullptr, *srcm = nullptr;
   std::vector<EFace> h_efaces;      // interior + boundary part (shared faces added by finalize)
@@ -1043,6 +1044,11 @@ struct PdesCtx {
     int restart = 0, nblk = 0;
     double *V = nullptr, *w = nullptr, *b = nullptr, *x = nullptr, *partials = nullptr, *hdev = nullptr;
     double* hhost = nullptr;     // pinned: [3*(restart+2)]
+    // element-block Jacobi right preconditioner (pdes_set_krylov_pc)
+    int pc_type = 0, ncolours = 0;
+    bool pc_ready = false;
+    double *pc_blocks = nullptr, *pcz = nullptr, *pcu = nullptr;
+    int32_t* colour = nullptr;
   } kry;
   // CUDA graphs of one RK4 step, one per state-buffer rotation; key = (h, norm?, res_tol, pseudo_time)
   cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr};
@@ -1910,7 +1916,9 @@ int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int 
 // shared-face values of the direction travel first (the reference's complex-step product exchanges the perturbed complex
 // state, newton_setup.jl:632-662 with parallel_data from read_input.jl:250-258): ncclSend/ncclRecv in stream order -- these
 // products serve the Krylov loop, not the RK4 hot loop.
-int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev) {
+// halo_mode 0: exchange states and directions; 1: exchange the states only, the direction is zero on the neighbours' side
+// (probing of the element-diagonal blocks); 2: no exchange at all (states and the zero direction of a previous mode-1 call)
+int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev, int halo_mode = 0) {
   const PdesConfig& c = ctx->cfg;
   ElemArgs a;
   fill_args(ctx, &a, ctx->qbuf[ctx->cur]);
@@ -1931,22 +1939,29 @@ int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev) {
       CUDA_TRY(ctx, cudaMalloc((void**)&ctx->v_send, sizeof(double) * nsend));
       CUDA_TRY(ctx, cudaMalloc((void**)&ctx->v_recv, sizeof(double) * nsend));
     }
-    CUDA_TRY(ctx, ctx->ops->launch_pack(a.q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, nullptr, ctx->ctl, ctx->stream));
-    CUDA_TRY(ctx, ctx->ops->launch_pack(vdev, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->v_send, nullptr, ctx->ctl, ctx->stream));
-    ctx->launches += 2;
-    ncclResult_t r = g_nccl.GroupStart();
-    for (auto& p : ctx->peers) {
-      if (r != ncclSuccess) break;
-      const size_t off = (size_t)p.offset * per_face, cnt = (size_t)p.nfaces * per_face;
-      r = g_nccl.Recv(ctx->q_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
-      if (r == ncclSuccess) r = g_nccl.Send(ctx->q_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
-      if (r == ncclSuccess) r = g_nccl.Recv(ctx->v_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
-      if (r == ncclSuccess) r = g_nccl.Send(ctx->v_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
-    }
-    ncclResult_t r2 = g_nccl.GroupEnd();
-    if (r != ncclSuccess || r2 != ncclSuccess) {
-      set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
-      return PDES_ERR_COMM;
+    if (halo_mode < 2) {
+      CUDA_TRY(ctx, ctx->ops->launch_pack(a.q, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->q_send, nullptr, ctx->ctl, ctx->stream));
+      if (halo_mode == 0)
+        CUDA_TRY(ctx, ctx->ops->launch_pack(vdev, ctx->sh_el, ctx->sh_face, ctx->nS, ctx->v_send, nullptr, ctx->ctl, ctx->stream));
+      else
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->v_recv, 0, sizeof(double) * nsend, ctx->stream));
+      ctx->launches += 2;
+      ncclResult_t r = g_nccl.GroupStart();
+      for (auto& p : ctx->peers) {
+        if (r != ncclSuccess) break;
+        const size_t off = (size_t)p.offset * per_face, cnt = (size_t)p.nfaces * per_face;
+        r = g_nccl.Recv(ctx->q_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+        if (r == ncclSuccess) r = g_nccl.Send(ctx->q_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+        if (halo_mode == 0) {
+          if (r == ncclSuccess) r = g_nccl.Recv(ctx->v_recv + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+          if (r == ncclSuccess) r = g_nccl.Send(ctx->v_send + off, cnt, ncclFloat64, p.rank, ctx->comm, ctx->stream);
+        }
+      }
+      ncclResult_t r2 = g_nccl.GroupEnd();
+      if (r != ncclSuccess || r2 != ncclSuccess) {
+        set_err(ctx, "NCCL send/recv failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+        return PDES_ERR_COMM;
+      }
     }
     fa.v_recv = ctx->v_recv;
     fa.ng = c.nF + c.nB + ctx->nS;
@@ -2073,11 +2088,11 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->d_norm_slots) cudaFree(ctx->d_norm_slots);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
-                  ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev,
+                  ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev, ctx->Q_dev,
                   ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->el_send_list, ctx->qel_send, ctx->qel_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
                   ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
-                  ctx->kry.partials, ctx->kry.hdev};
+                  ctx->kry.partials, ctx->kry.hdev, ctx->kry.pc_blocks, ctx->kry.pcz, ctx->kry.pcu, ctx->kry.colour};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -2117,6 +2132,7 @@ int pdes_set_operator(PdesCtx* ctx, const double* Q, const double* w, const doub
   ctx->ops->build_tables(c, Q, w, interp, perm, nbrperm, wface, c.index_base);
   ctx->h_w.assign(w, w + c.nn);
   CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->w_dev, w, (size_t)c.nn));
+  CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->Q_dev, Q, (size_t)c.nn * c.nn * c.dim));
   ctx->have_op = true;
   ctx->finalized = false;
   return PDES_OK;
@@ -2613,7 +2629,13 @@ int kry_alloc(PdesCtx* ctx, int restart) {
   void* old[] = {k.V, k.w, k.b, k.x, k.partials, k.hdev};
   for (void* p : old) if (p) cudaFree(p);
   if (k.hhost) cudaFreeHost(k.hhost);
-  k = PdesCtx::Krylov();
+  {
+    // (the preconditioner's buffers do not depend on the restart length)
+    PdesCtx::Krylov fresh;
+    fresh.pc_type = k.pc_type; fresh.ncolours = k.ncolours; fresh.pc_ready = k.pc_ready;
+    fresh.pc_blocks = k.pc_blocks; fresh.pcz = k.pcz; fresh.pcu = k.pcu; fresh.colour = k.colour;
+    k = fresh;
+  }
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2657,6 +2679,54 @@ int kry_fetch(PdesCtx* ctx, int count) {
   return PDES_OK;
 }
 
+// Element-block Jacobi preconditioner of the current state (see krylov_kernels.cuh): colours, probing products, inversion.
+int build_block_pc(PdesCtx* ctx) {
+  PdesCtx::Krylov& k = ctx->kry;
+  const PdesConfig& c = ctx->cfg;
+  const int EL = c.nn * ctx->nd;
+  const int64_t nE = c.nE, n = ctx->ndof;
+  const size_t smem = sizeof(double) * (size_t)EL * EL + sizeof(int) * (size_t)EL;
+  if (smem > 200 * 1024) { set_err(ctx, "element-block preconditioner: %d dofs per element exceed the shared-memory inversion", EL); return PDES_ERR_UNSUPPORTED; }
+  if (!k.colour) {
+    // greedy colouring of the face-adjacency graph (<= dim + 2 colours on a simplex mesh)
+    std::vector<std::vector<int32_t>> adj((size_t)nE);
+    for (const FaceRec& f : ctx->h_faces)
+      if (f.kind == FK_INTERIOR) { adj[f.elL].push_back(f.elR); adj[f.elR].push_back(f.elL); }
+    std::vector<int32_t> col((size_t)nE, -1);
+    int nc = 0;
+    for (int64_t e = 0; e < nE; ++e) {
+      unsigned used = 0;
+      for (int32_t o : adj[e]) if (col[o] >= 0) used |= 1u << col[o];
+      int cc = 0;
+      while (used & (1u << cc)) ++cc;
+      col[e] = cc;
+      nc = std::max(nc, cc + 1);
+    }
+    k.ncolours = nc;
+    CUDA_TRY(ctx, dev_upload(ctx->stream, &k.colour, col.data(), col.size()));
+    CUDA_TRY(ctx, cudaMalloc((void**)&k.pc_blocks, sizeof(double) * (size_t)nE * EL * EL));
+    CUDA_TRY(ctx, cudaMalloc((void**)&k.pcz, sizeof(double) * n));
+    CUDA_TRY(ctx, cudaMalloc((void**)&k.pcu, sizeof(double) * n));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_block_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int nb = k.nblk;
+  bool first = true;
+  for (int col = 0; col < k.ncolours; ++col)
+    for (int cdof = 0; cdof < EL; ++cdof) {
+      k_probe_set<<<nb, KRY_T, 0, ctx->stream>>>(k.pcz, k.colour, col, cdof, EL, nE);
+      int rc = enqueue_jvp(ctx, k.pcz, k.pcu, first ? 1 : 2);
+      if (rc) return rc;
+      first = false;
+      k_probe_get<<<nb, KRY_T, 0, ctx->stream>>>(k.pcu, k.colour, col, cdof, EL, nE, k.pc_blocks);
+      ctx->launches += 2;
+    }
+  k_block_invert<<<(unsigned)nE, 64, smem, ctx->stream>>>(k.pc_blocks, EL, nE);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  k.pc_ready = true;
+  return PDES_OK;
+}
+
 // Restarted GMRES on device vectors: solves dR/dq(q) x = b, x0 = 0; classical Gram-Schmidt applied twice (CGS2): two
 // batched dot kernels instead of j+1 dependent ones.  Convergence as PETSc's default test: rnorm <= max(reltol*|b|,
 // abstol); divergence when rnorm >= dtol*|b|.  reason: 1 rtol, 2 abstol, 3 exact breakdown, -1 itermax, -2 dtol.
@@ -2667,6 +2737,10 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
   PdesCtx::Krylov& k = ctx->kry;
   const int64_t n = ctx->ndof;
   const int m = restart, S = restart + 2;
+  // right preconditioning (-ksp_pc_side right): J M^-1 y = b, x = M^-1 y; the residual norms are those of the true system
+  const bool pc = k.pc_type == 1;
+  if (pc && !k.pc_ready) { rc = build_block_pc(ctx); if (rc) return rc; }
+  const int EL = ctx->cfg.nn * ctx->nd;
   double* h1 = k.hdev;           // first projection coefficients
   double* h2 = k.hdev + S;       // second pass
   double* nq = k.hdev + 2 * S;   // squared norms
@@ -2709,7 +2783,11 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
     g[0] = beta;
     int j = 0;
     for (; j < m && !reason; ++j) {
-      rc = enqueue_jvp(ctx, k.V + (size_t)j * n, k.w);
+      if (pc) {
+        k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.V + (size_t)j * n, k.pcz);
+        ctx->launches++;
+      }
+      rc = enqueue_jvp(ctx, pc ? k.pcz : k.V + (size_t)j * n, k.w);
       if (rc) return rc;
       rc = kry_dots(ctx, k.V, j + 1, k.w, h1);
       if (rc) return rc;
@@ -2756,6 +2834,14 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
       y[i] = H[(size_t)i * m + i] != 0.0 ? sacc / H[(size_t)i * m + i] : 0.0;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(h1, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
+    if (pc) {
+      // x += M^-1 (V y)
+      CUDA_TRY(ctx, cudaMemsetAsync(k.pcu, 0, sizeof(double) * n, st));
+      k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj, h1, 1.0, k.pcu, n);
+      k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.pcu, k.pcz);
+      k_axpby<<<nb, KRY_T, 0, st>>>(1.0, k.pcz, 1.0, x, n);
+      ctx->launches += 2;
+    } else
     k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj, h1, 1.0, x, n);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));     // y is a host temporary
@@ -2789,6 +2875,14 @@ int newton_rhs(PdesCtx* ctx, double* norm_out) {
 
 extern "C" {
 
+int pdes_set_krylov_pc(PdesCtx* ctx, int32_t pc_type) {
+  if (!ctx) return usage(ctx, "pdes_set_krylov_pc: null ctx");
+  if (pc_type != PDES_PC_NONE && pc_type != PDES_PC_ELEMENT_BLOCK_JACOBI) return usage(ctx, "pdes_set_krylov_pc: unknown preconditioner");
+  ctx->kry.pc_type = pc_type;
+  ctx->kry.pc_ready = false;
+  return PDES_OK;
+}
+
 int pdes_gmres(PdesCtx* ctx, const double* b, double* x, double reltol, double abstol, double dtol, int64_t itermax,
                int32_t restart, int64_t* iters_out, double* rnorm_out, int32_t* reason_out) {
   if (!ctx || !b || !x || !iters_out || !rnorm_out || !reason_out) return usage(ctx, "pdes_gmres: null argument");
@@ -2801,6 +2895,7 @@ int pdes_gmres(PdesCtx* ctx, const double* b, double* x, double reltol, double a
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kry.b, b, sizeof(double) * ctx->ndof, cudaMemcpyHostToDevice, ctx->stream));
   int reason = 0;
+  ctx->kry.pc_ready = false;          // the blocks belong to the state of this call
   rc = gmres_dev(ctx, ctx->kry.b, ctx->kry.x, reltol, abstol, dtol, itermax, restart, iters_out, rnorm_out, &reason);
   if (rc) return rc;
   *reason_out = reason;
@@ -2844,6 +2939,7 @@ int pdes_newton_krylov(PdesCtx* ctx, const PdesNewtonOpts* o, double* res_norms_
     int64_t kits = 0;
     double krn = 0.0;
     int reason = 0;
+    k.pc_ready = false;               // recalculated for every Newton iterate (recalc policy "always")
     rc = gmres_dev(ctx, k.b, k.x, o->krylov_reltol, o->krylov_abstol, o->krylov_dtol, o->krylov_itermax,
                    o->krylov_restart, &kits, &krn, &reason);
     if (rc) return rc;
@@ -2888,24 +2984,34 @@ int pdes_diagnostics(PdesCtx* ctx, double* out) {
   if (!ctx->diag_buf || ctx->diag_B != B) {
     if (ctx->diag_buf) cudaFree(ctx->diag_buf);
     ctx->diag_buf = nullptr;
-    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->diag_buf, sizeof(double) * (size_t)nv * (B + 1)));
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->diag_buf, sizeof(double) * (size_t)(nv + 1) * (B + 1)));
     ctx->diag_B = B;
   }
   double* partials = ctx->diag_buf;
-  double* sums = ctx->diag_buf + (size_t)nv * B;
+  double* sums = ctx->diag_buf + (size_t)(nv + 1) * B;        // [nv + 1]: the last entry is the enstrophy
   if (ctx->cfg.dim == 2)
     k_diag_partials<2><<<B, DIAG_T, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->res, ctx->mass, n_nodes, ctx->cfg.gamma, partials);
   else
     k_diag_partials<3><<<B, DIAG_T, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->res, ctx->mass, n_nodes, ctx->cfg.gamma, partials);
-  k_reduce_rows<<<nv, KRY_T, 0, ctx->stream>>>(partials, B, sums);
+  if (ctx->cfg.dim == 3) {
+    const int dd = 9;
+    k_enstrophy_partials<<<B, DIAG_T, 0, ctx->stream>>>(ctx->qbuf[ctx->cur], ctx->Q_dev, ctx->w_dev, ctx->dxidx,
+                                                        ctx->dx_compact ? dd : (int64_t)ctx->cfg.nn * dd, ctx->mass, ctx->cfg.nn,
+                                                        ctx->cfg.nE, partials + (size_t)nv * B);
+    ctx->launches++;
+  } else {
+    CUDA_TRY(ctx, cudaMemsetAsync(partials + (size_t)nv * B, 0, sizeof(double) * B, ctx->stream));
+  }
+  k_reduce_rows<<<nv + 1, KRY_T, 0, ctx->stream>>>(partials, B, sums);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches += 2;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out, sums, sizeof(double) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, sums, sizeof(double) * (nv + 1), cudaMemcpyDeviceToHost, ctx->stream));
   rc = pdes_sync(ctx);
   if (rc) return rc;
   const double volume = out[4];
   out[2] = 0.5 * out[2] / volume;
   out[3] = out[3] / volume;
+  out[nv] = 0.5 * out[nv] / volume;
   return PDES_OK;
 }
 

@@ -271,12 +271,20 @@ def diagnostics(mesh, sbp, eqn: EulerData, opts):
     device in one reduction pass after one residual evaluation: ``calcEntropyIntegral``, ``contractResEntropyVars``
     (``w^T R``), ``calcKineticEnergy``, ``calcKineticEnergydt`` (solver/euler/entropy_flux.jl:141-186, 414-485),
     ``volume`` and ``integrateQ`` (:231-247).  ``eqn.res`` is left holding R(q) on the device side only."""
-    out = np.zeros(5 + eqn.q.shape[0])
+    nd = eqn.q.shape[0]
+    out = np.zeros(6 + nd)
     L, ctx = eqn._L, eqn._ctx
     eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
     eqn._check(L.pdes_diagnostics(ctx, _ptr(out)))
     return {"entropy_integral": out[0], "wT_res": out[1], "kinetic_energy": out[2], "kinetic_energy_dt": out[3],
-            "volume": out[4], "integral_q": out[5:].copy()}
+            "volume": out[4], "integral_q": out[5:5 + nd].copy(), "enstrophy": out[5 + nd]}
+
+
+def calcEnstrophy(mesh, sbp, eqn: EulerData, opts, q_arr=None):
+    """solver/euler/entropy_flux.jl:322-355 (3D; ``write_enstrophy`` in majorIterationCallback, euler.jl:370-376)"""
+    if mesh.dim != 3:
+        raise PDESolverError("calcEnstrophy: 3D only (entropy_flux.jl:326)")
+    return diagnostics(mesh, sbp, eqn, opts)["enstrophy"]
 
 
 def calcEntropyIntegral(mesh, sbp, eqn: EulerData, opts, q_vec=None):
@@ -311,6 +319,18 @@ def _krylov_opts(opts):
                 restart=int(opts.get("krylov_restart", 30)))
 
 
+PC_IDS = {"none": 0, "PCNone": 0, "element_block_jacobi": 1, "bjacobi": 1}
+
+
+def _set_pc(eqn, opts):
+    """``opts["krylov_pc"]``: "none" (default) or "element_block_jacobi" -- the right preconditioner standing in for the
+    reference's PETSc ``-pc_type bjacobi -ksp_pc_side right`` (input/read_input.jl:560-570)."""
+    name = opts.get("krylov_pc", "none")
+    if name not in PC_IDS:
+        raise PDESolverError(f"unsupported preconditioner {name!r}")
+    eqn._check(eqn._L.pdes_set_krylov_pc(eqn._ctx, PC_IDS[name]))
+
+
 def linearSolve(mesh, sbp, eqn: EulerData, opts, b, x=None):
     """``linearSolve(ls, b, x)`` (linearsolvers) for the matrix-free operator of jac_type 4: solves
     ``dR/dq(eqn.q) x = b`` by restarted GMRES on the device (no preconditioner), zero initial guess.
@@ -321,6 +341,7 @@ def linearSolve(mesh, sbp, eqn: EulerData, opts, b, x=None):
     k = _krylov_opts(opts)
     L, ctx = eqn._L, eqn._ctx
     its, rn, reason = C.c_int64(0), C.c_double(0.0), C.c_int32(0)
+    _set_pc(eqn, opts)
     eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
     eqn._check(L.pdes_gmres(ctx, _ptr(b), _ptr(x), k["reltol"], k["abstol"], k["dtol"], k["itermax"], k["restart"],
                             C.byref(its), C.byref(rn), C.byref(reason)))
@@ -352,6 +373,7 @@ def newton(func, mesh, sbp, eqn: EulerData, opts, pmesh=None, t=0.0):
     r = PdesNewtonResult()
     L, ctx = eqn._L, eqn._ctx
     eqn.params.t = t
+    _set_pc(eqn, opts)
     eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
     eqn._check(L.pdes_newton_krylov(ctx, C.byref(o), _ptr(res_norms), _ptr(step_norms), C.byref(r)))
     eqn._check(L.pdes_get_q(ctx, _ptr(eqn.q)))
