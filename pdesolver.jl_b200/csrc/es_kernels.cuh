@@ -32,9 +32,9 @@ struct OpTabS {
 
 enum FluxId { FLUX_ROE = 1, FLUX_IR = 2, FLUX_IRSLF = 3 };
 
-template <int DIM>
-__device__ __forceinline__ void numerical_flux(int flux_id, const double* qL, const double* qR, const double* n,
-                                               double gamma, double* F) {
+template <int DIM, typename T>
+__device__ __forceinline__ void numerical_flux(int flux_id, const T* qL, const T* qR, const double* n,
+                                               double gamma, T* F) {
   if (flux_id == FLUX_IRSLF) irslf_flux<DIM>(qL, qR, n, gamma, F);
   else if (flux_id == FLUX_IR) ir_flux_single<DIM>(qL, qR, n, gamma, F);
   else roe_flux<DIM>(qL, qR, n, gamma, F);

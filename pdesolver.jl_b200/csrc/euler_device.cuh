@@ -74,6 +74,14 @@ __device__ __forceinline__ Dual absvalue3(Dual x) {
   return Dual(((x.v * x.v) / delta + delta) / 2, x.v * x.d / delta);
 }
 
+// elementary functions on dual numbers (entropy-stable fluxes in J*v); val(): the real part (comparisons, branch selection)
+using ::sqrt;
+using ::log;
+__device__ __forceinline__ double val(double x) { return x; }
+__device__ __forceinline__ double val(const Dual& x) { return x.v; }
+__device__ __forceinline__ Dual sqrt(Dual x) { const double s = ::sqrt(x.v); return Dual(s, 0.5 * x.d / s); }
+__device__ __forceinline__ Dual log(Dual x) { return Dual(::log(x.v), x.d / x.v); }
+
 // euler_funcs.jl:856-863 / 897-903 calcPressure
 template <int DIM, typename T>
 __device__ __forceinline__ T calc_pressure(const T* q, double gami) {
@@ -176,25 +184,26 @@ __device__ __forceinline__ void roe_flux(const T* q, const T* qg, const double* 
 
 // bc_solvers.jl:942-956 logavg(aL, aR) = (aL + aR) / (2 F) with log(aL/aR) supplied as lL - lR (logs tabulated per node:
 // two per node instead of two per node pair); f = (xi-1)/(xi+1) is evaluated as (aL-aR)/(aL+aR).  Returns 2 F.
-__device__ __forceinline__ double logavg_2F(double aL, double aR, double lL, double lR, double inv_sum) {
-  const double f = (aL - aR) * inv_sum;
-  const double u = f * f;
-  double F;
-  if (u < 1e-3) F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0 + u * (1.0 / 9.0))));
+template <typename T>
+__device__ __forceinline__ T logavg_2F(T aL, T aR, T lL, T lR, T inv_sum) {
+  const T f = (aL - aR) * inv_sum;
+  const T u = f * f;
+  T F;
+  if (val(u) < 1e-3) F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0 + u * (1.0 / 9.0))));
   else F = 0.5 * (lL - lR) * fast_rcp(f);
   return 2.0 * F;
 }
 // per-node quantities of the Ismail-Roe flux: z1 = sqrt(rho/p), z_{1+d} = z1*u_d, z5 = sqrt(rho*p), log z1, log z5
-template <int DIM>
+template <int DIM, typename T = double>
 struct IRNode {
-  double z1, zv[DIM], z5, l1, l5;
+  T z1, zv[DIM], z5, l1, l5;
 };
 
-template <int DIM>
-__device__ __forceinline__ IRNode<DIM> ir_node(const double* q, double gami) {
-  IRNode<DIM> z;
-  const double p = calc_pressure<DIM>(q, gami);
-  const double rinv = fast_rcp(q[0]);
+template <int DIM, typename T>
+__device__ __forceinline__ IRNode<DIM, T> ir_node(const T* q, double gami) {
+  IRNode<DIM, T> z;
+  const T p = calc_pressure<DIM>(q, gami);
+  const T rinv = fast_rcp(q[0]);
   z.z1 = sqrt(q[0] * fast_rcp(p));
   z.z5 = sqrt(q[0] * p);
 #pragma unroll
@@ -205,32 +214,32 @@ __device__ __forceinline__ IRNode<DIM> ir_node(const double* q, double gami) {
 }
 
 // bc_solvers.jl:776-805 (2D) / 842-874 (3D) calcEulerFlux_IR for NDIR directions (dir[d][:]), F[d][:]
-template <int DIM, int NDIR>
-__device__ __forceinline__ void ir_flux(const IRNode<DIM>& L, const IRNode<DIM>& R, const double (*dir)[DIM],
-                                        double gamma, double (*F)[DIM + 2]) {
+template <int DIM, int NDIR, typename T>
+__device__ __forceinline__ void ir_flux(const IRNode<DIM, T>& L, const IRNode<DIM, T>& R, const double (*dir)[DIM],
+                                        double gamma, T (*F)[DIM + 2]) {
   const double gamma_1 = gamma - 1.0;
-  const double s1 = L.z1 + R.z1, s5 = L.z5 + R.z5;
-  const double is1 = fast_rcp(s1), is5 = fast_rcp(s5);
+  const T s1 = L.z1 + R.z1, s5 = L.z5 + R.z5;
+  const T is1 = fast_rcp(s1), is5 = fast_rcp(s5);
   // with logavg(a) = s_a / (2 F_a) the quotients of the reference formulas need three reciprocals instead of six
   // (the two-point flux is FP64-pipe bound: the reciprocals were 21 % of k_element_split_n's samples):
   //   z5_ln / z1_ln = p1_hat * (2 F_1) / (2 F_5),   1 / rho_hat = 2 (2 F_5) / (s1 s5)
-  const double tF5 = logavg_2F(L.z5, R.z5, L.l5, R.l5, is5);
-  const double tF1 = logavg_2F(L.z1, R.z1, L.l1, R.l1, is1);
-  const double itF5 = fast_rcp(tF5);
-  const double la5 = s5 * itF5;                       // z5_ln
-  const double rho_hat = 0.5 * s1 * la5;
-  double vh[DIM], vv = 0.0;
+  const T tF5 = logavg_2F(L.z5, R.z5, L.l5, R.l5, is5);
+  const T tF1 = logavg_2F(L.z1, R.z1, L.l1, R.l1, is1);
+  const T itF5 = fast_rcp(tF5);
+  const T la5 = s5 * itF5;                       // z5_ln
+  const T rho_hat = 0.5 * s1 * la5;
+  T vh[DIM], vv = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { vh[d] = (L.zv[d] + R.zv[d]) * is1; vv += vh[d] * vh[d]; }
-  const double p1_hat = s5 * is1;
-  const double p2_hat = ((gamma + 1) / (2 * gamma)) * (p1_hat * tF1 * itF5) + (gamma_1 / (2 * gamma)) * p1_hat;
-  const double h_hat = (gamma / gamma_1) * p2_hat * (2.0 * tF5 * is1 * is5) + 0.5 * vv;
+  const T p1_hat = s5 * is1;
+  const T p2_hat = ((gamma + 1) / (2 * gamma)) * (p1_hat * tF1 * itF5) + (gamma_1 / (2 * gamma)) * p1_hat;
+  const T h_hat = (gamma / gamma_1) * p2_hat * (2.0 * tF5 * is1 * is5) + 0.5 * vv;
 #pragma unroll
   for (int i = 0; i < NDIR; ++i) {
-    double un = 0.0;
+    T un = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) un += dir[i][d] * vh[d];
-    const double mv_n = rho_hat * un;
+    const T mv_n = rho_hat * un;
     F[i][0] = mv_n;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) F[i][1 + d] = mv_n * vh[d] + dir[i][d] * p1_hat;
@@ -261,72 +270,66 @@ __device__ __forceinline__ void convert_to_ir(const double* qc, double gamma, do
 // convertToIR_ with the logarithms of the Ismail-Roe parameter vector: z1 = sqrt(rho/p), z5 = sqrt(rho p) give
 // log rho = l1 + l5, log p = l5 - l1, and gamma_1 rho_int = p, so the physical entropy s = log(p / rho^gamma) needs neither
 // the pow nor the log of conversion.jl:170-175 (they were ~40 % of k_face_flux_sparse's instructions)
-template <int DIM>
-__device__ __forceinline__ void convert_to_ir_z(const double* qc, const IRNode<DIM>& z, double gamma, double* qe) {
+template <int DIM, typename T>
+__device__ __forceinline__ void convert_to_ir_z(const T* qc, const IRNode<DIM, T>& z, double gamma, T* qe) {
   const double gamma_1 = gamma - 1.0, gamma_1i = 1.0 / gamma_1;
-  double k1 = 0.0;
+  T k1 = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) k1 += qc[1 + d] * qc[1 + d];
   k1 = 0.5 * k1 * fast_rcp(qc[0]);
-  const double rho_int = qc[DIM + 1] - k1;
-  const double s = (z.l5 - z.l1) - gamma * (z.l1 + z.l5);
-  const double fac = fast_rcp(rho_int);
+  const T rho_int = qc[DIM + 1] - k1;
+  const T s = (z.l5 - z.l1) - gamma * (z.l1 + z.l5);
+  const T fac = fast_rcp(rho_int);
   qe[0] = ((rho_int * (gamma + 1 - s) - qc[DIM + 1]) * fac) * gamma_1i;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) qe[1 + d] = qc[1 + d] * fac * gamma_1i;
   qe[DIM + 1] = -qc[0] * fac * gamma_1i;
 }
 
-template <int DIM>
-__device__ __forceinline__ void irslf_flux(const double* qL, const double* qR, const double* n, double gamma, double* F) {
+template <int DIM, typename T>
+__device__ __forceinline__ void irslf_flux(const T* qL, const T* qR, const double* n, double gamma, T* F) {
   constexpr int ND = DIM + 2;
   const double gami = gamma - 1.0;
-  const IRNode<DIM> zL = ir_node<DIM>(qL, gami), zR = ir_node<DIM>(qR, gami);
-  double dirs[1][DIM], Fi[1][ND];
+  const IRNode<DIM, T> zL = ir_node<DIM>(qL, gami), zR = ir_node<DIM>(qR, gami);
+  double dirs[1][DIM];
+  T Fi[1][ND];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) dirs[0][d] = n[d];
   ir_flux<DIM, 1>(zL, zR, dirs, gamma, Fi);
-  double qa[ND], vL[ND], vR[ND];
+  T qa[ND], vL[ND], vR[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) qa[i] = 0.5 * (qL[i] + qR[i]);
-#ifdef PDES_IRSLF_POW
-  convert_to_ir<DIM>(qL, gamma, vL);
-  convert_to_ir<DIM>(qR, gamma, vR);
-#else
   convert_to_ir_z<DIM>(qL, zL, gamma, vL);
   convert_to_ir_z<DIM>(qR, zR, gamma, vR);
-#endif
 #pragma unroll
   for (int i = 0; i < ND; ++i) vL[i] -= vR[i];
   // A0 = dq/dw at q_avg (symmetric), applied to delta w
-  const double p = calc_pressure<DIM>(qa, gami);
-  const double rho = qa[0], rhoe = qa[DIM + 1], rhoinv = fast_rcp(rho);
-  const double h = (rhoe + p) * rhoinv, a2 = gamma * p * rhoinv;
-  double out[ND];
+  const T p = calc_pressure<DIM>(qa, gami);
+  const T rho = qa[0], rhoe = qa[DIM + 1], rhoinv = fast_rcp(rho);
+  const T h = (rhoe + p) * rhoinv, a2 = gamma * p * rhoinv;
+  T out[ND];
   out[0] = rho * vL[0] + rhoe * vL[DIM + 1];
   out[DIM + 1] = rhoe * vL[0] + (rho * h * h - a2 * p / gami) * vL[DIM + 1];
 #pragma unroll
   for (int c = 0; c < DIM; ++c) {
     out[0] += qa[1 + c] * vL[1 + c];
     out[DIM + 1] += qa[1 + c] * h * vL[1 + c];
-    double r = qa[1 + c] * vL[0] + h * qa[1 + c] * vL[DIM + 1];
+    T r = qa[1 + c] * vL[0] + h * qa[1 + c] * vL[DIM + 1];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-      double a = qa[1 + d] * qa[1 + c] * rhoinv;
+      T a = qa[1 + d] * qa[1 + c] * rhoinv;
       if (d == c) a += p;
       r += a * vL[1 + d];
     }
     out[1 + c] = r;
   }
   // lambda_max = absvalue3(Un) + dA * a
-  double Un = 0.0, dA = 0.0;
+  T Un = 0.0;
+  double dA = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { Un += n[d] * qa[1 + d] * rhoinv; dA += n[d] * n[d]; }
-  dA = sqrt(dA);
-  const double delta = 1e-7;
-  const double v1 = fabs(Un);
-  const double aUn = v1 > delta ? v1 : ((Un * Un) / delta + delta) / 2;
-  const double lambda_max = aUn + dA * sqrt(a2);
+  dA = ::sqrt(dA);
+  const T lambda_max = absvalue3(Un) + dA * sqrt(a2);
 #pragma unroll
   for (int i = 0; i < ND; ++i) F[i] = Fi[0][i] + out[i] * lambda_max;
 }
@@ -501,11 +504,12 @@ __device__ __forceinline__ void lw2_entropy_kernel(const double* qa, const doubl
   }
 }
 
-template <int DIM>
-__device__ __forceinline__ void ir_flux_single(const double* qL, const double* qR, const double* n, double gamma, double* F) {
+template <int DIM, typename T>
+__device__ __forceinline__ void ir_flux_single(const T* qL, const T* qR, const double* n, double gamma, T* F) {
   constexpr int ND = DIM + 2;
-  const IRNode<DIM> zL = ir_node<DIM>(qL, gamma - 1.0), zR = ir_node<DIM>(qR, gamma - 1.0);
-  double dirs[1][DIM], Fi[1][ND];
+  const IRNode<DIM, T> zL = ir_node<DIM>(qL, gamma - 1.0), zR = ir_node<DIM>(qR, gamma - 1.0);
+  double dirs[1][DIM];
+  T Fi[1][ND];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) dirs[0][d] = n[d];
   ir_flux<DIM, 1>(zL, zR, dirs, gamma, Fi);

@@ -11,7 +11,7 @@
 //
 //   dense faces, Roe flux     k_gen_face<DIM, T>  + k_gen_element<DIM, MODE>        (T = Dual: the tangent records of J*v)
 //                                                   k_gen_jvp_element<DIM>
-//   sparse faces, split form  k_gen_face_sparse<DIM> + k_gen_element_split<DIM, MODE>
+//   sparse faces, split form  k_gen_face_sparse<DIM, T> + k_gen_element_split<DIM, MODE>, k_gen_jvp_element_split<DIM>
 //                             (calcVolumeIntegralsSplitFormLinear euler_funcs.jl:240-288, IR / IRSLF / Roe interface flux)
 //   halo                      k_gen_pack (getSendDataFace, Utils/parallel.jl:249-258) on any vector (q, or the J*v direction)
 #pragma once
@@ -116,11 +116,13 @@ k_gen_face(const GenTab op, const __grid_constant__ FaceArgs a, const double* __
   }
 }
 
-// sparse faces: face node i of face f IS volume node perm[i,f] (sbp_sat_reduced_sc.jl:969-972)
-template <int DIM>
+// sparse faces: face node i of face f IS volume node perm[i,f] (sbp_sat_reduced_sc.jl:969-972).  T = Dual: tangent records.
+template <int DIM, typename T>
 __global__ void __launch_bounds__(128)
-k_gen_face_sparse(const GenTab op, const __grid_constant__ FaceArgs a, int flux_id) {
+k_gen_face_sparse(const GenTab op, const __grid_constant__ FaceArgs a, int flux_id, const double* __restrict__ v,
+                  const double* __restrict__ v_recv) {
   constexpr int ND = DIM + 2, NF = DIM + 1;
+  constexpr bool DUAL = !std::is_same<T, double>::value;
   if (a.ctl->stop) return;
   const int nn = op.nn, nfn = op.nfn, EL = nn * ND, FL = nfn * ND;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,11 +130,15 @@ k_gen_face_sparse(const GenTab op, const __grid_constant__ FaceArgs a, int flux_
   const int64_t g = a.g0 + t / nfn;
   const int i = (int)(t % nfn);
   const FaceRec r = a.faces[g];
-  double qL[ND], qR[ND], nrm[DIM], flux[ND];
+  T qL[ND], qR[ND], flux[ND];
+  double nrm[DIM];
   {
-    const double* b = a.q + (int64_t)r.elL * EL + (int64_t)op.perm[r.fL * nfn + i] * ND;
+    const int64_t o = (int64_t)r.elL * EL + (int64_t)op.perm[r.fL * nfn + i] * ND;
 #pragma unroll
-    for (int k = 0; k < ND; ++k) qL[k] = b[k];
+    for (int k = 0; k < ND; ++k) {
+      if constexpr (DUAL) qL[k] = Dual(a.q[o + k], v[o + k]);
+      else qL[k] = a.q[o + k];
+    }
     const double* np_ = a.nrm + g * a.nrm_face_stride + i * a.nrm_node_stride;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) nrm[d] = np_[d];
@@ -143,23 +149,29 @@ k_gen_face_sparse(const GenTab op, const __grid_constant__ FaceArgs a, int flux_
     double xb[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) xb[d] = xp[d];
-    bc_flux_any<DIM>(r.aux, qL, xb, nrm, a.ph, flux);
+    if constexpr (DUAL) bc_flux_dual<DIM>(r.aux, qL, xb, nrm, a.ph, flux);
+    else bc_flux_any<DIM>(r.aux, qL, xb, nrm, a.ph, flux);
   } else {
     iR = op.nbrperm[r.orient * nfn + i];
-    const double* b = r.kind == FK_INTERIOR ? a.q + (int64_t)r.elR * EL + (int64_t)op.perm[r.fR * nfn + iR] * ND
-                                            : a.q_recv + ((int64_t)r.aux * nfn + iR) * ND;
+    const bool interior = r.kind == FK_INTERIOR;
+    const int64_t o = interior ? (int64_t)r.elR * EL + (int64_t)op.perm[r.fR * nfn + iR] * ND : ((int64_t)r.aux * nfn + iR) * ND;
+    const double* bq = interior ? a.q : a.q_recv;
+    const double* bv = interior ? v : v_recv;
 #pragma unroll
-    for (int k = 0; k < ND; ++k) qR[k] = b[k];
-    numerical_flux<DIM>(flux_id, qL, qR, nrm, a.ph.gamma, flux);
+    for (int k = 0; k < ND; ++k) {
+      if constexpr (DUAL) qR[k] = Dual(bq[o + k], bv[o + k]);
+      else qR[k] = bq[o + k];
+    }
+    numerical_flux<DIM, T>(flux_id, qL, qR, nrm, a.ph.gamma, flux);
   }
   const double w = op.wface[i];
   double* dl = a.fluxe + ((int64_t)r.elL * NF + r.fL) * FL + i * ND;
 #pragma unroll
-  for (int k = 0; k < ND; ++k) dl[k] = -w * flux[k];
+  for (int k = 0; k < ND; ++k) dl[k] = -w * GenScal<T>::out(flux[k]);
   if (r.kind == FK_INTERIOR) {
     double* dr = a.fluxe + ((int64_t)r.elR * NF + r.fR) * FL + iR * ND;
 #pragma unroll
-    for (int k = 0; k < ND; ++k) dr[k] = w * flux[k];
+    for (int k = 0; k < ND; ++k) dr[k] = w * GenScal<T>::out(flux[k]);
   }
 }
 
@@ -316,66 +328,113 @@ k_gen_jvp_element(const GenTab op, const __grid_constant__ ElemArgs a, const dou
   for (int k = 0; k < ND; ++k) out[(e * nn + i) * ND + k] = acc[k];
 }
 
-// split form with the Ismail-Roe flux (euler_funcs.jl:240-288): res[:, i] -= sum_m 2 S[i,m,d] F_d(q_hi, q_lo), the pair's
-// flux taken with the metrics of its higher-numbered node, as the reference's (i, j < i) loop does; sparse-face records
+// split form with the Ismail-Roe flux (euler_funcs.jl:240-288): acc[:] = -sum_m 2 S[i,m,d] F_d(q_hi, q_lo), the pair's
+// flux taken with the metrics of its higher-numbered node, as the reference's (i, j < i) loop does
+template <int DIM, typename T>
+__device__ __forceinline__ void gen_split_volume(const GenTab& op, const ElemArgs& a, const double* __restrict__ v, int64_t e,
+                                                 int i, double* acc, bool check) {
+  constexpr int ND = DIM + 2;
+  constexpr bool DUAL = !std::is_same<T, double>::value;
+  const int nn = op.nn, EL = nn * ND;
+  const double gami = a.ph.gamma - 1.0;
+  double qv[ND];
+  T qi[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) qv[k] = a.q[e * EL + i * ND + k];
+  bool ok = true;
+  if (check) ok = gen_check_node<DIM>(a, qv, e, i);
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    if (!ok) qv[k] = (k == 0 || k == ND - 1) ? 1.0 : 0.0;
+    if constexpr (DUAL) qi[k] = Dual(qv[k], v[e * EL + i * ND + k]);
+    else qi[k] = qv[k];
+  }
+  const IRNode<DIM, T> zi = ir_node<DIM>(qi, gami);
+  for (int m = 0; m < nn; ++m) {
+    if (m == i) continue;
+    double qmv[ND];
+    T qm[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      qmv[k] = a.q[e * EL + m * ND + k];
+      if constexpr (DUAL) qm[k] = Dual(qmv[k], v[e * EL + m * ND + k]);
+      else qm[k] = qmv[k];
+    }
+    const double pm = calc_pressure<DIM>(qmv, gami);
+    if (!(qmv[0] > 0.0) || !(pm > 0.0)) continue;        // reported by the thread of node m; keeps the logarithms finite
+    const IRNode<DIM, T> zm = ir_node<DIM>(qm, gami);
+    const int hi = m > i ? m : i;
+    const double* dx = a.dxidx + e * a.dx_el_stride + hi * a.dx_node_stride;
+    double dirs[DIM][DIM];
+    T F[DIM][ND];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int p = 0; p < DIM; ++p) dirs[d][p] = dx[d + DIM * p];
+    if (m > i) ir_flux<DIM, DIM>(zm, zi, dirs, a.ph.gamma, F);
+    else ir_flux<DIM, DIM>(zi, zm, dirs, a.ph.gamma, F);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const double sc = -op.S2[((int64_t)d * nn + i) * nn + m];
+#pragma unroll
+      for (int c = 0; c < ND; ++c) acc[c] = fma(sc, GenScal<T>::out(F[d][c]), acc[c]);
+    }
+  }
+}
+
+// sparse-face records: the face-node slots that coincide with volume node i
+template <int DIM>
+__device__ __forceinline__ void gen_sparse_gather(const GenTab& op, const ElemArgs& a, int64_t e, int i, double* acc) {
+  constexpr int ND = DIM + 2, NF = DIM + 1;
+  const double* G = a.fluxe + e * (NF * op.nfn * ND);
+  for (int u = 0; u < NF; ++u) {
+    const int slot = op.inv[i * NF + u];
+    if (slot < 0) break;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) acc[c] += G[slot * ND + c];
+  }
+}
+
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(128)
 k_gen_element_split(const GenTab op, const __grid_constant__ ElemArgs a) {
-  constexpr int ND = DIM + 2, NF = DIM + 1;
+  constexpr int ND = DIM + 2;
   if (a.ctl->stop) return;
-  const int nn = op.nn, nfn = op.nfn, EL = nn * ND, FL = nfn * ND;
+  const int nn = op.nn;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool act = t < (a.nE - a.e_begin) * nn;
   double nrm2 = 0.0;
   if (act) {
     const int64_t e = a.e_begin + t / nn;
     const int i = (int)(t % nn);
-    const double gami = a.ph.gamma - 1.0;
-    double qi[ND];
-#pragma unroll
-    for (int k = 0; k < ND; ++k) qi[k] = a.q[e * EL + i * ND + k];
-    if (!gen_check_node<DIM>(a, qi, e, i)) {
-#pragma unroll
-      for (int k = 0; k < ND; ++k) qi[k] = (k == 0 || k == ND - 1) ? 1.0 : 0.0;
-    }
-    const IRNode<DIM> zi = ir_node<DIM>(qi, gami);
     double acc[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) acc[k] = 0.0;
-    for (int m = 0; m < nn; ++m) {
-      if (m == i) continue;
-      double qm[ND];
-#pragma unroll
-      for (int k = 0; k < ND; ++k) qm[k] = a.q[e * EL + m * ND + k];
-      const double pm = calc_pressure<DIM>(qm, gami);
-      if (!(qm[0] > 0.0) || !(pm > 0.0)) continue;        // reported by the thread of node m; keeps the logarithms finite
-      const IRNode<DIM> zm = ir_node<DIM>(qm, gami);
-      const int hi = m > i ? m : i;
-      const double* dx = a.dxidx + e * a.dx_el_stride + hi * a.dx_node_stride;
-      double dirs[DIM][DIM], F[DIM][ND];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d)
-#pragma unroll
-        for (int p = 0; p < DIM; ++p) dirs[d][p] = dx[d + DIM * p];
-      if (m > i) ir_flux<DIM, DIM>(zm, zi, dirs, a.ph.gamma, F);
-      else ir_flux<DIM, DIM>(zi, zm, dirs, a.ph.gamma, F);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const double sc = -op.S2[((int64_t)d * nn + i) * nn + m];
-#pragma unroll
-        for (int c = 0; c < ND; ++c) acc[c] = fma(sc, F[d][c], acc[c]);
-      }
-    }
-    const double* G = a.fluxe + e * (NF * FL);
-    for (int u = 0; u < NF; ++u) {
-      const int slot = op.inv[i * NF + u];
-      if (slot < 0) break;
-#pragma unroll
-      for (int c = 0; c < ND; ++c) acc[c] += G[slot * ND + c];
-    }
+    gen_split_volume<DIM, double>(op, a, nullptr, e, i, acc, true);
+    gen_sparse_gather<DIM>(op, a, e, i, acc);
     nrm2 = gen_epilogue<DIM, MODE>(a, e * nn + i, acc);
   }
   if (MODE == EPI_RK && a.stage == 1) gen_block_norm(a, nrm2);
+}
+
+// out = dR/dq * v for the split form (tangent records from k_gen_face_sparse<DIM, Dual>)
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_gen_jvp_element_split(const GenTab op, const __grid_constant__ ElemArgs a, const double* __restrict__ v,
+                        double* __restrict__ out) {
+  constexpr int ND = DIM + 2;
+  const int nn = op.nn;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nE * nn) return;
+  const int64_t e = t / nn;
+  const int i = (int)(t % nn);
+  double acc[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) acc[k] = 0.0;
+  gen_split_volume<DIM, Dual>(op, a, v, e, i, acc, false);
+  gen_sparse_gather<DIM>(op, a, e, i, acc);
+#pragma unroll
+  for (int k = 0; k < ND; ++k) out[(e * nn + i) * ND + k] = acc[k];
 }
 
 // getSendDataFace (Utils/parallel.jl:249-258) of any element vector (the state, or the direction of a J*v product):

@@ -505,6 +505,8 @@ struct OpsImpl : Ops {
   }
 };
 
+Ops* make_generic_ops(const PdesConfig& c);
+
 // SBPDiagonalE operators (sparse faces) with the split-form entropy-stable volume integral (config 2)
 template <int DIM, int NN, int NFN, int E>
 struct OpsImplS : Ops {
@@ -533,12 +535,18 @@ struct OpsImplS : Ops {
     for (int i = 0; i < NFN; ++i) tab.wface[i] = wface[i];
     for (int o = 0; o < Tab::NOR; ++o)
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
-    (void)w; (void)interp;
+    jv.reset(make_generic_ops(c));
+    if (jv) jv->build_tables(c, Q, w, interp, perm, nbrperm, wface, base);
   }
   int64_t grid_for(int64_t nelems) const override { return (nelems + E - 1) / E; }
   int tile_elems() const override { return E; }
   int resident_element_ctas() override { return 0; }
   int resident_face_ctas() override { return 0; }
+  // J*v of the entropy-stable configuration: the dual-number instantiations of the size-generic kernels
+  std::unique_ptr<Ops> jv;
+  cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) override {
+    return jv ? jv->launch_jvp(fa, a, v, out, s) : cudaErrorNotSupported;
+  }
   cudaError_t launch_faces(const FaceArgs& a, cudaStream_t s) override {
     if (a.ng <= 0) return cudaSuccess;
     const int64_t n = a.ng * NFN;
@@ -834,7 +842,7 @@ struct OpsGeneric : Ops {
     if (a.ng <= 0) return cudaSuccess;
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     const unsigned nb = (unsigned)((a.ng * tab.nfn + 127) / 128);
-    if (tab.sparse) k_gen_face_sparse<DIM><<<nb, 128, 0, s>>>(tab, a, flux_id);
+    if (tab.sparse) k_gen_face_sparse<DIM, double><<<nb, 128, 0, s>>>(tab, a, flux_id, nullptr, nullptr);
     else k_gen_face<DIM, double><<<nb, 128, 0, s>>>(tab, a, nullptr, nullptr);
     return cudaGetLastError();
   }
@@ -860,9 +868,15 @@ struct OpsGeneric : Ops {
     return cudaGetLastError();
   }
   cudaError_t launch_jvp(const FaceArgs& fa, const ElemArgs& a, const double* v, double* out, cudaStream_t s) override {
-    if (tab.sparse || split) return cudaErrorNotSupported;
+    if (tab.sparse != (split ? 1 : 0)) return cudaErrorNotSupported;
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     const int64_t nfn = fa.ng * tab.nfn, nen = a.nE * tab.nn;
+    if (split) {
+      // entropy-stable configuration: IR / IRSLF / Roe interface flux and the split-form volume terms on dual numbers
+      if (nfn > 0) k_gen_face_sparse<DIM, Dual><<<(unsigned)((nfn + 127) / 128), 128, 0, s>>>(tab, fa, flux_id, v, fa.v_recv);
+      k_gen_jvp_element_split<DIM><<<(unsigned)((nen + 127) / 128), 128, 0, s>>>(tab, a, v, out);
+      return cudaGetLastError();
+    }
     if (nfn > 0) k_gen_face<DIM, Dual><<<(unsigned)((nfn + 127) / 128), 128, 0, s>>>(tab, fa, v, fa.v_recv);
     k_gen_jvp_element<DIM><<<(unsigned)((nen + 127) / 128), 128, 0, s>>>(tab, a, v, out);
     return cudaGetLastError();
@@ -1968,7 +1982,7 @@ int enqueue_jvp(PdesCtx* ctx, const double* vdev, double* odev, int halo_mode = 
   }
   cudaError_t e = ctx->ops->launch_jvp(fa, a, vdev, odev, ctx->stream);
   if (e == cudaErrorNotSupported) {
-    set_err(ctx, "pdes_eval_jvp is implemented for dense-face operators with the Roe flux only");
+    set_err(ctx, "pdes_eval_jvp is not implemented for face_integral_type 2 (face-element integrals)");
     return PDES_ERR_UNSUPPORTED;
   }
   CUDA_TRY(ctx, e);
