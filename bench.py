@@ -112,6 +112,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on (and first-touch host buffers from) the CPUs of the GPU's NUMA node, so that the pinned
+    eqn.q / eqn.res of this rank are local to the PCIe root its GPU hangs off (torchrun does not place its children).
+    Returns a short description for the JSON line; silently does nothing where sysfs has no answer (VMs)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:      # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 def build_problem(wl, rank, nranks, scaling="weak"):
     import pdesolver_jl_b200 as pd
     from pdesolver_jl_b200 import ic
@@ -315,6 +341,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle checks (kernel A/B runs)")
     ap.add_argument("--e2e-rk-steps", type=int, default=10, help="RK4 steps per public rk4() call in the e2e leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the NUMA node of its GPU")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.scaling == "strong" and args.workload == "c3_3d_p2_roe":
@@ -334,6 +361,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = "off" if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
@@ -490,6 +518,7 @@ def main():
                 "h2d_bytes_per_call": int(ndof * 8), "d2h_bytes_per_call": int(ndof * 8 + S * 8),
                 "rk4_steps_per_call": S, "calls": e2e_calls,
                 "api": "rk4(evalResidual, h, t_max, mesh, sbp, eqn, opts): eqn.q up and down once per call of S steps",
+                "host_numa_binding": numa,
                 "evalResidual_call_ms": dt_res * 1e3,
                 "evalResidual_dof_per_s": ndof_total / dt_res},
         "gpu_launches": int(launches),
@@ -497,7 +526,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "kernel": ("k_face_flux_sparse + k_element_split_r<EPI_RK>" if wl.get("kind") == "diage"
-                                else "k_face_flux + k_element_rk<EPI_RK>") + " (one residual evaluation + RK4 stage)",
+                                else "k_face_tma + k_element_tma<EPI_RK>") + " (one residual evaluation + RK4 stage)",
                      "algorithmic_bytes_per_dof": b_stage,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
     }

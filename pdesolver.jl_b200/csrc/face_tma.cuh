@@ -49,7 +49,8 @@ struct FaceTmaWCfg {
   static constexpr int max_warps(int smem_budget) { return (smem_budget - 512) / (WS * 8); }
 };
 
-template <int DIM, int NN, int NFN, int NW, bool EXTBC>
+// HALO: the launch carries the halo exchange of a partitioned mesh (HaloArgs); the single-GPU instantiation has none of it
+template <int DIM, int NN, int NFN, int NW, bool EXTBC, bool HALO = false>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
   using Cfg = FaceTmaWCfg<DIM, NN, NFN>;
@@ -60,7 +61,7 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
   if (a.ctl->stop) {
     // a rank stopped by an error never sends: tell the neighbours (abort slots) instead of letting them wait for the
     // time-out (a res_tol stop is taken by every rank at the same step head: nobody waits)
-    if (hx.on && a.ctl->err_code != 0 && blockIdx.x == 0 && (int)threadIdx.x < hx.npeers) {
+    if (HALO && a.ctl->err_code != 0 && blockIdx.x == 0 && (int)threadIdx.x < hx.npeers) {
       __threadfence_system();
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hx.peer_flags[threadIdx.x] + 32), "r"(1u) : "memory");
     }
@@ -72,15 +73,54 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
   double* wbase = reinterpret_cast<double*>(smem_ftma + 512) + (size_t)warp * Cfg::WS;
   double* sL = wbase + 2 * Cfg::STAGE;
   double* sR = sL + FW * FS;
-  // fused halo: the first npk tiles are the SEND pass over this rank's shared faces; the shared faces come again, as the
-  // last tiles of the face list, for their fluxes
-  const int64_t npk = hx.on ? (hx.nS + FW - 1) / FW : 0;
-  const int64_t ntiles = npk + (a.ng + FW - 1) / FW;
-  const unsigned hE = hx.on ? ld_relaxed_u32(hx.ctr) + 1u : 0u;          // number of this evaluation
-  const double* q_recv = hx.on ? hx.recv_base + (size_t)(hE & 1u) * hx.nsend : a.q_recv;
-  bool h_waited = false;
+  const int64_t ntiles = (a.ng + FW - 1) / FW;
   const int64_t W = (int64_t)gridDim.x * NW;
   const int64_t gw = (int64_t)blockIdx.x * NW + warp;
+  const unsigned hE = HALO ? ld_relaxed_u32(hx.ctr) + 1u : 0u;          // number of this evaluation
+  const double* q_recv = HALO ? hx.recv_base + (size_t)(hE & 1u) * hx.nsend : a.q_recv;
+  bool h_waited = false;
+  if (HALO) {
+    // ---- SEND pass (getSendDataFace, Utils/parallel.jl:249-258) before anything else: npk tiles of FW shared faces, dealt
+    // to the warps from the END of the grid (the tiles of the main loop are dealt from its start: the warps that own one
+    // tile less take the send tiles).  Variable lanes (face, k) interpolate this rank's side and store the states, in its
+    // own face-node order, straight into the neighbour's receive buffer (peer memory over NVLink); the warp that completes
+    // the pass publishes the evaluation number in every neighbour's flag slot (fence.sys by every storing warp, cumulative
+    // through the counter, fence.sys + release by the last one).
+    const int64_t npk = (hx.nS + FW - 1) / FW;
+    for (int64_t j = W - 1 - gw; j < npk; j += W) {
+      const int fi = lane / ND, k = lane - fi * ND;
+      const int64_t u = j * FW + fi;
+      if (lane < FW * ND && u < hx.nS) {
+        const FaceRec r = a.faces[hx.s0 + u];
+        const unsigned long long pk = op.perm_pk[r.fL];
+        const double* b = a.q + (int64_t)r.elL * EL + k;
+        double sv[NFN];
+#pragma unroll
+        for (int i = 0; i < NFN; ++i) sv[i] = 0.0;
+#pragma unroll
+        for (int jn = 0; jn < NN; ++jn) {
+          const double ql = __ldg(b + (int)((pk >> (4 * jn)) & 15ull) * ND);
+#pragma unroll
+          for (int i = 0; i < NFN; ++i) sv[i] = fma(op.interp[jn][i], ql, sv[i]);
+        }
+        double* dst = hx.face_dst[(size_t)(hE & 1u) * hx.nS + u];
+#pragma unroll
+        for (int i = 0; i < NFN; ++i) dst[i * ND + k] = sv[i];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_system();
+        const unsigned old = atomicAdd(hx.ctr + 1, 1u);
+        if (old + 1u == (unsigned)npk) {
+          hx.ctr[1] = 0u;
+          __threadfence_system();
+          for (int p = 0; p < hx.npeers; ++p)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hx.peer_flags[p]), "r"(hE) : "memory");
+        }
+      }
+      __syncwarp();
+    }
+  }
   if (gw >= ntiles) return;
   if (lane == 0) {
     mbar_init(&bars[0], 1);
@@ -93,18 +133,17 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
   // lane fi < FW carries the record of face fi of a tile as the raw 16 bytes {elL, elR, fL | fR<<8 | orient<<16 | kind<<24,
   // aux}; fields are unpacked where they are used, two iterations after the load was issued (unpacking at the load
   // exposed its full latency: 9 % of the samples of the first version)
+  // (volatile: the load keeps its place at the top of an iteration -- left to the scheduler it sinks to the register moves
+  // at the end of the loop body, where its full latency is exposed: 10 % of the samples of the halo instantiation)
+  auto ld_rec = [](const FaceRec* p) {
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+  };
   auto load_rec = [&](int64_t t) {
     int4 v = make_int4(0, 0, (int)(255u << 24), 0);
-    if (t < npk) {
-      const int64_t u = t * FW + lane;
-      if (lane < FW && u < hx.nS) {
-        v = __ldg(reinterpret_cast<const int4*>(a.faces + hx.s0 + u));
-        v.z = (int)(((unsigned)v.z & 0x00ffffffu) | ((unsigned)FK_PACK << 24));
-      }
-      return v;
-    }
-    const int64_t g = a.g0 + (t - npk) * FW + lane;
-    if (t < ntiles && lane < FW && g < gend) v = __ldg(reinterpret_cast<const int4*>(a.faces + g));
+    const int64_t g = a.g0 + t * FW + lane;
+    if (t < ntiles && lane < FW && g < gend) v = ld_rec(a.faces + g);
     return v;
   };
   // one bulk copy per staged element: lane l < 2*FW fetches slot l (left element of face l/2 for even l, right for odd l)
@@ -152,12 +191,10 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
     const bool more = t + W < ntiles;
     if (more) issue(rn, st ^ 1);
     const int4 rn2 = load_rec(t + 2 * W);         // records of the tile after next (consumed two iterations later)
-    const bool is_pack = t < npk;
-    const int64_t g0 = is_pack ? hx.s0 + t * FW : a.g0 + (t - npk) * FW;
-    const int64_t gstop = is_pack ? hx.s0 + hx.nS : gend;
-    const int nf = (int)((gstop - g0) < FW ? (gstop - g0) : FW);
+    const int64_t g0 = a.g0 + t * FW;
+    const int nf = (int)((gend - g0) < FW ? (gend - g0) : FW);
     const double* sQ = wbase + st * Cfg::STAGE;
-    if (hx.on && !is_pack && !h_waited && __any_sync(0xffffffffu, lane < FW && ((unsigned)rc.z >> 24) == FK_SHARED)) {
+    if (HALO && !h_waited && g0 + nf > hx.s0) {      // (the shared faces are the tail of the face list)
       // finishExchangeData: every neighbour's states of evaluation hE are in the local receive buffer
       if (lane < hx.npeers) {
         unsigned long long t0, t1;
@@ -183,7 +220,7 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
 
     // ---- node lanes: the normal of this lane's face node (depends on the face number only), requested before the wait
     const int nfi = lane / NFN, ni = lane - nfi * NFN;
-    const bool nact = !is_pack && lane < nf * NFN;
+    const bool nact = lane < nf * NFN;
     double nrm[DIM];
     if (nact) {
       const double* np_ = a.nrm + (g0 + nfi) * a.nrm_face_stride + ni * a.nrm_node_stride;
@@ -236,12 +273,7 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
           }
         }
       }
-      if (vact && kind == FK_PACK) {
-        // getSendDataFace (Utils/parallel.jl:249-258): own face-node order, straight into the neighbour's receive buffer
-        double* dst = hx.face_dst[(size_t)(hE & 1u) * hx.nS + (g0 - hx.s0) + fi];
-#pragma unroll
-        for (int i = 0; i < NFN; ++i) dst[i * ND + k] = sLv[i];
-      } else if (vact) {
+      if (vact) {
 #pragma unroll
         for (int i = 0; i < NFN; ++i) {
           sL[fi * FS + i * ND + k] = sLv[i];
@@ -258,24 +290,6 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
       }
     }
     __syncwarp();
-    if (is_pack) {
-      // this tile's states are on their way: the warp that completes the send pass publishes the evaluation number in
-      // every neighbour's flag slot (fence.sys by the storing warp, cumulative through the counter, fence.sys + release)
-      if (lane == 0) {
-        __threadfence_system();
-        const unsigned old = atomicAdd(hx.ctr + 1, 1u);
-        if (old + 1u == (unsigned)npk) {
-          hx.ctr[1] = 0u;
-          __threadfence_system();
-          for (int p = 0; p < hx.npeers; ++p)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hx.peer_flags[p]), "r"(hE) : "memory");
-        }
-      }
-      __syncwarp();
-      rc = rn;
-      rn = rn2;
-      continue;
-    }
 
     // ---- B: numerical flux at every face node (node lanes) ----------------------------------------------------------
     // results overwrite the face-state tiles: sL <- -w f* in elementL's node order, sR <- +w f* in elementR's node order

@@ -198,15 +198,19 @@ struct OpsImpl : Ops {
   // k_face_tma (default): warp-autonomous face tiles, element blocks staged by bulk copies
   using TabF = FaceTabP<DIM, NN, NFN>;
   using FWCfg = FaceTmaWCfg<DIM, NN, NFN>;
-  static constexpr int NWF = FWCfg::max_warps(SMEM_MAX) > 16 ? 16 : FWCfg::max_warps(SMEM_MAX);
+#ifndef PDES_FACE_NW
+#define PDES_FACE_NW 16       // warps per CTA of k_face_tma: 16 caps the kernel at 128 registers per thread
+#endif
+  static constexpr int NWF = FWCfg::max_warps(SMEM_MAX) > PDES_FACE_NW ? PDES_FACE_NW : FWCfg::max_warps(SMEM_MAX);
   TabF tabf;
   bool use_tma_face = true;
   template <bool EXTBC>
   cudaError_t launch_faces_tma(const FaceArgs& a, cudaStream_t s) {
-    const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW + (a.halo.on ? (a.halo.nS + FWCfg::FW - 1) / FWCfg::FW : 0);
+    const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW;      // (ng includes the shared faces: >= the send tiles)
     const int64_t nblk = std::min<int64_t>((ntiles + NWF - 1) / NWF, (int64_t)sm_count);
     const size_t smem = 512 + (size_t)NWF * FWCfg::WS * sizeof(double);
-    k_face_tma<DIM, NN, NFN, NWF, EXTBC><<<dim3((unsigned)nblk), dim3(32 * NWF), smem, s>>>(tabf, a);
+    if (a.halo.on) k_face_tma<DIM, NN, NFN, NWF, EXTBC, true><<<dim3((unsigned)nblk), dim3(32 * NWF), smem, s>>>(tabf, a);
+    else k_face_tma<DIM, NN, NFN, NWF, EXTBC, false><<<dim3((unsigned)nblk), dim3(32 * NWF), smem, s>>>(tabf, a);
     return cudaGetLastError();
   }
   bool use_tma_elem = true;
@@ -414,8 +418,10 @@ struct OpsImpl : Ops {
       if (sm_count <= 0) sm_count = 148;
       {
         const int fsm = (int)(512 + (size_t)NWF * FWCfg::WS * sizeof(double));
-        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_face_tma<DIM, NN, NFN, NWF, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return e;
       }
       if ((e = prepare_tma<EPI_RES, false, NW0>()) != cudaSuccess) return e;
       if ((e = prepare_tma<EPI_RK, false, NW0>()) != cudaSuccess) return e;
