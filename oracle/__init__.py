@@ -23,9 +23,8 @@ FEI_IDS = {"ECFaceIntegral": 1, "ELFPenaltyFaceIntegral": 2, "ESLFFaceIntegral":
 
 
 def build(force=False):
-    """Compile liborc.so / liborc_omp.so with the committed Makefile."""
-    if force or not (os.path.exists(os.path.join(_HERE, "liborc.so"))
-                     and os.path.exists(os.path.join(_HERE, "liborc_omp.so"))):
+    """Compile liborc.so / liborc_omp.so / liborc_cs.so with the committed Makefile."""
+    if force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liborc.so", "liborc_omp.so", "liborc_cs.so")):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
 
 
@@ -49,6 +48,17 @@ class OrcPeer(C.Structure):
 
 
 _libs = {}
+
+
+def lib_cs():
+    """liborc_cs.so: the complex-step J*v restatement (euler_oracle_cs.c)."""
+    if "cs" not in _libs:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "liborc_cs.so"))
+        L.orc_eval_jvp_complex_step.restype = C.c_int
+        L.orc_eval_jvp_complex_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        _libs["cs"] = L
+    return _libs["cs"]
 
 
 def lib(omp=False):
@@ -207,6 +217,17 @@ class Problem:
         if st == 2:
             raise FloatingPointError(f"Negative pressure detected at element {err[0]} node {err[1]}")
         return res
+
+    def eval_jvp_complex_step(self, q, v, eps=1e-20):
+        """The reference's own J*v: imag(R(q + i eps v))/eps with the residual in complex arithmetic (liborc_cs.so,
+        euler_oracle_cs.c; newton_setup.jl:632-662).  Dense-face Roe configurations."""
+        q = np.asfortranarray(q, dtype=np.float64)
+        v = np.asfortranarray(v, dtype=np.float64)
+        out = np.zeros(self.shape, order="F")
+        L = lib_cs()
+        if L.orc_eval_jvp_complex_step(self.ref(), _ptr(q), _ptr(v), float(eps), _ptr(out)) != 0:
+            raise NotImplementedError("complex-step oracle: dense-face Roe path only")
+        return out
 
     def volume_integrals(self, q, precompute=True):
         res = np.zeros(self.shape, order="F")

@@ -930,6 +930,23 @@ def test_jvp_with_more_boundary_functors(bc):
     eps = 1e-6
     fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
     assert rel_l2(Jv, fd) < 1e-8
+    # and to round-off against the reference's own method: the complex-step residual (oracle/euler_oracle_cs.c)
+    assert rel_l2(Jv, orc.eval_jvp_complex_step(q0, v)) < 1e-12
+
+
+@pytest.mark.parametrize("case,n", [("c1_2d_p1_roe", 8), ("c3_3d_p2_roe_src", 3), ("2d_p2_roe", 5), ("3d_p1_roe_src", 4),
+                                    ("2d_p2_alt_roe", 4), ("3d_p2_alt_roe_src", 2)])
+def test_jvp_matches_complex_step_oracle(case, n):
+    """The reference obtains J*v as imag(R(q + i eps v))/eps, eps = 1e-20, with evalResidual in Complex128
+    (newton_setup.jl:632-662, Utils/complexify.jl); the oracle restates exactly that (C99 complex) and the device's
+    dual-number product must agree with it to round-off -- central differences only reach 1e-8."""
+    sides = [0, 1, 0, 1] if CASES[case][0] == 2 else [0, 1, 0, 1, 0, 1]
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=6, extra={"BC2_name": "noPenetrationBC"}, bc_sides=sides)
+    rng = np.random.RandomState(11)
+    v = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+    eqn.q[...] = q0
+    Jv = pd.evaldRdqProduct(mesh, op, eqn, opts, v)
+    assert rel_l2(Jv, orc.eval_jvp_complex_step(q0, v)) < 1e-12
 
 
 # ---- size-generic kernels (generic_kernels.cuh): any operator createSBPOperator can build (solver/common.jl:276-390) --------

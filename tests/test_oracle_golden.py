@@ -580,3 +580,27 @@ def test_calc_norm_matches_reference_definition():
     assert np.isclose(L.orc_calc_norm(10, _ptr(M), _ptr(data)), np.sqrt(np.sum(data * M * data)), rtol=1e-15)
     Minv = 1.0 / M
     assert np.isclose(L.orc_calc_norm(10, _ptr(Minv), _ptr(data)), np.sqrt(np.sum(data * Minv * data)), rtol=1e-15)
+
+
+def test_complex_step_oracle_against_central_differences():
+    """oracle/euler_oracle_cs.c (the reference's J*v: complex step through the Complex128 residual) vs central differences
+    of the real oracle, and its linearity in v -- the checker of the device's dual-number product."""
+    import pdesolver_jl_b200 as pd
+    from common import CASES, perturbed, rel_l2
+    for case, n, bcs in [("c1_2d_p1_roe", 4, ("isentropicVortexBC", "noPenetrationBC")),
+                         ("c3_3d_p2_roe_src", 2, ("ExpBC", "noPenetrationESBC")), ("2d_p2_roe", 3, ("FreeStreamBC", "allOnesBC"))]:
+        dim, p, ic, opts = CASES[case]
+        op = pd.build_operator(dim, p)
+        sides = [0, 1, 0, 1] if dim == 2 else [0, 1, 0, 1, 0, 1]
+        opts = dict(opts, BC1_name=bcs[0], BC2_name=bcs[1], Ma=0.5, aoa=5.0)
+        mesh = pd.structured_mesh(op, n, shuffle_seed=6, bc_sides=sides)
+        orc = oracle.Problem(mesh, op, opts)
+        q0 = perturbed(orc.exact_state(ic))
+        rng = np.random.RandomState(0)
+        v = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+        w = np.asfortranarray(rng.standard_normal(q0.shape) * np.abs(q0))
+        Jv, Jw = orc.eval_jvp_complex_step(q0, v), orc.eval_jvp_complex_step(q0, w)
+        eps = 1e-6
+        fd = (orc.eval_residual(np.asfortranarray(q0 + eps * v)) - orc.eval_residual(np.asfortranarray(q0 - eps * v))) / (2 * eps)
+        assert rel_l2(Jv, fd) < 1e-8
+        assert rel_l2(orc.eval_jvp_complex_step(q0, 2.0 * v - 3.0 * w), 2.0 * Jv - 3.0 * Jw) < 1e-13

@@ -68,6 +68,13 @@ def main():
     out.append(dict(what="newton() on the C1 mesh (perf/input_vals_2d_newton.jl problem, matrix-free; reference: 51.55 s with an "
                          "explicit Jacobian + sparse direct solves, perf/perf_history_2d_newton.txt:5)", s_total=dt,
                     residual_norms=[float(x) for x in eqn.convergence], **eqn.newton_info))
+    # the same Newton solve with the element-block Jacobi right preconditioner (the reference: -pc_type bjacobi, right side)
+    eqn.q[...] = q0
+    t0 = time.perf_counter()
+    pd.newton(pd.evalResidual, mesh, op, eqn, dict(nopts, krylov_pc="element_block_jacobi"))
+    dt = time.perf_counter() - t0
+    out.append(dict(what="newton() on the C1 mesh with the element-block Jacobi right preconditioner", s_total=dt,
+                    residual_norms=[float(x) for x in eqn.convergence], **eqn.newton_info))
     dt = timed(lambda: pd.diagnostics(mesh, op, eqn, opts), 20)
     out.append(dict(what="diagnostics() (host q in, residual + 5 functionals)", dof=int(mesh.numDof), s_per_call=dt))
     eqn.close()
