@@ -318,6 +318,233 @@ k_face_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_cons
   }
 }
 
+// k_face_element_b: the same integrals, FB faces per CTA.  One face per CTA (k_face_element) leaves most of the 128 threads
+// idle outside the pair stage and meets twelve block barriers per face (profiles/r1_n2_face_element_3d_p2.txt: FP64 pipe 26 %,
+// barrier the top stall, 5 CTAs per SM by registers); here every stage loops over (face, item) pairs of the FB faces, so the
+// barriers are paid once per FB faces and every stage has FB times the parallel work.  Same arithmetic, same summation order.
+template <int DIM, int NN, int NFN, int FB>
+struct FaceElemBCfg {
+  static constexpr int ND = DIM + 2;
+  // doubles per face: sq 2*NN*ND | sZ 2*NN*(DIM+4) | sw 2*NN*ND | sG NN*NN*ND | sc DIM*NFN | spen NFN*ND | srec 2*NN*ND |
+  //                   sB NN*DIM*NFN | sWf, sQf 2 * 2*NFN*ND
+  static constexpr int PER = 2 * NN * ND + 2 * NN * (DIM + 4) + 2 * NN * ND + NN * NN * ND + DIM * NFN + NFN * ND + 2 * NN * ND +
+                             NN * DIM * NFN + 4 * NFN * ND;
+  static constexpr size_t smem_bytes = sizeof(double) * ((size_t)FB * PER + NN * NFN + NFN) + sizeof(int) * (size_t)FB * (2 * NN + NFN + 4);
+};
+
+template <int DIM, int NN, int NFN, int FB>
+__global__ void __launch_bounds__(128)
+k_face_element_b(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a, int fei) {
+  using Cfg = FaceElemBCfg<DIM, NN, NFN, FB>;
+  constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, T = 128, NZ = DIM + 4;
+  extern __shared__ __align__(16) unsigned char smem_feb[];
+  double* base = reinterpret_cast<double*>(smem_feb);
+  // per-face tiles (face-major), then the operator tables shared by all faces
+  auto Fq = [&](int f) { return base + (size_t)f * Cfg::PER; };                    // [2][NN][ND]
+  auto Fz = [&](int f) { return Fq(f) + 2 * NN * ND; };                              // [2][NN][NZ]
+  auto Fw = [&](int f) { return Fz(f) + 2 * NN * NZ; };                              // [2][NN][ND]
+  auto Fg = [&](int f) { return Fw(f) + 2 * NN * ND; };                              // [NN*NN][ND]
+  auto Fc = [&](int f) { return Fg(f) + NN * NN * ND; };                             // [DIM][NFN]
+  auto Fp = [&](int f) { return Fc(f) + DIM * NFN; };                                // [NFN][ND]
+  auto Fr = [&](int f) { return Fp(f) + NFN * ND; };                                 // [2][NN][ND]
+  auto Fb = [&](int f) { return Fr(f) + 2 * NN * ND; };                              // [NN][DIM][NFN]
+  auto Fwf = [&](int f) { return Fb(f) + NN * DIM * NFN; };                          // [2][NFN][ND]
+  auto Fqf = [&](int f) { return Fwf(f) + 2 * NFN * ND; };                           // [2][NFN][ND]
+  double* sA = base + (size_t)FB * Cfg::PER;                                         // [NN][NFN] interp
+  double* swf = sA + NN * NFN;                                                       // [NFN]     wface
+  int* si = reinterpret_cast<int*>(swf + NFN);
+  auto IpL = [&](int f) { return si + f * (2 * NN + NFN + 4); };                      // perm[:, fL]
+  auto IpR = [&](int f) { return IpL(f) + NN; };                                      // perm[:, fR]
+  auto Inb = [&](int f) { return IpR(f) + NN; };                                      // nbrperm[:, orient]
+  auto Ikd = [&](int f) { return Inb(f) + NFN; };                                     // kind | -1: no face
+  if (a.ctl->stop) return;
+  const int tid = threadIdx.x;
+  const int64_t g0 = a.g0 + (int64_t)blockIdx.x * FB;
+  const int nfc = (int)((a.g0 + a.ng - g0) < FB ? (a.g0 + a.ng - g0) : FB);
+  const double gami = a.ph.gamma - 1.0;
+
+  for (int idx = tid; idx < NN * NFN + NFN; idx += T) sA[idx] = __ldg(a.optab_dev + idx);      // interp | wface (contiguous)
+  for (int idx = tid; idx < nfc * (2 * NN + NFN); idx += T) {
+    const int f = idx / (2 * NN + NFN), x = idx - f * (2 * NN + NFN);
+    const FaceRec r = a.faces[g0 + f];
+    const bool two = r.kind != FK_BOUNDARY;
+    int v;
+    if (x < NN) v = __ldg(a.tab_dev + r.fL * NN + x);
+    else if (x < 2 * NN) v = two ? __ldg(a.tab_dev + r.fR * NN + (x - NN)) : 0;
+    else v = __ldg(a.tab_dev + NF * NN + (two ? r.orient : 0) * NFN + (x - 2 * NN));
+    IpL(f)[x] = v;
+    if (x == 0) Ikd(f)[0] = r.kind;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nfc * NN * ND; idx += T) {
+    const int f = idx / (NN * ND), x = idx - f * (NN * ND), j = x / ND, k = x - j * ND;
+    const FaceRec r = a.faces[g0 + f];
+    const bool shared = r.kind == FK_SHARED, two = r.kind != FK_BOUNDARY;
+    Fq(f)[x] = __ldg(a.q + (int64_t)r.elL * EL + IpL(f)[j] * ND + k);
+    Fq(f)[NN * ND + x] = two ? __ldg((shared ? a.q_recv : a.q) + (int64_t)r.elR * EL + IpR(f)[j] * ND + k) : 0.0;
+    Fr(f)[x] = 0.0;
+    Fr(f)[NN * ND + x] = 0.0;
+  }
+  for (int idx = tid; idx < nfc * DIM * NFN; idx += T) {
+    const int f = idx / (DIM * NFN), x = idx - f * (DIM * NFN), d = x / NFN, k = x - d * NFN;
+    Fc(f)[x] = swf[k] * __ldg(a.nrm + (g0 + f) * a.nrm_face_stride + k * a.nrm_node_stride + d);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nfc * NN * DIM * NFN; idx += T) {
+    const int f = idx / (NN * DIM * NFN), x = idx - f * (NN * DIM * NFN);
+    const int j = x / (DIM * NFN), d = (x / NFN) % DIM, k = x % NFN;
+    Fb(f)[x] = sA[j * NFN + Inb(f)[k]] * Fc(f)[d * NFN + k];
+  }
+  // ---- boundary faces: interpolateBoundary + BC functor + boundaryintegrate! ------------------------------------------
+  for (int idx = tid; idx < nfc * NFN; idx += T) {
+    const int f = idx / NFN, k = idx - f * NFN;
+    if (Ikd(f)[0] != FK_BOUNDARY) continue;
+    const FaceRec r = a.faces[g0 + f];
+    double qb[ND], xb[DIM], nb_[DIM], fb[ND];
+#pragma unroll
+    for (int p = 0; p < ND; ++p) qb[p] = 0.0;
+    for (int j = 0; j < NN; ++j) {
+      const double c = sA[j * NFN + k];
+#pragma unroll
+      for (int p = 0; p < ND; ++p) qb[p] = fma(c, Fq(f)[j * ND + p], qb[p]);
+    }
+    const double* xp = a.coords_bndry + ((int64_t)r.elR * NFN + k) * DIM;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { xb[d] = xp[d]; nb_[d] = __ldg(a.nrm + (g0 + f) * a.nrm_face_stride + k * a.nrm_node_stride + d); }
+    bc_flux_any<DIM>(r.aux, qb, xb, nb_, a.ph, fb);
+#pragma unroll
+    for (int p = 0; p < ND; ++p) Fp(f)[k * ND + p] = swf[k] * fb[p];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nfc * NN * ND; idx += T) {
+    const int f = idx / (NN * ND), x = idx - f * (NN * ND), j = x / ND, p = x - j * ND;
+    if (Ikd(f)[0] != FK_BOUNDARY) continue;
+    double s_ = 0.0;
+    for (int k = 0; k < NFN; ++k) s_ = fma(sA[j * NFN + k], Fp(f)[k * ND + p], s_);
+    Fr(f)[x] = -s_;
+  }
+  // ---- two-sided faces -------------------------------------------------------------------------------------------------
+  if (fei == FEI_EC || fei == FEI_ESLF || fei == FEI_ESLW2) {
+    for (int idx = tid; idx < nfc * 2 * NN; idx += T) {
+      const int f = idx / (2 * NN), x = idx - f * (2 * NN);
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      const IRNode<DIM> z = ir_node<DIM>(Fq(f) + x * ND, gami);
+      double* zz = Fz(f) + x * NZ;
+      zz[0] = z.z1;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) zz[1 + d] = z.zv[d];
+      zz[DIM + 1] = z.z5; zz[DIM + 2] = z.l1; zz[DIM + 3] = z.l5;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * NN * NN; idx += T) {
+      const int f = idx / (NN * NN), pr = idx - f * (NN * NN), i = pr / NN, j = pr - i * NN;
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      IRNode<DIM> zi, zj;
+      const double* za = Fz(f) + i * NZ;
+      const double* zb = Fz(f) + (NN + j) * NZ;
+      zi.z1 = za[0]; zj.z1 = zb[0];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) { zi.zv[d] = za[1 + d]; zj.zv[d] = zb[1 + d]; }
+      zi.z5 = za[DIM + 1]; zi.l1 = za[DIM + 2]; zi.l5 = za[DIM + 3];
+      zj.z5 = zb[DIM + 1]; zj.l1 = zb[DIM + 2]; zj.l5 = zb[DIM + 3];
+      double dirs[DIM][DIM], F[DIM][ND];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int e = 0; e < DIM; ++e) dirs[d][e] = d == e ? 1.0 : 0.0;
+      ir_flux<DIM, DIM>(zi, zj, dirs, a.ph.gamma, F);
+      double gsum[ND];
+#pragma unroll
+      for (int p = 0; p < ND; ++p) gsum[p] = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double Eij = 0.0;
+#pragma unroll
+        for (int k = 0; k < NFN; ++k) Eij = fma(sA[i * NFN + k], Fb(f)[(j * DIM + d) * NFN + k], Eij);
+#pragma unroll
+        for (int p = 0; p < ND; ++p) gsum[p] = fma(Eij, F[d][p], gsum[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < ND; ++p) Fg(f)[pr * ND + p] = gsum[p];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * NN * ND; idx += T) {
+      const int f = idx / (NN * ND), x = idx - f * (NN * ND), i = x / ND, p = x - i * ND;
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      double sl = 0.0, sr = 0.0;
+      for (int j = 0; j < NN; ++j) { sl += Fg(f)[(i * NN + j) * ND + p]; sr += Fg(f)[(j * NN + i) * ND + p]; }
+      Fr(f)[x] = -sl;
+      Fr(f)[NN * ND + x] = sr;
+    }
+    __syncthreads();
+  }
+  if (fei != FEI_EC) {      // ELF / ELW2 penalty, alone or on top of the entropy-conservative integral
+    for (int idx = tid; idx < nfc * 2 * NN; idx += T) {
+      const int f = idx / (2 * NN), x = idx - f * (2 * NN);
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      convert_to_ir<DIM>(Fq(f) + x * ND, a.ph.gamma, Fw(f) + x * ND);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * 2 * NFN * ND; idx += T) {
+      const int f = idx / (2 * NFN * ND), x = idx - f * (2 * NFN * ND);
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      const int sd = x / (NFN * ND), k = (x / ND) % NFN, p = x % ND;
+      const int kk = sd == 0 ? k : Inb(f)[k];
+      double w = 0.0;
+      for (int j = 0; j < NN; ++j) w += sA[j * NFN + kk] * Fw(f)[(sd * NN + j) * ND + p];
+      Fwf(f)[x] = w;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * 2 * NFN; idx += T) {
+      const int f = idx / (2 * NFN), x = idx - f * (2 * NFN);
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      double wv[ND], qv[ND];
+#pragma unroll
+      for (int p = 0; p < ND; ++p) wv[p] = Fwf(f)[x * ND + p];
+      convert_from_ir<DIM>(wv, a.ph.gamma, qv);
+#pragma unroll
+      for (int p = 0; p < ND; ++p) Fqf(f)[x * ND + p] = qv[p];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * NFN; idx += T) {
+      const int f = idx / NFN, k = idx - f * NFN;
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      double qa[ND], dw[ND], fl[ND], nrm[DIM];
+#pragma unroll
+      for (int p = 0; p < ND; ++p) {
+        qa[p] = 0.5 * (Fqf(f)[k * ND + p] + Fqf(f)[(NFN + k) * ND + p]);
+        dw[p] = Fwf(f)[k * ND + p] - Fwf(f)[(NFN + k) * ND + p];
+      }
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(a.nrm + (g0 + f) * a.nrm_face_stride + k * a.nrm_node_stride + d);
+      if (fei == FEI_ELW2_PENALTY || fei == FEI_ESLW2) lw2_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
+      else lf_entropy_kernel<DIM>(qa, dw, nrm, a.ph.gamma, fl);
+#pragma unroll
+      for (int p = 0; p < ND; ++p) Fp(f)[k * ND + p] = fl[p] * swf[k];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nfc * NN * ND; idx += T) {
+      const int f = idx / (NN * ND), x = idx - f * (NN * ND), j = x / ND, p = x - j * ND;
+      if (Ikd(f)[0] == FK_BOUNDARY) continue;
+      double sl = Fr(f)[x], sr = Fr(f)[NN * ND + x];
+      for (int k = 0; k < NFN; ++k) {
+        sl -= sA[j * NFN + k] * Fp(f)[k * ND + p];
+        sr += sA[j * NFN + Inb(f)[k]] * Fp(f)[k * ND + p];
+      }
+      Fr(f)[x] = sl;
+      Fr(f)[NN * ND + x] = sr;
+    }
+  }
+  __syncthreads();
+  // records in element node order: stencil node j of face f is volume node perm[f][j]
+  for (int idx = tid; idx < nfc * NN * ND; idx += T) {
+    const int f = idx / (NN * ND), x = idx - f * (NN * ND), j = x / ND, p = x - j * ND;
+    const FaceRec r = a.faces[g0 + f];
+    a.fluxe[((int64_t)r.elL * NF + r.fL) * EL + IpL(f)[j] * ND + p] = Fr(f)[x];
+    if (r.kind == FK_INTERIOR) a.fluxe[((int64_t)r.elR * NF + r.fR) * EL + IpR(f)[j] * ND + p] = Fr(f)[NN * ND + x];
+  }
+}
+
 template <int DIM, int NN, int NFN, int E>
 struct SplitCfg {
   static constexpr int ND = DIM + 2, NF = DIM + 1;

@@ -678,11 +678,27 @@ struct OpsImplE : Ops {
   int record_doubles() const override { return NN * (DIM + 2); }
   int32_t* d_ftab = nullptr;       // perm | nbrperm
   double* d_otab = nullptr;        // interp | wface
+  // faces per CTA of k_face_element_b: as many as fit in ~48 KB of shared memory (4 CTAs per SM), at most 16.  Measured
+  // (tools/r2_fei_fb.sh, ESLF, DOF-evals/s with 2 / 4 / 8 faces): p=2 tets 2.9 / 3.8 / 3.0e9 (8 faces = 94 KB: 2 CTAs per SM),
+  // p=2 triangles 3.3 / 5.5 / 7.6e9, p=1 tets 1.8 / 3.2 / 4.8e9; one face per CTA (k_face_element): 2.7 / 2.4 / 1.3e9
+#ifdef PDES_FEI_FB
+  static constexpr int FEB = PDES_FEI_FB;
+#else
+  static constexpr int feb_fit = (int)(49152 / (FaceElemBCfg<DIM, NN, NFN, 1>::PER * sizeof(double)));
+  static constexpr int FEB = feb_fit > 16 ? 16 : (feb_fit < 2 ? 2 : (feb_fit & ~1));
+#endif
   cudaError_t launch_faces(const FaceArgs& a_in, cudaStream_t s) override {
     if (a_in.ng <= 0) return cudaSuccess;
     { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
     FaceArgs a = a_in;
     a.tab_dev = d_ftab; a.optab_dev = d_otab;
+    // FB faces per CTA (default; PDES_FEI_BATCH=0: the one-face-per-CTA kernel)
+    static const int batch = env_int("PDES_FEI_BATCH", 1);
+    if (batch) {
+      using BC = FaceElemBCfg<DIM, NN, NFN, FEB>;
+      k_face_element_b<DIM, NN, NFN, FEB><<<(unsigned)((a.ng + FEB - 1) / FEB), 128, BC::smem_bytes, s>>>(tab, a, fei);
+      return cudaGetLastError();
+    }
     k_face_element<DIM, NN, NFN><<<(unsigned)a.ng, 128, 0, s>>>(tab, a, fei);
     return cudaGetLastError();
   }
@@ -690,6 +706,9 @@ struct OpsImplE : Ops {
     if (attr_set) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RES, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_face_element_b<DIM, NN, NFN, FEB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)FaceElemBCfg<DIM, NN, NFN, FEB>::smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_element_split<DIM, NN, NFN, E, EPI_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Cfg::smem_bytes);
