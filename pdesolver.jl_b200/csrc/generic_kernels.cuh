@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128)
 k_gen_face(const GenTab op, const __grid_constant__ FaceArgs a, const double* __restrict__ v, const double* __restrict__ v_recv) {
   constexpr int ND = DIM + 2, NF = DIM + 1;
   constexpr bool DUAL = !std::is_same<T, double>::value;
-  if (a.ctl->stop) return;
+  if (a.ctl->stop || a.ctl->kry_done) return;
   const int nn = op.nn, nfn = op.nfn, ss = op.ss, EL = nn * ND, FL = nfn * ND;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.ng * nfn) return;
@@ -123,7 +123,7 @@ k_gen_face_sparse(const GenTab op, const __grid_constant__ FaceArgs a, int flux_
                   const double* __restrict__ v_recv) {
   constexpr int ND = DIM + 2, NF = DIM + 1;
   constexpr bool DUAL = !std::is_same<T, double>::value;
-  if (a.ctl->stop) return;
+  if (a.ctl->stop || a.ctl->kry_done) return;
   const int nn = op.nn, nfn = op.nfn, EL = nn * ND, FL = nfn * ND;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.ng * nfn) return;
@@ -291,7 +291,7 @@ template <int DIM, int MODE>
 __global__ void __launch_bounds__(128)
 k_gen_element(const GenTab op, const __grid_constant__ ElemArgs a) {
   constexpr int ND = DIM + 2;
-  if (a.ctl->stop) return;
+  if (a.ctl->stop || a.ctl->kry_done) return;
   const int nn = op.nn;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool act = t < (a.nE - a.e_begin) * nn;
@@ -314,6 +314,7 @@ template <int DIM>
 __global__ void __launch_bounds__(128)
 k_gen_jvp_element(const GenTab op, const __grid_constant__ ElemArgs a, const double* __restrict__ v, double* __restrict__ out) {
   constexpr int ND = DIM + 2;
+  if (a.ctl->kry_done) return;
   const int nn = op.nn;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nE * nn) return;
@@ -399,7 +400,7 @@ template <int DIM, int MODE>
 __global__ void __launch_bounds__(128)
 k_gen_element_split(const GenTab op, const __grid_constant__ ElemArgs a) {
   constexpr int ND = DIM + 2;
-  if (a.ctl->stop) return;
+  if (a.ctl->stop || a.ctl->kry_done) return;
   const int nn = op.nn;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool act = t < (a.nE - a.e_begin) * nn;
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(128)
 k_gen_jvp_element_split(const GenTab op, const __grid_constant__ ElemArgs a, const double* __restrict__ v,
                         double* __restrict__ out) {
   constexpr int ND = DIM + 2;
+  if (a.ctl->kry_done) return;
   const int nn = op.nn;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nE * nn) return;

@@ -61,6 +61,7 @@ template <int DIM, int NN, int NFN>
 __global__ void __launch_bounds__(128)
 k_jvp_face(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a, const double* __restrict__ v) {
   constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, FL = NFN * ND;
+  if (a.ctl->kry_done) return;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.ng * NFN) return;
   const int64_t g = a.g0 + t / NFN;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(128)
 k_jvp_element(const __grid_constant__ OpTab<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a,
               const double* __restrict__ v, double* __restrict__ out) {
   constexpr int ND = DIM + 2, NF = DIM + 1, EL = NN * ND, FL = NFN * ND;
+  if (a.ctl->kry_done) return;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nE * NN) return;
   const int64_t e = t / NN;

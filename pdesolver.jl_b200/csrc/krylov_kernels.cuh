@@ -17,7 +17,8 @@ constexpr int KRY_VB = 8;      // basis vectors per CTA row of k_multi_dot
 // partials[i * gridDim.x + blockIdx.x] = sum over this CTA's dofs of V_i[idx] * w[idx],  i in [8*blockIdx.y, +8)
 __global__ void __launch_bounds__(KRY_T)
 k_multi_dot(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ w, int64_t n,
-            double* __restrict__ partials) {
+            double* __restrict__ partials, const int* done = nullptr) {
+  if (done && *done) return;
   const int i0 = blockIdx.y * KRY_VB;
   double acc[KRY_VB];
 #pragma unroll
@@ -84,7 +85,8 @@ k_reduce_rows(const double* __restrict__ partials, int B, double* __restrict__ o
 // w -= sum_i h[i] V_i   (Gram-Schmidt projection; h lives on the device: no host round trip between the dot and the update)
 __global__ void __launch_bounds__(KRY_T)
 k_multi_axpy(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ h, double sign,
-             double* __restrict__ w, int64_t n) {
+             double* __restrict__ w, int64_t n, const int* done = nullptr) {
+  if (done && *done) return;
   for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T) {
     double s = 0.0;
     for (int i = 0; i < nv; ++i) s = fma(h[i], V[(int64_t)i * ld + idx], s);
@@ -94,7 +96,9 @@ k_multi_axpy(const double* __restrict__ V, int64_t ld, int nv, const double* __r
 
 // dst = src / sqrt(*norm_sq)   (next basis vector; a zero norm leaves zeros: happy breakdown is detected on the host)
 __global__ void __launch_bounds__(KRY_T)
-k_normalize(const double* __restrict__ src, const double* __restrict__ norm_sq, double* __restrict__ dst, int64_t n) {
+k_normalize(const double* __restrict__ src, const double* __restrict__ norm_sq, double* __restrict__ dst, int64_t n,
+            const int* done = nullptr) {
+  if (done && *done) return;
   const double nv = *norm_sq;
   const double s = nv > 0.0 ? 1.0 / sqrt(nv) : 0.0;
   for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T)
@@ -106,6 +110,52 @@ __global__ void __launch_bounds__(KRY_T)
 k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n) {
   for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * KRY_T)
     y[idx] = b == 0.0 ? a * x[idx] : fma(a, x[idx], b * y[idx]);
+}
+
+// ---- Hessenberg column + Givens rotations of one GMRES iteration, on the device ------------------------------------------
+// Round 1 read the projection coefficients back every iteration to update the rotations on the host (one stream
+// synchronisation per iteration, ~25 % of an iteration on the 60 k-DOF meshes).  Here one thread does that update right
+// behind the reductions: column j of H from the two Gram-Schmidt passes, the previous rotations, the new one, the
+// residual norm |g_{j+1}| and the convergence / divergence / breakdown / itermax tests (PETSc's default test as in
+// gmres_dev).  When a test fires it raises Ctl::kry_done, which turns every Krylov and J*v kernel enqueued behind it into a
+// no-op; the host enqueues several iterations per poll of this block.  H (column-major, (m+1) x m), cs, sn, g stay on the
+// device until the end of the restart cycle.
+struct GmresState {
+  double rnorm, bnorm;
+  long long its, itermax;
+  int32_t reason, jdone;      // jdone: columns of the current cycle that are complete
+};
+__global__ void k_gmres_update(int j, int m, const double* __restrict__ h1, const double* __restrict__ h2,
+                               const double* __restrict__ nq, double* __restrict__ H, double* __restrict__ cs,
+                               double* __restrict__ sn, double* __restrict__ g, GmresState* st, double reltol, double abstol,
+                               double dtol, int* done) {
+  if (*done) return;
+  for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = h1[i] + h2[i];
+  const double hn = sqrt(*nq);
+  H[(size_t)(j + 1) * m + j] = hn;
+  for (int i = 0; i < j; ++i) {
+    const double t = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
+    H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
+    H[(size_t)i * m + j] = t;
+  }
+  const double a0 = H[(size_t)j * m + j], a1 = hn, d = hypot(a0, a1);
+  if (d == 0.0) { cs[j] = 1.0; sn[j] = 0.0; }
+  else { cs[j] = a0 / d; sn[j] = a1 / d; }
+  H[(size_t)j * m + j] = d;
+  H[(size_t)(j + 1) * m + j] = 0.0;
+  g[j + 1] = -sn[j] * g[j];
+  g[j] = cs[j] * g[j];
+  const double rnorm = fabs(g[j + 1]);
+  st->rnorm = rnorm;
+  st->its += 1;
+  st->jdone = j + 1;
+  int reason = 0;
+  if (rnorm <= reltol * st->bnorm) reason = 1;
+  else if (rnorm <= abstol) reason = 2;
+  else if (hn == 0.0) reason = 3;
+  else if (rnorm >= dtol * st->bnorm) reason = -2;
+  else if (st->its >= st->itermax) reason = -1;
+  if (reason) { st->reason = reason; *done = 1; }
 }
 
 // ---- element-block Jacobi right preconditioner --------------------------------------------------------------------
@@ -182,7 +232,9 @@ k_block_invert(double* __restrict__ blocks, int EL, int64_t nE) {
 }
 // z_e = Binv_e r_e: one thread per (element, row); consecutive rows read consecutive addresses of every column
 __global__ void __launch_bounds__(KRY_T)
-k_block_apply(const double* __restrict__ blocks, int EL, int64_t nE, const double* __restrict__ r, double* __restrict__ z) {
+k_block_apply(const double* __restrict__ blocks, int EL, int64_t nE, const double* __restrict__ r, double* __restrict__ z,
+              const int* done = nullptr) {
+  if (done && *done) return;
   for (int64_t idx = (int64_t)blockIdx.x * KRY_T + threadIdx.x; idx < nE * EL; idx += (int64_t)gridDim.x * KRY_T) {
     const int64_t e = idx / EL;
     const int row = (int)(idx - e * EL);

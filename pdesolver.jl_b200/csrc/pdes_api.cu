@@ -1083,6 +1083,10 @@ struct PdesCtx {
     int restart = 0, nblk = 0;
     double *V = nullptr, *w = nullptr, *b = nullptr, *x = nullptr, *partials = nullptr, *hdev = nullptr;
     double* hhost = nullptr;     // pinned: [3*(restart+2)]
+    // Hessenberg matrix, Givens rotations, right-hand side and solver state on the device (k_gmres_update)
+    double *gH = nullptr, *gcs = nullptr, *gsn = nullptr, *gg = nullptr;
+    GmresState* gstate = nullptr;
+    GmresState* hstate = nullptr;   // pinned
     // element-block Jacobi right preconditioner (pdes_set_krylov_pc)
     int pc_type = 0, ncolours = 0;
     bool pc_ready = false;
@@ -1145,7 +1149,7 @@ PhysPar phys_of(const PdesConfig& c) {
 
 int reset_ctl(PdesCtx* ctx) {
   Ctl z;
-  z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.norm_count = 0;
+  z.stop = 0; z.err_code = 0; z.err_loc = ~0ull; z.converged_step = -1; z.norm_count = 0; z.kry_done = 0;
   *ctx->h_ctl = z;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
   if (ctx->pipe_ctr) {
@@ -2131,9 +2135,10 @@ void pdes_destroy(PdesCtx* ctx) {
                   ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->el_send_list, ctx->qel_send, ctx->qel_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
                   ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
                   ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
-                  ctx->kry.partials, ctx->kry.hdev, ctx->kry.pc_blocks, ctx->kry.pcz, ctx->kry.pcu, ctx->kry.colour};
+                  ctx->kry.partials, ctx->kry.hdev, ctx->kry.gH, ctx->kry.gcs, ctx->kry.gsn, ctx->kry.gg, ctx->kry.gstate, ctx->kry.pc_blocks, ctx->kry.pcz, ctx->kry.pcu, ctx->kry.colour};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
+  if (ctx->kry.hstate) cudaFreeHost(ctx->kry.hstate);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
   if (ctx->ev_q) cudaEventDestroy(ctx->ev_q);
@@ -2665,9 +2670,10 @@ namespace {
 int kry_alloc(PdesCtx* ctx, int restart) {
   PdesCtx::Krylov& k = ctx->kry;
   if (k.restart >= restart && k.V) return PDES_OK;
-  void* old[] = {k.V, k.w, k.b, k.x, k.partials, k.hdev};
+  void* old[] = {k.V, k.w, k.b, k.x, k.partials, k.hdev, k.gH, k.gcs, k.gsn, k.gg, k.gstate};
   for (void* p : old) if (p) cudaFree(p);
   if (k.hhost) cudaFreeHost(k.hhost);
+  if (k.hstate) cudaFreeHost(k.hstate);
   {
     // (the preconditioner's buffers do not depend on the restart length)
     PdesCtx::Krylov fresh;
@@ -2687,6 +2693,12 @@ int kry_alloc(PdesCtx* ctx, int restart) {
   CUDA_TRY(ctx, cudaMalloc((void**)&k.partials, sizeof(double) * (size_t)(restart + 2) * k.nblk));
   CUDA_TRY(ctx, cudaMalloc((void**)&k.hdev, sizeof(double) * 3 * (size_t)(restart + 2)));
   CUDA_TRY(ctx, cudaMallocHost((void**)&k.hhost, sizeof(double) * 3 * (size_t)(restart + 2)));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.gH, sizeof(double) * (size_t)(restart + 1) * restart));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.gcs, sizeof(double) * restart));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.gsn, sizeof(double) * restart));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.gg, sizeof(double) * (restart + 1)));
+  CUDA_TRY(ctx, cudaMalloc((void**)&k.gstate, sizeof(GmresState)));
+  CUDA_TRY(ctx, cudaMallocHost((void**)&k.hstate, sizeof(GmresState)));
   k.restart = restart;
   return PDES_OK;
 }
@@ -2701,10 +2713,10 @@ int kry_allreduce(PdesCtx* ctx, double* dev, int count) {
 }
 
 // out[0..nv) = V[0..nv)^T w  (device results)
-int kry_dots(PdesCtx* ctx, const double* V, int nv, const double* w, double* out) {
+int kry_dots(PdesCtx* ctx, const double* V, int nv, const double* w, double* out, const int* done = nullptr) {
   PdesCtx::Krylov& k = ctx->kry;
   dim3 grid(k.nblk, (nv + KRY_VB - 1) / KRY_VB);
-  k_multi_dot<<<grid, KRY_T, 0, ctx->stream>>>(V, ctx->ndof, nv, w, ctx->ndof, k.partials);
+  k_multi_dot<<<grid, KRY_T, 0, ctx->stream>>>(V, ctx->ndof, nv, w, ctx->ndof, k.partials, done);
   k_reduce_rows<<<nv, KRY_T, 0, ctx->stream>>>(k.partials, k.nblk, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches += 2;
@@ -2785,8 +2797,12 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
   double* nq = k.hdev + 2 * S;   // squared norms
   const int nb = k.nblk;
   cudaStream_t st = ctx->stream;
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m);
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1), y(m);
+  int* done = &ctx->ctl->kry_done;
+  // iterations enqueued per poll of the device-side solver state (PDES_GMRES_POLL; 1 = a read-back per iteration)
+  static const int poll = std::max(1, env_int("PDES_GMRES_POLL", 8));
   CUDA_TRY(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(done, 0, sizeof(int), st));
   rc = kry_dots(ctx, b, 1, b, nq);
   if (rc) return rc;
   rc = kry_fetch(ctx, 3 * S);
@@ -2818,55 +2834,55 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
     rnorm = beta;
     if (!first && beta <= tol) { reason = beta <= reltol * bnorm ? 1 : 2; break; }
     first = false;
-    std::fill(g.begin(), g.end(), 0.0);
-    g[0] = beta;
+    // the cycle's Hessenberg system lives on the device: g = beta e_1, state = {its so far, no reason, no column}
+    {
+      std::fill(g.begin(), g.end(), 0.0);
+      g[0] = beta;
+      GmresState hs;
+      hs.rnorm = beta; hs.bnorm = bnorm; hs.its = its; hs.itermax = itermax; hs.reason = 0; hs.jdone = 0;
+      *k.hstate = hs;
+      CUDA_TRY(ctx, cudaMemcpyAsync(k.gstate, k.hstate, sizeof(GmresState), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpyAsync(k.gg, g.data(), sizeof(double) * (m + 1), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));       // g and hstate are host temporaries
+    }
     int j = 0;
-    for (; j < m && !reason; ++j) {
-      if (pc) {
-        k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.V + (size_t)j * n, k.pcz);
-        ctx->launches++;
+    while (j < m && !reason) {
+      const int jb = std::min(poll, m - j);
+      for (int u = 0; u < jb; ++u) {
+        const int jj = j + u;
+        if (pc) {
+          k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.V + (size_t)jj * n, k.pcz, done);
+          ctx->launches++;
+        }
+        rc = enqueue_jvp(ctx, pc ? k.pcz : k.V + (size_t)jj * n, k.w);
+        if (rc) return rc;
+        rc = kry_dots(ctx, k.V, jj + 1, k.w, h1, done);
+        if (rc) return rc;
+        k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h1, -1.0, k.w, n, done);
+        rc = kry_dots(ctx, k.V, jj + 1, k.w, h2, done);
+        if (rc) return rc;
+        k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h2, -1.0, k.w, n, done);
+        rc = kry_dots(ctx, k.w, 1, k.w, nq, done);
+        if (rc) return rc;
+        k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V + (size_t)(jj + 1) * n, n, done);
+        // Hessenberg column, rotations, residual norm and the stopping tests: on the device, no read-back
+        k_gmres_update<<<1, 1, 0, st>>>(jj, m, h1, h2, nq, k.gH, k.gcs, k.gsn, k.gg, k.gstate, reltol, abstol, dtol, done);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 4;
       }
-      rc = enqueue_jvp(ctx, pc ? k.pcz : k.V + (size_t)j * n, k.w);
-      if (rc) return rc;
-      rc = kry_dots(ctx, k.V, j + 1, k.w, h1);
-      if (rc) return rc;
-      k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, j + 1, h1, -1.0, k.w, n);
-      rc = kry_dots(ctx, k.V, j + 1, k.w, h2);
-      if (rc) return rc;
-      k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, j + 1, h2, -1.0, k.w, n);
-      rc = kry_dots(ctx, k.w, 1, k.w, nq);
-      if (rc) return rc;
-      k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V + (size_t)(j + 1) * n, n);
-      CUDA_TRY(ctx, cudaGetLastError());
-      ctx->launches += 3;
-      rc = kry_fetch(ctx, 3 * S);
-      if (rc) return rc;
-      for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = k.hhost[i] + k.hhost[S + i];
-      const double hn = sqrt(k.hhost[2 * S]);
-      H[(size_t)(j + 1) * m + j] = hn;
-      // previous Givens rotations, then the new one
-      for (int i = 0; i < j; ++i) {
-        const double t = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
-        H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
-        H[(size_t)i * m + j] = t;
-      }
-      const double a0 = H[(size_t)j * m + j], a1 = hn, d = hypot(a0, a1);
-      if (d == 0.0) { cs[j] = 1.0; sn[j] = 0.0; }
-      else { cs[j] = a0 / d; sn[j] = a1 / d; }
-      H[(size_t)j * m + j] = d;
-      H[(size_t)(j + 1) * m + j] = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
-      rnorm = fabs(g[j + 1]);
-      ++its;
-      if (rnorm <= reltol * bnorm) reason = 1;
-      else if (rnorm <= abstol) reason = 2;
-      else if (hn == 0.0) reason = 3;
-      else if (rnorm >= dtol * bnorm) reason = -2;
-      else if (its >= itermax) reason = -1;
+      CUDA_TRY(ctx, cudaMemcpyAsync(k.hstate, k.gstate, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      j = k.hstate->jdone;
+      its = k.hstate->its;
+      rnorm = k.hstate->rnorm;
+      reason = k.hstate->reason;
     }
     // x += V y with H y = g (back substitution over the j columns built in this cycle)
     const int jj = j;
+    CUDA_TRY(ctx, cudaMemsetAsync(done, 0, sizeof(int), st));        // the update kernels below must run
+    CUDA_TRY(ctx, cudaMemcpyAsync(H.data(), k.gH, sizeof(double) * (size_t)(m + 1) * m, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g.data(), k.gg, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     for (int i = jj - 1; i >= 0; --i) {
       double sacc = g[i];
       for (int c2 = i + 1; c2 < jj; ++c2) sacc -= H[(size_t)i * m + c2] * y[c2];

@@ -59,6 +59,7 @@ struct Ctl {               // device-resident control block
   unsigned long long err_loc;  // ((code-1) << 62) | (element << 8) | node of the lowest offending location
   int32_t converged_step;  // step head at which norm < res_tol (or -1)
   int32_t norm_count;      // step heads whose norm has been committed (the slot the next commit writes)
+  int32_t kry_done;        // GMRES: the convergence test passed on the device; the Krylov / J*v kernels enqueued behind it are no-ops
 };
 
 template <int DIM, int NN, int NFN>
