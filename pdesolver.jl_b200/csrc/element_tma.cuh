@@ -49,9 +49,12 @@ struct ElemTmaCfg {
   static constexpr int QSTAGE = QW + MW + XW;
   static constexpr int UOW = UW > QW ? UW : QW;
   static constexpr int WS_RSB = 2 * QSTAGE + RW + UOW;
+  // QSB layout (q single-buffered too: the next tile's q is requested when this tile's epilogue has read it; the other
+  // warps of the SM cover the latency -- 16 instead of 14 warps per SM, four per scheduler)
+  static constexpr int WS_QSB = QSTAGE + RW + UOW;
   static constexpr int HDR = 512;                            // mbarriers: 4 per group
-  static constexpr int ws(bool rsb) { return rsb ? WS_RSB : WS; }
-  static constexpr int max_groups_l(int smem_budget, bool rsb) { return (smem_budget - HDR) / (ws(rsb) * 8); }
+  static constexpr int ws(bool rsb, bool qsb = false) { return qsb ? WS_QSB : (rsb ? WS_RSB : WS); }
+  static constexpr int max_groups_l(int smem_budget, bool rsb, bool qsb = false) { return (smem_budget - HDR) / (ws(rsb, qsb) * 8); }
   static_assert(G >= 2 && QW % 2 == 0 && RW % 2 == 0 && MW % 2 == 0 && XW % 2 == 0, "bulk copies need 16-byte multiples");
   static_assert(RW >= QW, "the result rows are staged in the record tile");
   static constexpr int max_groups(int smem_budget) { return (smem_budget - 256) / (WS * 8); }
@@ -148,7 +151,7 @@ struct NodeSlice {
 };
 
 // NP groups of NS warps per CTA; one CTA per SM (persistent), tiles strided over the groups of the grid
-template <int DIM, int NN, int NFN, int MODE, bool DXN, int NP, int NS, bool RSB = false, bool HOIST = true>
+template <int DIM, int NN, int NFN, int MODE, bool DXN, int NP, int NS, bool RSB = false, bool HOIST = true, bool QSB = false>
 __global__ void __launch_bounds__(32 * NP * NS, 1)
 k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_constant__ ElemArgs a) {
   using Cfg = ElemTmaCfg<DIM, NN, NFN, DXN>;
@@ -156,7 +159,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   constexpr int NNP = OpTabP<DIM, NN, NFN>::NNP, UPN = Cfg::UPN;
   constexpr int NC = NS == 1 ? NNP : ((NNP / 2 + NS - 1) / NS) * 2;      // output nodes per warp of a group (even)
   static_assert(NS == 1 || NS == 2, "one or two warps per tile");
-  static_assert(NP <= 15, "one named barrier per group");
+  static_assert(NP <= 15 || NS == 1, "one named barrier per group");
   extern __shared__ __align__(128) unsigned char smem_tma[];
   if (a.ctl->stop) return;
   // fused halo: the face launch of this evaluation is complete (stream order) -- close the evaluation
@@ -167,9 +170,10 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   const int grp = warp / NS, half = warp - grp * NS;
   // mbarriers per group: [0,1] the two q stages, [2,3] the record tile(s)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_tma) + 4 * grp;
-  double* wbase = reinterpret_cast<double*>(smem_tma + Cfg::HDR) + (size_t)grp * (RSB ? Cfg::WS_RSB : Cfg::WS);
-  constexpr int QST = RSB ? Cfg::QSTAGE : Cfg::STAGE;        // stride of a q stage
-  double* sRbase = RSB ? wbase + 2 * Cfg::QSTAGE : wbase + Cfg::QW + Cfg::MW + Cfg::XW;   // record tile (of stage 0)
+  static_assert(!QSB || RSB, "QSB implies RSB");
+  double* wbase = reinterpret_cast<double*>(smem_tma + Cfg::HDR) + (size_t)grp * (QSB ? Cfg::WS_QSB : (RSB ? Cfg::WS_RSB : Cfg::WS));
+  constexpr int QST = QSB ? 0 : (RSB ? Cfg::QSTAGE : Cfg::STAGE);        // stride of a q stage
+  double* sRbase = RSB ? wbase + (QSB ? 1 : 2) * Cfg::QSTAGE : wbase + Cfg::QW + Cfg::MW + Cfg::XW;   // record tile (of stage 0)
   double* sU = RSB ? sRbase + Cfg::RW : wbase + 2 * Cfg::STAGE;
   const int64_t ntiles = (a.nE - a.e_begin + G - 1) / G;
   const int64_t W = (int64_t)gridDim.x * NP;
@@ -274,11 +278,11 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   int it = 0;
 #pragma unroll 1
   for (int64_t t = gw; t < ntiles; t += W, ++it) {
-    int st = it & 1;
+    int st = QSB ? 0 : (it & 1);
     asm volatile("" : "+r"(st));          // opaque: keeps ONE copy of the (fully unrolled) tile body in the instruction cache
     const bool more = t + W < ntiles;
     if (more) {
-      issue_q(t + W, st ^ 1);
+      if (!QSB) issue_q(t + W, st ^ 1);
       if (!RSB) issue_r(t + W, st ^ 1);
     }
     const int64_t e0 = tile_e0(t);
@@ -287,7 +291,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     double* sM = sQ + Cfg::QW;
     double* sX = sM + Cfg::MW;
     double* sR = r_tile(st);
-    mbar_wait_sleep(&bars[st], (unsigned)((it >> 1) & 1));
+    mbar_wait_sleep(&bars[st], (unsigned)(QSB ? (it & 1) : ((it >> 1) & 1)));
 
     // ---- S1 (node items, split over the group): density / pressure checks, pressure, U_d = dxidx[d,:].u ---------------
     // (all items of a lane in one unrolled pass: their shared-memory loads and dependent FP64 chains interleave; one
@@ -525,6 +529,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
       }
     }
     group_sync();              // the stage may be refilled by the next iteration's issue
+    if (QSB && more) issue_q(t + W, 0);
   }
 }
 

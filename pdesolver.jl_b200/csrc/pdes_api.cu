@@ -96,6 +96,9 @@ int env_int(const char* name, int dflt) {
 #ifndef PDES_TMA_RSB
 #define PDES_TMA_RSB 1      // k_element_tma: face records single-buffered (more resident warp groups)
 #endif
+#ifndef PDES_TMA_QSB
+#define PDES_TMA_QSB 1      // k_element_tma: the q / Minv / dxidx tile single-buffered as well (16 warps per SM: 0.908 -> 0.892 ms per step)
+#endif
 #ifndef PDES_TMA_HOIST
 #define PDES_TMA_HOIST 0    // k_element_tma: epilogue streams requested before the operator products (held in registers)
 #endif
@@ -190,10 +193,13 @@ struct OpsImpl : Ops {
   using PCfg1 = ElemTmaCfg<DIM, NN, NFN, true>;
   static constexpr int SMEM_MAX = 232448;      // 227 KB: the opt-in dynamic shared memory of an sm_100 CTA
   static constexpr int NSW = PDES_TMA_NS;                // warps per tile group (they split the output nodes of the operator products)
-  static constexpr int nw_cap(int m) { return m > 15 ? 15 : (m < 1 ? 1 : m); }     // groups per CTA (one named barrier each)
-  static constexpr bool RSB = PDES_TMA_RSB != 0, HOIST = PDES_TMA_HOIST != 0;
+#ifndef PDES_TMA_NWCAP
+#define PDES_TMA_NWCAP (PDES_TMA_NS == 1 ? 16 : 15)      // upper bound on the tile groups per CTA of k_element_tma (NS > 1: one named barrier each)
+#endif
+  static constexpr int nw_cap(int m) { return m > PDES_TMA_NWCAP ? PDES_TMA_NWCAP : (m < 1 ? 1 : m); }
+  static constexpr bool RSB = PDES_TMA_RSB != 0, HOIST = PDES_TMA_HOIST != 0, QSB = PDES_TMA_QSB != 0;
   static constexpr int nw_thr(int m) { return m * NSW > 32 ? 32 / NSW : m; }        // <= 1024 threads per CTA
-  static constexpr int NW0 = nw_thr(nw_cap(PCfg0::max_groups_l(SMEM_MAX, RSB))), NW1 = nw_thr(nw_cap(PCfg1::max_groups_l(SMEM_MAX, RSB)));
+  static constexpr int NW0 = nw_thr(nw_cap(PCfg0::max_groups_l(SMEM_MAX, RSB, QSB))), NW1 = nw_thr(nw_cap(PCfg1::max_groups_l(SMEM_MAX, RSB, QSB)));
   TabP tabp;
   // k_face_tma (default): warp-autonomous face tiles, element blocks staged by bulk copies
   using TabF = FaceTabP<DIM, NN, NFN>;
@@ -266,15 +272,15 @@ struct OpsImpl : Ops {
     using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
     const int64_t ntiles = (a.nE - a.e_begin + C::G - 1) / C::G;
     const int64_t nblk = std::min<int64_t>((ntiles + NW - 1) / NW, (int64_t)sm_count);
-    const size_t smem = C::HDR + (size_t)NW * C::ws(RSB) * sizeof(double);
-    k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST><<<dim3((unsigned)nblk), dim3(32 * NW * NSW), smem, s>>>(tabp, a);
+    const size_t smem = C::HDR + (size_t)NW * C::ws(RSB, QSB) * sizeof(double);
+    k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST, QSB><<<dim3((unsigned)nblk), dim3(32 * NW * NSW), smem, s>>>(tabp, a);
     return cudaGetLastError();
   }
   template <int MODE, bool DXN, int NW>
   cudaError_t prepare_tma() {
     using C = ElemTmaCfg<DIM, NN, NFN, DXN>;
-    return cudaFuncSetAttribute(k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C::HDR + (size_t)NW * C::ws(RSB) * sizeof(double)));
+    return cudaFuncSetAttribute(k_element_tma<DIM, NN, NFN, MODE, DXN, NW, NSW, RSB, HOIST, QSB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C::HDR + (size_t)NW * C::ws(RSB, QSB) * sizeof(double)));
   }
   int resident_element_ctas() override {
     int per_sm = 0, dev = 0, sms = 0;
