@@ -43,7 +43,7 @@ enum {
   PDES_ERR_UNSUPPORTED = -3,  /* euler.jl:653,796,855,863 ErrorException for option combos */
   PDES_ERR_COMM = -4
 };
-/* faceElementIntegrals.jl:735-741 FaceElementDict (face_integral_type 2; the Lax-Wendroff kernels are unsupported) */
+/* faceElementIntegrals.jl:735-741 FaceElementDict (face_integral_type 2): EC, Lax-Friedrichs and Lax-Wendroff entropy penalties */
 enum { PDES_FEI_EC = 1, PDES_FEI_ELF_PENALTY = 2, PDES_FEI_ESLF = 3, PDES_FEI_ELW2_PENALTY = 4, PDES_FEI_ESLW2 = 5 };
 
 
@@ -134,9 +134,10 @@ int pdes_inject_recv_elements(PdesCtx *ctx, int32_t peer_idx, const double *q_re
 
 /* Multi-GPU: NCCL communicator from a 128-byte ncclUniqueId the host broadcast
  * (replaces mesh.comm / MPI.Isend/Irecv!, parallel_types.jl:620-684).
- * The communicator carries the set-up and the 8-byte norm all-reduce.  The per-
- * evaluation halo (startSolutionExchange / finishExchangeData, Utils/parallel.jl:
- * 29-208) goes peer to peer: at the FIRST evaluation after this call -- which is
+ * The communicator carries the set-up, the halos of J*v and of the type-2 face
+ * integrals, and the Krylov inner products.  The per-evaluation halo
+ * (startSolutionExchange / finishExchangeData, Utils/parallel.jl:29-208) and the
+ * stage-1 norm all-reduce go peer to peer, from inside the face / norm kernels: at the FIRST evaluation after this call -- which is
  * therefore collective over all ranks -- every rank exports its receive buffer
  * through CUDA IPC (one process per GPU, same node) and maps its neighbours';
  * if any mapping fails all ranks fall back to ncclSend/ncclRecv together.  Every
@@ -163,7 +164,8 @@ int pdes_unpin_host(void *ptr);
 /* the library's compute stream (a cudaStream_t) so that a caller can bracket launches with its own events */
 void *pdes_stream(PdesCtx *ctx);
 
-/* evalResidual: q -> res (no Minv), synchronous.  euler.jl:111-175 */
+/* evalResidual: q -> res (no Minv), synchronous.  euler.jl:111-175.  `t` is accepted for the signature's sake: every
+ * restated source term and boundary functor (SRCExp, the eight BCs) is time independent, as in the named configurations. */
 int pdes_eval_residual(PdesCtx *ctx, double t);
 /* same, but returns after enqueueing; pdes_sync reports errors (bench / overlap) */
 int pdes_eval_residual_async(PdesCtx *ctx, double t);
@@ -171,7 +173,10 @@ int pdes_sync(PdesCtx *ctx);
 
 /* Jacobian-vector product out = dR/dq(q) * v at the resident q (no Minv), v/out [nd,nn,nE] host arrays: the
  * product the reference forms as imag(R(q + i*eps*v))/eps with eps = 1e-20 (evaldRdqProduct interface2.jl:454-498,
- * applyLinearOperator NonlinearSolvers/newton_setup.jl:632-662); evaluated here on dual numbers, exact to round-off. */
+ * applyLinearOperator NonlinearSolvers/newton_setup.jl:632-662); evaluated here on dual numbers, exact to round-off
+ * (pinned against a C99-complex restatement of the complex step, oracle/euler_oracle_cs.c).  Roe and entropy-stable
+ * (IR / IRSLF, diagonal-E) configurations, any operator size; on a partitioned mesh (needs pdes_set_comm) the shared-face
+ * states and directions are exchanged first -- collective.  PDES_ERR_UNSUPPORTED for face_integral_type 2. */
 int pdes_eval_jvp(PdesCtx *ctx, const double *v, double *out);
 
 /* Matrix-free Newton-Krylov on the resident q (configuration 5): the reference's

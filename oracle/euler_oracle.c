@@ -37,7 +37,7 @@ enum { ORC_BC_ISENTROPIC_VORTEX = 1, ORC_BC_EXP = 2, ORC_BC_FREESTREAM = 3,
        ORC_BC_NOPENETRATION = 4, ORC_BC_RHO1E2U3 = 5, ORC_BC_ALLONES = 6, ORC_BC_ZEROFLUX = 7,
        ORC_BC_NOPENETRATION_ES = 8 };
 enum { ORC_SRC_NONE = 0, ORC_SRC_EXP = 1 };
-/* faceElementIntegrals.jl:735-741 FaceElementDict (the Lax-Wendroff kernels are not restated) */
+/* faceElementIntegrals.jl:735-741 FaceElementDict */
 enum { ORC_FEI_EC = 1, ORC_FEI_ELF_PENALTY = 2, ORC_FEI_ESLF = 3, ORC_FEI_ELW2_PENALTY = 4, ORC_FEI_ESLW2 = 5 };
 
 typedef struct {
