@@ -530,6 +530,18 @@ def main():
                      "algorithmic_bytes_per_dof": b_stage,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
     }
+    if wl.get("kind") == "diage":
+        # the entropy-stable path is FP64-pipe bound, not HBM bound: secondary ceiling against the measured DFMA
+        # rate (profiles/r1_fp64_pipes_microbench.txt).  Algorithmic flops per element (fma = 2): nn(nn-1)/2 Ismail-Roe pair
+        # fluxes in dim directions (~100 each), per node the parameter vector (~40) and the S-weighted gather
+        # (2 (nn-1) dim nd), per face node an IRSLF flux (~300), (dim+1) nfn / 2 per element
+        fl_el = nn * (nn - 1) / 2 * 100 + nn * (40 + 2 * (nn - 1) * dim * (dim + 2)) + (dim + 1) * nfn / 2 * 300
+        fl_dof = fl_el / (nn * (dim + 2))
+        tf = value / nranks * fl_dof * 1e-12
+        line["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": 36.7, "unit": "TFLOP/s", "frac": tf / 36.7,
+                                 "algorithmic_flops_per_dof": fl_dof,
+                                 "note": "transcendentals (2 log, 2 sqrt per node; Newton-refined reciprocals) expand to many "
+                                         "FP64 instructions: ncu shows the pipe 49 % busy (profiles/r1_s4_es_kernels_c2.txt)"}
     if nranks == 1 and not args.no_cpu_baseline:
         _omp_threads(os.cpu_count() or 1)
         rate, spstep, cores, nd_s, n_s = cpu_reference_rate(wl, 1, 0)

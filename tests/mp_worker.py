@@ -145,6 +145,23 @@ def run_nccl_b200(rank, world, local_rank):
         # the parallel norm is reduced twice -> sqrt(P) * serial norm
         assert np.allclose(eqn.convergence, np.sqrt(world) * norms_ref, rtol=1e-11, atol=0), \
             f"rank {rank} {case}: norms"
+        # res_tol exit on a partitioned mesh (rk4.jl:258-267): every rank must stop at the same step head.  The norm the
+        # reference tests in parallel is the doubly reduced one (sqrt(P) x the serial norm, rk4.jl:451-453), so the serial
+        # oracle runs with res_tol / sqrt(P); lserk54 through the same halo.
+        if case == "c1_2d_p1_roe":
+            tol = float(np.sqrt(world) * 0.5 * (norms_ref[4] + norms_ref[5]))
+            eqn.q[...] = q_s[:, :, idx]
+            t = pd.rk4(pd.evalResidual, h, 40 * h, local, op, eqn, opts, res_tol=tol)
+            t_ref, q_ref, n_ref = orc_s.rk4(q_s, h, 40 * h, res_tol=tol / np.sqrt(world))
+            assert t == t_ref and len(eqn.convergence) == len(n_ref) < 40, (t, t_ref, len(eqn.convergence), len(n_ref))
+            errq = rel_l2(eqn.q, q_ref[:, :, idx])
+            assert errq < 1e-10, f"rank {rank} {case}: res_tol exit {errq:.2e}"
+            eqn.q[...] = q_s[:, :, idx]
+            t = pd.lserk54(pd.evalResidual, h, 8 * h, local, op, eqn, opts)
+            t_ref, q_ref, n_ref = orc_s.lserk54(q_s, h, 8 * h)
+            errq = rel_l2(eqn.q, q_ref[:, :, idx])
+            assert t == t_ref and errq < 1e-10, f"rank {rank} {case}: lserk54 {errq:.2e}"
+            assert np.allclose(eqn.convergence, np.sqrt(world) * n_ref, rtol=1e-11, atol=0)
         if case not in ("c2_2d_p2_es",):
             # J*v and the Newton-Krylov linear solve on the partitioned mesh (newton_setup.jl:632-662 is flux- and
             # partition-agnostic): the shared-face states AND directions are exchanged, the Krylov inner products are
