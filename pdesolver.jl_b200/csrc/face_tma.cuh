@@ -50,7 +50,17 @@ struct FaceTmaWCfg {
 };
 
 // HALO: the launch carries the halo exchange of a partitioned mesh (HaloArgs); the single-GPU instantiation has none of it
-template <int DIM, int NN, int NFN, int NW, bool EXTBC, bool HALO = false>
+// LANECPY: the staged elements arrive by lane-parallel 16-byte cp.async copies (three lanes per element, ten LDGSTS each,
+// one address computation per lane and tile) instead of one cp.async.bulk per element.  The bulk copy is a uniform-datapath
+// instruction: with per-lane operands ptxas wraps it into an ELECT / R2UR loop over the active lanes, ~14 instructions per
+// copy -- 142 of the ~1000 warp instructions of a tile and 15 % of the kernel's stall samples (profiles/r2_final_face_tma.txt).
+// Measured (same box): 1.237 vs 0.891 ms per RK4 step -- the 280 LDGSTS of a tile cost the LSU more than the issue loop costs the
+// schedulers, and the 128-register cap spills (424 bytes of stack).  Opt-in build switch, like the round-1 finding for
+// cp.async staging.
+#ifndef PDES_FACE_LANECPY
+#define PDES_FACE_LANECPY 0
+#endif
+template <int DIM, int NN, int NFN, int NW, bool EXTBC, bool HALO = false, bool LANECPY = (PDES_FACE_LANECPY != 0)>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_constant__ FaceArgs a) {
   using Cfg = FaceTmaWCfg<DIM, NN, NFN>;
@@ -122,7 +132,7 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
     }
   }
   if (gw >= ntiles) return;
-  if (lane == 0) {
+  if (!LANECPY && lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -146,8 +156,30 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
     if (t < ntiles && lane < FW && g < gend) v = ld_rec(a.faces + g);
     return v;
   };
-  // one bulk copy per staged element: lane l < 2*FW fetches slot l (left element of face l/2 for even l, right for odd l)
+  // slot s of a stage = left (s even) / right (s odd) element of face s/2
+  constexpr int LPS = 32 / (2 * FW);                               // lanes per slot (LANECPY)
+  constexpr int NCH = Cfg::CPY / 16;                               // 16-byte chunks per element
+  constexpr int CPL = (NCH + LPS - 1) / LPS;                       // chunks per lane
   auto issue = [&](const int4& rmine, int st) {
+    if (LANECPY) {
+      const int slot = lane / LPS, part = lane - slot * LPS;
+      const int fic = slot < 2 * FW ? (slot >> 1) : 0;
+      const int elL = __shfl_sync(0xffffffffu, rmine.x, fic);
+      const int elR = __shfl_sync(0xffffffffu, rmine.y, fic);
+      const int kind = (int)((unsigned)__shfl_sync(0xffffffffu, rmine.z, fic) >> 24);
+      int el = -1;
+      if (slot < 2 * FW && kind != 255) el = (slot & 1) ? (kind == FK_INTERIOR ? elR : -1) : elL;
+      if (el >= 0) {
+        const char* src = reinterpret_cast<const char*>(a.q) + (int64_t)el * (EL * 8) + part * (CPL * 16);
+        if (!Cfg::ALIGNED) src -= (el & 1) * 8;
+        char* dst = reinterpret_cast<char*>(wbase + st * Cfg::STAGE + slot * SLOTD) + part * (CPL * 16);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+          if (part * CPL + c < NCH) cp_async16(dst + 16 * c, src + 16 * c);
+      }
+      cp_async_commit();
+      return;
+    }
     const int fi = lane >> 1;
     const int elL = __shfl_sync(0xffffffffu, rmine.x, fi);
     const int elR = __shfl_sync(0xffffffffu, rmine.y, fi);
@@ -227,7 +259,14 @@ k_face_tma(const __grid_constant__ FaceTabP<DIM, NN, NFN> op, const __grid_const
 #pragma unroll
       for (int d = 0; d < DIM; ++d) nrm[d] = __ldg(np_ + d);
     }
-    mbar_wait_sleep(&bars[st], (unsigned)((it >> 1) & 1));
+    if (LANECPY) {
+      // this lane's copies of the current tile have landed (the group of the next tile may still be in flight);
+      // the warp barrier publishes every lane's part to the others
+      if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+    } else {
+      mbar_wait_sleep(&bars[st], (unsigned)((it >> 1) & 1));
+    }
 
     // ---- A: interpolate both sides to the face nodes (variable lanes: lane = (face fi, variable k)) ------------------
     {

@@ -208,6 +208,7 @@ struct OpsImpl : Ops {
 #define PDES_FACE_NW 16       // warps per CTA of k_face_tma: 16 caps the kernel at 128 registers per thread
 #endif
   static constexpr int NWF = FWCfg::max_warps(SMEM_MAX) > PDES_FACE_NW ? PDES_FACE_NW : FWCfg::max_warps(SMEM_MAX);
+  static_assert(32 / (2 * FWCfg::FW) >= 1, "k_face_tma: at least one copy lane per staged element");
   TabF tabf;
   bool use_tma_face = true;
   template <bool EXTBC>
