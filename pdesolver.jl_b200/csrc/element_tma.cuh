@@ -80,6 +80,15 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsign
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
+// the block [src, src + bytes) into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+#ifndef PDES_TMA_L2PF
+#define PDES_TMA_L2PF 1      // QSB: the inputs of a warp's NEXT tile are pulled into L2 while it works on the current one
+#endif
+
 template <int DIM, int NN, int NFN, int U0, int NC>
 struct NodeSlice {
   // operator products of one warp: rows (element, variable) x output nodes [U0, U0 + NC)
@@ -291,6 +300,17 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     double* sM = sQ + Cfg::QW;
     double* sX = sM + Cfg::MW;
     double* sR = r_tile(st);
+    if (QSB && PDES_TMA_L2PF && more && half == 0 && lane == 0) {
+      // single-buffered tiles are requested late (when their predecessor's rows have been consumed): have DRAM deliver them to
+      // L2 now, a whole tile period ahead, so that the bulk copies issued later are L2 hits
+      const int64_t e1 = tile_e0(t + W);
+      if (tile_ne(e1) == G) {
+        bulk_prefetch_l2(a.q + e1 * EL, Cfg::QW * 8);
+        bulk_prefetch_l2(a.fluxe + e1 * (NF * FL), Cfg::RW * 8);
+        if (MODE == EPI_RK) bulk_prefetch_l2(a.minv + e1 * NN, Cfg::MW * 8);
+        bulk_prefetch_l2(a.dxidx + e1 * a.dx_el_stride, Cfg::XW * 8);
+      }
+    }
     mbar_wait_sleep(&bars[st], (unsigned)(QSB ? (it & 1) : ((it >> 1) & 1)));
 
     // ---- S1 (node items, split over the group): density / pressure checks, pressure, U_d = dxidx[d,:].u ---------------
