@@ -1921,7 +1921,7 @@ int enqueue_lserk_step(PdesCtx* ctx, double h, double res_tol, int pseudo_time, 
   return PDES_OK;
 }
 
-// One full RK4 step as a CUDA graph (single-GPU, single-stream schedule): the ten launches of a step are
+// One full RK4 step as a CUDA graph: the nine launches of a step (at N > 1 with the fused halo: ten) are
 // captured once per buffer rotation (three graphs) and replayed; small meshes are launch-bound otherwise.
 int launch_rk4_step(PdesCtx* ctx, double h, bool with_norm, double res_tol, int pseudo_time) {
   // (collective one-time set-up of the peer-to-peer halo: not inside a capture)

@@ -50,8 +50,7 @@ struct __align__(16) FaceRec {
   uint8_t fL, fR, orient, kind;
   int32_t aux;       // boundary: BC functor id; shared: index into the receive buffer
 };
-enum FaceKind : uint8_t { FK_INTERIOR = 0, FK_BOUNDARY = 2, FK_SHARED = 3,
-                          FK_PACK = 4 /* k_face_tma only: a shared face in its send pass (never stored in the face list) */ };
+enum FaceKind : uint8_t { FK_INTERIOR = 0, FK_BOUNDARY = 2, FK_SHARED = 3 };
 
 struct Ctl {               // device-resident control block
   int32_t stop;            // kernels return immediately when set (physics error or res_tol reached)
