@@ -85,6 +85,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+#ifndef PDES_TMA_DYN
+#define PDES_TMA_DYN 1       // (0.890 -> 0.886 ms per step) tiles beyond a warp's first one are drawn from a device counter instead of a fixed stride
+#endif
 #ifndef PDES_TMA_L2PF
 #define PDES_TMA_L2PF 1      // QSB: the inputs of a warp's NEXT tile are pulled into L2 while it works on the current one
 #endif
@@ -285,14 +288,25 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
   // epilogue); a staggered start spreads the phases over the tile period
   if (a.stagger_ns > 0) __nanosleep((unsigned)(a.stagger_ns * (grp & 3)));
   int it = 0;
+  constexpr bool DYN = PDES_TMA_DYN != 0 && NS == 1;
+  // dynamic deal: the first tile of a warp is gw, every further one the next undealt tile (the draw for the tile after next is
+  // requested at the top of an iteration and consumed at its end: the atomic's latency is never exposed)
+  auto draw = [&]() -> int64_t {
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(a.tile_ctr, 1u);
+    return W + (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t tn = DYN ? draw() : gw + W;
 #pragma unroll 1
-  for (int64_t t = gw; t < ntiles; t += W, ++it) {
+  for (int64_t t = gw; t < ntiles; ++it) {
     int st = QSB ? 0 : (it & 1);
     asm volatile("" : "+r"(st));          // opaque: keeps ONE copy of the (fully unrolled) tile body in the instruction cache
-    const bool more = t + W < ntiles;
+    const bool more = tn < ntiles;
+    int64_t tn2 = tn + W;
+    if (DYN && more) tn2 = draw();
     if (more) {
-      if (!QSB) issue_q(t + W, st ^ 1);
-      if (!RSB) issue_r(t + W, st ^ 1);
+      if (!QSB) issue_q(tn, st ^ 1);
+      if (!RSB) issue_r(tn, st ^ 1);
     }
     const int64_t e0 = tile_e0(t);
     const int ne = tile_ne(e0);
@@ -303,7 +317,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     if (QSB && PDES_TMA_L2PF && more && half == 0 && lane == 0) {
       // single-buffered tiles are requested late (when their predecessor's rows have been consumed): have DRAM deliver them to
       // L2 now, a whole tile period ahead, so that the bulk copies issued later are L2 hits
-      const int64_t e1 = tile_e0(t + W);
+      const int64_t e1 = tile_e0(tn);
       if (tile_ne(e1) == G) {
         bulk_prefetch_l2(a.q + e1 * EL, Cfg::QW * 8);
         bulk_prefetch_l2(a.fluxe + e1 * (NF * FL), Cfg::RW * 8);
@@ -431,7 +445,7 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
     group_sync();              // every lane of the group has consumed its records and (U_d, p)
     // RSB: the record tile is free -- the next tile's records start to arrive while this tile is staged and written out;
     // the results are staged in the (dead) (U_d, p) tile.  Otherwise the (dead) record tile is the staging tile.
-    if (RSB && more) issue_r(t + W, 0);
+    if (RSB && more) issue_r(tn, 0);
     double* sOut = RSB ? sU : sR;
     if (act) {
 #pragma unroll
@@ -549,7 +563,14 @@ k_element_tma(const __grid_constant__ OpTabP<DIM, NN, NFN> op, const __grid_cons
       }
     }
     group_sync();              // the stage may be refilled by the next iteration's issue
-    if (QSB && more) issue_q(t + W, 0);
+    if (QSB && more) issue_q(tn, 0);
+    t = tn;
+    tn = tn2;
+  }
+  if (DYN && lane == 0) {
+    // the last warp to finish re-arms the counters for the next launch
+    const int64_t nwarps = ntiles < W ? ntiles : W;
+    if (atomicAdd(a.tile_ctr + 1, 1u) + 1u == (unsigned)nwarps) { a.tile_ctr[0] = 0u; a.tile_ctr[1] = 0u; }
   }
 }
 

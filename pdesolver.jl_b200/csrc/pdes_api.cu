@@ -1075,6 +1075,7 @@ struct PdesCtx {
   int prefetch_ahead_groups = 0, discard_records = 0, acquire_fence = 1;
   int rk4_nosum = 0;       // rk4 stages without the running sum of the k's (epilogue_tile scheme 2)
   int stagger_ns = 0;
+  unsigned* tile_ctr = nullptr;   // k_element_tma dynamic tile deal (PDES_TMA_DYN builds)
   int reverse_elems = 0, discard_split = 0;   // split kernels: element tiles swept last-to-first; consumed records dropped from L2
   // chunk pipeline (PDES_PIPE = number of chunks): F0 F1 E0 F2 E1 ... with programmatic dependent launches
   bool pipe = false;
@@ -1441,6 +1442,7 @@ void fill_args(PdesCtx* ctx, ElemArgs* a, const double* q) {
   a->prefetch_ahead = ctx->prefetch_ahead;
   a->reverse = ctx->reverse_elems;
   a->stagger_ns = ctx->stagger_ns;
+  a->tile_ctr = ctx->tile_ctr;
   a->discard_records = ctx->pipe ? ctx->pipe_discard : ctx->discard_split;
 }
 
@@ -2105,6 +2107,8 @@ int pdes_create(const PdesConfig* cfg, PdesCtx** out) {
   CUDA_TRY(c, cudaMalloc((void**)&c->ctl, sizeof(Ctl)));
   CUDA_TRY(c, cudaMallocHost((void**)&c->h_ctl, sizeof(Ctl)));
   CUDA_TRY(c, cudaMalloc((void**)&c->norm_sq, sizeof(double)));
+  CUDA_TRY(c, cudaMalloc((void**)&c->tile_ctr, 4 * sizeof(unsigned)));
+  CUDA_TRY(c, cudaMemset(c->tile_ctr, 0, 4 * sizeof(unsigned)));
   c->peers.resize(cfg->npeers > 0 ? cfg->npeers : 0);
   int rc = reset_ctl(c);
   if (rc) return rc;
@@ -2140,7 +2144,7 @@ void pdes_destroy(PdesCtx* ctx) {
   void* ptrs[] = {ctx->qbuf[0], ctx->qbuf[1], ctx->qbuf[2], ctx->ksum, ctx->res, ctx->dxidx, ctx->minv, ctx->srcw,
                   ctx->nrm_all, ctx->fluxe, ctx->srcm, ctx->faces, ctx->coords_bndry, ctx->w_dev, ctx->Q_dev,
                   ctx->q_send, ctx->q_recv, ctx->v_send, ctx->v_recv, ctx->el_send_list, ctx->qel_send, ctx->qel_recv, ctx->sh_el, ctx->sh_face, ctx->ctl, ctx->norm_partials,
-                  ctx->norm_sq, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
+                  ctx->norm_sq, ctx->tile_ctr, ctx->norms_dev, ctx->plan[0].tile_list, ctx->plan[0].need, ctx->plan[1].tile_list,
                   ctx->plan[1].need, ctx->flags, ctx->sched, ctx->mass, ctx->diag_buf, ctx->kry.V, ctx->kry.w, ctx->kry.b, ctx->kry.x,
                   ctx->kry.partials, ctx->kry.hdev, ctx->kry.gH, ctx->kry.gcs, ctx->kry.gsn, ctx->kry.gg, ctx->kry.gstate, ctx->kry.pc_blocks, ctx->kry.pcz, ctx->kry.pcu, ctx->kry.colour};
   for (void* p : ptrs) if (p) cudaFree(p);

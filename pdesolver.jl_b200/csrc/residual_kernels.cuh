@@ -156,6 +156,7 @@ struct ElemArgs {
   int32_t reverse;             // k_element_rk sweeps its tiles from the last to the first (see pdes_api.cu: L2 reuse)
   int32_t stagger_ns;          // k_element_tma: warp w starts (w mod 4) * stagger_ns later (de-synchronises the tile phases)
   unsigned* halo_epoch;        // fused halo (HaloArgs): the evaluation is complete -> ++*halo_epoch (block 0), or nullptr
+  unsigned* tile_ctr;          // k_element_tma, dynamic tile deal: {tiles handed out beyond the first round, warps finished}
   int64_t e_begin, nE;         // element range [e_begin, nE) of this launch (e_begin a multiple of the tile size)
   Ctl* ctl;
   PhysPar ph;
