@@ -167,6 +167,11 @@ void *pdes_stream(PdesCtx *ctx);
 /* evalResidual: q -> res (no Minv), synchronous.  euler.jl:111-175.  `t` is accepted for the signature's sake: every
  * restated source term and boundary functor (SRCExp, the eight BCs) is time independent, as in the named configurations. */
 int pdes_eval_residual(PdesCtx *ctx, double t);
+/* evalResidual with host arrays in one call: q[nd,nn,nE] in, res[nd,nn,nE] out (page-locked memory: pdes_pin_host).
+ * The evaluation is pipelined in chunks with the upload of q and the download of res (full-duplex PCIe), for the
+ * host-driven integrators that call evalResidual every stage; bit-identical to pdes_set_q + pdes_eval_residual +
+ * pdes_get_res, which is also what partitioned or small meshes fall back to. */
+int pdes_eval_residual_host(PdesCtx *ctx, const double *q, double *res, double t);
 /* same, but returns after enqueueing; pdes_sync reports errors (bench / overlap) */
 int pdes_eval_residual_async(PdesCtx *ctx, double t);
 int pdes_sync(PdesCtx *ctx);

@@ -37,6 +37,7 @@ EXPORTS = [
     "pdes_set_q_dev", "pdes_stream", "pdes_pin_host", "pdes_unpin_host", "pdes_eval_jvp", "pdes_lserk54",
     "pdes_newton_krylov", "pdes_gmres", "pdes_diagnostics",
     "pdes_set_peer_elements", "pdes_pack_send_elements", "pdes_inject_recv_elements", "pdes_set_krylov_pc",
+    "pdes_eval_residual_host",
 ]
 
 
@@ -95,6 +96,7 @@ def lib():
         L.pdes_get_unique_id.argtypes = [p]
         L.pdes_set_comm.argtypes = [p, p, i32, i32]
         L.pdes_set_krylov_pc.argtypes = [p, i32]
+        L.pdes_eval_residual_host.argtypes = [p, p, p, C.c_double]
         L.pdes_set_peer_elements.argtypes = [p, i32, i64, p, i64, i64]
         L.pdes_pack_send_elements.argtypes = [p, i32, p]
         L.pdes_inject_recv_elements.argtypes = [p, i32, p]

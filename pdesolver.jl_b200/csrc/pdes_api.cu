@@ -1076,6 +1076,16 @@ struct PdesCtx {
   int rk4_nosum = 0;       // rk4 stages without the running sum of the k's (epilogue_tile scheme 2)
   int stagger_ns = 0;
   unsigned* tile_ctr = nullptr;   // k_element_tma dynamic tile deal (PDES_TMA_DYN builds)
+  // pdes_eval_residual_host: evaluation pipelined with the upload of q and the download of res (HC chunks)
+#ifndef PDES_HOST_CHUNKS
+#define PDES_HOST_CHUNKS 8
+#endif
+  static const int HC = PDES_HOST_CHUNKS;
+  int host_chunks = 0;            // 0: not possible for this context (partitioned mesh, too small, other schedule)
+  int64_t hc_e[HC + 1] = {0}, hc_g[HC + 1] = {0};
+  int hc_updep[HC] = {0};
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t ev_up[HC] = {nullptr}, ev_el[HC] = {nullptr}, ev_idle = nullptr;
   int reverse_elems = 0, discard_split = 0;   // split kernels: element tiles swept last-to-first; consumed records dropped from L2
   // chunk pipeline (PDES_PIPE = number of chunks): F0 F1 E0 F2 E1 ... with programmatic dependent launches
   bool pipe = false;
@@ -1363,6 +1373,38 @@ int finalize(PdesCtx* ctx) {
       CUDA_TRY(ctx, dev_upload<unsigned>(ctx->stream, &ctx->flags, nullptr, nflags));
       Sched s0{0u, 0u, 0u, 1u};
       CUDA_TRY(ctx, dev_upload(ctx->stream, &ctx->sched, &s0, 1));
+    }
+  }
+  {
+    // chunks of pdes_eval_residual_host: HC element ranges of whole tiles; the faces whose lowest element lies in range k
+    // (the face list is sorted by it) form face chunk k; hc_updep[k] = the last element chunk those faces read
+    ctx->host_chunks = 0;
+    const int tile = ctx->ops->tile_elems();
+    const int64_t ntiles = (c.nE + tile - 1) / tile, nIB = c.nF + c.nB;
+    if (ctx->nS == 0 && ctx->nchunks == 1 && !ctx->fused && !ctx->pipe && ntiles >= 64 * PdesCtx::HC) {
+      auto key = [&](int64_t g) {
+        const FaceRec& r = faces[g];
+        return (r.kind == FK_INTERIOR && r.elR < r.elL) ? r.elR : r.elL;
+      };
+      int64_t g = 0;
+      for (int k = 0; k <= PdesCtx::HC; ++k) {
+        const int64_t e = k == PdesCtx::HC ? c.nE : (ntiles * k / PdesCtx::HC) * tile;
+        ctx->hc_e[k] = e;
+        while (g < nIB && key(g) < e) ++g;
+        ctx->hc_g[k] = k == PdesCtx::HC ? nIB : g;
+      }
+      ctx->hc_g[0] = 0;
+      for (int k = 0; k < PdesCtx::HC; ++k) {
+        int64_t emax = 0;
+        for (int64_t gg = ctx->hc_g[k]; gg < ctx->hc_g[k + 1]; ++gg) {
+          emax = std::max<int64_t>(emax, faces[gg].elL);
+          if (faces[gg].kind == FK_INTERIOR) emax = std::max<int64_t>(emax, faces[gg].elR);
+        }
+        int d = k;
+        while (d + 1 < PdesCtx::HC && ctx->hc_e[d + 1] <= emax) ++d;
+        ctx->hc_updep[k] = d;
+      }
+      ctx->host_chunks = PdesCtx::HC;
     }
   }
   for (int64_t e = 0; e < c.nE; ++e)
@@ -2159,6 +2201,13 @@ void pdes_destroy(PdesCtx* ctx) {
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   for (int i = 0; i < PdesCtx::MAXC; ++i) if (ctx->ev_face[i]) cudaEventDestroy(ctx->ev_face[i]);
   if (ctx->ev_elem) cudaEventDestroy(ctx->ev_elem);
+  for (int k = 0; k < PdesCtx::HC; ++k) {
+    if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
+    if (ctx->ev_el[k]) cudaEventDestroy(ctx->ev_el[k]);
+  }
+  if (ctx->ev_idle) cudaEventDestroy(ctx->ev_idle);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
   if (ctx->face_stream) cudaStreamDestroy(ctx->face_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -2510,6 +2559,83 @@ int pdes_eval_residual(PdesCtx* ctx, double t) {
   rc = pdes_sync(ctx);
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) ctx->tm.t_func += ms * 1e-3;   // Timings.t_func
+  return rc;
+}
+
+// evalResidual with host arrays in ONE call: the evaluation is cut into HC element / face chunks and pipelined with the
+// copies -- chunk k of q goes up while the faces and elements of the chunks before it are evaluated, chunk k of res comes
+// down (PCIe is full duplex) as soon as its elements are done.  A host-driven time integrator pays ~max(upload, download)
+// instead of upload + evaluation + download per call.  Same kernels on sub-ranges: bit-identical to pdes_set_q +
+// pdes_eval_residual + pdes_get_res, which is also the fall-back (partitioned meshes, small meshes).
+int pdes_eval_residual_host(PdesCtx* ctx, const double* q, double* res, double t) {
+  if (!ctx || !q || !res) return usage(ctx, "pdes_eval_residual_host: null argument");
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  static const bool pipelined = env_int("PDES_HOST_PIPE", 1) != 0;
+  if (!ctx->host_chunks || !pipelined) {
+    if ((rc = pdes_set_q(ctx, q))) return rc;
+    if ((rc = pdes_eval_residual(ctx, t))) return rc;
+    return pdes_get_res(ctx, res);
+  }
+  const int HC = PdesCtx::HC;
+  if (!ctx->up_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_idle, cudaEventDisableTiming));
+    for (int k = 0; k < HC; ++k) {
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_el[k], cudaEventDisableTiming));
+    }
+  }
+  const PdesConfig& c = ctx->cfg;
+  const size_t el = (size_t)c.nn * ctx->nd;
+  double* qd = ctx->qbuf[ctx->cur];
+  cudaEventRecord(ctx->ev_t0, ctx->stream);
+  // nothing enqueued earlier may still read the state buffer or write res
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_idle, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->up_stream, ctx->ev_idle, 0));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->ev_idle, 0));
+  for (int k = 0; k < HC; ++k) {
+    const size_t o = (size_t)ctx->hc_e[k] * el, n = (size_t)(ctx->hc_e[k + 1] - ctx->hc_e[k]) * el;
+    CUDA_TRY(ctx, cudaMemcpyAsync(qd + o, q + o, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->up_stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up[k], ctx->up_stream));
+  }
+  ElemArgs a;
+  fill_args(ctx, &a, qd);
+  a.res = ctx->res;
+  FaceArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.q = a.q; fa.faces = ctx->faces; fa.nrm = ctx->nrm_all; fa.coords_bndry = ctx->coords_bndry;
+  fa.q_recv = ctx->q_recv; fa.fluxe = ctx->fluxe; fa.ctl = ctx->ctl; fa.ph = a.ph;
+  fa.nrm_face_stride = ctx->nrm_compact ? c.dim : c.nfn * c.dim;
+  fa.nrm_node_stride = ctx->nrm_compact ? 0 : c.dim;
+  fa.prefetch_ahead = ctx->prefetch_ahead_faces;
+  fa.ext_bc = ctx->has_ext_bc ? 1 : 0;
+  int up_done = -1;
+  for (int k = 0; k < HC; ++k) {
+    if (ctx->hc_updep[k] > up_done) {
+      up_done = ctx->hc_updep[k];
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[up_done], 0));     // (uploads complete in order)
+    }
+    fa.g0 = ctx->hc_g[k]; fa.ng = ctx->hc_g[k + 1] - ctx->hc_g[k];
+    CUDA_TRY(ctx, ctx->ops->launch_faces(fa, ctx->stream));
+    a.e_begin = ctx->hc_e[k]; a.nE = ctx->hc_e[k + 1];
+    CUDA_TRY(ctx, ctx->ops->launch_elements(a, EPI_RES, ctx->stream));
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_el[k], ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->ev_el[k], 0));
+    const size_t o = (size_t)ctx->hc_e[k] * el, n = (size_t)(ctx->hc_e[k + 1] - ctx->hc_e[k]) * el;
+    CUDA_TRY(ctx, cudaMemcpyAsync(res + o, ctx->res + o, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->down_stream));
+  }
+  ctx->n_evals++;
+  cudaEventRecord(ctx->ev_t1, ctx->stream);
+  // the compute stream must not run ahead of the copies it shares buffers with
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->up_stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->down_stream));
+  rc = pdes_sync(ctx);
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) ctx->tm.t_func += ms * 1e-3;
   return rc;
 }
 

@@ -214,9 +214,8 @@ def evalResidual(mesh, sbp, eqn: EulerData, opts, t=0.0):
     """``evalResidual(mesh, sbp, eqn, opts, t)`` of the Euler module (euler.jl:111-175)."""
     eqn.params.t = t
     L, ctx = eqn._L, eqn._ctx
-    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
-    eqn._check(L.pdes_eval_residual(ctx, float(t)))
-    eqn._check(L.pdes_get_res(ctx, _ptr(eqn.res)))
+    # one call: eqn.q up, R(q), eqn.res down -- pipelined in chunks with the copies where the mesh allows it
+    eqn._check(L.pdes_eval_residual_host(ctx, _ptr(eqn.q), _ptr(eqn.res), float(t)))
     return None
 
 

@@ -1144,3 +1144,40 @@ def test_entropy_stable_jacobian_vector_product(case, n):
     rn = np.linalg.norm(pd.evaldRdqProduct(mesh, op, eqn, opts, x) - b)
     assert eqn.krylov_info["reason"] in (1, -1) and rn < np.linalg.norm(b)
     assert abs(rn - eqn.krylov_info["rnorm"]) < 1e-6 * np.linalg.norm(b) or eqn.krylov_info["reason"] == 1
+
+
+@pytest.mark.parametrize("case,n", [("c3_3d_p2_roe_src", 9), ("2d_p2_roe", 60), ("c2_2d_p2_es", 48), ("3d_p2_alt_roe_src", 9)])
+def test_pipelined_host_evaluation_is_bit_identical(case, n):
+    """pdes_eval_residual_host (what evalResidual calls): the evaluation cut into eight element / face chunks and pipelined
+    with the upload of q and the download of res must return exactly what pdes_set_q + pdes_eval_residual + pdes_get_res
+    return (same kernels on sub-ranges), match the oracle, and keep the reference's error semantics."""
+    op, mesh, opts, orc, q0, eqn = setup(case, n, shuffle_seed=8)
+    L, ctx = eqn._L, eqn._ctx
+    from pdesolver_jl_b200.euler import _ptr
+    eqn.q[...] = q0
+    eqn._check(L.pdes_set_q(ctx, _ptr(eqn.q)))
+    eqn._check(L.pdes_eval_residual(ctx, 0.0))
+    eqn._check(L.pdes_get_res(ctx, _ptr(eqn.res)))
+    res3 = eqn.res.copy(order="F")
+    n0 = eqn.kernel_launch_count()
+    eqn.res[...] = 0.0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert eqn.kernel_launch_count() - n0 == 16, "the pipelined path was not taken"      # 8 chunks x (faces, elements)
+    assert np.array_equal(eqn.res, res3)
+    assert rel_l2(eqn.res, orc.eval_residual(q0)) < RES_TOL
+    # a second evaluation right behind the first (buffers are reused while copies may still be in flight)
+    q1 = perturbed(q0, amp=2e-3)
+    eqn.q[...] = q1
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert rel_l2(eqn.res, orc.eval_residual(q1)) < RES_TOL
+    # negative density in the last chunk
+    bad = q0.copy(order="F")
+    e_bad = mesh.numEl - 3
+    bad[0, 1, e_bad] = -1.0
+    eqn.q[...] = bad
+    with pytest.raises(pd.PhysicsError) as ei:
+        pd.evalResidual(mesh, op, eqn, opts)
+    assert (ei.value.element, ei.value.node) == (e_bad, 1)
+    eqn.q[...] = q0
+    pd.evalResidual(mesh, op, eqn, opts)
+    assert np.array_equal(eqn.res, res3)
