@@ -122,14 +122,15 @@ k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y
 // device until the end of the restart cycle.
 struct GmresState {
   double rnorm, bnorm;
+  double reltol, abstol, dtol;   // (in device memory, not kernel arguments: the captured graph of an iteration serves every solve)
   long long its, itermax;
   int32_t reason, jdone;      // jdone: columns of the current cycle that are complete
 };
 __global__ void k_gmres_update(int j, int m, const double* __restrict__ h1, const double* __restrict__ h2,
                                const double* __restrict__ nq, double* __restrict__ H, double* __restrict__ cs,
-                               double* __restrict__ sn, double* __restrict__ g, GmresState* st, double reltol, double abstol,
-                               double dtol, int* done) {
+                               double* __restrict__ sn, double* __restrict__ g, GmresState* st, int* done) {
   if (*done) return;
+  const double reltol = st->reltol, abstol = st->abstol, dtol = st->dtol;
   for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = h1[i] + h2[i];
   const double hn = sqrt(*nq);
   H[(size_t)(j + 1) * m + j] = hn;

@@ -1105,6 +1105,10 @@ struct PdesCtx {
     double *gH = nullptr, *gcs = nullptr, *gsn = nullptr, *gg = nullptr;
     GmresState* gstate = nullptr;
     GmresState* hstate = nullptr;   // pinned
+    // one CUDA graph per Krylov iteration j of a restart cycle (its ~12 launches differ only in j): captured on first use,
+    // replayed by every later cycle and solve; key = (restart, preconditioner, state buffer)
+    std::vector<cudaGraphExec_t> itg;
+    int itg_pc = -1, itg_cur = -1;
     // element-block Jacobi right preconditioner (pdes_set_krylov_pc)
     int pc_type = 0, ncolours = 0;
     bool pc_ready = false;
@@ -1447,6 +1451,8 @@ int finalize(PdesCtx* ctx) {
   CUDA_TRY(ctx, dev_upload<double>(ctx->stream, &ctx->norm_partials, nullptr, (size_t)ctx->ops->grid_for(c.nE)));
   for (int i = 0; i < 3; ++i)
     if (ctx->step_graph[i]) { cudaGraphExecDestroy(ctx->step_graph[i]); ctx->step_graph[i] = nullptr; }
+  for (cudaGraphExec_t ge : ctx->kry.itg) if (ge) cudaGraphExecDestroy(ge);      // (captured with the old device arrays)
+  ctx->kry.itg.clear();
   ctx->no_graph = env_int("PDES_NO_GRAPH", 0) != 0;
   CUDA_TRY(ctx, ctx->ops->prepare());
   ctx->prefetch_ahead = env_int("PDES_PREFETCH_AHEAD", ctx->ops->resident_element_ctas() / 8);   // measured optimum: ~half a wave
@@ -2192,6 +2198,7 @@ void pdes_destroy(PdesCtx* ctx) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->kry.hhost) cudaFreeHost(ctx->kry.hhost);
   if (ctx->kry.hstate) cudaFreeHost(ctx->kry.hstate);
+  for (cudaGraphExec_t ge : ctx->kry.itg) if (ge) cudaGraphExecDestroy(ge);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
   if (ctx->ev_q) cudaEventDestroy(ctx->ev_q);
@@ -2811,6 +2818,8 @@ int kry_alloc(PdesCtx* ctx, int restart) {
   for (void* p : old) if (p) cudaFree(p);
   if (k.hhost) cudaFreeHost(k.hhost);
   if (k.hstate) cudaFreeHost(k.hstate);
+  for (cudaGraphExec_t ge : k.itg) if (ge) cudaGraphExecDestroy(ge);     // (they hold the old buffers)
+  k.itg.clear();
   {
     // (the preconditioner's buffers do not depend on the restart length)
     PdesCtx::Krylov fresh;
@@ -2936,6 +2945,17 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
   cudaStream_t st = ctx->stream;
   std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1), y(m);
   int* done = &ctx->ctl->kry_done;
+  // CUDA graph per iteration (one GPU: the partitioned J*v carries NCCL calls); cache valid for this (restart, pc, buffer)
+  const bool use_graph = !ctx->no_graph && !ctx->comm && ctx->nS == 0;
+  if (use_graph && ((int)k.itg.size() != m || k.itg_pc != (pc ? 1 : 0) || k.itg_cur != ctx->cur)) {
+    for (cudaGraphExec_t ge : k.itg) if (ge) cudaGraphExecDestroy(ge);
+    k.itg.assign(m, nullptr);
+    k.itg_pc = pc ? 1 : 0; k.itg_cur = ctx->cur;
+    // one product outside any capture: one-time set-up of the J*v kernels (table uploads, function attributes) must not
+    // happen while a stream is capturing
+    rc = enqueue_jvp(ctx, b, k.w);
+    if (rc) return rc;
+  }
   // iterations enqueued per poll of the device-side solver state (PDES_GMRES_POLL; 1 = a read-back per iteration)
   static const int poll = std::max(1, env_int("PDES_GMRES_POLL", 8));
   CUDA_TRY(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, st));
@@ -2977,6 +2997,7 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
       g[0] = beta;
       GmresState hs;
       hs.rnorm = beta; hs.bnorm = bnorm; hs.its = its; hs.itermax = itermax; hs.reason = 0; hs.jdone = 0;
+      hs.reltol = reltol; hs.abstol = abstol; hs.dtol = dtol;
       *k.hstate = hs;
       CUDA_TRY(ctx, cudaMemcpyAsync(k.gstate, k.hstate, sizeof(GmresState), cudaMemcpyHostToDevice, st));
       CUDA_TRY(ctx, cudaMemcpyAsync(k.gg, g.data(), sizeof(double) * (m + 1), cudaMemcpyHostToDevice, st));
@@ -2987,25 +3008,47 @@ int gmres_dev(PdesCtx* ctx, const double* b, double* x, double reltol, double ab
       const int jb = std::min(poll, m - j);
       for (int u = 0; u < jb; ++u) {
         const int jj = j + u;
-        if (pc) {
-          k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.V + (size_t)jj * n, k.pcz, done);
-          ctx->launches++;
+        auto enqueue_iteration = [&]() -> int {
+          int rci;
+          if (pc) {
+            k_block_apply<<<nb, KRY_T, 0, st>>>(k.pc_blocks, EL, ctx->cfg.nE, k.V + (size_t)jj * n, k.pcz, done);
+            ctx->launches++;
+          }
+          rci = enqueue_jvp(ctx, pc ? k.pcz : k.V + (size_t)jj * n, k.w);
+          if (rci) return rci;
+          rci = kry_dots(ctx, k.V, jj + 1, k.w, h1, done);
+          if (rci) return rci;
+          k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h1, -1.0, k.w, n, done);
+          rci = kry_dots(ctx, k.V, jj + 1, k.w, h2, done);
+          if (rci) return rci;
+          k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h2, -1.0, k.w, n, done);
+          rci = kry_dots(ctx, k.w, 1, k.w, nq, done);
+          if (rci) return rci;
+          k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V + (size_t)(jj + 1) * n, n, done);
+          // Hessenberg column, rotations, residual norm and the stopping tests: on the device, no read-back
+          k_gmres_update<<<1, 1, 0, st>>>(jj, m, h1, h2, nq, k.gH, k.gcs, k.gsn, k.gg, k.gstate, done);
+          if (cudaGetLastError() != cudaSuccess) return PDES_ERR_CUDA;
+          ctx->launches += 4;
+          return PDES_OK;
+        };
+        if (!use_graph) {
+          rc = enqueue_iteration();
+          if (rc) { if (rc == PDES_ERR_CUDA) set_err(ctx, "GMRES iteration launch failed"); return rc; }
+          continue;
         }
-        rc = enqueue_jvp(ctx, pc ? k.pcz : k.V + (size_t)jj * n, k.w);
-        if (rc) return rc;
-        rc = kry_dots(ctx, k.V, jj + 1, k.w, h1, done);
-        if (rc) return rc;
-        k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h1, -1.0, k.w, n, done);
-        rc = kry_dots(ctx, k.V, jj + 1, k.w, h2, done);
-        if (rc) return rc;
-        k_multi_axpy<<<nb, KRY_T, 0, st>>>(k.V, n, jj + 1, h2, -1.0, k.w, n, done);
-        rc = kry_dots(ctx, k.w, 1, k.w, nq, done);
-        if (rc) return rc;
-        k_normalize<<<nb, KRY_T, 0, st>>>(k.w, nq, k.V + (size_t)(jj + 1) * n, n, done);
-        // Hessenberg column, rotations, residual norm and the stopping tests: on the device, no read-back
-        k_gmres_update<<<1, 1, 0, st>>>(jj, m, h1, h2, nq, k.gH, k.gcs, k.gsn, k.gg, k.gstate, reltol, abstol, dtol, done);
-        CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches += 4;
+        if (!k.itg[jj]) {
+          const int64_t l0 = ctx->launches;
+          cudaGraph_t gr = nullptr;
+          CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          rc = enqueue_iteration();
+          cudaError_t ce = cudaStreamEndCapture(st, &gr);
+          ctx->launches = l0;
+          if (rc || ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); if (!rc) { CUDA_TRY(ctx, ce); } return rc; }
+          CUDA_TRY(ctx, cudaGraphInstantiate(&k.itg[jj], gr, 0));
+          cudaGraphDestroy(gr);
+        }
+        CUDA_TRY(ctx, cudaGraphLaunch(k.itg[jj], st));
+        ctx->launches += pc ? 13 : 12;
       }
       CUDA_TRY(ctx, cudaMemcpyAsync(k.hstate, k.gstate, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(ctx, cudaStreamSynchronize(st));
