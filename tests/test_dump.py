@@ -70,3 +70,24 @@ def test_julia_dump_gpu():
     eqn.q[...] = q
     pd.evalResidual(m, s, eqn, o)
     assert rel_l2(eqn.res, r) < 1e-12
+
+
+def test_julia_dump_script_matches_the_schema():
+    """tools/dump_pdesolver.jl cannot run here (no Julia): at least its record count and record names must agree with what the
+    Python writer of the same schema emits, so that load_dump finds every record it needs."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "tools", "dump_pdesolver.jl")).read()
+    body = jl[jl.index('write(io, "PDSDUMP1")'):]
+    declared = int(re.search(r'write\(io, "PDSDUMP1"\); write\(io, Int32\((\d+)\)\)', body).group(1))
+    names = re.findall(r'wrec\(io, "([A-Za-z_]+)"', body)
+    assert declared == len(names), (declared, names)
+    op = pd.build_operator(2, 1)
+    mesh = pd.structured_mesh(op, 2)
+    opts = {"Flux_name": "RoeFlux", "BC1_name": "isentropicVortexBC"}
+    q = np.zeros((4, 3, mesh.numEl), order="F")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "x.pds")
+        dump.save_dump(f, mesh, op, opts, q, q)
+        assert sorted(dump.read_records(f)) == sorted(names)
