@@ -211,6 +211,7 @@ struct OpsImpl : Ops {
   static_assert(32 / (2 * FWCfg::FW) >= 1, "k_face_tma: at least one copy lane per staged element");
   TabF tabf;
   bool use_tma_face = true;
+  bool face_small = true;
   template <bool EXTBC>
   cudaError_t launch_faces_tma(const FaceArgs& a, cudaStream_t s) {
     const int64_t ntiles = (a.ng + FWCfg::FW - 1) / FWCfg::FW;      // (ng includes the shared faces: >= the send tiles)
@@ -248,6 +249,7 @@ struct OpsImpl : Ops {
       for (int i = 0; i < NFN; ++i) tab.nbrperm[o][i] = (int)(nbrperm[i + NFN * o] - base);
     use_tma_face = env_int("PDES_FACE_WTMA", 1) != 0 && env_int("PDES_FUSED", 0) == 0 && env_int("PDES_PIPE", 0) <= 1 &&
                    env_int("PDES_FACE_TMA", 0) == 0 && env_int("PDES_FACE_W", 0) == 0 && env_int("PDES_FACE_P", 0) == 0;
+    face_small = env_int("PDES_FACE_SMALL", 1) != 0;
     memset(&tabf, 0, sizeof(tabf));
     for (int j = 0; j < NN; ++j)
       for (int i = 0; i < NFN; ++i) tabf.interp[j][i] = tab.interp[j][i];
@@ -337,7 +339,12 @@ struct OpsImpl : Ops {
     if (a.ng <= 0) return cudaSuccess;
     if (use_tma_face) {
       { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
-      return a.ext_bc ? launch_faces_tma<true>(a, s) : launch_faces_tma<false>(a, s);
+      // a launch with less than one tile per resident warp has nothing to pipeline: the plain tile kernel (same arithmetic,
+      // bit-identical records) starts 1.5 us sooner -- C1 (7,600 faces): 51.2 instead of 57.4 us per RK4 step
+      // (profiles/r2_c1_small_mesh_ab.txt).  PDES_FACE_SMALL=0 keeps the persistent kernel at every size (the tests do).
+      const bool small = face_small && !a.halo.on && (a.ng + FWCfg::FW - 1) / FWCfg::FW < (int64_t)NWF * sm_count;
+      if (!small) return a.ext_bc ? launch_faces_tma<true>(a, s) : launch_faces_tma<false>(a, s);
+      a.tab_dev = d_ftab;          // (allocated by prepare())
     }
     const int64_t ntiles = (a.ng + FT - 1) / FT;
     if (a.ext_bc) {

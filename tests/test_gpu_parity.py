@@ -910,12 +910,15 @@ def test_face_kernel_variants_bitwise_equal():
             "print('DIGEST', h.hexdigest())\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                    os.path.dirname(os.path.abspath(__file__)))
     digests = {}
-    for name, env in (("base", {}), ("warp", {"PDES_FACE_W": "2"}), ("persistent", {"PDES_FACE_P": "8"})):
+    for name, env in (("base", {}), ("warp", {"PDES_FACE_W": "2"}), ("persistent", {"PDES_FACE_P": "8"}),
+                      ("small", {"PDES_FACE_SMALL": "1"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                            env=dict(os.environ, **env))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         digests[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert digests["warp"] == digests["base"] and digests["persistent"] == digests["base"]
+    # the product default: launches with less than one tile per warp leave the persistent kernel for the plain one
+    assert digests["small"] == digests["base"]
 
 
 @pytest.mark.parametrize("bc", ["noPenetrationESBC", "Rho1E2U3BC", "ZeroFluxBC"])
